@@ -1,0 +1,142 @@
+"""Generate the committed golden vectors.  Run HERE (the build container), where
+/root/reference exists; the GPU box only reads the .npz files.
+
+    python tests/golden/make_golden.py
+
+1. heads_golden.npz -- outputs of the REFERENCE's own loss / metric functions on
+   seeded inputs.  The reference scripts run a training job at import time, so the
+   functions are lifted out of their source files by AST (only the named ``def``s
+   are compiled; no other reference statement runs):
+     angle_prediction/dinov2salad/dino_v2_gemini.py   angular_regression_loss, prediction_to_angle_deg
+     angle_prediction/dinov2salad/dino_angle_finetuning.py   angular_regression_loss (scalar variant)
+     angle_prediction/swin/swin_angle_finetuning_sin_cos.py   angular_loss, compute_angle_error
+     angle_prediction/swin/swin_angle_finetuning_gemini.py    mean_absolute_angular_error
+   plus torch's own nn.MSELoss / nn.HuberLoss(delta=1) which the reference
+   instantiates directly (dinov2salad_finetuning.py:96, dinov2salad_finetuning_2.py:154),
+   and the validation score expression of dinov2salad_validation.py:101 evaluated
+   with numpy exactly as written there.
+2. salad_golden.npz -- outputs of the CPU oracle (oracle/salad_ref.py) on seeded
+   inputs: regression fixtures for the restated SALAD (parity unpinned upstream).
+"""
+import ast
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F  # noqa: F401  (used by extracted functions)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+
+def lift(path, names):
+    """Compile only the named top-level functions of a reference script."""
+    src = open(os.path.join(REF, path)).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert len(keep) == len(names), (path, names, [k.name for k in keep])
+    mod = ast.Module(body=keep, type_ignores=[])
+    ns = {"torch": torch, "F": F, "np": np}
+    exec(compile(mod, path, "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def heads_inputs():
+    g = torch.Generator().manual_seed(20261018)
+    B = 37
+    sc = torch.randn(B, 2, generator=g)
+    sc[3] = torch.tensor([0.0, -1.0])          # atan2 branch cut neighbourhood
+    sc[4] = torch.tensor([1e-4, -2.0])
+    sc[5] = torch.tensor([-1e-4, -2.0])
+    tgt_deg = torch.rand(B, generator=g) * 750.0   # labels go up to 750 deg (SURVEY D-8)
+    pred_deg = torch.randn(B, generator=g) * 400.0
+    ll_pred = torch.randn(B, 2, generator=g) * 2.0
+    ll_tgt = torch.randn(B, 2, generator=g)
+    return sc, tgt_deg, pred_deg, ll_pred, ll_tgt
+
+
+def make_heads():
+    sc, tgt_deg, pred_deg, ll_pred, ll_tgt = heads_inputs()
+    (maae_deg, to_deg) = lift("angle_prediction/dinov2salad/dino_v2_gemini.py",
+                              ["angular_regression_loss", "prediction_to_angle_deg"])
+    (maae_scalar,) = lift("angle_prediction/dinov2salad/dino_angle_finetuning.py",
+                          ["angular_regression_loss"])
+    (acos_loss, angle_err) = lift("angle_prediction/swin/swin_angle_finetuning_sin_cos.py",
+                                  ["angular_loss", "compute_angle_error"])
+    (maae_sc,) = lift("angle_prediction/swin/swin_angle_finetuning_gemini.py",
+                      ["mean_absolute_angular_error"])
+    out = {}
+    out["deg_from_sincos"] = to_deg(sc).numpy()
+    out["maae_deg"] = maae_deg(pred_deg, tgt_deg).numpy()
+    out["maae_atan2"] = maae_deg(to_deg(sc), tgt_deg).numpy()
+    out["maae_scalar"] = maae_scalar(pred_deg % 360, tgt_deg).numpy()
+    r = torch.deg2rad(tgt_deg % 360)
+    tgt_sc = torch.stack([torch.sin(r), torch.cos(r)], dim=1)
+    unit = F.normalize(sc, dim=1, p=2, eps=1e-6)     # swin_angle_finetuning_sin_cos.py:62
+    out["acos_loss"] = acos_loss(unit, tgt_sc).numpy()
+    out["angle_err_atan2"] = angle_err(unit, tgt_sc).numpy()
+    out["maae_sincos_metric"] = maae_sc(sc, tgt_sc).numpy()
+    out["mse"] = torch.nn.MSELoss()(ll_pred, ll_tgt).numpy()
+    out["huber"] = torch.nn.HuberLoss(delta=1.0)(ll_pred, ll_tgt).numpy()
+    out["mse_sincos"] = torch.nn.MSELoss()(sc, tgt_sc).numpy()
+    # dinov2salad_validation.py:96-101, evaluated with numpy as written there
+    all_preds, all_targets = ll_pred.numpy(), ll_tgt.numpy()
+    out["val_score"] = np.asarray(
+        0.5 * (np.sum((all_preds[:, 0] - all_targets[:, 0]) ** 2)
+               + np.sum((all_preds[:, 1] - all_targets[:, 1]) ** 2)) / len(all_preds))
+    # gradients of the differentiable losses w.r.t. the head output (autograd through the
+    # reference functions themselves)
+    for name, fn in (("maae_atan2", lambda s: maae_deg(to_deg(s), tgt_deg)),
+                     ("acos_loss", lambda s: acos_loss(F.normalize(s, dim=1, p=2, eps=1e-6), tgt_sc)),
+                     ("mse_sincos", lambda s: torch.nn.MSELoss()(s, tgt_sc))):
+        s = sc.clone().requires_grad_(True)
+        fn(s).backward()
+        out["grad_" + name] = s.grad.numpy()
+    for name, fn in (("mse", torch.nn.MSELoss()), ("huber", torch.nn.HuberLoss(delta=1.0))):
+        p = ll_pred.clone().requires_grad_(True)
+        fn(p, ll_tgt).backward()
+        out["grad_" + name] = p.grad.numpy()
+    np.savez(os.path.join(HERE, "heads_golden.npz"), **out)
+    print("heads_golden.npz:", sorted(out))
+
+
+def salad_case(B, hw, seed):
+    from oracle.salad_ref import SaladRef, tokens_to_salad_input
+    torch.manual_seed(0)
+    mod = SaladRef(dropout=0.0)
+    g = torch.Generator().manual_seed(seed)
+    n = hw * hw
+    x = torch.randn(B, n, 768, generator=g)
+    t = torch.randn(B, 768, generator=g)
+    x.requires_grad_(True)
+    t.requires_grad_(True)
+    w = torch.randn(B, 8448, generator=g)
+    out = mod((tokens_to_salad_input(x, hw, hw), t))
+    (out * w).sum().backward()
+    return {
+        "desc": out.detach().numpy(),
+        "dx_rows": x.grad[:, :4].numpy().copy(),          # first 4 tokens of each image
+        "dt": t.grad.numpy(),
+        "g_score3_w": mod.score[3].weight.grad.flatten().numpy()[:4096].copy(),
+        "g_cluster0_b": mod.cluster_features[0].bias.grad.numpy(),
+        "g_token2_w_norm": np.asarray(mod.token_features[2].weight.grad.norm().item()),
+        "g_dust_bin": np.asarray(mod.dust_bin.grad.item()),
+    }
+
+
+def make_salad():
+    out = {}
+    for tag, (B, hw, seed) in {"n256": (2, 16, 1234), "n529": (2, 23, 4321)}.items():
+        for k, v in salad_case(B, hw, seed).items():
+            out[f"{tag}_{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "salad_golden.npz"), **out)
+    print("salad_golden.npz:", sorted(out))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    make_heads()
+    make_salad()
