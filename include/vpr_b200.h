@@ -1,0 +1,180 @@
+/* C-ABI of libvpr_b200.so: the B200 (sm_100a) implementation of the one hot path of
+ * anshium/visual-place-recognition-and-geopose-estimation -- SALAD aggregation head
+ * (forward + backward), geopose heads + losses, descriptor kNN.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer owned by the caller (PyTorch); the library
+ *    allocates nothing and keeps no state besides lazily-set kernel attributes.
+ *  - Every call is asynchronous on `stream`, re-entrant and does not synchronise.
+ *  - Return value 0 = success; otherwise vpr_last_error() (thread-local) explains.
+ *  - dtype: VPR_F32 = fp32 storage + fp32 FMA GEMMs (1e-4 parity mode),
+ *           VPR_BF16 = bf16 storage, tcgen05 bf16 GEMMs with fp32 accumulation;
+ *           Sinkhorn, norms and losses always compute in fp32.
+ *
+ * Reference interfaces replaced (paths under the reference repo):
+ *  - vpr_salad_fwd            : the aggregator call inside `self.feature_extractor(x)`,
+ *                               dinov2salad/dinov2salad_finetuning.py:36 and
+ *                               dinov2salad/dinov2salad_validation.py:81, i.e. upstream
+ *                               serizba/salad SALAD.forward reached through
+ *                               torch.hub.load (dinov2salad_finetuning.py:19,92).
+ *  - vpr_salad_bwd            : autograd through that call (the reference freezes it,
+ *                               dinov2salad_finetuning.py:25-26,35; north-star adds backward).
+ *  - vpr_sinkhorn_fwd / _bwd  : upstream get_matching_probs / log_otp_solver.
+ *  - vpr_heads_loss_fwd_bwd   : `self.regressor(features)` + `loss_fn(preds, targets)` +
+ *                               `loss.backward()`, dinov2salad_finetuning.py:28-32,37,120-124;
+ *                               Huber variant dinov2salad_finetuning_2.py:118-123,154; sin/cos
+ *                               angle head + losses angle_prediction/dinov2salad/dino_v2_gemini.py:
+ *                               106-141,243-249 and angle_prediction/swin/
+ *                               swin_angle_finetuning_sin_cos.py:56-69.
+ *  - vpr_knn_topk             : no reference call site (SURVEY.md section 0 finding 4);
+ *                               replaces torch.topk(Q @ G.T, k).
+ */
+#ifndef VPR_B200_H
+#define VPR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPR_ABI_VERSION 1
+#if defined(__GNUC__)
+#define VPR_API __attribute__((visibility("default")))
+#else
+#define VPR_API
+#endif
+#define VPR_F32 0
+#define VPR_BF16 1
+
+typedef struct {
+    int B;        /* images in the batch */
+    int n;        /* patch tokens per image (h*w); n > m */
+    int d;        /* num_channels (768 for ViT-B/14) */
+    int hidden;   /* hidden width of the three MLPs (512 upstream) */
+    int m;        /* num_clusters (64) */
+    int l;        /* cluster_dim (128) */
+    int g;        /* token_dim (256) */
+    int iters;    /* Sinkhorn iterations (3 upstream) */
+} VprSaladShape;
+
+/* fp32 master parameters in upstream state_dict layout (1x1 conv weights are [out,in]). */
+typedef struct {
+    const float* cluster_w0; const float* cluster_b0;   /* [hidden,d], [hidden] */
+    const float* cluster_w1; const float* cluster_b1;   /* [l,hidden], [l] */
+    const float* score_w0;   const float* score_b0;     /* [hidden,d], [hidden] */
+    const float* score_w1;   const float* score_b1;     /* [m,hidden], [m] */
+    const float* token_w0;   const float* token_b0;     /* [hidden,d], [hidden] */
+    const float* token_w1;   const float* token_b1;     /* [g,hidden], [g] */
+    const float* dust_bin;                              /* scalar */
+} VprSaladParams;
+
+/* fp32 gradients, same layout; every buffer is OVERWRITTEN by vpr_salad_bwd. */
+typedef struct {
+    float* cluster_w0; float* cluster_b0;
+    float* cluster_w1; float* cluster_b1;
+    float* score_w0;   float* score_b0;
+    float* score_w1;   float* score_b1;
+    float* token_w0;   float* token_b0;
+    float* token_w1;   float* token_b1;
+    float* dust_bin;
+} VprSaladGrads;
+
+VPR_API const char* vpr_last_error(void);
+VPR_API int vpr_abi_version(void);
+
+/* Bytes of the activation buffer forward fills and backward reads / of the scratch
+ * buffer either call may clobber. */
+VPR_API size_t vpr_salad_save_bytes(const VprSaladShape* s, int dtype);
+VPR_API size_t vpr_salad_workspace_bytes(const VprSaladShape* s, int dtype);
+
+/* x: [B, n, d] token-major contiguous (the memory of upstream's permuted [B,d,h,w] view),
+ * t: [B, d], out: [B, g + l*m] L2-normalised rows; all of `dtype`.
+ * dropout_p > 0 applies the two Dropout(p) layers of cluster_features / score with a
+ * counter-based mask keyed on `seed` (see vpr_dropout_mask). */
+VPR_API int vpr_salad_fwd(const VprSaladParams* p, const void* x, const void* t, void* out, void* save,
+                  void* workspace, size_t workspace_bytes, const VprSaladShape* s, int dtype,
+                  float dropout_p, uint64_t seed, cudaStream_t stream);
+
+/* d_out: [B, g + l*m]; dx: [B, n, d] or NULL; dt: [B, d] or NULL (all `dtype`). */
+VPR_API int vpr_salad_bwd(const VprSaladParams* p, const void* x, const void* t, const void* d_out,
+                  const void* save, void* workspace, size_t workspace_bytes, VprSaladGrads* grads,
+                  void* dx, void* dt, const VprSaladShape* s, int dtype, float dropout_p,
+                  cudaStream_t stream);
+
+/* The keep-mask ({0,1} bytes, [rows, cols]) the dropout epilogue uses for (seed). */
+VPR_API int vpr_dropout_mask(uint64_t seed, float p, int64_t rows, int64_t cols, uint8_t* out, cudaStream_t stream);
+
+/* Stand-alone Sinkhorn (upstream get_matching_probs + exp + drop dustbin row).
+ * S: [B, n, m] fp32 token-major scores; P: [B, n, m] (`p_dtype`); U: [B, iters, m+1] fp32,
+ * V: [B, iters, n] fp32 potentials kept for the backward.  dust_bin: device scalar. */
+VPR_API int vpr_sinkhorn_fwd(const float* S, const float* dust_bin, void* P, int p_dtype, float* U, float* V,
+                     int B, int n, int m, int iters, cudaStream_t stream);
+/* dP: [B, n, m] fp32 -> dS: [B, n, m] (`ds_dtype`); d_bias (nullable): [m] fp32 += sum_{b,j} dS. */
+VPR_API int vpr_sinkhorn_bwd(const float* S, const float* dust_bin, const float* U, const float* V,
+                     const float* dP, void* dS, int ds_dtype, float* d_bias, int B, int n, int m,
+                     int iters, cudaStream_t stream);
+
+/* ---- geopose heads + losses, forward and backward in one call --------------------------- */
+#define VPR_LATLON_MSE 0
+#define VPR_LATLON_HUBER 1
+#define VPR_ANGLE_NONE 0
+#define VPR_ANGLE_ATAN2_MAAE 1   /* dino_v2_gemini.py:117-141 */
+#define VPR_ANGLE_ACOS 2         /* swin_angle_finetuning_sin_cos.py:56-69 */
+#define VPR_ANGLE_MSE 3          /* swin_angle_finetuning_gemini.py:183 on [sin,cos] */
+
+typedef struct {
+    int B;          /* rows in this call */
+    int D;          /* descriptor width (8448) */
+    int hidden;     /* regressor hidden width (512) */
+    int latlon_loss;
+    int angle_loss;
+    float huber_delta;
+    float loss_scale;   /* multiplies every gradient (not the reported losses) */
+    int global_B;       /* denominator of the batch means (== B on one GPU; sum of B over ranks under DP) */
+    float reg_dropout_p;   /* Dropout between ReLU and Linear(hidden,2): dinov2salad_finetuning_2.py:121 */
+    uint64_t seed;
+} VprHeadsShape;
+
+typedef struct {
+    const float* reg_w0; const float* reg_b0;   /* [hidden, D], [hidden]  regressor.0 */
+    const float* reg_w1; const float* reg_b1;   /* [2, hidden], [2]       regressor.2 */
+    const float* ang_w;  const float* ang_b;    /* [2, D], [2]            head        */
+} VprHeadsParams;
+
+typedef struct {
+    float* reg_w0; float* reg_b0; float* reg_w1; float* reg_b1; float* ang_w; float* ang_b;
+} VprHeadsGrads;
+
+VPR_API size_t vpr_heads_workspace_bytes(const VprHeadsShape* s, int dtype);
+/* desc: [B, D] (`dtype`); latlon_target: [B,2] fp32 (z-scored); angle_target_deg: [B] fp32.
+ * Outputs: latlon_pred [B,2] fp32, sincos_pred [B,2] fp32, losses [2] fp32 (lat/lon, angle),
+ * grads (overwritten), d_desc [B, D] (`dtype`) or NULL. */
+VPR_API int vpr_heads_loss_fwd_bwd(const VprHeadsParams* p, const void* desc, const float* latlon_target,
+                           const float* angle_target_deg, float* latlon_pred, float* sincos_pred,
+                           float* losses, VprHeadsGrads* grads, void* d_desc, void* workspace,
+                           size_t workspace_bytes, const VprHeadsShape* s, int dtype, cudaStream_t stream);
+
+/* ---- descriptor kNN ------------------------------------------------------------------- */
+VPR_API size_t vpr_knn_workspace_bytes(int64_t Q, int64_t G, int D, int k);
+/* q: [Q, D] bf16, g: [G, D] bf16 (this rank's gallery shard), scores = q . g (fp32 accumulate).
+ * out_score [Q,k] fp32 descending, out_idx [Q,k] int64 = g_offset + local row; ties -> lower index. */
+VPR_API int vpr_knn_topk(const void* q, const void* g, int64_t Q, int64_t G, int D, int k, int64_t g_offset,
+                 float* out_score, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+                 cudaStream_t stream);
+/* Merge R per-rank results ([R, Q, k] score/idx, e.g. after an allgather) into the global top-k. */
+VPR_API int vpr_knn_merge(const float* scores, const int64_t* idx, int R, int64_t Q, int k, float* out_score,
+                  int64_t* out_idx, cudaStream_t stream);
+
+/* ---- test hook: the GEMM every dense step above is built from --------------------------- */
+VPR_API int vpr_gemm(int dtype, const void* A, int a_mn, int64_t lda, int64_t a_bs, const void* B, int b_mn,
+             int64_t ldb, int64_t b_bs, int M, int N, int K, int batch, void* out, int out_kind,
+             int64_t ldo, int64_t out_bs, const float* bias, int relu, const void* mask, int64_t ld_mask,
+             int64_t mask_bs, float mask_scale, float alpha, int k_splits, int bn, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPR_B200_H */

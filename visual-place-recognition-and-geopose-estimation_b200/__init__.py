@@ -1,0 +1,13 @@
+"""B200-native (sm_100a) SALAD aggregation head, geopose heads/losses and descriptor kNN: the one
+data-parallel hot path of anshium/visual-place-recognition-and-geopose-estimation, behind the
+reference's own module interface.  Importable as ``vpr_b200`` (see /vpr_b200.py at the repo root;
+the directory name carries the reference's hyphenated name)."""
+from ._lib import LIB_PATH, lib  # noqa: F401
+from .heads import GeoposeHeads, sincos_to_degrees  # noqa: F401
+from .knn import knn_topk, knn_topk_sharded, merge_topk  # noqa: F401
+from .parallel import DataParallelStep, allreduce_grads, init_distributed, shard_range  # noqa: F401
+from .salad import SaladHead, dropout_keep_mask, sinkhorn, sinkhorn_backward  # noqa: F401
+
+__all__ = ["SaladHead", "GeoposeHeads", "knn_topk", "knn_topk_sharded", "merge_topk", "sinkhorn",
+           "sinkhorn_backward", "dropout_keep_mask", "DataParallelStep", "allreduce_grads", "init_distributed",
+           "shard_range", "sincos_to_degrees", "lib", "LIB_PATH"]

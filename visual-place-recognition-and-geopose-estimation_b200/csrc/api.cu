@@ -1,0 +1,55 @@
+// Library-wide state: the error channel, device properties and the C-ABI test hook for the GEMM.
+#include "common.cuh"
+#include "gemm.h"
+#include "../../include/vpr_b200.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+
+namespace vpr {
+
+static thread_local char g_err[1024] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace vpr
+
+extern "C" {
+
+const char* vpr_last_error(void) { return vpr::g_err; }
+
+int vpr_abi_version(void) { return VPR_ABI_VERSION; }
+
+int vpr_gemm(int dtype, const void* A, int a_mn, int64_t lda, int64_t a_bs, const void* B, int b_mn, int64_t ldb,
+             int64_t b_bs, int M, int N, int K, int batch, void* out, int out_kind, int64_t ldo, int64_t out_bs,
+             const float* bias, int relu, const void* mask, int64_t ld_mask, int64_t mask_bs, float mask_scale,
+             float alpha, int k_splits, int bn, cudaStream_t stream) {
+    vpr::GemmDesc g;
+    g.dtype = dtype;
+    g.A = A; g.a_mn = a_mn; g.lda = lda; g.a_bs = a_bs;
+    g.B = B; g.b_mn = b_mn; g.ldb = ldb; g.b_bs = b_bs;
+    g.M = M; g.N = N; g.K = K; g.batch = batch;
+    g.out = out; g.out_kind = out_kind; g.ldo = ldo; g.out_bs = out_bs;
+    g.bias = bias; g.relu = relu;
+    g.mask = mask; g.ld_mask = ld_mask; g.mask_bs = mask_bs; g.mask_scale = mask_scale;
+    g.alpha = alpha; g.k_splits = k_splits; g.bn = bn;
+    return vpr::gemm_run(g, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,237 @@
+// Shared device/host helpers for the sm_100a kernels: PTX wrappers for mbarrier,
+// TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld) and the
+// library-wide error channel.  Everything here is written for sm_100a only.
+#pragma once
+
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched at run time)
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vpr {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------
+// error channel (api.cu)
+// ---------------------------------------------------------------------------
+int fail(int code, const char* fmt, ...);
+int num_sms();
+
+#define VPR_CUDA_OK(expr)                                                          \
+    do {                                                                           \
+        cudaError_t e__ = (expr);                                                  \
+        if (e__ != cudaSuccess)                                                    \
+            return ::vpr::fail(2, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,     \
+                               cudaGetErrorString(e__));                           \
+    } while (0)
+
+#define VPR_TRY(expr)                  \
+    do {                               \
+        int r__ = (expr);              \
+        if (r__ != 0) return r__;      \
+    } while (0)
+
+#define VPR_REQUIRE(cond, ...)                                   \
+    do {                                                         \
+        if (!(cond)) return ::vpr::fail(1, __VA_ARGS__);         \
+    } while (0)
+
+static inline int launch_ok(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(3, "launch %s: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+template <typename T>
+static inline T* carve(char*& p, size_t count) {
+    uintptr_t a = (reinterpret_cast<uintptr_t>(p) + 255) & ~uintptr_t(255);
+    T* r = reinterpret_cast<T*>(a);
+    p = reinterpret_cast<char*>(a + count * sizeof(T));
+    return r;
+}
+static inline size_t carve_size(size_t& off, size_t bytes) {
+    off = (off + 255) & ~size_t(255);
+    size_t r = off;
+    off += bytes;
+    return r;
+}
+
+// Counter-based dropout: splitmix64 of (seed, element index); keep iff hash >= p * 2^32.
+__host__ __device__ inline uint32_t dropout_hash(uint64_t seed, uint64_t idx) {
+    uint64_t z = idx + (seed + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (uint32_t)(z >> 32);
+}
+static inline uint32_t dropout_threshold(float p) {
+    double t = (double)p * 4294967296.0;
+    if (t < 0) t = 0;
+    if (t > 4294967295.0) t = 4294967295.0;
+    return (uint32_t)t;
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------
+// small device utilities
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// mbarrier
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a wedged pipeline traps (the launch fails with an error) instead of
+// hanging the GPU box.  ~4e9 SM cycles is two orders of magnitude above any
+// legitimate wait in these kernels.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    long long t0 = 0;
+    int spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (++spins == 64) t0 = clock64();
+        if (spins > 64 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// TMA
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                            int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// tcgen05 / TMEM
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// tcgen05.commit: arrives (count 1) on the mbarrier once all MMAs issued so far by
+// this thread have completed.  Implies fence::before_thread_sync.
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 in, fp32 accumulate).
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = lane i of
+// the warp's TMEM lane quarter).
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+        " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31},"
+        " [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(addr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor for tcgen05.mma, SWIZZLE_128B, 16-bit elements.
+//  K-major operand : rows of 128 B (64 elements of K), 8-row groups 1024 B apart (SBO);
+//                    LBO unused for swizzled K-major (encoded 1 like CUTLASS does).
+//  MN-major operand: rows of 128 B hold 64 consecutive M/N elements for one k; 8 k-rows
+//                    form a 1024 B group (SBO = 1024); the next 64 M/N elements start LBO
+//                    bytes further (one TMA box = 64 k-rows * 128 B = 8192 B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
+    d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= uint64_t(1) << 46;   // descriptor version (Blackwell)
+    d |= uint64_t(2) << 61;   // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor, kind::f16: bf16 x bf16 -> fp32.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_mn) << 15) | (uint32_t(b_mn) << 16) |
+           (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+#endif  // __CUDACC__
+
+}  // namespace vpr

@@ -1,0 +1,38 @@
+// One GEMM entry point for the whole library:
+//   out[b][m][n] (op)= epilogue( alpha * sum_k A(b,m,k) * B(b,n,k) )
+// dtype 1 (bf16 operands, fp32 accumulate) runs the persistent warp-specialised
+// TMA + tcgen05 kernel; dtype 0 (fp32 operands) runs a plain fp32 FMA kernel that
+// exists for the north-star's 1e-4 fp32 parity mode (tensor cores cannot give fp32
+// products).  Both share the epilogue semantics below.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace vpr {
+
+enum { OUT_F32 = 0, OUT_BF16 = 1, OUT_ATOMIC_F32 = 2 };
+enum { DT_F32 = 0, DT_BF16 = 1 };
+
+struct GemmDesc {
+    int dtype = DT_BF16;
+    // A(m,k): a_mn == 0 -> stored [M rows][K inner] ("K-major"), lda = row stride
+    //         a_mn == 1 -> stored [K rows][M inner] ("MN-major"), lda = row stride
+    const void* A = nullptr; int a_mn = 0; int64_t lda = 0; int64_t a_bs = 0;
+    // B(n,k): same convention with N in place of M.  b_bs == 0 -> shared by all batches.
+    const void* B = nullptr; int b_mn = 0; int64_t ldb = 0; int64_t b_bs = 0;
+    int M = 0, N = 0, K = 0, batch = 1;
+    void* out = nullptr; int out_kind = OUT_F32; int64_t ldo = 0; int64_t out_bs = 0;
+    const float* bias = nullptr;   // per-n, added before relu / mask
+    int relu = 0;
+    // v = mask(b,m,n) > 0 ? v * mask_scale : 0 ; mask has the operand dtype
+    const void* mask = nullptr; int64_t ld_mask = 0; int64_t mask_bs = 0; float mask_scale = 1.f;
+    float alpha = 1.f;
+    // inverted dropout on the output (after relu): keep iff dropout_hash(seed, (b*M+m)*N+n) >= p*2^32
+    float dropout_p = 0.f; uint64_t dropout_seed = 0;
+    int k_splits = 1;              // > 1 requires OUT_ATOMIC_F32 (caller zeroes out)
+    int bn = 0;                    // tcgen05 tile N (64/128/256); 0 = auto
+};
+
+int gemm_run(const GemmDesc& g, cudaStream_t stream);
+
+}  // namespace vpr

@@ -1,0 +1,319 @@
+// Descriptor kNN: scores = Q G^T on tcgen05 with a fused per-row top-k epilogue (SURVEY.md
+// section 8 row a10).  The [Q, G] score matrix is never written: each epilogue thread owns one
+// query row of the 128-row tile, keeps that row's current k-th best score in a register as a
+// threshold and inserts the (rare) survivors into a sorted list in shared memory.
+//
+// Work decomposition: one work item = (128-query tile, gallery chunk); a CTA streams every
+// 256-row gallery tile of its chunk through the TMA/MMA pipeline, then writes the chunk-local
+// top-k of its 128 queries to the workspace; a small merge kernel combines the chunks (and, in
+// the sharded case, the per-rank results after the allgather).
+#include "common.cuh"
+#include "../../include/vpr_b200.h"
+
+#include <math.h>
+
+namespace vpr {
+
+static constexpr int KBM = 128, KBN = 256, KBK = 64;
+static constexpr int K_A_BYTES = KBM * KBK * 2, K_B_BYTES = KBN * KBK * 2;
+static constexpr int K_STAGE_BYTES = K_A_BYTES + K_B_BYTES;
+static constexpr int K_STAGES = 4;
+static constexpr int KMAX = 32;   // list capacity per row
+static constexpr int K_LIST_BYTES = KMAX * KBM * 8;
+static constexpr int K_SMEM_BYTES = K_STAGES * K_STAGE_BYTES + K_LIST_BYTES + 1024 + 256;
+static constexpr int K_THREADS = 192;
+
+struct KnnArgs {
+    int Q, G, D, k;
+    int tiles_m, chunks, tiles_per_chunk, tiles_n, kb_total;
+    float* ws_score;       // [Q, chunks, k]
+    int* ws_idx;           // [Q, chunks, k] local gallery row, -1 = empty
+};
+
+__global__ void __launch_bounds__(K_THREADS, 1)
+knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG, const KnnArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    float* lscore = reinterpret_cast<float*>(smem_al + K_STAGES * K_STAGE_BYTES);      // [KMAX][128]
+    int* lidx = reinterpret_cast<int*>(lscore + KMAX * KBM);                             // [KMAX][128]
+    const uint32_t bar_base = smem_base + K_STAGES * K_STAGE_BYTES + K_LIST_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (K_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * K_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * K_STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * K_STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmG); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < K_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+            for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+            mbar_fence_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int total_work = args.tiles_m * args.chunks;
+
+    auto tile_range = [&](int w, int& mt, int& ch, int& nt0, int& nt1) {
+        ch = w % args.chunks;
+        mt = w / args.chunks;
+        nt0 = ch * args.tiles_per_chunk;
+        nt1 = nt0 + args.tiles_per_chunk;
+        if (nt1 > args.tiles_n) nt1 = args.tiles_n;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                int mt, ch, nt0, nt1;
+                tile_range(w, mt, ch, nt0, nt1);
+                for (int nt = nt0; nt < nt1; ++nt)
+                    for (int kb = 0; kb < args.kb_total; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        const uint32_t sa = smem_base + stage * K_STAGE_BYTES, sb = sa + K_A_BYTES;
+                        mbar_expect_tx(full_bar(stage), K_STAGE_BYTES);
+                        tma_load_3d(sa, &tmQ, full_bar(stage), kb * KBK, mt * KBM, 0);
+                        tma_load_3d(sb, &tmG, full_bar(stage), kb * KBK, nt * KBN, 0);
+                        if (++stage == K_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(KBM, KBN, false, false);
+            int stage = 0; uint32_t phase = 0; int it = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                int mt, ch, nt0, nt1;
+                tile_range(w, mt, ch, nt0, nt1);
+                for (int nt = nt0; nt < nt1; ++nt, ++it) {
+                    const int as = it & 1;
+                    const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+                    mbar_wait(tempty_bar(as), aphase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * KBN);
+                    for (int kb = 0; kb < args.kb_total; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + stage * K_STAGE_BYTES, sb = sa + K_A_BYTES;
+#pragma unroll
+                        for (int k = 0; k < KBK / 16; ++k)
+                            tc_mma_bf16(d_tmem, make_smem_desc(sa + k * 32, 16u, 1024u),
+                                        make_smem_desc(sb + k * 32, 16u, 1024u), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        tc_commit(empty_bar(stage));
+                        if (++stage == K_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    tc_commit(tfull_bar(as));
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;              // this thread's query row within the tile
+        const int kk = args.k;
+        int it = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            int mt, ch, nt0, nt1;
+            tile_range(w, mt, ch, nt0, nt1);
+            for (int s = 0; s < kk; ++s) { lscore[s * KBM + row] = -INFINITY; lidx[s * KBM + row] = -1; }
+            float thr = -INFINITY;                   // current k-th best of this row
+            for (int nt = nt0; nt < nt1; ++nt, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(tfull_bar(as), aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * KBN);
+#pragma unroll 1
+                for (int c = 0; c < KBN / 32; ++c) {
+                    const int n0 = nt * KBN + c * 32;
+                    if (n0 >= args.G) break;
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float v = __uint_as_float(r[i]);
+                        if (v > thr && n0 + i < args.G) {
+                            // insert (v, n0+i) into the descending list; equal scores keep the earlier index first
+                            int pos = kk - 1;
+                            while (pos > 0 && lscore[(pos - 1) * KBM + row] < v) {
+                                lscore[pos * KBM + row] = lscore[(pos - 1) * KBM + row];
+                                lidx[pos * KBM + row] = lidx[(pos - 1) * KBM + row];
+                                --pos;
+                            }
+                            lscore[pos * KBM + row] = v;
+                            lidx[pos * KBM + row] = n0 + i;
+                            thr = lscore[(kk - 1) * KBM + row];
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(as));
+            }
+            const int qrow = mt * KBM + row;
+            if (qrow < args.Q) {
+                float* os = args.ws_score + ((size_t)qrow * args.chunks + ch) * kk;
+                int* oi = args.ws_idx + ((size_t)qrow * args.chunks + ch) * kk;
+                for (int s = 0; s < kk; ++s) { os[s] = lscore[s * KBM + row]; oi[s] = lidx[s * KBM + row]; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// Merge R sorted-or-not candidate lists of k entries per query into the global top-k
+// (score descending, ties -> lower index).  One warp per query, k selection rounds.
+template <typename IdxT>
+__global__ void __launch_bounds__(256) knn_merge_kernel(const float* __restrict__ scores, const IdxT* __restrict__ idx,
+                                                        int R, long long Q, int k, long long q_stride_lists,
+                                                        long long list_stride, long long idx_offset,
+                                                        float* __restrict__ out_score, long long* __restrict__ out_idx) {
+    // candidate (r, s) of query q lives at q*q_stride_lists + r*list_stride + s
+    const long long q = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    const int total = R * k;
+    float prev_s = INFINITY;
+    long long prev_i = -1;
+    for (int sel = 0; sel < k; ++sel) {
+        float best_s = -INFINITY;
+        long long best_i = 0x7fffffffffffffffLL;
+        for (int e = lane; e < total; e += 32) {
+            const int r = e / k, s = e - r * k;
+            const long long off = q * q_stride_lists + (long long)r * list_stride + s;
+            const long long ii = (long long)idx[off];
+            if (ii < 0) continue;
+            const float sc = scores[off];
+            // strictly after (prev_s, prev_i) in (score desc, idx asc) order
+            const bool after = (sc < prev_s) || (sc == prev_s && ii > prev_i);
+            if (!after) continue;
+            if (sc > best_s || (sc == best_s && ii < best_i)) { best_s = sc; best_i = ii; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, best_s, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            if (os > best_s || (os == best_s && oi < best_i)) { best_s = os; best_i = oi; }
+        }
+        if (lane == 0) {
+            const bool found = best_i != 0x7fffffffffffffffLL;
+            out_score[q * k + sel] = found ? best_s : -INFINITY;
+            out_idx[q * k + sel] = found ? best_i + idx_offset : -1;
+        }
+        prev_s = best_s;
+        prev_i = best_i;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int knn_map(CUtensorMap* map, const void* ptr, int64_t rows, int D, int box_rows) {
+    static EncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return fail(1, "cuTensorMapEncodeTiled not available from the driver");
+        enc = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    VPR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "kNN operand must be 16-byte aligned");
+    cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)rows, 1};
+    cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)D * 2 * (cuuint64_t)rows};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VPR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for kNN operand rows=%lld D=%d", (int)r,
+                (long long)rows, D);
+    return 0;
+}
+
+static void knn_plan(int64_t Q, int64_t G, int& tiles_m, int& tiles_n, int& chunks, int& tiles_per_chunk) {
+    tiles_m = (int)((Q + KBM - 1) / KBM);
+    tiles_n = (int)((G + KBN - 1) / KBN);
+    // aim for >= 8 work items per SM so the last wave is short, but keep >= 8 gallery tiles per chunk
+    int want = (8 * num_sms() + tiles_m - 1) / tiles_m;
+    if (want < 1) want = 1;
+    int max_chunks = (tiles_n + 7) / 8;
+    if (max_chunks < 1) max_chunks = 1;
+    chunks = want < max_chunks ? want : max_chunks;
+    if (chunks > 64) chunks = 64;
+    tiles_per_chunk = (tiles_n + chunks - 1) / chunks;
+    chunks = (tiles_n + tiles_per_chunk - 1) / tiles_per_chunk;
+}
+
+}  // namespace vpr
+
+using namespace vpr;
+
+extern "C" {
+
+size_t vpr_knn_workspace_bytes(int64_t Q, int64_t G, int D, int k) {
+    (void)D;
+    int tm, tn, ch, tpc;
+    knn_plan(Q, G, tm, tn, ch, tpc);
+    size_t off = 0;
+    carve_size(off, (size_t)Q * ch * k * 4);
+    carve_size(off, (size_t)Q * ch * k * 4);
+    return (off + 255) & ~size_t(255);
+}
+
+int vpr_knn_topk(const void* q, const void* g, int64_t Q, int64_t G, int D, int k, int64_t g_offset, float* out_score,
+                 int64_t* out_idx, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    VPR_REQUIRE(q && g && out_score && out_idx && workspace, "null argument");
+    VPR_REQUIRE(Q > 0 && G > 0, "empty kNN problem (Q=%lld, G=%lld)", (long long)Q, (long long)G);
+    VPR_REQUIRE(k >= 1 && k <= KMAX, "k must be in [1, %d]", KMAX);
+    VPR_REQUIRE(D % 8 == 0, "descriptor width must be a multiple of 8");
+    VPR_REQUIRE(G < (1ll << 31) - KBN && Q < (1ll << 31) - KBM, "shard too large for 32-bit local indices");
+    VPR_REQUIRE(workspace_bytes >= vpr_knn_workspace_bytes(Q, G, D, k), "workspace too small");
+    KnnArgs a;
+    a.Q = (int)Q; a.G = (int)G; a.D = D; a.k = k;
+    knn_plan(Q, G, a.tiles_m, a.tiles_n, a.chunks, a.tiles_per_chunk);
+    a.kb_total = (D + KBK - 1) / KBK;
+    size_t off = 0;
+    a.ws_score = (float*)((char*)workspace + carve_size(off, (size_t)Q * a.chunks * k * 4));
+    a.ws_idx = (int*)((char*)workspace + carve_size(off, (size_t)Q * a.chunks * k * 4));
+    CUtensorMap tq, tg;
+    VPR_TRY(knn_map(&tq, q, Q, D, KBM));
+    VPR_TRY(knn_map(&tg, g, G, D, KBN));
+    static bool attr = false;
+    if (!attr) {
+        VPR_CUDA_OK(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K_SMEM_BYTES));
+        attr = true;
+    }
+    long long total = (long long)a.tiles_m * a.chunks;
+    int grid = (int)(total < num_sms() ? total : num_sms());
+    knn_tc_kernel<<<grid, K_THREADS, K_SMEM_BYTES, stream>>>(tq, tg, a);
+    VPR_TRY(launch_ok("knn_tc_kernel"));
+    const long long warps = Q;
+    knn_merge_kernel<int><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(
+        a.ws_score, a.ws_idx, a.chunks, Q, k, (long long)a.chunks * k, k, g_offset, out_score, (long long*)out_idx);
+    return launch_ok("knn_merge_kernel");
+}
+
+int vpr_knn_merge(const float* scores, const int64_t* idx, int R, int64_t Q, int k, float* out_score, int64_t* out_idx,
+                  cudaStream_t stream) {
+    VPR_REQUIRE(scores && idx && out_score && out_idx && R > 0 && Q > 0 && k > 0, "bad argument");
+    // input layout [R, Q, k]
+    knn_merge_kernel<long long><<<(unsigned)((Q * 32 + 255) / 256), 256, 0, stream>>>(
+        scores, (const long long*)idx, R, Q, k, (long long)k, (long long)Q * k, 0, out_score, (long long*)out_idx);
+    return launch_ok("knn_merge_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,781 @@
+// SALAD aggregation head, forward and backward.
+//
+// Data layout in HBM (T = B*n patch tokens, everything token-major so that every GEMM has
+// the tokens on the 128-lane M side of the tcgen05 tile):
+//   X   [T, d]        input tokens (the memory behind upstream's permuted [B,d,h,w] view)
+//   H   [T, 2*hidden] relu(dropout(X W0^T + b0)); columns [0,hidden) cluster MLP, [hidden,2h) score MLP
+//   F   [T, l]        cluster features          S [T, m] fp32 scores
+//   P   [T, m]        Sinkhorn assignment (dustbin row never materialised)
+//   AGG [B, l, m]     fp32  sum_j F[j,l] P[j,c]
+//   out [B, g + l*m]  normalize(cat(normalize(TF), normalize(AGG, over l).flatten))
+#include "common.cuh"
+#include "gemm.h"
+#include "../../include/vpr_b200.h"
+
+#include <math.h>
+
+namespace vpr {
+
+// ---------------------------------------------------------------------------
+// scalar load/store helpers over the two storage types
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// block-wide reductions for 256-thread blocks (8 warps); red must hold >= 8 floats
+__device__ __forceinline__ float block_sum256(float v, float* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r += red[i];
+    return r;
+}
+__device__ __forceinline__ float block_max256(float v, float* red) {
+    v = warp_max(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) r = fmaxf(r, red[i]);
+    return r;
+}
+
+// ---------------------------------------------------------------------------
+// parameter packing: fp32 master weights -> run dtype, first layers concatenated
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_params_kernel(const VprSaladParams p, int d, int h, int l, int m, int g, T* w0cat, T* w1c,
+                                   T* w1s, T* wt0, T* wt1, float* b0cat) {
+    const long long n0 = (long long)h * d, n1 = (long long)l * h, n2 = (long long)m * h, n3 = (long long)g * h;
+    const long long total = 2 * n0 + n1 + n2 + n0 + n3 + 2 * h;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long e = i;
+        if (e < n0) { stf(w0cat + e, p.cluster_w0[e]); continue; }
+        e -= n0;
+        if (e < n0) { stf(w0cat + n0 + e, p.score_w0[e]); continue; }
+        e -= n0;
+        if (e < n1) { stf(w1c + e, p.cluster_w1[e]); continue; }
+        e -= n1;
+        if (e < n2) { stf(w1s + e, p.score_w1[e]); continue; }
+        e -= n2;
+        if (e < n0) { stf(wt0 + e, p.token_w0[e]); continue; }
+        e -= n0;
+        if (e < n3) { stf(wt1 + e, p.token_w1[e]); continue; }
+        e -= n3;
+        b0cat[e] = e < h ? p.cluster_b0[e] : p.score_b0[e - h];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Sinkhorn forward.  One CTA (256 threads) per image; the [n, m] score tile stays in shared
+// memory (pitch m+1 -> conflict-free in both reduction directions) for all iterations.
+// The dustbin row is a constant z, so it is never stored: it enters each column
+// logsumexp as one scalar per image.
+// ---------------------------------------------------------------------------
+struct SinkConst {
+    float norm;      // -log(n+m)  (fp32 like upstream's torch.tensor(math.log(..)))
+    float log_a_m;   // norm + log(n-m)
+};
+
+template <typename TP>
+__global__ void __launch_bounds__(256) sinkhorn_fwd_kernel(const float* __restrict__ S, const float* __restrict__ dust_bin,
+                                                           TP* __restrict__ P, float* __restrict__ U,
+                                                           float* __restrict__ V, int n, int m, int iters,
+                                                           SinkConst k) {
+    extern __shared__ float sm[];
+    const int pitch = m + 1;
+    float* Ms = sm;                       // [n][pitch]
+    float* vs = Ms + (size_t)n * pitch;   // [n]
+    float* us = vs + n;                   // [m+1]
+    float* red = us + (m + 1);            // [256] partials
+    float* red2 = red + 256;              // [8]
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float z = __ldg(dust_bin);
+    const float* Sb = S + (size_t)b * n * m;
+    for (int e = tid; e < n * m; e += 256) {
+        const int j = e / m, c = e - j * m;
+        Ms[j * pitch + c] = __ldg(Sb + e);
+    }
+    for (int j = tid; j < n; j += 256) vs[j] = 0.f;
+    __syncthreads();
+    const int parts = 256 / m;            // m in {16,32,64,128}
+    const int c = tid % m, part = tid / m;
+    float lse_v = logf((float)n);         // logsumexp_j(v_j) with v = 0
+    for (int it = 0; it < iters; ++it) {
+        // ---- u_c = log_a - LSE_j(M_jc + v_j) ----
+        float mx = -INFINITY;
+        for (int j = part; j < n; j += parts) mx = fmaxf(mx, Ms[j * pitch + c] + vs[j]);
+        red[tid] = mx;
+        __syncthreads();
+        mx = red[c];
+        for (int q = 1; q < parts; ++q) mx = fmaxf(mx, red[q * m + c]);
+        __syncthreads();
+        float sum = 0.f;
+        for (int j = part; j < n; j += parts) sum += expf(Ms[j * pitch + c] + vs[j] - mx);
+        red[tid] = sum;
+        __syncthreads();
+        if (part == 0) {
+            float tot = red[c];
+            for (int q = 1; q < parts; ++q) tot += red[q * m + c];
+            us[c] = k.norm - (logf(tot) + mx);
+        }
+        if (tid == 0) us[m] = k.log_a_m - (z + lse_v);
+        __syncthreads();
+        // ---- v_j = log_b - LSE_{c<=m}(M_jc + u_c) ----
+        float vmax = -INFINITY;
+        for (int j = tid; j < n; j += 256) {
+            const float* row = Ms + j * pitch;
+            float cmx = z + us[m];
+            for (int cc = 0; cc < m; ++cc) cmx = fmaxf(cmx, row[cc] + us[cc]);
+            float cs = expf(z + us[m] - cmx);
+            for (int cc = 0; cc < m; ++cc) cs += expf(row[cc] + us[cc] - cmx);
+            const float vj = k.norm - (logf(cs) + cmx);
+            vs[j] = vj;
+            vmax = fmaxf(vmax, vj);
+        }
+        vmax = block_max256(vmax, red2);
+        float vsum = 0.f;
+        for (int j = tid; j < n; j += 256) vsum += expf(vs[j] - vmax);
+        vsum = block_sum256(vsum, red2);
+        lse_v = logf(vsum) + vmax;
+        // save potentials for the backward
+        if (tid <= m) U[((size_t)b * iters + it) * (m + 1) + tid] = us[tid];
+        for (int j = tid; j < n; j += 256) V[((size_t)b * iters + it) * n + j] = vs[j];
+        __syncthreads();
+    }
+    TP* Pb = P + (size_t)b * n * m;
+    for (int e = tid; e < n * m; e += 256) {
+        const int j = e / m, cc = e - j * m;
+        stf(Pb + e, expf(Ms[j * pitch + cc] + us[cc] + vs[j] - k.norm));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Sinkhorn backward: reverse-unrolled recurrence on the potentials'
+// adjoints (du, dv); the per-element dM is assembled once at the end from the saved
+// per-iteration adjoints, so only the score tile itself has to stay in shared memory.
+// ---------------------------------------------------------------------------
+template <typename TD>
+__global__ void __launch_bounds__(256) sinkhorn_bwd_kernel(const float* __restrict__ S, const float* __restrict__ dust_bin,
+                                                           const float* __restrict__ U, const float* __restrict__ V,
+                                                           const float* __restrict__ dP, TD* __restrict__ dS,
+                                                           float* __restrict__ d_bias, int n, int m, int iters,
+                                                           SinkConst k) {
+    extern __shared__ float sm[];
+    const int pitch = m + 1;
+    float* Ms = sm;                                // [n][pitch]
+    float* vs = Ms + (size_t)n * pitch;            // [iters+1][n]   v^0 .. v^K
+    float* us = vs + (size_t)(iters + 1) * n;      // [iters][m+1]   u^1 .. u^K
+    float* DV = us + (size_t)iters * (m + 1);      // [iters][n]     dv used in the v-step of iteration k
+    float* DU = DV + (size_t)iters * n;            // [iters][m+1]   du used in the u-step of iteration k
+    float* red = DU + (size_t)iters * (m + 1);     // [256]
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float z = __ldg(dust_bin);
+    const float* Sb = S + (size_t)b * n * m;
+    const float* dPb = dP + (size_t)b * n * m;
+    for (int e = tid; e < n * m; e += 256) {
+        const int j = e / m, c = e - j * m;
+        Ms[j * pitch + c] = __ldg(Sb + e);
+    }
+    for (int j = tid; j < n; j += 256) vs[j] = 0.f;
+    for (int e = tid; e < iters * n; e += 256) vs[n + e] = __ldg(V + (size_t)b * iters * n + e);
+    for (int e = tid; e < iters * (m + 1); e += 256) us[e] = __ldg(U + (size_t)b * iters * (m + 1) + e);
+    __syncthreads();
+    const int parts = 256 / m;
+    const int c = tid % m, part = tid / m;
+    const float* uK = us + (size_t)(iters - 1) * (m + 1);
+    const float* vK = vs + (size_t)iters * n;
+    // G_jc = dP_jc * P_jc, P_jc = exp(M_jc + uK_c + vK_j - norm);  du_c = sum_j G, dv_j = sum_c G
+    {
+        float acc = 0.f;
+        for (int j = part; j < n; j += parts)
+            acc += __ldg(dPb + j * m + c) * expf(Ms[j * pitch + c] + uK[c] + vK[j] - k.norm);
+        red[tid] = acc;
+        __syncthreads();
+        if (part == 0) {
+            float tot = red[c];
+            for (int q = 1; q < parts; ++q) tot += red[q * m + c];
+            DU[(size_t)(iters - 1) * (m + 1) + c] = tot;
+        }
+        if (tid == 0) DU[(size_t)(iters - 1) * (m + 1) + m] = 0.f;
+        for (int j = tid; j < n; j += 256) {
+            const float* row = Ms + j * pitch;
+            float acc2 = 0.f;
+            for (int cc = 0; cc < m; ++cc)
+                acc2 += __ldg(dPb + j * m + cc) * expf(row[cc] + uK[cc] + vK[j] - k.norm);
+            DV[(size_t)(iters - 1) * n + j] = acc2;
+        }
+        __syncthreads();
+    }
+    for (int it = iters - 1; it >= 0; --it) {
+        const float* uk = us + (size_t)it * (m + 1);
+        const float* vk = vs + (size_t)(it + 1) * n;     // v^k
+        const float* vkm1 = vs + (size_t)it * n;         // v^{k-1}
+        float* du = DU + (size_t)it * (m + 1);
+        const float* dv = DV + (size_t)it * n;
+        // du_c -= sum_j dv_j * Wv_jc,  Wv_jc = exp(M_jc + u_c + v_j - log_b)
+        float acc = 0.f;
+        for (int j = part; j < n; j += parts) acc += dv[j] * expf(Ms[j * pitch + c] + uk[c] + vk[j] - k.norm);
+        red[tid] = acc;
+        __syncthreads();
+        if (part == 0) {
+            float tot = red[c];
+            for (int q = 1; q < parts; ++q) tot += red[q * m + c];
+            du[c] -= tot;
+        }
+        __syncthreads();
+        {   // dustbin row: Wv_jm = exp(z + u_m + v_j - log_b)
+            float a2 = 0.f;
+            for (int j = tid; j < n; j += 256) a2 += dv[j] * expf(z + uk[m] + vk[j] - k.norm);
+            a2 = block_sum256(a2, red);
+            if (tid == 0) du[m] -= a2;
+            __syncthreads();
+        }
+        // dv^{k-1}_j = - sum_{c<=m} du_c * Wu_jc,  Wu_jc = exp(M_jc + v^{k-1}_j + u_c - log_a_c)
+        if (it > 0) {
+            float* dvn = DV + (size_t)(it - 1) * n;
+            float* dun = DU + (size_t)(it - 1) * (m + 1);
+            for (int j = tid; j < n; j += 256) {
+                const float* row = Ms + j * pitch;
+                float a3 = du[m] * expf(z + vkm1[j] + uk[m] - k.log_a_m);
+                for (int cc = 0; cc < m; ++cc) a3 += du[cc] * expf(row[cc] + vkm1[j] + uk[cc] - k.norm);
+                dvn[j] = -a3;
+            }
+            if (tid <= m) dun[tid] = 0.f;
+            __syncthreads();
+        }
+    }
+    // dM_jc = G_jc - sum_k ( DV[k][j] * Wv^k_jc + DU[k][c] * Wu^k_jc )
+    TD* dSb = dS + (size_t)b * n * m;
+    float bsum = 0.f;
+    for (int e = tid; e < n * m; e += 256) {
+        const int j = e / m, cc = e - j * m;   // cc == c because 256 % m == 0
+        const float mv = Ms[j * pitch + cc];
+        float g = __ldg(dPb + e) * expf(mv + uK[cc] + vK[j] - k.norm);
+        for (int it = 0; it < iters; ++it) {
+            const float u = us[(size_t)it * (m + 1) + cc];
+            g -= DV[(size_t)it * n + j] * expf(mv + u + vs[(size_t)(it + 1) * n + j] - k.norm);
+            g -= DU[(size_t)it * (m + 1) + cc] * expf(mv + u + vs[(size_t)it * n + j] - k.norm);
+        }
+        stf(dSb + e, g);
+        bsum += g;
+    }
+    if (d_bias != nullptr) {
+        __syncthreads();
+        red[tid] = bsum;
+        __syncthreads();
+        if (part == 0) {
+            float tot = red[c];
+            for (int q = 1; q < parts; ++q) tot += red[q * m + c];
+            atomicAdd(d_bias + c, tot);
+        }
+    }
+}
+
+static SinkConst sink_consts(int n, int m) {
+    SinkConst k;
+    k.norm = (float)(-log((double)(n + m)));
+    k.log_a_m = k.norm + (float)log((double)(n - m));
+    return k;
+}
+static size_t sink_fwd_smem(int n, int m) { return ((size_t)n * (m + 1) + n + (m + 1) + 256 + 8) * sizeof(float); }
+static size_t sink_bwd_smem(int n, int m, int iters) {
+    return ((size_t)n * (m + 1) + (size_t)(iters + 1) * n + (size_t)iters * (m + 1) + (size_t)iters * n +
+            (size_t)iters * (m + 1) + 256) * sizeof(float);
+}
+
+static int sinkhorn_fwd(const float* S, const float* dust_bin, void* P, int p_dtype, float* U, float* V, int B, int n,
+                        int m, int iters, cudaStream_t st) {
+    VPR_REQUIRE(m == 16 || m == 32 || m == 64 || m == 128, "num_clusters must be 16/32/64/128 (got %d)", m);
+    VPR_REQUIRE(n > m, "Sinkhorn needs n > m (n=%d, m=%d)", n, m);
+    VPR_REQUIRE(iters >= 1 && iters <= 8, "iters out of range");
+    const size_t smem = sink_fwd_smem(n, m);
+    VPR_REQUIRE(smem <= 227 * 1024, "score tile [%d,%d] does not fit in shared memory", n, m);
+    const SinkConst k = sink_consts(n, m);
+    if (p_dtype == VPR_BF16) {
+        VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sinkhorn_fwd_kernel<bf16><<<B, 256, smem, st>>>(S, dust_bin, (bf16*)P, U, V, n, m, iters, k);
+    } else {
+        VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sinkhorn_fwd_kernel<float><<<B, 256, smem, st>>>(S, dust_bin, (float*)P, U, V, n, m, iters, k);
+    }
+    return launch_ok("sinkhorn_fwd_kernel");
+}
+
+static int sinkhorn_bwd(const float* S, const float* dust_bin, const float* U, const float* V, const float* dP, void* dS,
+                        int ds_dtype, float* d_bias, int B, int n, int m, int iters, cudaStream_t st) {
+    VPR_REQUIRE(m == 16 || m == 32 || m == 64 || m == 128, "num_clusters must be 16/32/64/128 (got %d)", m);
+    VPR_REQUIRE(n > m, "Sinkhorn needs n > m");
+    const size_t smem = sink_bwd_smem(n, m, iters);
+    VPR_REQUIRE(smem <= 227 * 1024, "score tile [%d,%d] does not fit in shared memory", n, m);
+    const SinkConst k = sink_consts(n, m);
+    if (ds_dtype == VPR_BF16) {
+        VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sinkhorn_bwd_kernel<bf16><<<B, 256, smem, st>>>(S, dust_bin, U, V, dP, (bf16*)dS, d_bias, n, m, iters, k);
+    } else {
+        VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sinkhorn_bwd_kernel<float><<<B, 256, smem, st>>>(S, dust_bin, U, V, dP, (float*)dS, d_bias, n, m, iters, k);
+    }
+    return launch_ok("sinkhorn_bwd_kernel");
+}
+
+// ---------------------------------------------------------------------------
+// descriptor assembly: intra-cluster L2 norm (over l), token L2 norm, concat, global L2 norm
+// ---------------------------------------------------------------------------
+#define NORM_EPS 1e-12f
+
+template <typename T>
+__global__ void __launch_bounds__(256) finalize_fwd_kernel(const float* __restrict__ AGG, const float* __restrict__ TF,
+                                                           T* __restrict__ out, int l, int m, int g) {
+    __shared__ float red[256];
+    __shared__ float inv_c[128];
+    __shared__ float red2[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float* A = AGG + (size_t)b * l * m;
+    const float* t = TF + (size_t)b * g;
+    const int parts = 256 / m, c = tid % m, part = tid / m;
+    float acc = 0.f;
+    for (int li = part; li < l; li += parts) { const float v = A[li * m + c]; acc += v * v; }
+    red[tid] = acc;
+    __syncthreads();
+    float zz = 0.f;   // ||z||^2 contribution of this thread's cluster
+    if (part == 0) {
+        float tot = red[c];
+        for (int q = 1; q < parts; ++q) tot += red[q * m + c];
+        const float nc = fmaxf(sqrtf(tot), NORM_EPS);
+        inv_c[c] = 1.f / nc;
+        zz = tot / (nc * nc);
+    }
+    float ts = 0.f;
+    for (int i = tid; i < g; i += 256) { const float v = t[i]; ts += v * v; }
+    ts = block_sum256(ts, red2);
+    const float nt = fmaxf(sqrtf(ts), NORM_EPS);
+    zz = block_sum256(zz, red2) + ts / (nt * nt);
+    const float invN = 1.f / fmaxf(sqrtf(zz), NORM_EPS);
+    T* o = out + (size_t)b * (g + l * m);
+    const float invt = invN / nt;
+    for (int i = tid; i < g; i += 256) stf(o + i, t[i] * invt);
+    for (int e = tid; e < l * m; e += 256) stf(o + g + e, A[e] * inv_c[e % m] * invN);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) finalize_bwd_kernel(const float* __restrict__ AGG, const float* __restrict__ TF,
+                                                           const T* __restrict__ d_out, T* __restrict__ dAGG,
+                                                           T* __restrict__ dTF, int l, int m, int g) {
+    __shared__ float red[256];
+    __shared__ float inv_c[128];
+    __shared__ float dot_c[128];
+    __shared__ float red2[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float* A = AGG + (size_t)b * l * m;
+    const float* t = TF + (size_t)b * g;
+    const T* dy = d_out + (size_t)b * (g + l * m);
+    const int parts = 256 / m, c = tid % m, part = tid / m;
+    // norms (recomputed)
+    float acc = 0.f;
+    for (int li = part; li < l; li += parts) { const float v = A[li * m + c]; acc += v * v; }
+    red[tid] = acc;
+    __syncthreads();
+    float zz = 0.f;
+    if (part == 0) {
+        float tot = red[c];
+        for (int q = 1; q < parts; ++q) tot += red[q * m + c];
+        const float nc = fmaxf(sqrtf(tot), NORM_EPS);
+        inv_c[c] = 1.f / nc;
+        zz = tot / (nc * nc);
+    }
+    float ts = 0.f;
+    for (int i = tid; i < g; i += 256) { const float v = t[i]; ts += v * v; }
+    ts = block_sum256(ts, red2);
+    const float nt = fmaxf(sqrtf(ts), NORM_EPS);
+    const float invt = 1.f / nt;
+    zz = block_sum256(zz, red2) + ts * invt * invt;
+    const float invN = 1.f / fmaxf(sqrtf(zz), NORM_EPS);
+    // s = y . dy   with y = z * invN
+    float s = 0.f;
+    for (int i = tid; i < g; i += 256) s += t[i] * invt * invN * ldf(dy + i);
+    for (int e = tid; e < l * m; e += 256) s += A[e] * inv_c[e % m] * invN * ldf(dy + g + e);
+    s = block_sum256(s, red2);
+    // dz = (dy - y s) * invN ; token part: dt = (dz - that (that . dz)) / nt
+    float dt_dot = 0.f;
+    for (int i = tid; i < g; i += 256) {
+        const float th = t[i] * invt;
+        const float dz = (ldf(dy + i) - th * invN * s) * invN;
+        dt_dot += th * dz;
+    }
+    dt_dot = block_sum256(dt_dot, red2);
+    T* dT = dTF + (size_t)b * g;
+    for (int i = tid; i < g; i += 256) {
+        const float th = t[i] * invt;
+        const float dz = (ldf(dy + i) - th * invN * s) * invN;
+        stf(dT + i, (dz - th * dt_dot) * invt);
+    }
+    // cluster part: per column c, dot_c = sum_l ahat_lc dz_lc
+    float dc = 0.f;
+    for (int li = part; li < l; li += parts) {
+        const float ah = A[li * m + c] * inv_c[c];
+        const float dz = (ldf(dy + g + li * m + c) - ah * invN * s) * invN;
+        dc += ah * dz;
+    }
+    __syncthreads();
+    red[tid] = dc;
+    __syncthreads();
+    if (part == 0) {
+        float tot = red[c];
+        for (int q = 1; q < parts; ++q) tot += red[q * m + c];
+        dot_c[c] = tot;
+    }
+    __syncthreads();
+    T* dA = dAGG + (size_t)b * l * m;
+    for (int e = tid; e < l * m; e += 256) {
+        const int cc = e % m;
+        const float ah = A[e] * inv_c[cc];
+        const float dz = (ldf(dy + g + e) - ah * invN * s) * invN;
+        stf(dA + e, (dz - ah * dot_c[cc]) * inv_c[cc]);
+    }
+}
+
+// column sums of a [R, C] matrix into fp32 (atomic): bias gradients
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, long long ld, long long R, int C,
+                                                     int rows_per_block, float* __restrict__ out) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + tx;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > R) r1 = R;
+    float acc = 0.f;
+    if (col < C)
+        for (long long r = r0 + ty; r < r1; r += 8) acc += ldf(X + r * ld + col);
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && col < C) {
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += red[i][tx];
+        atomicAdd(out + col, tot);
+    }
+}
+
+template <typename T>
+static int colsum(const T* X, long long ld, long long R, int C, float* out, cudaStream_t st) {
+    const int rpb = 512;
+    dim3 grid((C + 31) / 32, (unsigned)((R + rpb - 1) / rpb));
+    colsum_kernel<T><<<grid, 256, 0, st>>>(X, ld, R, C, rpb, out);
+    return launch_ok("colsum_kernel");
+}
+
+__global__ void dropout_mask_kernel(unsigned long long seed, uint32_t thr, long long total, uint8_t* out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        out[i] = dropout_hash(seed, (unsigned long long)i) >= thr ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------
+// buffer plans
+// ---------------------------------------------------------------------------
+struct SavePlan {
+    size_t w0cat, w1c, w1s, wt0, wt1, b0cat, H, F, S, P, U, V, AGG, HT, TF, total;
+};
+struct WorkPlan {
+    size_t dAGG, dTF, dF, dP, dS, dH, dHT, total;
+};
+
+static SavePlan save_plan(const VprSaladShape& s, int dtype) {
+    const size_t e = dtype == VPR_BF16 ? 2 : 4;
+    const size_t T = (size_t)s.B * s.n, h = s.hidden;
+    SavePlan p;
+    size_t off = 0;
+    p.w0cat = carve_size(off, 2 * h * s.d * e);
+    p.w1c = carve_size(off, (size_t)s.l * h * e);
+    p.w1s = carve_size(off, (size_t)s.m * h * e);
+    p.wt0 = carve_size(off, h * s.d * e);
+    p.wt1 = carve_size(off, (size_t)s.g * h * e);
+    p.b0cat = carve_size(off, 2 * h * 4);
+    p.H = carve_size(off, T * 2 * h * e);
+    p.F = carve_size(off, T * s.l * e);
+    p.S = carve_size(off, T * s.m * 4);
+    p.P = carve_size(off, T * s.m * e);
+    p.U = carve_size(off, (size_t)s.B * s.iters * (s.m + 1) * 4);
+    p.V = carve_size(off, (size_t)s.B * s.iters * s.n * 4);
+    p.AGG = carve_size(off, (size_t)s.B * s.l * s.m * 4);
+    p.HT = carve_size(off, (size_t)s.B * h * e);
+    p.TF = carve_size(off, (size_t)s.B * s.g * 4);
+    p.total = (off + 255) & ~size_t(255);
+    return p;
+}
+
+static WorkPlan work_plan(const VprSaladShape& s, int dtype) {
+    const size_t e = dtype == VPR_BF16 ? 2 : 4;
+    const size_t T = (size_t)s.B * s.n, h = s.hidden;
+    WorkPlan p;
+    size_t off = 0;
+    p.dAGG = carve_size(off, (size_t)s.B * s.l * s.m * e);
+    p.dTF = carve_size(off, (size_t)s.B * s.g * e);
+    p.dF = carve_size(off, T * s.l * e);
+    p.dP = carve_size(off, T * s.m * 4);
+    p.dS = carve_size(off, T * s.m * e);
+    p.dH = carve_size(off, T * 2 * h * e);
+    p.dHT = carve_size(off, (size_t)s.B * h * e);
+    p.total = (off + 255) & ~size_t(255);
+    return p;
+}
+
+static int check_shape(const VprSaladShape& s, int dtype) {
+    VPR_REQUIRE(dtype == VPR_F32 || dtype == VPR_BF16, "dtype must be VPR_F32 or VPR_BF16");
+    VPR_REQUIRE(s.B > 0 && s.n > 0, "empty batch (B=%d, n=%d)", s.B, s.n);
+    VPR_REQUIRE(s.n > s.m, "SALAD needs more patch tokens than clusters (n=%d, m=%d)", s.n, s.m);
+    VPR_REQUIRE(s.m == 16 || s.m == 32 || s.m == 64 || s.m == 128, "num_clusters must be 16/32/64/128");
+    VPR_REQUIRE(s.d % 8 == 0 && s.hidden % 8 == 0 && s.l % 8 == 0 && s.g % 8 == 0,
+                "channel counts must be multiples of 8 (d=%d hidden=%d l=%d g=%d)", s.d, s.hidden, s.l, s.g);
+    VPR_REQUIRE(s.iters >= 1 && s.iters <= 8, "iters out of range");
+    return 0;
+}
+
+template <typename T>
+static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, char* save, const VprSaladShape& s,
+                       int dtype, float drop_p, uint64_t seed, cudaStream_t st) {
+    const SavePlan sp = save_plan(s, dtype);
+    const int h = s.hidden;
+    const long long Tk = (long long)s.B * s.n;
+    T* w0cat = (T*)(save + sp.w0cat); T* w1c = (T*)(save + sp.w1c); T* w1s = (T*)(save + sp.w1s);
+    T* wt0 = (T*)(save + sp.wt0); T* wt1 = (T*)(save + sp.wt1); float* b0cat = (float*)(save + sp.b0cat);
+    T* H = (T*)(save + sp.H); T* F = (T*)(save + sp.F); float* S = (float*)(save + sp.S); T* P = (T*)(save + sp.P);
+    float* U = (float*)(save + sp.U); float* V = (float*)(save + sp.V); float* AGG = (float*)(save + sp.AGG);
+    T* HT = (T*)(save + sp.HT); float* TF = (float*)(save + sp.TF);
+    const int okT = dtype == VPR_BF16 ? OUT_BF16 : OUT_F32;
+
+    pack_params_kernel<T><<<num_sms() * 2, 256, 0, st>>>(p, s.d, h, s.l, s.m, s.g, w0cat, w1c, w1s, wt0, wt1, b0cat);
+    VPR_TRY(launch_ok("pack_params_kernel"));
+
+    GemmDesc g;
+    // H = dropout(relu(X W0cat^T + b0cat))           [T, 2h]
+    g = GemmDesc(); g.dtype = dtype;
+    g.A = x; g.lda = s.d; g.B = w0cat; g.ldb = s.d; g.M = (int)Tk; g.N = 2 * h; g.K = s.d;
+    g.out = H; g.out_kind = okT; g.ldo = 2 * h; g.bias = b0cat; g.relu = 1;
+    g.dropout_p = drop_p; g.dropout_seed = seed;
+    VPR_REQUIRE(Tk < (1ll << 31), "too many tokens");
+    VPR_TRY(gemm_run(g, st));
+    // F = H[:, :h] W1c^T + b1c                        [T, l]
+    g = GemmDesc(); g.dtype = dtype;
+    g.A = H; g.lda = 2 * h; g.B = w1c; g.ldb = h; g.M = (int)Tk; g.N = s.l; g.K = h;
+    g.out = F; g.out_kind = okT; g.ldo = s.l; g.bias = p.cluster_b1;
+    VPR_TRY(gemm_run(g, st));
+    // S = H[:, h:] W1s^T + b1s                        [T, m] fp32
+    g = GemmDesc(); g.dtype = dtype;
+    g.A = H + h; g.lda = 2 * h; g.B = w1s; g.ldb = h; g.M = (int)Tk; g.N = s.m; g.K = h;
+    g.out = S; g.out_kind = OUT_F32; g.ldo = s.m; g.bias = p.score_b1;
+    VPR_TRY(gemm_run(g, st));
+    // token features
+    g = GemmDesc(); g.dtype = dtype;
+    g.A = t; g.lda = s.d; g.B = wt0; g.ldb = s.d; g.M = s.B; g.N = h; g.K = s.d;
+    g.out = HT; g.out_kind = okT; g.ldo = h; g.bias = p.token_b0; g.relu = 1;
+    VPR_TRY(gemm_run(g, st));
+    g = GemmDesc(); g.dtype = dtype;
+    g.A = HT; g.lda = h; g.B = wt1; g.ldb = h; g.M = s.B; g.N = s.g; g.K = h;
+    g.out = TF; g.out_kind = OUT_F32; g.ldo = s.g; g.bias = p.token_b1;
+    VPR_TRY(gemm_run(g, st));
+    // P = sinkhorn(S)
+    VPR_TRY(sinkhorn_fwd(S, p.dust_bin, P, dtype, U, V, s.B, s.n, s.m, s.iters, st));
+    // AGG[b][l][c] = sum_j F[b][j][l] P[b][j][c]      both operands MN-major, K = tokens of image b
+    g = GemmDesc(); g.dtype = dtype;
+    g.A = F; g.a_mn = 1; g.lda = s.l; g.a_bs = (int64_t)s.n * s.l;
+    g.B = P; g.b_mn = 1; g.ldb = s.m; g.b_bs = (int64_t)s.n * s.m;
+    g.M = s.l; g.N = s.m; g.K = s.n; g.batch = s.B;
+    g.out = AGG; g.out_kind = OUT_F32; g.ldo = s.m; g.out_bs = (int64_t)s.l * s.m;
+    VPR_TRY(gemm_run(g, st));
+    finalize_fwd_kernel<T><<<s.B, 256, 0, st>>>(AGG, TF, out, s.l, s.m, s.g);
+    return launch_ok("finalize_fwd_kernel");
+}
+
+template <typename T>
+static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T* d_out, const char* save, char* ws,
+                       VprSaladGrads& gr, T* dx, T* dt, const VprSaladShape& s, int dtype, float drop_p,
+                       cudaStream_t st) {
+    const SavePlan sp = save_plan(s, dtype);
+    const WorkPlan wp = work_plan(s, dtype);
+    const int h = s.hidden;
+    const long long Tk = (long long)s.B * s.n;
+    const T* w0cat = (const T*)(save + sp.w0cat); const T* w1c = (const T*)(save + sp.w1c);
+    const T* w1s = (const T*)(save + sp.w1s); const T* wt0 = (const T*)(save + sp.wt0);
+    const T* wt1 = (const T*)(save + sp.wt1);
+    const T* H = (const T*)(save + sp.H); const T* F = (const T*)(save + sp.F); const float* S = (const float*)(save + sp.S);
+    const T* P = (const T*)(save + sp.P); const float* U = (const float*)(save + sp.U);
+    const float* V = (const float*)(save + sp.V); const float* AGG = (const float*)(save + sp.AGG);
+    const T* HT = (const T*)(save + sp.HT); const float* TF = (const float*)(save + sp.TF);
+    T* dAGG = (T*)(ws + wp.dAGG); T* dTF = (T*)(ws + wp.dTF); T* dF = (T*)(ws + wp.dF); float* dP = (float*)(ws + wp.dP);
+    T* dS = (T*)(ws + wp.dS); T* dH = (T*)(ws + wp.dH); T* dHT = (T*)(ws + wp.dHT);
+    const int okT = dtype == VPR_BF16 ? OUT_BF16 : OUT_F32;
+    const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const int nsm = num_sms();
+
+    // zero every gradient buffer that is accumulated with atomics
+    VPR_CUDA_OK(cudaMemsetAsync(gr.cluster_w0, 0, sizeof(float) * (size_t)h * s.d, st));
+    VPR_CUDA_OK(cudaMemsetAsync(gr.cluster_b0, 0, sizeof(float) * h, st));
+    VPR_CUDA_OK(cudaMemsetAsync(gr.cluster_w1, 0, sizeof(float) * (size_t)s.l * h, st));
+    VPR_CUDA_OK(cudaMemsetAsync(gr.cluster_b1, 0, sizeof(float) * s.l, st));
+    VPR_CUDA_OK(cudaMemsetAsync(gr.score_w0, 0, sizeof(float) * (size_t)h * s.d, st));
+    VPR_CUDA_OK(cudaMemsetAsync(gr.score_b0, 0, sizeof(float) * h, st));
+    VPR_CUDA_OK(cudaMemsetAsync(gr.score_w1, 0, sizeof(float) * (size_t)s.m * h, st));
+    VPR_CUDA_OK(cudaMemsetAsync(gr.score_b1, 0, sizeof(float) * s.m, st));
+    VPR_CUDA_OK(cudaMemsetAsync(gr.token_w0, 0, sizeof(float) * (size_t)h * s.d, st));
+    VPR_CUDA_OK(cudaMemsetAsync(gr.token_b0, 0, sizeof(float) * h, st));
+    VPR_CUDA_OK(cudaMemsetAsync(gr.token_w1, 0, sizeof(float) * (size_t)s.g * h, st));
+    VPR_CUDA_OK(cudaMemsetAsync(gr.token_b1, 0, sizeof(float) * s.g, st));
+    VPR_CUDA_OK(cudaMemsetAsync(gr.dust_bin, 0, sizeof(float), st));   // d/d dust_bin == 0 (SURVEY A-3b)
+
+    // norms backward: d_out -> dAGG [B,l,m], dTF [B,g]
+    finalize_bwd_kernel<T><<<s.B, 256, 0, st>>>(AGG, TF, d_out, dAGG, dTF, s.l, s.m, s.g);
+    VPR_TRY(launch_ok("finalize_bwd_kernel"));
+
+    GemmDesc g;
+    // ---- token-feature MLP backward ----
+    VPR_TRY(colsum<T>(dTF, s.g, s.B, s.g, gr.token_b1, st));
+    g = GemmDesc(); g.dtype = dtype;    // dWt1[g,h] = dTF^T HT
+    g.A = dTF; g.a_mn = 1; g.lda = s.g; g.B = HT; g.b_mn = 1; g.ldb = h; g.M = s.g; g.N = h; g.K = s.B;
+    g.out = gr.token_w1; g.out_kind = OUT_ATOMIC_F32; g.ldo = h;
+    VPR_TRY(gemm_run(g, st));
+    g = GemmDesc(); g.dtype = dtype;    // dHT = (dTF Wt1) * (HT > 0)
+    g.A = dTF; g.lda = s.g; g.B = wt1; g.b_mn = 1; g.ldb = h; g.M = s.B; g.N = h; g.K = s.g;
+    g.out = dHT; g.out_kind = okT; g.ldo = h; g.mask = HT; g.ld_mask = h;
+    VPR_TRY(gemm_run(g, st));
+    VPR_TRY(colsum<T>(dHT, h, s.B, h, gr.token_b0, st));
+    g = GemmDesc(); g.dtype = dtype;    // dWt0[h,d] = dHT^T t
+    g.A = dHT; g.a_mn = 1; g.lda = h; g.B = t; g.b_mn = 1; g.ldb = s.d; g.M = h; g.N = s.d; g.K = s.B;
+    g.out = gr.token_w0; g.out_kind = OUT_ATOMIC_F32; g.ldo = s.d;
+    VPR_TRY(gemm_run(g, st));
+    if (dt != nullptr) {                // dt = dHT Wt0
+        g = GemmDesc(); g.dtype = dtype;
+        g.A = dHT; g.lda = h; g.B = wt0; g.b_mn = 1; g.ldb = s.d; g.M = s.B; g.N = s.d; g.K = h;
+        g.out = dt; g.out_kind = okT; g.ldo = s.d;
+        VPR_TRY(gemm_run(g, st));
+    }
+
+    // ---- aggregation backward ----
+    g = GemmDesc(); g.dtype = dtype;    // dF[b][j][l] = sum_c P[b][j][c] dAGG[b][l][c]
+    g.A = P; g.lda = s.m; g.a_bs = (int64_t)s.n * s.m; g.B = dAGG; g.ldb = s.m; g.b_bs = (int64_t)s.l * s.m;
+    g.M = s.n; g.N = s.l; g.K = s.m; g.batch = s.B;
+    g.out = dF; g.out_kind = okT; g.ldo = s.l; g.out_bs = (int64_t)s.n * s.l;
+    VPR_TRY(gemm_run(g, st));
+    g = GemmDesc(); g.dtype = dtype;    // dP[b][j][c] = sum_l F[b][j][l] dAGG[b][l][c]
+    g.A = F; g.lda = s.l; g.a_bs = (int64_t)s.n * s.l; g.B = dAGG; g.b_mn = 1; g.ldb = s.m; g.b_bs = (int64_t)s.l * s.m;
+    g.M = s.n; g.N = s.m; g.K = s.l; g.batch = s.B;
+    g.out = dP; g.out_kind = OUT_F32; g.ldo = s.m; g.out_bs = (int64_t)s.n * s.m;
+    VPR_TRY(gemm_run(g, st));
+    // ---- Sinkhorn backward: dP -> dS (+ score bias gradient) ----
+    VPR_TRY(sinkhorn_bwd(S, p.dust_bin, U, V, dP, dS, dtype, gr.score_b1, s.B, s.n, s.m, s.iters, st));
+    VPR_TRY(colsum<T>(dF, s.l, Tk, s.l, gr.cluster_b1, st));
+
+    // ---- second-layer weight gradients (K = all tokens, split-K + fp32 atomics) ----
+    const int kb_tok = (int)((Tk + 63) / 64);
+    g = GemmDesc(); g.dtype = dtype;    // dW1c[l,h] = dF^T H[:, :h]
+    g.A = dF; g.a_mn = 1; g.lda = s.l; g.B = H; g.b_mn = 1; g.ldb = 2 * h; g.M = s.l; g.N = h; g.K = (int)Tk;
+    g.out = gr.cluster_w1; g.out_kind = OUT_ATOMIC_F32; g.ldo = h;
+    {
+        int tiles = ((s.l + 127) / 128) * ((h + 255) / 256);
+        g.k_splits = nsm / tiles; if (g.k_splits < 1) g.k_splits = 1; if (g.k_splits > kb_tok) g.k_splits = kb_tok;
+    }
+    VPR_TRY(gemm_run(g, st));
+    g = GemmDesc(); g.dtype = dtype;    // dW1s[m,h] = dS^T H[:, h:]
+    g.A = dS; g.a_mn = 1; g.lda = s.m; g.B = H + h; g.b_mn = 1; g.ldb = 2 * h; g.M = s.m; g.N = h; g.K = (int)Tk;
+    g.out = gr.score_w1; g.out_kind = OUT_ATOMIC_F32; g.ldo = h;
+    {
+        int tiles = ((s.m + 127) / 128) * ((h + 255) / 256);
+        g.k_splits = nsm / tiles; if (g.k_splits < 1) g.k_splits = 1; if (g.k_splits > kb_tok) g.k_splits = kb_tok;
+    }
+    VPR_TRY(gemm_run(g, st));
+
+    // ---- dH = [dF W1c | dS W1s] * (H > 0) * keep_scale ----
+    g = GemmDesc(); g.dtype = dtype;
+    g.A = dF; g.lda = s.l; g.B = w1c; g.b_mn = 1; g.ldb = h; g.M = (int)Tk; g.N = h; g.K = s.l;
+    g.out = dH; g.out_kind = okT; g.ldo = 2 * h; g.mask = H; g.ld_mask = 2 * h; g.mask_scale = keep_scale;
+    VPR_TRY(gemm_run(g, st));
+    g = GemmDesc(); g.dtype = dtype;
+    g.A = dS; g.lda = s.m; g.B = w1s; g.b_mn = 1; g.ldb = h; g.M = (int)Tk; g.N = h; g.K = s.m;
+    g.out = dH + h; g.out_kind = okT; g.ldo = 2 * h; g.mask = H + h; g.ld_mask = 2 * h; g.mask_scale = keep_scale;
+    VPR_TRY(gemm_run(g, st));
+    // first-layer bias gradients
+    VPR_TRY(colsum<T>(dH, 2 * h, Tk, h, gr.cluster_b0, st));
+    VPR_TRY(colsum<T>(dH + h, 2 * h, Tk, h, gr.score_b0, st));
+    // ---- first-layer weight gradients: dW0[h,d] = dH^T X (two halves: separate parameter tensors) ----
+    for (int half = 0; half < 2; ++half) {
+        g = GemmDesc(); g.dtype = dtype;
+        g.A = dH + half * h; g.a_mn = 1; g.lda = 2 * h; g.B = x; g.b_mn = 1; g.ldb = s.d; g.M = h; g.N = s.d; g.K = (int)Tk;
+        g.out = half == 0 ? gr.cluster_w0 : gr.score_w0; g.out_kind = OUT_ATOMIC_F32; g.ldo = s.d;
+        int tiles = ((h + 127) / 128) * ((s.d + 255) / 256);
+        g.k_splits = nsm / tiles; if (g.k_splits < 1) g.k_splits = 1; if (g.k_splits > kb_tok) g.k_splits = kb_tok;
+        VPR_TRY(gemm_run(g, st));
+    }
+    // ---- input gradient dX = dH W0cat ----
+    if (dx != nullptr) {
+        g = GemmDesc(); g.dtype = dtype;
+        g.A = dH; g.lda = 2 * h; g.B = w0cat; g.b_mn = 1; g.ldb = s.d; g.M = (int)Tk; g.N = s.d; g.K = 2 * h;
+        g.out = dx; g.out_kind = okT; g.ldo = s.d;
+        VPR_TRY(gemm_run(g, st));
+    }
+    return 0;
+}
+
+}  // namespace vpr
+
+using namespace vpr;
+
+extern "C" {
+
+size_t vpr_salad_save_bytes(const VprSaladShape* s, int dtype) { return save_plan(*s, dtype).total; }
+size_t vpr_salad_workspace_bytes(const VprSaladShape* s, int dtype) { return work_plan(*s, dtype).total; }
+
+int vpr_salad_fwd(const VprSaladParams* p, const void* x, const void* t, void* out, void* save, void* workspace,
+                  size_t workspace_bytes, const VprSaladShape* s, int dtype, float dropout_p, uint64_t seed,
+                  cudaStream_t stream) {
+    (void)workspace; (void)workspace_bytes;
+    VPR_REQUIRE(p && x && t && out && save && s, "null argument");
+    VPR_TRY(check_shape(*s, dtype));
+    VPR_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout_p out of range");
+    if (dtype == VPR_BF16)
+        return salad_fwd_t<bf16>(*p, (const bf16*)x, (const bf16*)t, (bf16*)out, (char*)save, *s, dtype, dropout_p, seed, stream);
+    return salad_fwd_t<float>(*p, (const float*)x, (const float*)t, (float*)out, (char*)save, *s, dtype, dropout_p, seed, stream);
+}
+
+int vpr_salad_bwd(const VprSaladParams* p, const void* x, const void* t, const void* d_out, const void* save,
+                  void* workspace, size_t workspace_bytes, VprSaladGrads* grads, void* dx, void* dt,
+                  const VprSaladShape* s, int dtype, float dropout_p, cudaStream_t stream) {
+    VPR_REQUIRE(p && x && t && d_out && save && workspace && grads && s, "null argument");
+    VPR_TRY(check_shape(*s, dtype));
+    VPR_REQUIRE(workspace_bytes >= work_plan(*s, dtype).total, "workspace too small: %zu < %zu", workspace_bytes,
+                work_plan(*s, dtype).total);
+    if (dtype == VPR_BF16)
+        return salad_bwd_t<bf16>(*p, (const bf16*)x, (const bf16*)t, (const bf16*)d_out, (const char*)save,
+                                 (char*)workspace, *grads, (bf16*)dx, (bf16*)dt, *s, dtype, dropout_p, stream);
+    return salad_bwd_t<float>(*p, (const float*)x, (const float*)t, (const float*)d_out, (const char*)save,
+                              (char*)workspace, *grads, (float*)dx, (float*)dt, *s, dtype, dropout_p, stream);
+}
+
+int vpr_dropout_mask(uint64_t seed, float p, int64_t rows, int64_t cols, uint8_t* out, cudaStream_t stream) {
+    VPR_REQUIRE(out && rows > 0 && cols > 0, "bad argument");
+    dropout_mask_kernel<<<num_sms() * 4, 256, 0, stream>>>(seed, p > 0.f ? dropout_threshold(p) : 0u, rows * cols, out);
+    return launch_ok("dropout_mask_kernel");
+}
+
+int vpr_sinkhorn_fwd(const float* S, const float* dust_bin, void* P, int p_dtype, float* U, float* V, int B, int n,
+                     int m, int iters, cudaStream_t stream) {
+    VPR_REQUIRE(S && dust_bin && P && U && V && B > 0, "bad argument");
+    return sinkhorn_fwd(S, dust_bin, P, p_dtype, U, V, B, n, m, iters, stream);
+}
+
+int vpr_sinkhorn_bwd(const float* S, const float* dust_bin, const float* U, const float* V, const float* dP, void* dS,
+                     int ds_dtype, float* d_bias, int B, int n, int m, int iters, cudaStream_t stream) {
+    VPR_REQUIRE(S && dust_bin && U && V && dP && dS && B > 0, "bad argument");
+    return sinkhorn_bwd(S, dust_bin, U, V, dP, dS, ds_dtype, d_bias, B, n, m, iters, stream);
+}
+
+}  // extern "C"

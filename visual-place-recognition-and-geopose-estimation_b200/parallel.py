@@ -1,0 +1,116 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch on the
+GPU box, gloo in the CPU tests).  Only the two exchanges the path really has:
+  * fine-tuning shards the batch -> one sum-allreduce of the head gradients per step, bucketed so
+    the geopose-head gradients (ready first, 75 % of the bytes) fly while the SALAD backward runs;
+  * retrieval shards the gallery -> allgather of per-rank top-k lists (knn.knn_topk_sharded).
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend: str | None = None) -> tuple[int, int, int]:
+    """Initialise from torchrun's environment.  Returns (rank, local_rank, world_size)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, local, world
+
+
+def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous [begin, end) of ``total`` rows owned by ``rank`` (first ``total % world`` ranks
+    get one extra row).  Used for batch shards and gallery shards alike."""
+    base, rem = divmod(total, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def _flatten(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+    return torch.cat([t.reshape(-1) for t in tensors])
+
+
+def allreduce_grads(params: Iterable[torch.nn.Parameter], group=None, bucket_bytes: int = 32 << 20,
+                    average: bool = False, async_op: bool = False):
+    """Sum-allreduce ``p.grad`` of every parameter that has one, in flat buckets of about
+    ``bucket_bytes``.  Returns a finaliser that waits and scatters the reduced values back."""
+    ps = [p for p in params if p.grad is not None]
+    if not ps or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return lambda: None
+    world = dist.get_world_size(group)
+    buckets: List[List[torch.nn.Parameter]] = [[]]
+    size = 0
+    for p in ps:
+        nb = p.grad.numel() * p.grad.element_size()
+        if buckets[-1] and size + nb > bucket_bytes:
+            buckets.append([])
+            size = 0
+        buckets[-1].append(p)
+        size += nb
+    pending = []
+    for b in buckets:
+        flat = _flatten([p.grad for p in b])
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        pending.append((b, flat, work))
+
+    def finish():
+        for b, flat, work in pending:
+            work.wait()
+            if average:
+                flat.div_(world)
+            off = 0
+            for p in b:
+                n = p.grad.numel()
+                p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                off += n
+
+    if async_op:
+        return finish
+    finish()
+    return lambda: None
+
+
+class DataParallelStep:
+    """One fine-tuning step of SALAD head + geopose heads over a batch shard (BASELINE config 3).
+
+    The loss is the global-batch mean (each rank divides by the global batch), so the reduction
+    across ranks is a plain sum.  The geopose-head gradients come out of the fused heads kernel
+    before the SALAD backward starts; their allreduce is launched first and overlaps it.
+    """
+
+    def __init__(self, salad, heads, group=None):
+        self.salad, self.heads, self.group = salad, heads, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def grad_elements(self) -> int:
+        return sum(p.numel() for p in list(self.salad.parameters()) + list(self.heads.parameters()))
+
+    def step(self, f, t, latlon_target, angle_target_deg, global_B: int | None = None):
+        B = t.shape[0]
+        gB = global_B if global_B is not None else B * self.world
+        for p in list(self.salad.parameters()) + list(self.heads.parameters()):
+            p.grad = None
+        desc = self.salad((f, t))
+        d = desc.detach().requires_grad_(True)
+        total, losses, latlon_pred, sincos_pred = self.heads(d, latlon_target, angle_target_deg, global_B=gB)
+        total.backward()                       # heads grads + d(desc): already computed by the fused call
+        fin_heads = allreduce_grads(self.heads.parameters(), self.group, async_op=True)
+        desc.backward(d.grad)                  # SALAD backward overlaps the heads-gradient allreduce
+        fin_salad = allreduce_grads(self.salad.parameters(), self.group, async_op=True)
+        fin_heads()
+        fin_salad()
+        return total.detach(), losses

@@ -1,0 +1,194 @@
+"""SaladHead: drop-in for the SALAD aggregator the reference pulls in through
+``torch.hub.load("serizba/salad", "dinov2_salad")`` (reference
+dinov2salad/dinov2salad_finetuning.py:19,92; dinov2salad/dinov2salad_validation.py:65).
+
+Same constructor arguments, parameter names/shapes and ``forward((patch_map, cls_token)) ->
+[B, token_dim + cluster_dim*num_clusters]`` L2-normalised descriptor contract as upstream
+``SALAD``, with an autograd backward.  All arithmetic runs in
+libvpr_b200.so (hand-written sm_100a kernels); this file only marshals pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+_PARAM_ORDER = (
+    ("cluster_w0", "cluster_features.0.weight"), ("cluster_b0", "cluster_features.0.bias"),
+    ("cluster_w1", "cluster_features.3.weight"), ("cluster_b1", "cluster_features.3.bias"),
+    ("score_w0", "score.0.weight"), ("score_b0", "score.0.bias"),
+    ("score_w1", "score.3.weight"), ("score_b1", "score.3.bias"),
+    ("token_w0", "token_features.0.weight"), ("token_b0", "token_features.0.bias"),
+    ("token_w1", "token_features.2.weight"), ("token_b1", "token_features.2.bias"),
+    ("dust_bin", "dust_bin"),
+)
+
+
+def _params_struct(cls, tensors):
+    s = cls()
+    for (field, _), t in zip(_PARAM_ORDER, tensors):
+        setattr(s, field, t.data_ptr())
+    return s
+
+
+class _SaladFn(torch.autograd.Function):
+    """x_tok: [B, n, d] contiguous, t: [B, d]; params in _PARAM_ORDER (fp32, contiguous)."""
+
+    @staticmethod
+    def forward(ctx, x_tok, t, shape_tuple, dropout_p, seed, *params):
+        lib = L.lib()
+        B, n, d, hidden, m, l, g, iters = shape_tuple
+        dt = L.dtype_code(x_tok.dtype)
+        shape = L.SaladShape(B, n, d, hidden, m, l, g, iters)
+        dev = x_tok.device
+        save = torch.empty(lib.vpr_salad_save_bytes(C.byref(shape), dt), dtype=torch.uint8, device=dev)
+        out = torch.empty(B, g + l * m, dtype=x_tok.dtype, device=dev)
+        ps = _params_struct(L.SaladParams, params)
+        L.check(lib.vpr_salad_fwd(C.byref(ps), L.ptr(x_tok), L.ptr(t), L.ptr(out), L.ptr(save), None, 0,
+                                  C.byref(shape), dt, float(dropout_p), int(seed), L.stream_ptr(dev)),
+                "vpr_salad_fwd")
+        ctx.shape_tuple = shape_tuple
+        ctx.dropout_p = float(dropout_p)
+        ctx.save_for_backward(x_tok, t, save, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = L.lib()
+        x_tok, t, save, *params = ctx.saved_tensors
+        B, n, d, hidden, m, l, g, iters = ctx.shape_tuple
+        dt = L.dtype_code(x_tok.dtype)
+        shape = L.SaladShape(B, n, d, hidden, m, l, g, iters)
+        dev = x_tok.device
+        d_out = d_out.contiguous()
+        if d_out.dtype != x_tok.dtype:
+            d_out = d_out.to(x_tok.dtype)
+        ws_bytes = lib.vpr_salad_workspace_bytes(C.byref(shape), dt)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        sizes = [p.numel() for p in params]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        grads = list(torch.split(flat, sizes))
+        gs = _params_struct(L.SaladGrads, grads)
+        ps = _params_struct(L.SaladParams, params)
+        dx = torch.empty_like(x_tok) if ctx.needs_input_grad[0] else None
+        dtok = torch.empty_like(t) if ctx.needs_input_grad[1] else None
+        L.check(lib.vpr_salad_bwd(C.byref(ps), L.ptr(x_tok), L.ptr(t), L.ptr(d_out), L.ptr(save), L.ptr(ws),
+                                  ws_bytes, C.byref(gs), L.ptr(dx), L.ptr(dtok), C.byref(shape), dt,
+                                  ctx.dropout_p, L.stream_ptr(dev)),
+                "vpr_salad_bwd")
+        pg = [gr.view_as(p) if ctx.needs_input_grad[5 + i] else None
+              for i, (gr, p) in enumerate(zip(grads, params))]
+        return (dx, dtok, None, None, None, *pg)
+
+
+class SaladHead(nn.Module):
+    """B200-native SALAD aggregation head.
+
+    ``forward((f, t))``: ``f`` is the patch-token map, either ``[B, C, h, w]`` (any strides; the
+    permuted channels-last view upstream's DINOv2 wrapper produces is consumed without a copy)
+    or ``[B, n, C]``; ``t`` is the CLS token ``[B, C]``.  fp32 inputs run the fp32 parity path,
+    bf16 inputs the tcgen05 path; the descriptor has the input dtype.
+    """
+
+    def __init__(self, num_channels: int = 768, num_clusters: int = 64, cluster_dim: int = 128,
+                 token_dim: int = 256, dropout: float = 0.3, sinkhorn_iters: int = 3):
+        super().__init__()
+        self.num_channels = num_channels
+        self.num_clusters = num_clusters
+        self.cluster_dim = cluster_dim
+        self.token_dim = token_dim
+        self.dropout_p = float(dropout)
+        self.sinkhorn_iters = sinkhorn_iters
+        drop = nn.Dropout(dropout) if dropout > 0 else nn.Identity()
+        # parameter containers with upstream's names; the modules themselves are never called
+        self.token_features = nn.Sequential(nn.Linear(num_channels, 512), nn.ReLU(), nn.Linear(512, token_dim))
+        self.cluster_features = nn.Sequential(nn.Conv2d(num_channels, 512, 1), drop, nn.ReLU(),
+                                              nn.Conv2d(512, cluster_dim, 1))
+        self.score = nn.Sequential(nn.Conv2d(num_channels, 512, 1), drop, nn.ReLU(),
+                                   nn.Conv2d(512, num_clusters, 1))
+        self.dust_bin = nn.Parameter(torch.tensor(1.0))
+        self._step = 0
+        self.seed = 0x5A1AD
+
+    @property
+    def out_dim(self) -> int:
+        return self.token_dim + self.cluster_dim * self.num_clusters
+
+    def _param_list(self):
+        sd = dict(self.named_parameters())
+        return [sd[name] for _, name in _PARAM_ORDER]
+
+    @staticmethod
+    def tokens_from_map(f: torch.Tensor) -> torch.Tensor:
+        if f.dim() == 3:
+            return f.contiguous()
+        if f.dim() != 4:
+            raise ValueError(f"patch tokens must be [B,C,h,w] or [B,n,C], got {tuple(f.shape)}")
+        B, Cc, h, w = f.shape
+        return f.permute(0, 2, 3, 1).reshape(B, h * w, Cc).contiguous()   # no copy for channels-last views
+
+    def forward(self, x: Tuple[torch.Tensor, torch.Tensor]) -> torch.Tensor:
+        f, t = x
+        L.require_cuda(f, "patch tokens")
+        L.require_cuda(t, "cls token")
+        x_tok = self.tokens_from_map(f)
+        B, n, d = x_tok.shape
+        if d != self.num_channels:
+            raise ValueError(f"expected {self.num_channels} channels, got {d}")
+        if t.shape != (B, d):
+            raise ValueError(f"cls token must be [{B},{d}], got {tuple(t.shape)}")
+        if n <= self.num_clusters:
+            raise ValueError(f"SALAD needs more patch tokens ({n}) than clusters ({self.num_clusters})")
+        t = t.to(x_tok.dtype).contiguous()
+        params = self._param_list()
+        for p in params:
+            if p.dtype != torch.float32 or not p.is_cuda:
+                raise RuntimeError("SaladHead parameters must be fp32 CUDA tensors (master weights)")
+        p_drop = self.dropout_p if self.training else 0.0
+        seed = (self.seed * 1000003 + self._step) & 0xFFFFFFFFFFFFFFFF
+        if self.training:
+            self._step += 1
+        shape = (B, n, d, 512, self.num_clusters, self.cluster_dim, self.token_dim, self.sinkhorn_iters)
+        self.last_seed = seed
+        return _SaladFn.apply(x_tok, t, shape, p_drop, seed, *[p.contiguous() for p in params])
+
+
+def dropout_keep_mask(seed: int, p: float, rows: int, cols: int, device="cuda") -> torch.Tensor:
+    """The {0,1} keep mask the fused dropout epilogue used for ``seed`` over the [rows, cols] hidden
+    activation (cols = 1024: cluster half then score half).  Test support."""
+    out = torch.empty(rows, cols, dtype=torch.uint8, device=device)
+    L.check(L.lib().vpr_dropout_mask(int(seed), float(p), rows, cols, L.ptr(out), L.stream_ptr(out.device)),
+            "vpr_dropout_mask")
+    return out
+
+
+def sinkhorn(S: torch.Tensor, dust_bin: torch.Tensor, iters: int = 3, out_dtype=torch.float32):
+    """Stand-alone log-domain Sinkhorn (upstream get_matching_probs + exp, dustbin row dropped).
+    S: [B, n, m] fp32 token-major -> (P [B,n,m], U [B,iters,m+1], V [B,iters,n])."""
+    L.require_cuda(S, "S")
+    S = S.contiguous().float()
+    B, n, m = S.shape
+    P = torch.empty(B, n, m, dtype=out_dtype, device=S.device)
+    U = torch.empty(B, iters, m + 1, dtype=torch.float32, device=S.device)
+    V = torch.empty(B, iters, n, dtype=torch.float32, device=S.device)
+    db = dust_bin.detach().float().reshape(1).to(S.device)
+    L.check(L.lib().vpr_sinkhorn_fwd(L.ptr(S), L.ptr(db), L.ptr(P), L.dtype_code(out_dtype), L.ptr(U), L.ptr(V),
+                                     B, n, m, iters, L.stream_ptr(S.device)), "vpr_sinkhorn_fwd")
+    return P, U, V
+
+
+def sinkhorn_backward(S, dust_bin, U, V, dP, iters: int = 3, out_dtype=torch.float32):
+    S = S.contiguous().float()
+    dP = dP.contiguous().float()
+    B, n, m = S.shape
+    dS = torch.empty(B, n, m, dtype=out_dtype, device=S.device)
+    dbias = torch.zeros(m, dtype=torch.float32, device=S.device)
+    db = dust_bin.detach().float().reshape(1).to(S.device)
+    L.check(L.lib().vpr_sinkhorn_bwd(L.ptr(S), L.ptr(db), L.ptr(U), L.ptr(V), L.ptr(dP), L.ptr(dS),
+                                     L.dtype_code(out_dtype), L.ptr(dbias), B, n, m, iters,
+                                     L.stream_ptr(S.device)), "vpr_sinkhorn_bwd")
+    return dS, dbias
