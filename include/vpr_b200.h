@@ -84,6 +84,8 @@ typedef struct {
 
 VPR_API const char* vpr_last_error(void);
 VPR_API int vpr_abi_version(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+VPR_API unsigned long long vpr_launch_count(void);
 
 /* Bytes of the activation buffer forward fills and backward reads / of the scratch
  * buffer either call may clobber. */

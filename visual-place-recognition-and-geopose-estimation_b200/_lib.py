@@ -52,6 +52,7 @@ class HeadsGrads(C.Structure):
 EXPORTS = {
     "vpr_last_error": (C.c_char_p, []),
     "vpr_abi_version": (C.c_int, []),
+    "vpr_launch_count": (C.c_ulonglong, []),
     "vpr_salad_save_bytes": (C.c_size_t, [C.POINTER(SaladShape), C.c_int]),
     "vpr_salad_workspace_bytes": (C.c_size_t, [C.POINTER(SaladShape), C.c_int]),
     "vpr_salad_fwd": (C.c_int, [C.POINTER(SaladParams), _fp, _fp, _fp, _fp, _fp, C.c_size_t,

@@ -3,6 +3,7 @@
 #include "gemm.h"
 #include "../../include/vpr_b200.h"
 
+#include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -17,6 +18,9 @@ int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int num_sms() {
     static int n = 0;
@@ -35,6 +39,8 @@ extern "C" {
 const char* vpr_last_error(void) { return vpr::g_err; }
 
 int vpr_abi_version(void) { return VPR_ABI_VERSION; }
+
+unsigned long long vpr_launch_count(void) { return vpr::g_launches.load(); }
 
 int vpr_gemm(int dtype, const void* A, int a_mn, int64_t lda, int64_t a_bs, const void* B, int b_mn, int64_t ldb,
              int64_t b_bs, int M, int N, int K, int batch, void* out, int out_kind, int64_t ldo, int64_t out_bs,

@@ -17,6 +17,7 @@ typedef __nv_bfloat16 bf16;
 // ---------------------------------------------------------------------------
 int fail(int code, const char* fmt, ...);
 int num_sms();
+void note_launch();   // counts kernel launches (vpr_launch_count)
 
 #define VPR_CUDA_OK(expr)                                                          \
     do {                                                                           \
@@ -40,6 +41,7 @@ int num_sms();
 static inline int launch_ok(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(3, "launch %s: %s", what, cudaGetErrorString(e));
+    note_launch();
     return 0;
 }
 
