@@ -1,0 +1,418 @@
+"""GPU parity tests (run with -m gpu on a B200): every CUDA path, called through the C-ABI
+library, against the CPU oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): descriptors and gradients within 1e-4 relative in fp32 and
+2e-2 in bf16; kNN top-k index sets exact outside ties within 1e-6.  "Relative" is the Frobenius
+norm of the difference over the Frobenius norm of the oracle tensor.
+
+bf16 mode stores weights and activations in bf16, so its oracle is the fp32 oracle evaluated on
+the same bf16-rounded inputs AND bf16-rounded weights (exactly what the kernels consume; fp32
+accumulation everywhere).  Against the un-rounded fp32 weights only the descriptor is held to
+2e-2: gradients then differ by whole ReLU units whose pre-activation changes sign under weight
+rounding (about one unit per token), which no bf16 implementation can avoid.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import salad_ref as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def vpr():
+    import __graft_entry__ as g
+    if not os.path.exists(os.path.join(g.PKG_DIR, "libvpr_b200.so")):
+        g.build()
+    import vpr_b200
+    assert torch.cuda.is_available()
+    return vpr_b200
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+# ------------------------------------------------------------------ GEMM building block
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("shape", [(128, 64, 64, 1), (384, 192, 320, 1), (200, 104, 72, 1), (1024, 1024, 768, 1),
+                                   (256, 128, 192, 3), (536, 64, 128, 2)])
+def test_tcgen05_gemm_all_operand_layouts(vpr, a_mn, b_mn, shape):
+    from vpr_b200 import ops
+    M, N, K, batch = shape
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(batch, M, K, device="cuda", generator=g).bfloat16()
+    B = torch.randn(batch, N, K, device="cuda", generator=g).bfloat16()
+    ref = torch.einsum("bmk,bnk->bmn", A.float(), B.float())
+    Ast = A.transpose(1, 2).contiguous() if a_mn else A
+    Bst = B.transpose(1, 2).contiguous() if b_mn else B
+    out = ops.gemm(Ast, Bst, M, N, K, a_mn=a_mn, b_mn=b_mn, batch=batch, a_bs=Ast.stride(0) if batch > 1 else 0,
+                   b_bs=Bst.stride(0) if batch > 1 else 0)
+    assert rel(out, ref) < 2e-6          # products of bf16 are exact in fp32; only summation order differs
+
+
+def test_gemm_epilogues_and_split_k(vpr):
+    from vpr_b200 import ops, _lib as L
+    g = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.randn(1, 300, 512, device="cuda", generator=g).bfloat16()
+    B = torch.randn(1, 256, 512, device="cuda", generator=g).bfloat16()
+    bias = torch.randn(256, device="cuda", generator=g)
+    mask = torch.randn(1, 300, 256, device="cuda", generator=g).bfloat16()
+    ref = (torch.einsum("bmk,bnk->bmn", A.float(), B.float()) + bias).clamp_min(0)
+    ref = torch.where(mask.float() > 0, ref * 0.5, torch.zeros_like(ref))
+    out = ops.gemm(A, B, 300, 256, 512, out_kind=L.OUT_BF16, bias=bias, relu=True, mask=mask, mask_scale=0.5)
+    assert rel(out, ref) < 4e-3                                    # one bf16 rounding of the output
+    At = torch.randn(1, 4096, 128, device="cuda", generator=g).bfloat16()    # MN-major A: [K, M]
+    Bt = torch.randn(1, 4096, 512, device="cuda", generator=g).bfloat16()    # MN-major B: [K, N]
+    ref2 = torch.einsum("bkm,bkn->bmn", At.float(), Bt.float())
+    out2 = ops.gemm(At, Bt, 128, 512, 4096, a_mn=True, b_mn=True, out_kind=L.OUT_ATOMIC_F32, k_splits=16)
+    assert rel(out2, ref2) < 2e-6
+
+
+def test_fp32_gemm_parity_mode(vpr):
+    from vpr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.randn(2, 200, 529, device="cuda", generator=g)
+    B = torch.randn(2, 100, 529, device="cuda", generator=g)
+    out = ops.gemm(A, B, 200, 100, 529, batch=2, a_bs=A.stride(0), b_bs=B.stride(0))
+    assert rel(out, torch.einsum("bmk,bnk->bmn", A.double(), B.double())) < 1e-6
+
+
+# ------------------------------------------------------------------ Sinkhorn
+@pytest.mark.parametrize("B,n,m", [(2, 256, 64), (3, 529, 64), (1, 65, 64), (2, 100, 64), (2, 300, 32)])
+def test_sinkhorn_forward_backward(vpr, B, n, m):
+    g = torch.Generator().manual_seed(n + m)
+    S = torch.randn(B, m, n, generator=g) * 2.0
+    db = torch.tensor(1.0)
+    Sd = S.double().requires_grad_(True)
+    Pd = O.get_matching_probs(Sd, db.double(), 3, const_dtype=torch.float64).exp()
+    St = S.transpose(1, 2).contiguous().cuda()
+    P, U, V = vpr.sinkhorn(St, db.cuda(), 3)
+    assert rel(P, Pd[:, :m].transpose(1, 2)) < 1e-5
+    # known answers: columns of the augmented plan sum to 1 -> token rows of P sum to 1 - dustbin share
+    dust = Pd[:, m].float()
+    np.testing.assert_allclose(P.sum(2).cpu().numpy(), (1 - dust).numpy(), atol=2e-6)
+    dP = torch.randn(B, n, m, generator=g)
+    (Pd[:, :m] * dP.double().transpose(1, 2)).sum().backward()
+    dS, _ = vpr.sinkhorn_backward(St, db.cuda(), U, V, dP.cuda(), 3)
+    assert rel(dS, Sd.grad.transpose(1, 2)) < 1e-5
+    # explicit recurrence (SURVEY A-3) agrees too
+    dS2 = O.sinkhorn_backward_explicit(S.double(), dP.double().transpose(1, 2), 3)
+    assert rel(dS, dS2.transpose(1, 2)) < 1e-5
+
+
+def test_sinkhorn_dustbin_value_is_irrelevant(vpr):
+    g = torch.Generator().manual_seed(3)
+    S = torch.randn(2, 256, 64, generator=g).cuda()
+    P1, _, _ = vpr.sinkhorn(S, torch.tensor(1.0).cuda(), 3)
+    P2, _, _ = vpr.sinkhorn(S, torch.tensor(-7.3).cuda(), 3)
+    assert rel(P1, P2) < 1e-5
+
+
+# ------------------------------------------------------------------ SALAD head
+def _pair(vpr, dropout=0.0, round_weights=False):
+    torch.manual_seed(0)
+    ref = O.SaladRef(dropout=dropout)
+    if round_weights:
+        with torch.no_grad():
+            for p in ref.parameters():
+                p.copy_(p.bfloat16().float())
+    mod = vpr.SaladHead(dropout=dropout).cuda()
+    mod.load_state_dict(ref.state_dict())
+    return ref, mod
+
+
+def _run_pair(vpr, ref, mod, B, hw, seed, dtype, train=False, nchw=False):
+    ref.train(train)
+    mod.train(train)
+    g = torch.Generator().manual_seed(seed)
+    n = hw * hw
+    x = torch.randn(B, n, 768, generator=g)
+    t = torch.randn(B, 768, generator=g)
+    w = torch.randn(B, 8448, generator=g)
+    if dtype == torch.bfloat16:
+        x, t = x.bfloat16().float(), t.bfloat16().float()
+    xg = x.cuda().to(dtype).requires_grad_(True)
+    tg = t.cuda().to(dtype).requires_grad_(True)
+    f = O.tokens_to_salad_input(xg, hw, hw)
+    if nchw:
+        f = f.contiguous()
+    out = mod((f, tg))
+    (out.float() * w.cuda()).sum().backward()
+    mask = None
+    if train and mod.dropout_p > 0:
+        keep = vpr.dropout_keep_mask(mod.last_seed, mod.dropout_p, B * n, 1024).cpu().float()
+        mask = keep.reshape(B, hw, hw, 1024).permute(0, 3, 1, 2)
+    xr = x.clone().requires_grad_(True)
+    tr = t.clone().requires_grad_(True)
+    oref = ref((O.tokens_to_salad_input(xr, hw, hw), tr), drop_mask=mask)
+    (oref * w).sum().backward()
+    errs = {"desc": rel(out, oref), "dx": rel(xg.grad, xr.grad), "dt": rel(tg.grad, tr.grad)}
+    for (name, p), (_, pr) in zip(mod.named_parameters(), ref.named_parameters()):
+        if pr.grad.norm() > 1e-6:           # dust_bin and score.3.bias have identically-zero gradients
+            errs[name] = rel(p.grad, pr.grad)
+        else:
+            assert p.grad.abs().max() < 1e-5, name
+    return errs, out
+
+
+@pytest.mark.parametrize("B,hw", [(2, 16), (2, 23), (1, 9), (5, 10)])
+def test_salad_fp32_matches_oracle(vpr, B, hw):
+    ref, mod = _pair(vpr)
+    errs, out = _run_pair(vpr, ref, mod, B, hw, 1234, torch.float32)
+    assert max(errs.values()) < 1e-4, errs
+    np.testing.assert_allclose(out.float().norm(dim=1).cpu().numpy(), 1.0, atol=1e-5)
+
+
+def test_salad_fp32_matches_committed_golden(vpr, golden_dir):
+    sg = np.load(os.path.join(golden_dir, "salad_golden.npz"))
+    ref, mod = _pair(vpr)
+    for tag, (B, hw, seed) in {"n256": (2, 16, 1234), "n529": (2, 23, 4321)}.items():
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(B, hw * hw, 768, generator=g)
+        t = torch.randn(B, 768, generator=g)
+        w = torch.randn(B, 8448, generator=g)
+        xg = x.cuda().requires_grad_(True)
+        tg = t.cuda().requires_grad_(True)
+        out = mod((O.tokens_to_salad_input(xg, hw, hw), tg))
+        (out * w.cuda()).sum().backward()
+        assert rel(out, torch.from_numpy(sg[f"{tag}_desc"])) < 1e-4
+        assert rel(xg.grad[:, :4], torch.from_numpy(sg[f"{tag}_dx_rows"])) < 1e-4
+        assert rel(tg.grad, torch.from_numpy(sg[f"{tag}_dt"])) < 1e-4
+        assert rel(mod.cluster_features[0].bias.grad, torch.from_numpy(sg[f"{tag}_g_cluster0_b"])) < 1e-4
+        assert rel(mod.score[3].weight.grad.flatten()[:4096], torch.from_numpy(sg[f"{tag}_g_score3_w"])) < 1e-4
+        for p in mod.parameters():
+            p.grad = None
+
+
+def test_salad_fp32_training_dropout_with_exported_mask(vpr):
+    ref, mod = _pair(vpr, dropout=0.3)
+    errs, _ = _run_pair(vpr, ref, mod, 3, 16, 77, torch.float32, train=True)
+    assert max(errs.values()) < 1e-4, errs
+    keep = vpr.dropout_keep_mask(mod.last_seed, 0.3, 3 * 256, 1024).float().mean().item()
+    assert abs(keep - 0.7) < 0.01
+    s1 = mod.last_seed
+    _run_pair(vpr, ref, mod, 3, 16, 77, torch.float32, train=True)
+    assert mod.last_seed != s1                                   # a fresh mask every training step
+
+
+@pytest.mark.parametrize("B,hw", [(2, 16), (4, 23)])
+def test_salad_bf16_matches_oracle_on_same_rounded_operands(vpr, B, hw):
+    ref, mod = _pair(vpr, round_weights=True)
+    errs, out = _run_pair(vpr, ref, mod, B, hw, 4321, torch.bfloat16)
+    assert max(errs.values()) < 2e-2, errs
+    assert out.dtype == torch.bfloat16
+
+
+def test_salad_bf16_descriptor_vs_unrounded_fp32_oracle(vpr):
+    ref, mod = _pair(vpr)
+    errs, _ = _run_pair(vpr, ref, mod, 4, 16, 99, torch.bfloat16)
+    assert errs["desc"] < 2e-2, errs
+
+
+def test_salad_accepts_true_nchw_and_token_major_inputs(vpr):
+    ref, mod = _pair(vpr)
+    e1, o1 = _run_pair(vpr, ref, mod, 2, 16, 5, torch.float32, nchw=True)
+    assert max(e1.values()) < 1e-4
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 256, 768, generator=g).cuda()
+    t = torch.randn(2, 768, generator=g).cuda()
+    o2 = mod((x, t))                                             # [B, n, C] form
+    assert rel(o2, o1) < 1e-6
+
+
+def test_salad_no_grad_and_frozen_use(vpr):
+    """The reference freezes the aggregator and runs it under no_grad (dinov2salad_finetuning.py:25-26,35)."""
+    _, mod = _pair(vpr)
+    for p in mod.parameters():
+        p.requires_grad = False
+    mod.eval()
+    x = torch.randn(2, 768, 16, 16, device="cuda")
+    t = torch.randn(2, 768, device="cuda")
+    with torch.no_grad():
+        out = mod((x, t))
+    assert out.shape == (2, 8448) and not out.requires_grad
+
+
+def test_salad_error_behaviour(vpr):
+    mod = vpr.SaladHead().cuda()
+    with pytest.raises(ValueError, match="more patch tokens"):
+        mod((torch.randn(1, 768, 8, 8, device="cuda"), torch.randn(1, 768, device="cuda")))      # n == m
+    with pytest.raises(ValueError, match="channels"):
+        mod((torch.randn(1, 384, 16, 16, device="cuda"), torch.randn(1, 384, device="cuda")))
+    with pytest.raises(RuntimeError, match="unsupported dtype"):
+        mod((torch.randn(1, 768, 16, 16, device="cuda").half(), torch.randn(1, 768, device="cuda").half()))
+
+
+def test_salad_full_size_properties_bf16(vpr):
+    """BASELINE configs[1] size (B=256, n=256): size-independent properties instead of the oracle."""
+    torch.manual_seed(0)
+    mod = vpr.SaladHead(dropout=0.0).cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    B = 256
+    x = torch.randn(B, 256, 768, device="cuda", generator=g).bfloat16().requires_grad_(True)
+    t = torch.randn(B, 768, device="cuda", generator=g).bfloat16().requires_grad_(True)
+    out = mod((x, t))
+    o = out.float()
+    np.testing.assert_allclose(o.norm(dim=1).cpu().numpy(), 1.0, atol=4e-3)
+    np.testing.assert_allclose(o[:, :256].norm(dim=1).cpu().numpy(), 1 / math.sqrt(65), rtol=1e-2)
+    cl = o[:, 256:].reshape(B, 128, 64).norm(dim=1)
+    np.testing.assert_allclose(cl.cpu().numpy(), 1 / math.sqrt(65), rtol=1e-2)
+    # images are independent: the first 8 images alone give the same descriptors
+    out8 = mod((x[:8].detach(), t[:8].detach()))
+    assert rel(out8, out[:8]) < 1e-6
+    # backward is linear in d_out
+    g1 = torch.randn(B, 8448, device="cuda", generator=g).bfloat16()
+    g2 = torch.randn(B, 8448, device="cuda", generator=g).bfloat16()
+    def grads(go):
+        for p in mod.parameters():
+            p.grad = None
+        x.grad = None
+        out.backward(go, retain_graph=True)
+        return x.grad.float().clone(), mod.cluster_features[0].weight.grad.clone()
+    a_x, a_w = grads(g1)
+    b_x, b_w = grads(g2)
+    c_x, c_w = grads((g1.float() + g2.float()).bfloat16())
+    assert rel(c_w, a_w + b_w) < 2e-2 and rel(c_x, a_x + b_x) < 2e-2
+    # per-image descriptors have zero gradient w.r.t. radial direction: <y, J^T g> structure -> sum_b y.dy == 0
+    assert mod.dust_bin.grad.abs().item() == 0.0
+
+
+# ------------------------------------------------------------------ geopose heads
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("latlon,angle", [("mse", "atan2_maae"), ("huber", "acos"), ("mse", "mse"), ("mse", None)])
+def test_heads_losses_and_gradients(vpr, dtype, latlon, angle):
+    torch.manual_seed(3)
+    B, D = 48, 8448
+    ll, ah = O.LatLonRegressorRef(D, 512), O.SinCosHeadRef(D)
+    if dtype == torch.bfloat16:      # the GEMM operands are bf16: round the big matrix in the oracle too
+        with torch.no_grad():
+            ll.regressor[0].weight.copy_(ll.regressor[0].weight.bfloat16().float())
+            ah.head.weight.copy_(ah.head.weight.bfloat16().float())
+    heads = vpr.GeoposeHeads(D, 512, latlon_loss=latlon, angle_loss=angle).cuda()
+    heads.regressor.load_state_dict(ll.regressor.state_dict())
+    heads.head.load_state_dict(ah.head.state_dict())
+    g = torch.Generator().manual_seed(5)
+    desc = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=1) * 8.0
+    lt = torch.randn(B, 2, generator=g) * 2
+    at = torch.rand(B, generator=g) * 720.0
+    if dtype == torch.bfloat16:
+        desc = desc.bfloat16().float()
+    dg = desc.cuda().to(dtype).requires_grad_(True)
+    total, losses, llp, scp = heads(dg, lt.cuda(), at.cuda() if angle else None)
+    total.backward()
+    dr = desc.clone().requires_grad_(True)
+    if angle:
+        tot_r, l1, l2, llr, scr = O.geopose_loss(dr, ll, ah, lt, at, latlon, angle)
+    else:
+        llr = ll(dr)
+        tot_r = O.mse_loss(llr, lt)
+    tot_r.backward()
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    assert abs(total.item() - tot_r.item()) <= tol * abs(tot_r.item())
+    assert rel(llp, llr) < tol
+    assert rel(dg.grad, dr.grad) < tol
+    pairs = [(heads.regressor[0].weight, ll.regressor[0].weight), (heads.regressor[0].bias, ll.regressor[0].bias),
+             (heads.regressor[2].weight, ll.regressor[2].weight), (heads.regressor[2].bias, ll.regressor[2].bias)]
+    if angle:
+        assert rel(scp, scr) < tol
+        pairs += [(heads.head.weight, ah.head.weight), (heads.head.bias, ah.head.bias)]
+    for p, pr in pairs:
+        assert rel(p.grad, pr.grad) < tol
+
+
+def test_heads_predict_and_golden_loss_values(vpr, golden_dir):
+    """Loss kernels against the vectors produced by the REFERENCE's own functions."""
+    from tests.golden.make_golden import heads_inputs
+    hg = np.load(os.path.join(golden_dir, "heads_golden.npz"))
+    sc, tgt_deg, _, ll_pred, ll_tgt = heads_inputs()
+    B = sc.shape[0]
+    D = 64
+    # identity-like heads: descriptor carries the wanted head outputs in its first columns
+    for angle, key, gkey in (("atan2_maae", "maae_atan2", "grad_maae_atan2"), ("acos", "acos_loss", "grad_acos_loss"),
+                             ("mse", "mse_sincos", "grad_mse_sincos")):
+        heads = vpr.GeoposeHeads(D, 8, latlon_loss="mse", angle_loss=angle).cuda()
+        with torch.no_grad():
+            for p in heads.parameters():
+                p.zero_()
+            heads.head.weight[0, 0] = 1.0
+            heads.head.weight[1, 1] = 1.0
+        desc = torch.zeros(B, D)
+        desc[:, :2] = sc
+        dg = desc.cuda().requires_grad_(True)
+        total, losses, llp, scp = heads(dg, torch.zeros(B, 2).cuda(), tgt_deg.cuda())
+        total.backward()
+        np.testing.assert_allclose(losses[1].item(), float(hg[key]), rtol=2e-5)
+        np.testing.assert_allclose(dg.grad[:, :2].cpu().numpy(), hg[gkey], rtol=2e-4, atol=1e-6)
+    for latlon, key, gkey in (("mse", "mse", "grad_mse"), ("huber", "huber", "grad_huber")):
+        heads = vpr.GeoposeHeads(D, 8, latlon_loss=latlon, angle_loss=None).cuda()
+        with torch.no_grad():
+            for p in heads.parameters():
+                p.zero_()
+            heads.regressor[0].weight[0, 0] = 1.0
+            heads.regressor[0].weight[1, 1] = 1.0
+            heads.regressor[0].weight[2, 0] = -1.0
+            heads.regressor[0].weight[3, 1] = -1.0
+            w1 = heads.regressor[2].weight
+            w1[0, 0], w1[0, 2], w1[1, 1], w1[1, 3] = 1.0, -1.0, 1.0, -1.0      # relu(x) - relu(-x) == x
+        desc = torch.zeros(B, D)
+        desc[:, :2] = ll_pred
+        dg = desc.cuda().requires_grad_(True)
+        total, losses, llp, _ = heads(dg, ll_tgt.cuda())
+        total.backward()
+        np.testing.assert_allclose(llp.cpu().numpy(), ll_pred.numpy(), rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(losses[0].item(), float(hg[key]), rtol=1e-5)
+        np.testing.assert_allclose(dg.grad[:, :2].cpu().numpy(), hg[gkey], rtol=1e-4, atol=1e-7)
+
+
+# ------------------------------------------------------------------ kNN
+def _near_tie_free(scores, k, tol=1e-6):
+    """rows whose k-th and (k+1)-th oracle scores are separated by more than tol"""
+    s, _ = torch.sort(scores, dim=1, descending=True)
+    return (s[:, k - 1] - s[:, k]) > tol
+
+
+@pytest.mark.parametrize("Q,G,D,k", [(64, 1000, 256, 25), (300, 5000, 8448, 25), (1000, 30000, 512, 10),
+                                      (7, 26, 64, 25), (130, 257, 64, 1)])
+def test_knn_matches_oracle(vpr, Q, G, D, k):
+    g = torch.Generator().manual_seed(Q + G)
+    q = torch.nn.functional.normalize(torch.randn(Q, D, generator=g), dim=1).bfloat16()
+    ga = torch.nn.functional.normalize(torch.randn(G, D, generator=g), dim=1).bfloat16()
+    s, i = vpr.knn_topk(q.cuda(), ga.cuda(), k, g_offset=1000)
+    rs, ri = O.knn_topk_ref(q, ga, k, g_offset=1000)
+    ok = _near_tie_free(q.float() @ ga.float().T, k) if G > k else torch.ones(Q, dtype=torch.bool)
+    for r in range(Q):
+        if ok[r]:
+            assert set(i[r].tolist()) == set(ri[r].tolist()), r
+    np.testing.assert_allclose(s.cpu().numpy(), rs.numpy(), atol=2e-6)
+    assert (s[:, :-1] >= s[:, 1:]).all()
+
+
+def test_knn_ties_prefer_lower_index_and_short_gallery(vpr):
+    g = torch.Generator().manual_seed(2)
+    ga = torch.randn(600, 128, generator=g).bfloat16()
+    ga[400] = ga[7]
+    ga[599] = ga[7]
+    q = ga[7:8].clone()
+    s, i = vpr.knn_topk(q.cuda(), ga.cuda(), 5)
+    assert i[0, :3].tolist() == [7, 400, 599] and s[0, 0] == s[0, 1] == s[0, 2]
+    s2, i2 = vpr.knn_topk(q.cuda(), ga[:3].cuda(), 5)            # fewer gallery rows than k
+    assert sorted(i2[0, :3].tolist()) == [0, 1, 2] and i2[0, 3:].tolist() == [-1, -1]
+
+
+def test_knn_sharded_merge_equals_unsharded(vpr):
+    """Gallery sharded over R ranks, emulated sequentially on one GPU."""
+    g = torch.Generator().manual_seed(11)
+    q = torch.nn.functional.normalize(torch.randn(200, 512, generator=g), dim=1).bfloat16().cuda()
+    ga = torch.nn.functional.normalize(torch.randn(9000, 512, generator=g), dim=1).bfloat16().cuda()
+    full_s, full_i = vpr.knn_topk(q, ga, 25)
+    for R in (2, 3, 8):
+        parts = [vpr.knn_topk(q, ga[b:e], 25, g_offset=b) for b, e in (vpr.shard_range(9000, r, R) for r in range(R))]
+        ms, mi = vpr.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), 25)
+        assert torch.equal(mi, full_i) and torch.equal(ms, full_s)

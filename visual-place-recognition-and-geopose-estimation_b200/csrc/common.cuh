@@ -59,18 +59,21 @@ static inline size_t carve_size(size_t& off, size_t bytes) {
     return r;
 }
 
-// Counter-based dropout: splitmix64 of (seed, element index); keep iff hash >= p * 2^32.
-__host__ __device__ inline uint32_t dropout_hash(uint64_t seed, uint64_t idx) {
-    uint64_t z = idx + (seed + 1) * 0x9E3779B97F4A7C15ull;
+// Counter-based dropout: one splitmix64 of (seed, element index / 4) yields four 16-bit lanes;
+// element e is kept iff lane (e & 3) >= p * 65536.
+__host__ __device__ inline uint64_t dropout_hash64(uint64_t seed, uint64_t group) {
+    uint64_t z = group + (seed + 1) * 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    return (uint32_t)(z >> 32);
+    return z ^ (z >> 31);
+}
+__host__ __device__ inline bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t thr16) {
+    return (uint32_t)((dropout_hash64(seed, idx >> 2) >> (16 * (idx & 3))) & 0xFFFFu) >= thr16;
 }
 static inline uint32_t dropout_threshold(float p) {
-    double t = (double)p * 4294967296.0;
+    double t = (double)p * 65536.0 + 0.5;
     if (t < 0) t = 0;
-    if (t > 4294967295.0) t = 4294967295.0;
+    if (t > 65535.0) t = 65535.0;
     return (uint32_t)t;
 }
 

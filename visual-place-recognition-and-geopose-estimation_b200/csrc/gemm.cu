@@ -18,7 +18,8 @@ namespace vpr {
 static constexpr int BM = 128;
 static constexpr int BK = 64;                 // 64 bf16 = 128 B = one swizzle span
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
-static constexpr int GEMM_THREADS = 192;
+static constexpr int GEMM_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
+static constexpr int EPI_WARPS = 8;
 static constexpr int SMEM_BUDGET = 196608;    // operand ring; barriers live above it
 
 struct TcArgs {
@@ -55,9 +56,17 @@ __device__ __forceinline__ void epilogue_store32(const TcArgs& a, const uint32_t
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * a.alpha;
     if (a.bias != nullptr) {
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (full || n0 + i < N) v[i] += __ldg(a.bias + n0 + i);
+            for (int j = 0; j < 8; ++j) {
+                const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n0) + j);
+                v[4 * j] += bq.x; v[4 * j + 1] += bq.y; v[4 * j + 2] += bq.z; v[4 * j + 3] += bq.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (n0 + i < N) v[i] += __ldg(a.bias + n0 + i);
+        }
     }
     if (a.relu) {
 #pragma unroll
@@ -65,9 +74,19 @@ __device__ __forceinline__ void epilogue_store32(const TcArgs& a, const uint32_t
     }
     if (a.drop_thr != 0u) {
         const unsigned long long base = ((unsigned long long)b * a.M + m) * (unsigned long long)N + n0;
+        if ((base & 3ull) == 0ull) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            v[i] = (dropout_hash(a.drop_seed, base + i) >= a.drop_thr) ? v[i] * a.drop_scale : 0.f;
+            for (int j = 0; j < 8; ++j) {
+                const unsigned long long h = dropout_hash64(a.drop_seed, (base >> 2) + j);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    v[4 * j + i] = ((uint32_t)(h >> (16 * i)) & 0xFFFFu) >= a.drop_thr ? v[4 * j + i] * a.drop_scale : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                v[i] = dropout_keep(a.drop_seed, base + i, a.drop_thr) ? v[i] * a.drop_scale : 0.f;
+        }
     }
     if (a.mask != nullptr) {
         const bf16* mp = a.mask + (long long)b * a.mask_bs + (long long)m * a.ld_mask + n0;
@@ -118,9 +137,17 @@ __device__ __forceinline__ void epilogue_store32(const TcArgs& a, const uint32_t
         }
     } else {
         float* op = reinterpret_cast<float*>(a.out) + off;
+        if (full && ((a.ldo & 3) == 0)) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (full || n0 + i < N) atomicAdd(op + i, v[i]);
+            for (int j = 0; j < 8; ++j)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + 4 * j), "f"(v[4 * j]),
+                             "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                             : "memory");
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (n0 + i < N) atomicAdd(op + i, v[i]);
+        }
     }
 }
 
@@ -157,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(tfull_bar(s), 1);
-                mbar_init(tempty_bar(s), 4);
+                mbar_init(tempty_bar(s), EPI_WARPS);
             }
             mbar_fence_init();
         }
@@ -253,7 +280,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ------------------------------ epilogue ------------------------------
-        const int q = warp & 3;   // TMEM lane quarter this warp may touch
+        const int q = warp & 3;            // TMEM lane quarter this warp may touch
+        const int chalf = (warp - 2) >> 2;   // two warps share a quarter: even / odd 32-column chunks
         int it = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
             int b, mt, nt, kb0, kb1;
@@ -265,7 +293,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m = mt * BM + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = chalf; c < BN / 32; c += 2) {
                 const int n0 = nt * BN + c * 32;
                 if (n0 >= args.N) break;
                 uint32_t r[32];
@@ -354,7 +382,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs a) {
             if (a.bias) v += a.bias[n];
             if (a.relu) v = fmaxf(v, 0.f);
             if (a.drop_thr != 0u)
-                v = (dropout_hash(a.drop_seed, ((unsigned long long)b * a.M + m) * (unsigned long long)a.N + n) >= a.drop_thr)
+                v = dropout_keep(a.drop_seed, ((unsigned long long)b * a.M + m) * (unsigned long long)a.N + n, a.drop_thr)
                         ? v * a.drop_scale : 0.f;
             if (a.mask) {
                 float mk = a.mask[(long long)b * a.mask_bs + (long long)m * a.ld_mask + n];

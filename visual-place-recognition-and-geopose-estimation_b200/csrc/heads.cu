@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128) heads_tail_kernel(const TailArgs a) {
     for (int i = tid; i < a.hid; i += 128) {
         float z = fmaxf(zrow[i] + a.b0[i], 0.f);
         if (a.drop_thr != 0u)
-            z = dropout_hash(a.seed, (unsigned long long)b * a.hid + i) >= a.drop_thr ? z * a.drop_scale : 0.f;
+            z = dropout_keep(a.seed, (unsigned long long)b * a.hid + i, a.drop_thr) ? z * a.drop_scale : 0.f;
         p0 += z * a.w1[i];
         p1 += z * a.w1[a.hid + i];
     }
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(128) heads_tail_kernel(const TailArgs a) {
             float z = fmaxf(zrow[i] + a.b0[i], 0.f);
             float keep = 1.f;
             if (a.drop_thr != 0u)
-                keep = dropout_hash(a.seed, (unsigned long long)b * a.hid + i) >= a.drop_thr ? a.drop_scale : 0.f;
+                keep = dropout_keep(a.seed, (unsigned long long)b * a.hid + i, a.drop_thr) ? a.drop_scale : 0.f;
             const float zd = z * keep;
             atomicAdd(a.g_w1 + i, g0 * zd);
             atomicAdd(a.g_w1 + a.hid + i, g1 * zd);

@@ -10,6 +10,7 @@
 //   out [B, g + l*m]  normalize(cat(normalize(TF), normalize(AGG, over l).flatten))
 #include "common.cuh"
 #include "gemm.h"
+#include "sinkhorn_fast.cuh"
 #include "../../include/vpr_b200.h"
 
 #include <math.h>
@@ -298,6 +299,21 @@ static int sinkhorn_fwd(const float* S, const float* dust_bin, void* P, int p_dt
     VPR_REQUIRE(m == 16 || m == 32 || m == 64 || m == 128, "num_clusters must be 16/32/64/128 (got %d)", m);
     VPR_REQUIRE(n > m, "Sinkhorn needs n > m (n=%d, m=%d)", n, m);
     VPR_REQUIRE(iters >= 1 && iters <= 8, "iters out of range");
+    if (m == 64) {
+        const size_t fs = sinkfast_fwd_floats<64>(n) * sizeof(float);
+        VPR_REQUIRE(fs <= 227 * 1024, "score tile [%d,%d] does not fit in shared memory", n, m);
+        SinkConst2 k2;
+        k2.norm2 = (float)(-log2((double)(n + m)));
+        k2.log_a_m2 = k2.norm2 + (float)log2((double)(n - m));
+        if (p_dtype == VPR_BF16) {
+            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_fast<bf16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+            sinkhorn_fwd_fast<bf16, 64><<<B, SK_NT, fs, st>>>(S, dust_bin, (bf16*)P, U, V, n, iters, k2);
+        } else {
+            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_fast<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+            sinkhorn_fwd_fast<float, 64><<<B, SK_NT, fs, st>>>(S, dust_bin, (float*)P, U, V, n, iters, k2);
+        }
+        return launch_ok("sinkhorn_fwd_fast");
+    }
     const size_t smem = sink_fwd_smem(n, m);
     VPR_REQUIRE(smem <= 227 * 1024, "score tile [%d,%d] does not fit in shared memory", n, m);
     const SinkConst k = sink_consts(n, m);
@@ -315,6 +331,21 @@ static int sinkhorn_bwd(const float* S, const float* dust_bin, const float* U, c
                         int ds_dtype, float* d_bias, int B, int n, int m, int iters, cudaStream_t st) {
     VPR_REQUIRE(m == 16 || m == 32 || m == 64 || m == 128, "num_clusters must be 16/32/64/128 (got %d)", m);
     VPR_REQUIRE(n > m, "Sinkhorn needs n > m");
+    if (m == 64) {
+        const size_t fs = sinkfast_bwd_floats<64>(n, iters) * sizeof(float);
+        VPR_REQUIRE(fs <= 227 * 1024, "score tile [%d,%d] does not fit in shared memory", n, m);
+        SinkConst2 k2;
+        k2.norm2 = (float)(-log2((double)(n + m)));
+        k2.log_a_m2 = k2.norm2 + (float)log2((double)(n - m));
+        if (ds_dtype == VPR_BF16) {
+            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_bwd_fast<bf16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+            sinkhorn_bwd_fast<bf16, 64><<<B, SK_NT, fs, st>>>(S, dust_bin, U, V, dP, (bf16*)dS, d_bias, n, iters, k2);
+        } else {
+            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_bwd_fast<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+            sinkhorn_bwd_fast<float, 64><<<B, SK_NT, fs, st>>>(S, dust_bin, U, V, dP, (float*)dS, d_bias, n, iters, k2);
+        }
+        return launch_ok("sinkhorn_bwd_fast");
+    }
     const size_t smem = sink_bwd_smem(n, m, iters);
     VPR_REQUIRE(smem <= 227 * 1024, "score tile [%d,%d] does not fit in shared memory", n, m);
     const SinkConst k = sink_consts(n, m);
@@ -444,40 +475,72 @@ __global__ void __launch_bounds__(256) finalize_bwd_kernel(const float* __restri
     }
 }
 
-// column sums of a [R, C] matrix into fp32 (atomic): bias gradients
+// column sums of a [R, C] matrix into fp32 (atomic): bias gradients.  16-byte loads, consecutive
+// threads on consecutive vectors of a row; columns >= split go to out1 (two parameter tensors).
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, long long ld, long long R, int C,
-                                                     int rows_per_block, float* __restrict__ out) {
-    __shared__ float red[8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int col = blockIdx.x * 32 + tx;
+                                                     int rows_per_block, float* __restrict__ out0,
+                                                     float* __restrict__ out1, int split) {
+    constexpr int VEC = 16 / sizeof(T);
+    __shared__ float red[256 * VEC];
+    const int ncv = C / VEC;                       // vectors per row (C % VEC == 0 checked on host)
+    const int groups = 256 / ncv > 0 ? 256 / ncv : 1;
     const long long r0 = (long long)blockIdx.y * rows_per_block;
     long long r1 = r0 + rows_per_block;
     if (r1 > R) r1 = R;
-    float acc = 0.f;
-    if (col < C)
-        for (long long r = r0 + ty; r < r1; r += 8) acc += ldf(X + r * ld + col);
-    red[ty][tx] = acc;
-    __syncthreads();
-    if (ty == 0 && col < C) {
-        float tot = 0.f;
+    for (int cv0 = blockIdx.x * 256; cv0 < ncv; cv0 += gridDim.x * 256) {
+        const int cv = cv0 + (ncv >= 256 ? threadIdx.x : threadIdx.x % ncv);
+        const int rg = ncv >= 256 ? 0 : threadIdx.x / ncv;
+        float acc[VEC];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) tot += red[i][tx];
-        atomicAdd(out + col, tot);
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        if (cv < ncv && rg < groups) {
+#pragma unroll 4
+            for (long long r = r0 + rg; r < r1; r += groups) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(X + r * ld) + cv);
+                const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] += ldf(e + i);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) red[threadIdx.x * VEC + i] = acc[i];
+        __syncthreads();
+        if (rg == 0 && cv < ncv) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                float tot = 0.f;
+                for (int g2 = 0; g2 < groups; ++g2) {
+                    const int t2 = g2 * ncv + (threadIdx.x % (ncv >= 256 ? 256 : ncv));
+                    if (ncv >= 256 && g2 > 0) break;
+                    tot += red[t2 * VEC + i];
+                }
+                const int col = cv * VEC + i;
+                if (col < split) atomicAdd(out0 + col, tot); else atomicAdd(out1 + (col - split), tot);
+            }
+        }
     }
 }
 
 template <typename T>
-static int colsum(const T* X, long long ld, long long R, int C, float* out, cudaStream_t st) {
-    const int rpb = 512;
-    dim3 grid((C + 31) / 32, (unsigned)((R + rpb - 1) / rpb));
-    colsum_kernel<T><<<grid, 256, 0, st>>>(X, ld, R, C, rpb, out);
+static int colsum(const T* X, long long ld, long long R, int C, float* out, cudaStream_t st, float* out1 = nullptr,
+                  int split = 0) {
+    constexpr int VEC = 16 / sizeof(T);
+    VPR_REQUIRE(C % VEC == 0 && ld % VEC == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "colsum needs 16-byte rows");
+    if (out1 == nullptr) split = C;
+    const int ncv = C / VEC;
+    int rpb = 256;
+    long long nblk = (R + rpb - 1) / rpb;
+    while (nblk > 4 * num_sms() && rpb < 4096) { rpb *= 2; nblk = (R + rpb - 1) / rpb; }
+    dim3 grid((ncv + 255) / 256, (unsigned)nblk);
+    colsum_kernel<T><<<grid, 256, 0, st>>>(X, ld, R, C, rpb, out, out1, split);
     return launch_ok("colsum_kernel");
 }
 
 __global__ void dropout_mask_kernel(unsigned long long seed, uint32_t thr, long long total, uint8_t* out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
-        out[i] = dropout_hash(seed, (unsigned long long)i) >= thr ? 1 : 0;
+        out[i] = dropout_keep(seed, (unsigned long long)i, thr) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -618,20 +681,24 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
     const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     const int nsm = num_sms();
 
-    // zero every gradient buffer that is accumulated with atomics
-    VPR_CUDA_OK(cudaMemsetAsync(gr.cluster_w0, 0, sizeof(float) * (size_t)h * s.d, st));
-    VPR_CUDA_OK(cudaMemsetAsync(gr.cluster_b0, 0, sizeof(float) * h, st));
-    VPR_CUDA_OK(cudaMemsetAsync(gr.cluster_w1, 0, sizeof(float) * (size_t)s.l * h, st));
-    VPR_CUDA_OK(cudaMemsetAsync(gr.cluster_b1, 0, sizeof(float) * s.l, st));
-    VPR_CUDA_OK(cudaMemsetAsync(gr.score_w0, 0, sizeof(float) * (size_t)h * s.d, st));
-    VPR_CUDA_OK(cudaMemsetAsync(gr.score_b0, 0, sizeof(float) * h, st));
-    VPR_CUDA_OK(cudaMemsetAsync(gr.score_w1, 0, sizeof(float) * (size_t)s.m * h, st));
-    VPR_CUDA_OK(cudaMemsetAsync(gr.score_b1, 0, sizeof(float) * s.m, st));
-    VPR_CUDA_OK(cudaMemsetAsync(gr.token_w0, 0, sizeof(float) * (size_t)h * s.d, st));
-    VPR_CUDA_OK(cudaMemsetAsync(gr.token_b0, 0, sizeof(float) * h, st));
-    VPR_CUDA_OK(cudaMemsetAsync(gr.token_w1, 0, sizeof(float) * (size_t)s.g * h, st));
-    VPR_CUDA_OK(cudaMemsetAsync(gr.token_b1, 0, sizeof(float) * s.g, st));
-    VPR_CUDA_OK(cudaMemsetAsync(gr.dust_bin, 0, sizeof(float), st));   // d/d dust_bin == 0 (SURVEY A-3b)
+    // zero every gradient buffer that is accumulated with atomics (adjacent buffers -> one memset)
+    {
+        struct Rng { float* p; size_t n; };
+        const Rng r[13] = {{gr.cluster_w0, (size_t)h * s.d}, {gr.cluster_b0, (size_t)h}, {gr.cluster_w1, (size_t)s.l * h},
+                           {gr.cluster_b1, (size_t)s.l}, {gr.score_w0, (size_t)h * s.d}, {gr.score_b0, (size_t)h},
+                           {gr.score_w1, (size_t)s.m * h}, {gr.score_b1, (size_t)s.m}, {gr.token_w0, (size_t)h * s.d},
+                           {gr.token_b0, (size_t)h}, {gr.token_w1, (size_t)s.g * h}, {gr.token_b1, (size_t)s.g},
+                           {gr.dust_bin, 1}};    // d/d dust_bin == 0 identically (SURVEY A-3b)
+        int i = 0;
+        while (i < 13) {
+            float* p0 = r[i].p;
+            size_t cnt = r[i].n;
+            int j = i + 1;
+            while (j < 13 && r[j].p == p0 + cnt) { cnt += r[j].n; ++j; }
+            VPR_CUDA_OK(cudaMemsetAsync(p0, 0, cnt * sizeof(float), st));
+            i = j;
+        }
+    }
 
     // norms backward: d_out -> dAGG [B,l,m], dTF [B,g]
     finalize_bwd_kernel<T><<<s.B, 256, 0, st>>>(AGG, TF, d_out, dAGG, dTF, s.l, s.m, s.g);
@@ -704,8 +771,7 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
     g.out = dH + h; g.out_kind = okT; g.ldo = 2 * h; g.mask = H + h; g.ld_mask = 2 * h; g.mask_scale = keep_scale;
     VPR_TRY(gemm_run(g, st));
     // first-layer bias gradients
-    VPR_TRY(colsum<T>(dH, 2 * h, Tk, h, gr.cluster_b0, st));
-    VPR_TRY(colsum<T>(dH + h, 2 * h, Tk, h, gr.score_b0, st));
+    VPR_TRY(colsum<T>(dH, 2 * h, Tk, 2 * h, gr.cluster_b0, st, gr.score_b0, h));
     // ---- first-layer weight gradients: dW0[h,d] = dH^T X (two halves: separate parameter tensors) ----
     for (int half = 0; half < 2; ++half) {
         g = GemmDesc(); g.dtype = dtype;
