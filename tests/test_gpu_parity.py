@@ -66,8 +66,10 @@ def test_gemm_epilogues_and_split_k(vpr):
     mask = torch.randn(1, 300, 256, device="cuda", generator=g).bfloat16()
     ref = (torch.einsum("bmk,bnk->bmn", A.float(), B.float()) + bias).clamp_min(0)
     ref = torch.where(mask.float() > 0, ref * 0.5, torch.zeros_like(ref))
-    out = ops.gemm(A, B, 300, 256, 512, out_kind=L.OUT_BF16, bias=bias, relu=True, mask=mask, mask_scale=0.5)
+    cs = torch.zeros(256, device="cuda")
+    out = ops.gemm(A, B, 300, 256, 512, out_kind=L.OUT_BF16, bias=bias, relu=True, mask=mask, mask_scale=0.5, colsum=cs)
     assert rel(out, ref) < 4e-3                                    # one bf16 rounding of the output
+    assert rel(cs, out.float().sum((0, 1))) < 1e-5                 # fused column sums of the stored values
     At = torch.randn(1, 4096, 128, device="cuda", generator=g).bfloat16()    # MN-major A: [K, M]
     Bt = torch.randn(1, 4096, 512, device="cuda", generator=g).bfloat16()    # MN-major B: [K, N]
     ref2 = torch.einsum("bkm,bkn->bmn", At.float(), Bt.float())
@@ -97,7 +99,7 @@ def test_sinkhorn_forward_backward(vpr, B, n, m):
     assert rel(P, Pd[:, :m].transpose(1, 2)) < 1e-5
     # known answers: columns of the augmented plan sum to 1 -> token rows of P sum to 1 - dustbin share
     dust = Pd[:, m].float()
-    np.testing.assert_allclose(P.sum(2).cpu().numpy(), (1 - dust).numpy(), atol=2e-6)
+    np.testing.assert_allclose(P.sum(2).cpu().numpy(), (1 - dust).detach().numpy(), atol=2e-6)
     dP = torch.randn(B, n, m, generator=g)
     (Pd[:, :m] * dP.double().transpose(1, 2)).sum().backward()
     dS, _ = vpr.sinkhorn_backward(St, db.cuda(), U, V, dP.cuda(), 3)

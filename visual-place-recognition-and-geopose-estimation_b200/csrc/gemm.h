@@ -29,10 +29,14 @@ struct GemmDesc {
     float alpha = 1.f;
     // inverted dropout on the output (after relu): keep iff dropout_hash(seed, (b*M+m)*N+n) >= p*2^32
     float dropout_p = 0.f; uint64_t dropout_seed = 0;
+    // colsum[n] += sum over (b, m) of the stored output (after mask / rounding); caller zeroes it
+    float* colsum = nullptr;
     int k_splits = 1;              // > 1 requires OUT_ATOMIC_F32 (caller zeroes out)
     int bn = 0;                    // tcgen05 tile N (64/128/256); 0 = auto
 };
 
 int gemm_run(const GemmDesc& g, cudaStream_t stream);
+// Up to 4 independent problems with the same dtype and operand layout in ONE launch.
+int gemm_run_group(const GemmDesc* gs, int count, cudaStream_t stream);
 
 }  // namespace vpr

@@ -401,7 +401,8 @@ __global__ void __launch_bounds__(256) finalize_fwd_kernel(const float* __restri
 template <typename T>
 __global__ void __launch_bounds__(256) finalize_bwd_kernel(const float* __restrict__ AGG, const float* __restrict__ TF,
                                                            const T* __restrict__ d_out, T* __restrict__ dAGG,
-                                                           T* __restrict__ dTF, int l, int m, int g) {
+                                                           T* __restrict__ dTF, float* __restrict__ g_bias_tok, int l,
+                                                           int m, int g) {
     __shared__ float red[256];
     __shared__ float inv_c[128];
     __shared__ float dot_c[128];
@@ -448,7 +449,9 @@ __global__ void __launch_bounds__(256) finalize_bwd_kernel(const float* __restri
     for (int i = tid; i < g; i += 256) {
         const float th = t[i] * invt;
         const float dz = (ldf(dy + i) - th * invN * s) * invN;
-        stf(dT + i, (dz - th * dt_dot) * invt);
+        const float dti = (dz - th * dt_dot) * invt;
+        stf(dT + i, dti);
+        if (g_bias_tok != nullptr) atomicAdd(g_bias_tok + i, dti);
     }
     // cluster part: per column c, dot_c = sum_l ahat_lc dz_lc
     float dc = 0.f;
@@ -473,69 +476,6 @@ __global__ void __launch_bounds__(256) finalize_bwd_kernel(const float* __restri
         const float dz = (ldf(dy + g + e) - ah * invN * s) * invN;
         stf(dA + e, (dz - ah * dot_c[cc]) * inv_c[cc]);
     }
-}
-
-// column sums of a [R, C] matrix into fp32 (atomic): bias gradients.  16-byte loads, consecutive
-// threads on consecutive vectors of a row; columns >= split go to out1 (two parameter tensors).
-template <typename T>
-__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, long long ld, long long R, int C,
-                                                     int rows_per_block, float* __restrict__ out0,
-                                                     float* __restrict__ out1, int split) {
-    constexpr int VEC = 16 / sizeof(T);
-    __shared__ float red[256 * VEC];
-    const int ncv = C / VEC;                       // vectors per row (C % VEC == 0 checked on host)
-    const int groups = 256 / ncv > 0 ? 256 / ncv : 1;
-    const long long r0 = (long long)blockIdx.y * rows_per_block;
-    long long r1 = r0 + rows_per_block;
-    if (r1 > R) r1 = R;
-    for (int cv0 = blockIdx.x * 256; cv0 < ncv; cv0 += gridDim.x * 256) {
-        const int cv = cv0 + (ncv >= 256 ? threadIdx.x : threadIdx.x % ncv);
-        const int rg = ncv >= 256 ? 0 : threadIdx.x / ncv;
-        float acc[VEC];
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-        if (cv < ncv && rg < groups) {
-#pragma unroll 4
-            for (long long r = r0 + rg; r < r1; r += groups) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(X + r * ld) + cv);
-                const T* e = reinterpret_cast<const T*>(&q);
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) acc[i] += ldf(e + i);
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) red[threadIdx.x * VEC + i] = acc[i];
-        __syncthreads();
-        if (rg == 0 && cv < ncv) {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                float tot = 0.f;
-                for (int g2 = 0; g2 < groups; ++g2) {
-                    const int t2 = g2 * ncv + (threadIdx.x % (ncv >= 256 ? 256 : ncv));
-                    if (ncv >= 256 && g2 > 0) break;
-                    tot += red[t2 * VEC + i];
-                }
-                const int col = cv * VEC + i;
-                if (col < split) atomicAdd(out0 + col, tot); else atomicAdd(out1 + (col - split), tot);
-            }
-        }
-    }
-}
-
-template <typename T>
-static int colsum(const T* X, long long ld, long long R, int C, float* out, cudaStream_t st, float* out1 = nullptr,
-                  int split = 0) {
-    constexpr int VEC = 16 / sizeof(T);
-    VPR_REQUIRE(C % VEC == 0 && ld % VEC == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "colsum needs 16-byte rows");
-    if (out1 == nullptr) split = C;
-    const int ncv = C / VEC;
-    int rpb = 256;
-    long long nblk = (R + rpb - 1) / rpb;
-    while (nblk > 4 * num_sms() && rpb < 4096) { rpb *= 2; nblk = (R + rpb - 1) / rpb; }
-    dim3 grid((ncv + 255) / 256, (unsigned)nblk);
-    colsum_kernel<T><<<grid, 256, 0, st>>>(X, ld, R, C, rpb, out, out1, split);
-    return launch_ok("colsum_kernel");
 }
 
 __global__ void dropout_mask_kernel(unsigned long long seed, uint32_t thr, long long total, uint8_t* out) {
@@ -620,42 +560,37 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
     pack_params_kernel<T><<<num_sms() * 2, 256, 0, st>>>(p, s.d, h, s.l, s.m, s.g, w0cat, w1c, w1s, wt0, wt1, b0cat);
     VPR_TRY(launch_ok("pack_params_kernel"));
 
-    GemmDesc g;
-    // H = dropout(relu(X W0cat^T + b0cat))           [T, 2h]
-    g = GemmDesc(); g.dtype = dtype;
-    g.A = x; g.lda = s.d; g.B = w0cat; g.ldb = s.d; g.M = (int)Tk; g.N = 2 * h; g.K = s.d;
-    g.out = H; g.out_kind = okT; g.ldo = 2 * h; g.bias = b0cat; g.relu = 1;
-    g.dropout_p = drop_p; g.dropout_seed = seed;
     VPR_REQUIRE(Tk < (1ll << 31), "too many tokens");
-    VPR_TRY(gemm_run(g, st));
-    // F = H[:, :h] W1c^T + b1c                        [T, l]
-    g = GemmDesc(); g.dtype = dtype;
-    g.A = H; g.lda = 2 * h; g.B = w1c; g.ldb = h; g.M = (int)Tk; g.N = s.l; g.K = h;
-    g.out = F; g.out_kind = okT; g.ldo = s.l; g.bias = p.cluster_b1;
-    VPR_TRY(gemm_run(g, st));
-    // S = H[:, h:] W1s^T + b1s                        [T, m] fp32
-    g = GemmDesc(); g.dtype = dtype;
-    g.A = H + h; g.lda = 2 * h; g.B = w1s; g.ldb = h; g.M = (int)Tk; g.N = s.m; g.K = h;
-    g.out = S; g.out_kind = OUT_F32; g.ldo = s.m; g.bias = p.score_b1;
-    VPR_TRY(gemm_run(g, st));
-    // token features
-    g = GemmDesc(); g.dtype = dtype;
-    g.A = t; g.lda = s.d; g.B = wt0; g.ldb = s.d; g.M = s.B; g.N = h; g.K = s.d;
-    g.out = HT; g.out_kind = okT; g.ldo = h; g.bias = p.token_b0; g.relu = 1;
-    VPR_TRY(gemm_run(g, st));
-    g = GemmDesc(); g.dtype = dtype;
-    g.A = HT; g.lda = h; g.B = wt1; g.ldb = h; g.M = s.B; g.N = s.g; g.K = h;
-    g.out = TF; g.out_kind = OUT_F32; g.ldo = s.g; g.bias = p.token_b1;
-    VPR_TRY(gemm_run(g, st));
+    GemmDesc g[3];
+    // launch 1: H = dropout(relu(X W0cat^T + b0cat)) [T, 2h]   +   HT = relu(t Wt0^T + bt0) [B, h]
+    g[0] = GemmDesc(); g[0].dtype = dtype;
+    g[0].A = x; g[0].lda = s.d; g[0].B = w0cat; g[0].ldb = s.d; g[0].M = (int)Tk; g[0].N = 2 * h; g[0].K = s.d;
+    g[0].out = H; g[0].out_kind = okT; g[0].ldo = 2 * h; g[0].bias = b0cat; g[0].relu = 1;
+    g[0].dropout_p = drop_p; g[0].dropout_seed = seed;
+    g[1] = GemmDesc(); g[1].dtype = dtype;
+    g[1].A = t; g[1].lda = s.d; g[1].B = wt0; g[1].ldb = s.d; g[1].M = s.B; g[1].N = h; g[1].K = s.d;
+    g[1].out = HT; g[1].out_kind = okT; g[1].ldo = h; g[1].bias = p.token_b0; g[1].relu = 1;
+    VPR_TRY(gemm_run_group(g, 2, st));
+    // launch 2: F = H[:, :h] W1c^T + b1c [T, l]   S = H[:, h:] W1s^T + b1s [T, m] fp32   TF = HT Wt1^T + bt1 [B, g] fp32
+    g[0] = GemmDesc(); g[0].dtype = dtype;
+    g[0].A = H; g[0].lda = 2 * h; g[0].B = w1c; g[0].ldb = h; g[0].M = (int)Tk; g[0].N = s.l; g[0].K = h;
+    g[0].out = F; g[0].out_kind = okT; g[0].ldo = s.l; g[0].bias = p.cluster_b1;
+    g[1] = GemmDesc(); g[1].dtype = dtype;
+    g[1].A = H + h; g[1].lda = 2 * h; g[1].B = w1s; g[1].ldb = h; g[1].M = (int)Tk; g[1].N = s.m; g[1].K = h;
+    g[1].out = S; g[1].out_kind = OUT_F32; g[1].ldo = s.m; g[1].bias = p.score_b1;
+    g[2] = GemmDesc(); g[2].dtype = dtype;
+    g[2].A = HT; g[2].lda = h; g[2].B = wt1; g[2].ldb = h; g[2].M = s.B; g[2].N = s.g; g[2].K = h;
+    g[2].out = TF; g[2].out_kind = OUT_F32; g[2].ldo = s.g; g[2].bias = p.token_b1;
+    VPR_TRY(gemm_run_group(g, 3, st));
     // P = sinkhorn(S)
     VPR_TRY(sinkhorn_fwd(S, p.dust_bin, P, dtype, U, V, s.B, s.n, s.m, s.iters, st));
     // AGG[b][l][c] = sum_j F[b][j][l] P[b][j][c]      both operands MN-major, K = tokens of image b
-    g = GemmDesc(); g.dtype = dtype;
-    g.A = F; g.a_mn = 1; g.lda = s.l; g.a_bs = (int64_t)s.n * s.l;
-    g.B = P; g.b_mn = 1; g.ldb = s.m; g.b_bs = (int64_t)s.n * s.m;
-    g.M = s.l; g.N = s.m; g.K = s.n; g.batch = s.B;
-    g.out = AGG; g.out_kind = OUT_F32; g.ldo = s.m; g.out_bs = (int64_t)s.l * s.m;
-    VPR_TRY(gemm_run(g, st));
+    g[0] = GemmDesc(); g[0].dtype = dtype;
+    g[0].A = F; g[0].a_mn = 1; g[0].lda = s.l; g[0].a_bs = (int64_t)s.n * s.l;
+    g[0].B = P; g[0].b_mn = 1; g[0].ldb = s.m; g[0].b_bs = (int64_t)s.n * s.m;
+    g[0].M = s.l; g[0].N = s.m; g[0].K = s.n; g[0].batch = s.B;
+    g[0].out = AGG; g[0].out_kind = OUT_F32; g[0].ldo = s.m; g[0].out_bs = (int64_t)s.l * s.m;
+    VPR_TRY(gemm_run(g[0], st));
     finalize_fwd_kernel<T><<<s.B, 256, 0, st>>>(AGG, TF, out, s.l, s.m, s.g);
     return launch_ok("finalize_fwd_kernel");
 }
@@ -700,93 +635,88 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         }
     }
 
-    // norms backward: d_out -> dAGG [B,l,m], dTF [B,g]
-    finalize_bwd_kernel<T><<<s.B, 256, 0, st>>>(AGG, TF, d_out, dAGG, dTF, s.l, s.m, s.g);
+    // norms backward: d_out -> dAGG [B,l,m], dTF [B,g] (+ token_features.2.bias gradient)
+    finalize_bwd_kernel<T><<<s.B, 256, 0, st>>>(AGG, TF, d_out, dAGG, dTF, gr.token_b1, s.l, s.m, s.g);
     VPR_TRY(launch_ok("finalize_bwd_kernel"));
 
-    GemmDesc g;
-    // ---- token-feature MLP backward ----
-    VPR_TRY(colsum<T>(dTF, s.g, s.B, s.g, gr.token_b1, st));
-    g = GemmDesc(); g.dtype = dtype;    // dWt1[g,h] = dTF^T HT
-    g.A = dTF; g.a_mn = 1; g.lda = s.g; g.B = HT; g.b_mn = 1; g.ldb = h; g.M = s.g; g.N = h; g.K = s.B;
-    g.out = gr.token_w1; g.out_kind = OUT_ATOMIC_F32; g.ldo = h;
-    VPR_TRY(gemm_run(g, st));
-    g = GemmDesc(); g.dtype = dtype;    // dHT = (dTF Wt1) * (HT > 0)
-    g.A = dTF; g.lda = s.g; g.B = wt1; g.b_mn = 1; g.ldb = h; g.M = s.B; g.N = h; g.K = s.g;
-    g.out = dHT; g.out_kind = okT; g.ldo = h; g.mask = HT; g.ld_mask = h;
-    VPR_TRY(gemm_run(g, st));
-    VPR_TRY(colsum<T>(dHT, h, s.B, h, gr.token_b0, st));
-    g = GemmDesc(); g.dtype = dtype;    // dWt0[h,d] = dHT^T t
-    g.A = dHT; g.a_mn = 1; g.lda = h; g.B = t; g.b_mn = 1; g.ldb = s.d; g.M = h; g.N = s.d; g.K = s.B;
-    g.out = gr.token_w0; g.out_kind = OUT_ATOMIC_F32; g.ldo = s.d;
-    VPR_TRY(gemm_run(g, st));
-    if (dt != nullptr) {                // dt = dHT Wt0
-        g = GemmDesc(); g.dtype = dtype;
-        g.A = dHT; g.lda = h; g.B = wt0; g.b_mn = 1; g.ldb = s.d; g.M = s.B; g.N = s.d; g.K = h;
-        g.out = dt; g.out_kind = okT; g.ldo = s.d;
-        VPR_TRY(gemm_run(g, st));
-    }
-
+    GemmDesc g[3];
+    const int kb_tok = (int)((Tk + 63) / 64);
     // ---- aggregation backward ----
-    g = GemmDesc(); g.dtype = dtype;    // dF[b][j][l] = sum_c P[b][j][c] dAGG[b][l][c]
-    g.A = P; g.lda = s.m; g.a_bs = (int64_t)s.n * s.m; g.B = dAGG; g.ldb = s.m; g.b_bs = (int64_t)s.l * s.m;
-    g.M = s.n; g.N = s.l; g.K = s.m; g.batch = s.B;
-    g.out = dF; g.out_kind = okT; g.ldo = s.l; g.out_bs = (int64_t)s.n * s.l;
-    VPR_TRY(gemm_run(g, st));
-    g = GemmDesc(); g.dtype = dtype;    // dP[b][j][c] = sum_l F[b][j][l] dAGG[b][l][c]
-    g.A = F; g.lda = s.l; g.a_bs = (int64_t)s.n * s.l; g.B = dAGG; g.b_mn = 1; g.ldb = s.m; g.b_bs = (int64_t)s.l * s.m;
-    g.M = s.n; g.N = s.m; g.K = s.l; g.batch = s.B;
-    g.out = dP; g.out_kind = OUT_F32; g.ldo = s.m; g.out_bs = (int64_t)s.n * s.m;
-    VPR_TRY(gemm_run(g, st));
+    g[0] = GemmDesc(); g[0].dtype = dtype;    // dF[b][j][l] = sum_c P[b][j][c] dAGG[b][l][c]   (+ cluster bias gradient)
+    g[0].A = P; g[0].lda = s.m; g[0].a_bs = (int64_t)s.n * s.m; g[0].B = dAGG; g[0].ldb = s.m; g[0].b_bs = (int64_t)s.l * s.m;
+    g[0].M = s.n; g[0].N = s.l; g[0].K = s.m; g[0].batch = s.B;
+    g[0].out = dF; g[0].out_kind = okT; g[0].ldo = s.l; g[0].out_bs = (int64_t)s.n * s.l; g[0].colsum = gr.cluster_b1;
+    VPR_TRY(gemm_run(g[0], st));
+    g[0] = GemmDesc(); g[0].dtype = dtype;    // dP[b][j][c] = sum_l F[b][j][l] dAGG[b][l][c]
+    g[0].A = F; g[0].lda = s.l; g[0].a_bs = (int64_t)s.n * s.l; g[0].B = dAGG; g[0].b_mn = 1; g[0].ldb = s.m;
+    g[0].b_bs = (int64_t)s.l * s.m; g[0].M = s.n; g[0].N = s.m; g[0].K = s.l; g[0].batch = s.B;
+    g[0].out = dP; g[0].out_kind = OUT_F32; g[0].ldo = s.m; g[0].out_bs = (int64_t)s.n * s.m;
+    VPR_TRY(gemm_run(g[0], st));
     // ---- Sinkhorn backward: dP -> dS (+ score bias gradient) ----
     VPR_TRY(sinkhorn_bwd(S, p.dust_bin, U, V, dP, dS, dtype, gr.score_b1, s.B, s.n, s.m, s.iters, st));
-    VPR_TRY(colsum<T>(dF, s.l, Tk, s.l, gr.cluster_b1, st));
 
-    // ---- second-layer weight gradients (K = all tokens, split-K + fp32 atomics) ----
-    const int kb_tok = (int)((Tk + 63) / 64);
-    g = GemmDesc(); g.dtype = dtype;    // dW1c[l,h] = dF^T H[:, :h]
-    g.A = dF; g.a_mn = 1; g.lda = s.l; g.B = H; g.b_mn = 1; g.ldb = 2 * h; g.M = s.l; g.N = h; g.K = (int)Tk;
-    g.out = gr.cluster_w1; g.out_kind = OUT_ATOMIC_F32; g.ldo = h;
+    // ---- second-layer weight gradients (split-K + fp32 reductions), one launch ----
     {
-        int tiles = ((s.l + 127) / 128) * ((h + 255) / 256);
-        g.k_splits = nsm / tiles; if (g.k_splits < 1) g.k_splits = 1; if (g.k_splits > kb_tok) g.k_splits = kb_tok;
+        const int small = ((s.g + 127) / 128) * ((h + 255) / 256);
+        const int tiles = ((s.l + 127) / 128 + (s.m + 127) / 128) * ((h + 255) / 256);
+        int ks = (nsm - small) / tiles; if (ks < 1) ks = 1; if (ks > kb_tok) ks = kb_tok;
+        g[0] = GemmDesc(); g[0].dtype = dtype;    // dW1c[l,h] = dF^T H[:, :h]
+        g[0].A = dF; g[0].a_mn = 1; g[0].lda = s.l; g[0].B = H; g[0].b_mn = 1; g[0].ldb = 2 * h; g[0].M = s.l; g[0].N = h;
+        g[0].K = (int)Tk; g[0].out = gr.cluster_w1; g[0].out_kind = OUT_ATOMIC_F32; g[0].ldo = h; g[0].k_splits = ks;
+        g[1] = GemmDesc(); g[1].dtype = dtype;    // dW1s[m,h] = dS^T H[:, h:]
+        g[1].A = dS; g[1].a_mn = 1; g[1].lda = s.m; g[1].B = H + h; g[1].b_mn = 1; g[1].ldb = 2 * h; g[1].M = s.m; g[1].N = h;
+        g[1].K = (int)Tk; g[1].out = gr.score_w1; g[1].out_kind = OUT_ATOMIC_F32; g[1].ldo = h; g[1].k_splits = ks;
+        g[2] = GemmDesc(); g[2].dtype = dtype;    // dWt1[g,h] = dTF^T HT
+        g[2].A = dTF; g[2].a_mn = 1; g[2].lda = s.g; g[2].B = HT; g[2].b_mn = 1; g[2].ldb = h; g[2].M = s.g; g[2].N = h;
+        g[2].K = s.B; g[2].out = gr.token_w1; g[2].out_kind = OUT_ATOMIC_F32; g[2].ldo = h;
+        VPR_TRY(gemm_run_group(g, 3, st));
     }
-    VPR_TRY(gemm_run(g, st));
-    g = GemmDesc(); g.dtype = dtype;    // dW1s[m,h] = dS^T H[:, h:]
-    g.A = dS; g.a_mn = 1; g.lda = s.m; g.B = H + h; g.b_mn = 1; g.ldb = 2 * h; g.M = s.m; g.N = h; g.K = (int)Tk;
-    g.out = gr.score_w1; g.out_kind = OUT_ATOMIC_F32; g.ldo = h;
+    // ---- dH = [dF W1c | dS W1s] * (H > 0) * keep_scale,  dHT = (dTF Wt1) * (HT > 0); first-layer bias gradients ----
+    g[0] = GemmDesc(); g[0].dtype = dtype;
+    g[0].A = dF; g[0].lda = s.l; g[0].B = w1c; g[0].b_mn = 1; g[0].ldb = h; g[0].M = (int)Tk; g[0].N = h; g[0].K = s.l;
+    g[0].out = dH; g[0].out_kind = okT; g[0].ldo = 2 * h; g[0].mask = H; g[0].ld_mask = 2 * h; g[0].mask_scale = keep_scale;
+    g[0].colsum = gr.cluster_b0;
+    g[1] = GemmDesc(); g[1].dtype = dtype;
+    g[1].A = dS; g[1].lda = s.m; g[1].B = w1s; g[1].b_mn = 1; g[1].ldb = h; g[1].M = (int)Tk; g[1].N = h; g[1].K = s.m;
+    g[1].out = dH + h; g[1].out_kind = okT; g[1].ldo = 2 * h; g[1].mask = H + h; g[1].ld_mask = 2 * h; g[1].mask_scale = keep_scale;
+    g[1].colsum = gr.score_b0;
+    g[2] = GemmDesc(); g[2].dtype = dtype;
+    g[2].A = dTF; g[2].lda = s.g; g[2].B = wt1; g[2].b_mn = 1; g[2].ldb = h; g[2].M = s.B; g[2].N = h; g[2].K = s.g;
+    g[2].out = dHT; g[2].out_kind = okT; g[2].ldo = h; g[2].mask = HT; g[2].ld_mask = h; g[2].colsum = gr.token_b0;
+    VPR_TRY(gemm_run_group(g, 3, st));
+    // ---- first-layer weight gradients: dW0[h,d] = dH^T X (two parameter tensors) and dWt0 = dHT^T t ----
     {
-        int tiles = ((s.m + 127) / 128) * ((h + 255) / 256);
-        g.k_splits = nsm / tiles; if (g.k_splits < 1) g.k_splits = 1; if (g.k_splits > kb_tok) g.k_splits = kb_tok;
+        const int small = ((h + 127) / 128) * ((s.d + 255) / 256);
+        const int tiles = 2 * small;
+        int ks = (nsm - small) / tiles; if (ks < 1) ks = 1; if (ks > kb_tok) ks = kb_tok;
+        for (int half = 0; half < 2; ++half) {
+            g[half] = GemmDesc(); g[half].dtype = dtype;
+            g[half].A = dH + half * h; g[half].a_mn = 1; g[half].lda = 2 * h; g[half].B = x; g[half].b_mn = 1; g[half].ldb = s.d;
+            g[half].M = h; g[half].N = s.d; g[half].K = (int)Tk;
+            g[half].out = half == 0 ? gr.cluster_w0 : gr.score_w0; g[half].out_kind = OUT_ATOMIC_F32; g[half].ldo = s.d;
+            g[half].k_splits = ks;
+        }
+        g[2] = GemmDesc(); g[2].dtype = dtype;
+        g[2].A = dHT; g[2].a_mn = 1; g[2].lda = h; g[2].B = t; g[2].b_mn = 1; g[2].ldb = s.d; g[2].M = h; g[2].N = s.d; g[2].K = s.B;
+        g[2].out = gr.token_w0; g[2].out_kind = OUT_ATOMIC_F32; g[2].ldo = s.d;
+        VPR_TRY(gemm_run_group(g, 3, st));
     }
-    VPR_TRY(gemm_run(g, st));
-
-    // ---- dH = [dF W1c | dS W1s] * (H > 0) * keep_scale ----
-    g = GemmDesc(); g.dtype = dtype;
-    g.A = dF; g.lda = s.l; g.B = w1c; g.b_mn = 1; g.ldb = h; g.M = (int)Tk; g.N = h; g.K = s.l;
-    g.out = dH; g.out_kind = okT; g.ldo = 2 * h; g.mask = H; g.ld_mask = 2 * h; g.mask_scale = keep_scale;
-    VPR_TRY(gemm_run(g, st));
-    g = GemmDesc(); g.dtype = dtype;
-    g.A = dS; g.lda = s.m; g.B = w1s; g.b_mn = 1; g.ldb = h; g.M = (int)Tk; g.N = h; g.K = s.m;
-    g.out = dH + h; g.out_kind = okT; g.ldo = 2 * h; g.mask = H + h; g.ld_mask = 2 * h; g.mask_scale = keep_scale;
-    VPR_TRY(gemm_run(g, st));
-    // first-layer bias gradients
-    VPR_TRY(colsum<T>(dH, 2 * h, Tk, 2 * h, gr.cluster_b0, st, gr.score_b0, h));
-    // ---- first-layer weight gradients: dW0[h,d] = dH^T X (two halves: separate parameter tensors) ----
-    for (int half = 0; half < 2; ++half) {
-        g = GemmDesc(); g.dtype = dtype;
-        g.A = dH + half * h; g.a_mn = 1; g.lda = 2 * h; g.B = x; g.b_mn = 1; g.ldb = s.d; g.M = h; g.N = s.d; g.K = (int)Tk;
-        g.out = half == 0 ? gr.cluster_w0 : gr.score_w0; g.out_kind = OUT_ATOMIC_F32; g.ldo = s.d;
-        int tiles = ((h + 127) / 128) * ((s.d + 255) / 256);
-        g.k_splits = nsm / tiles; if (g.k_splits < 1) g.k_splits = 1; if (g.k_splits > kb_tok) g.k_splits = kb_tok;
-        VPR_TRY(gemm_run(g, st));
-    }
-    // ---- input gradient dX = dH W0cat ----
-    if (dx != nullptr) {
-        g = GemmDesc(); g.dtype = dtype;
-        g.A = dH; g.lda = 2 * h; g.B = w0cat; g.b_mn = 1; g.ldb = s.d; g.M = (int)Tk; g.N = s.d; g.K = 2 * h;
-        g.out = dx; g.out_kind = okT; g.ldo = s.d;
-        VPR_TRY(gemm_run(g, st));
+    // ---- input gradients: dX = dH W0cat, dt = dHT Wt0 ----
+    {
+        int cnt = 0;
+        if (dx != nullptr) {
+            g[cnt] = GemmDesc(); g[cnt].dtype = dtype;
+            g[cnt].A = dH; g[cnt].lda = 2 * h; g[cnt].B = w0cat; g[cnt].b_mn = 1; g[cnt].ldb = s.d; g[cnt].M = (int)Tk; g[cnt].N = s.d;
+            g[cnt].K = 2 * h; g[cnt].out = dx; g[cnt].out_kind = okT; g[cnt].ldo = s.d;
+            ++cnt;
+        }
+        if (dt != nullptr) {
+            g[cnt] = GemmDesc(); g[cnt].dtype = dtype;
+            g[cnt].A = dHT; g[cnt].lda = h; g[cnt].B = wt0; g[cnt].b_mn = 1; g[cnt].ldb = s.d; g[cnt].M = s.B; g[cnt].N = s.d; g[cnt].K = h;
+            g[cnt].out = dt; g[cnt].out_kind = okT; g[cnt].ldo = s.d;
+            ++cnt;
+        }
+        if (cnt > 0) VPR_TRY(gemm_run_group(g, cnt, st));
     }
     return 0;
 }

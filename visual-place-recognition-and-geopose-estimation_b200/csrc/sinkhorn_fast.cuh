@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(SK_NT) sinkhorn_bwd_fast(const float* __restri
     {
         const float uc = uK[c] - k.norm2;
         float acc = 0.f;
+#pragma unroll 4
         for (int j = part; j < n; j += PARTS) {
             const float g = __ldg(dPb + j * M_ + c) * fex2(Ms[j * PITCH + c] + uc + vK[j]);
             acc += g;
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(SK_NT) sinkhorn_bwd_fast(const float* __restri
     // dM_jc = G_jc - sum_k ( DV[k][j] * Wv^k_jc + DU[k][c] * Wu^k_jc )
     TD* dSb = dS + (size_t)b * n * M_;
     float bsum = 0.f;
+#pragma unroll 2
     for (int e = tid; e < n * M_; e += NT) {      // e % M_ == c because NT % M_ == 0
         const int j = e / M_;
         const float mv = Ms[j * PITCH + c] - k.norm2;
