@@ -169,7 +169,7 @@ def test_salad_fp32_matches_oracle(vpr, B, hw):
     ref, mod = _pair(vpr)
     errs, out = _run_pair(vpr, ref, mod, B, hw, 1234, torch.float32)
     assert max(errs.values()) < 1e-4, errs
-    np.testing.assert_allclose(out.float().norm(dim=1).cpu().numpy(), 1.0, atol=1e-5)
+    np.testing.assert_allclose(out.detach().float().norm(dim=1).cpu().numpy(), 1.0, atol=1e-5)
 
 
 def test_salad_fp32_matches_committed_golden(vpr, golden_dir):

@@ -401,48 +401,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             const int seg_cols = 256 / esize;                                // columns staged per round
             const int rounds = (BN + seg_cols - 1) / seg_cols;
             const int round_chunks = (BN < seg_cols ? BN : seg_cols) / 32;    // 32-column chunks per round
+            int valid_rounds = (args.N - nt * BN + seg_cols - 1) / seg_cols;      // rounds that hold real columns
+            if (valid_rounds > rounds) valid_rounds = rounds;
 #pragma unroll 1
-            for (int rd = 0; rd < rounds; ++rd) {
+            for (int rd = 0; rd < valid_rounds; ++rd) {
                 const int col0 = nt * BN + rd * seg_cols;
-                if (col0 < args.N) {
-                    // ---- phase A: TMEM -> registers -> epilogue math -> swizzled staging tile ----
+                // ---- phase A: TMEM -> registers -> epilogue math -> swizzled staging tile ----
 #pragma unroll 1
-                    for (int c = chalf; c < round_chunks; c += 2) {
-                        const int n0 = col0 + c * 32;
-                        if (n0 >= args.N) break;
-                        uint32_t r[32];
-                        float v[32];
-                        tmem_ld32(taddr + rd * seg_cols + c * 32, r);
-                        tmem_ld_wait();
-                        epilogue_math32(args, r, v, b, m, n0);
-                        if (esize == 2) {
+                for (int c = chalf; c < round_chunks; c += 2) {
+                    const int n0 = col0 + c * 32;
+                    if (n0 >= args.N) break;
+                    uint32_t r[32];
+                    float v[32];
+                    tmem_ld32(taddr + rd * seg_cols + c * 32, r);
+                    tmem_ld_wait();
+                    epilogue_math32(args, r, v, b, m, n0);
+                    if (esize == 2) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint32_t pk[4];
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t pk[4];
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j * 8 + 2 * i], v[j * 8 + 2 * i + 1]);
-                                    pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-                                }
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(staging, row, c * 4 + j)),
-                                             "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                            for (int i = 0; i < 4; ++i) {
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j * 8 + 2 * i], v[j * 8 + 2 * i + 1]);
+                                pk[i] = *reinterpret_cast<uint32_t*>(&h2);
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(staging, row, c * 8 + j)),
-                                             "r"(__float_as_uint(v[4 * j])), "r"(__float_as_uint(v[4 * j + 1])),
-                                             "r"(__float_as_uint(v[4 * j + 2])), "r"(__float_as_uint(v[4 * j + 3])) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(staging, row, c * 4 + j)),
+                                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
                         }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(staging, row, c * 8 + j)),
+                                         "r"(__float_as_uint(v[4 * j])), "r"(__float_as_uint(v[4 * j + 1])),
+                                         "r"(__float_as_uint(v[4 * j + 2])), "r"(__float_as_uint(v[4 * j + 3])) : "memory");
                     }
                 }
-                if (rd == rounds - 1 || col0 + seg_cols >= args.N) {
+                if (rd == valid_rounds - 1) {
                     // every tcgen05.ld of this tile has completed: hand the accumulator back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar(as));
                 }
-                if (col0 >= args.N) break;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 // ---- phase B: coalesced flush ----
                 int seg_n = args.N - col0;                                       // valid columns of this round

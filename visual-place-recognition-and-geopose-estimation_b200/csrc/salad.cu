@@ -580,7 +580,7 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
     g[1].out = S; g[1].out_kind = OUT_F32; g[1].ldo = s.m; g[1].bias = p.score_b1;
     g[2] = GemmDesc(); g[2].dtype = dtype;
     g[2].A = HT; g[2].lda = h; g[2].B = wt1; g[2].ldb = h; g[2].M = s.B; g[2].N = s.g; g[2].K = h;
-    g[2].out = TF; g[2].out_kind = OUT_F32; g[2].ldo = s.g; g[2].bias = p.token_b1;
+    g[2].out = TF; g[2].out_kind = OUT_F32; g[2].ldo = s.g; g[2].bias = p.token_b1; g[2].bn = 128;
     VPR_TRY(gemm_run_group(g, 3, st));
     // P = sinkhorn(S)
     VPR_TRY(sinkhorn_fwd(S, p.dust_bin, P, dtype, U, V, s.B, s.n, s.m, s.iters, st));
