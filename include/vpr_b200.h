@@ -175,7 +175,7 @@ VPR_API int vpr_gemm(int dtype, const void* A, int a_mn, int64_t lda, int64_t a_
              int64_t ldb, int64_t b_bs, int M, int N, int K, int batch, void* out, int out_kind,
              int64_t ldo, int64_t out_bs, const float* bias, int relu, const void* mask, int64_t ld_mask,
              int64_t mask_bs, float mask_scale, float alpha, int k_splits, int bn, float* colsum,
-             cudaStream_t stream);
+             float dropout_p, uint64_t dropout_seed, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

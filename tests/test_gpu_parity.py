@@ -262,6 +262,7 @@ def test_salad_full_size_properties_bf16(vpr):
     t = torch.randn(B, 768, device="cuda", generator=g).bfloat16().requires_grad_(True)
     out = mod((x, t))
     o = out.float()
+    o = o.detach()
     np.testing.assert_allclose(o.norm(dim=1).cpu().numpy(), 1.0, atol=4e-3)
     np.testing.assert_allclose(o[:, :256].norm(dim=1).cpu().numpy(), 1 / math.sqrt(65), rtol=1e-2)
     cl = o[:, 256:].reshape(B, 128, 64).norm(dim=1)

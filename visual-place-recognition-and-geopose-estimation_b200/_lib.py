@@ -73,7 +73,8 @@ EXPORTS = {
     "vpr_knn_merge": (C.c_int, [_fp, _fp, C.c_int, C.c_int64, C.c_int, _fp, _fp, _fp]),
     "vpr_gemm": (C.c_int, [C.c_int, _fp, C.c_int, C.c_int64, C.c_int64, _fp, C.c_int, C.c_int64, C.c_int64,
                            C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_int64, C.c_int64, _fp, C.c_int,
-                           _fp, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_int, C.c_int, _fp, _fp]),
+                           _fp, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_int, C.c_int, _fp, C.c_float,
+                           C.c_uint64, _fp]),
 }
 
 _lib = None

@@ -45,7 +45,8 @@ unsigned long long vpr_launch_count(void) { return vpr::g_launches.load(); }
 int vpr_gemm(int dtype, const void* A, int a_mn, int64_t lda, int64_t a_bs, const void* B, int b_mn, int64_t ldb,
              int64_t b_bs, int M, int N, int K, int batch, void* out, int out_kind, int64_t ldo, int64_t out_bs,
              const float* bias, int relu, const void* mask, int64_t ld_mask, int64_t mask_bs, float mask_scale,
-             float alpha, int k_splits, int bn, float* colsum, cudaStream_t stream) {
+             float alpha, int k_splits, int bn, float* colsum, float dropout_p, uint64_t dropout_seed,
+             cudaStream_t stream) {
     vpr::GemmDesc g;
     g.dtype = dtype;
     g.A = A; g.a_mn = a_mn; g.lda = lda; g.a_bs = a_bs;
@@ -55,6 +56,7 @@ int vpr_gemm(int dtype, const void* A, int a_mn, int64_t lda, int64_t a_bs, cons
     g.bias = bias; g.relu = relu;
     g.mask = mask; g.ld_mask = ld_mask; g.mask_bs = mask_bs; g.mask_scale = mask_scale;
     g.alpha = alpha; g.k_splits = k_splits; g.bn = bn; g.colsum = colsum;
+    g.dropout_p = dropout_p; g.dropout_seed = dropout_seed;
     return vpr::gemm_run(g, stream);
 }
 

@@ -54,6 +54,8 @@ struct TcGroup {
     int count;
     int total_work;
 };
+static_assert(sizeof(TcArgs) % 8 == 0, "TcArgs is copied to shared memory in 4-byte words");
+static constexpr int ARGS_SMEM_BYTES = ((MAX_GROUP * (int)sizeof(TcArgs) + 127) / 128) * 128;
 
 template <int BN>
 struct TcCfg {
@@ -63,7 +65,7 @@ struct TcCfg {
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                      : (2 * BN <= 256) ? 256 : 512;
     // ring + staging + barriers/tmem slot (256) + column-sum scratch (512) + alignment slack
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 512 + 1024;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 512 + ARGS_SMEM_BYTES + 1024;
 };
 
 // Per-thread epilogue math on one 32-column chunk of one output row.
@@ -239,6 +241,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
     float* cs = reinterpret_cast<float*>(smem_al + (bar_base + 256 - smem_base));      // [128] column-sum scratch
+    // per-problem arguments in shared memory: dynamically indexed by every role without touching param space
+    TcArgs* sargs = reinterpret_cast<TcArgs*>(smem_al + (bar_base + 256 + 512 - smem_base));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -266,6 +270,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         tmem_relinquish();
     }
     if (warp >= 2 && threadIdx.x - 64 < 128) cs[threadIdx.x - 64] = 0.f;
+    for (int i = threadIdx.x; i < grp.count * (int)(sizeof(TcArgs) / 4); i += GEMM_THREADS) {
+        const int gi = i / (int)(sizeof(TcArgs) / 4), wi = i % (int)(sizeof(TcArgs) / 4);
+        reinterpret_cast<uint32_t*>(sargs + gi)[wi] = reinterpret_cast<const uint32_t*>(&grp.p[gi].args)[wi];
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -277,8 +285,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         g = 0;
 #pragma unroll
         for (int i = 1; i < MAX_GROUP; ++i)
-            if (i < grp.count && w >= grp.p[i].args.work_begin) g = i;
-        const TcArgs& a = grp.p[g].args;
+            if (i < grp.count && w >= sargs[i].work_begin) g = i;
+        const TcArgs& a = sargs[g];
         w -= a.work_begin;
         nt = w % a.tiles_n;
         w /= a.tiles_n;
@@ -286,8 +294,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         w /= a.k_splits;
         mt = w % a.tiles_m;
         b = w / a.tiles_m;
-        kb0 = (int)((long long)ks * a.kb_total / a.k_splits);
-        kb1 = (int)((long long)(ks + 1) * a.kb_total / a.k_splits);
+        kb0 = (ks * a.kb_total) / a.k_splits;          // ks < 148, kb_total < 2^20: no overflow
+        kb1 = ((ks + 1) * a.kb_total) / a.k_splits;
     };
 
     if (warp == 0) {
@@ -300,7 +308,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 decode(w, g, b, mt, nt, kb0, kb1);
                 const CUtensorMap* tmA = &grp.p[g].tmA;
                 const CUtensorMap* tmB = &grp.p[g].tmB;
-                const int bb = grp.p[g].args.b_batched ? b : 0;
+                const int bb = sargs[g].b_batched ? b : 0;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -370,7 +378,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
             int g, b, mt, nt, kb0, kb1;
             decode(w, g, b, mt, nt, kb0, kb1);
-            const TcArgs& args = grp.p[g].args;
+            const TcArgs& args = sargs[g];
             const int as = it & 1;
             const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
             mbar_wait(tfull_bar(as), aphase);
