@@ -109,6 +109,29 @@ def test_sinkhorn_forward_backward(vpr, B, n, m):
     assert rel(dS, dS2.transpose(1, 2)) < 1e-5
 
 
+@pytest.mark.parametrize("n,iters", [(256, 3), (529, 3), (200, 5)])
+def test_sinkhorn_wide_score_range_takes_the_log_domain_guard_path(vpr, n, iters):
+    """Image 0 has ordinary scores (scaled-tile path), image 1 a spread of several hundred nats, far outside
+    what an exponentiated tile can hold in fp32: its CTA must fall back to the element-wise log-domain body."""
+    g = torch.Generator().manual_seed(n)
+    S = torch.randn(2, 64, n, generator=g) * 2.0
+    S[1] *= 40.0
+    db = torch.tensor(1.0)
+    Sd = S.double().requires_grad_(True)
+    Pd = O.get_matching_probs(Sd, db.double(), iters, const_dtype=torch.float64).exp()
+    St = S.transpose(1, 2).contiguous().cuda()
+    P, U, V = vpr.sinkhorn(St, db.cuda(), iters)
+    assert torch.isfinite(P).all() and torch.isfinite(U).all() and torch.isfinite(V).all()
+    for b in range(2):
+        assert rel(P[b], Pd[b, :64].transpose(0, 1)) < 1e-4, b
+    dP = torch.randn(2, n, 64, generator=g)
+    (Pd[:, :64] * dP.double().transpose(1, 2)).sum().backward()
+    dS, _ = vpr.sinkhorn_backward(St, db.cuda(), U, V, dP.cuda(), iters)
+    assert torch.isfinite(dS).all()
+    for b in range(2):
+        assert rel(dS[b], Sd.grad[b].transpose(0, 1)) < 1e-4, b
+
+
 def test_sinkhorn_dustbin_value_is_irrelevant(vpr):
     g = torch.Generator().manual_seed(3)
     S = torch.randn(2, 256, 64, generator=g).cuda()

@@ -1,0 +1,63 @@
+"""Per-kernel device times of one SALAD fwd+bwd step (CUPTI via torch.profiler; warm, pipelined --
+complements the cold, serialised ncu launch list).  python tools/step_profile.py [B] [n]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+import vpr_b200  # noqa: E402
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+    hw = int(round(n ** 0.5))
+    torch.manual_seed(0)
+    head = vpr_b200.SaladHead(dropout=0.3).cuda().train()
+    x = torch.randn(B, n, 768, device="cuda").bfloat16()
+    t = torch.randn(B, 768, device="cuda").bfloat16()
+    w = torch.randn(B, 8448, device="cuda").bfloat16()
+
+    def step():
+        for p in head.parameters():
+            p.grad = None
+        xg = x.detach().requires_grad_(True)
+        tg = t.detach().requires_grad_(True)
+        out = head((xg.view(B, hw, hw, 768).permute(0, 3, 1, 2), tg))
+        out.backward(w)
+
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    steps = 10
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+    rows = []
+    for e in prof.key_averages():
+        dt = getattr(e, "device_time_total", None)
+        if dt is None:
+            dt = e.cuda_time_total
+        if dt > 0:
+            rows.append((dt / steps, e.count / steps, e.key))
+    rows.sort(reverse=True)
+    tot = sum(r[0] for r in rows)
+    print(f"B={B} n={n}: sum of kernel time per step {tot:.1f} us")
+    for dt, cnt, key in rows:
+        print(f"{dt:9.1f} us  x{cnt:4.1f}  {key[:150]}")
+    # in-order trace of the last step
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    per = len(evs) // steps
+    print("--- last step, launch order ---")
+    t0 = evs[-per].time_range.start
+    for e in evs[-per:]:
+        print(f"{e.time_range.start - t0:9.1f} +{e.time_range.end - e.time_range.start:8.1f} us  {e.name[:120]}")
+
+
+if __name__ == "__main__":
+    main()

@@ -10,7 +10,7 @@
 //   out [B, g + l*m]  normalize(cat(normalize(TF), normalize(AGG, over l).flatten))
 #include "common.cuh"
 #include "gemm.h"
-#include "sinkhorn_fast.cuh"
+#include "sinkhorn_scaled.cuh"
 #include "../../include/vpr_b200.h"
 
 #include <math.h>
@@ -300,17 +300,29 @@ static int sinkhorn_fwd(const float* S, const float* dust_bin, void* P, int p_dt
     VPR_REQUIRE(n > m, "Sinkhorn needs n > m (n=%d, m=%d)", n, m);
     VPR_REQUIRE(iters >= 1 && iters <= 8, "iters out of range");
     if (m == 64) {
-        const size_t fs = sinkfast_fwd_floats<64>(n) * sizeof(float);
-        VPR_REQUIRE(fs <= 227 * 1024, "score tile [%d,%d] does not fit in shared memory", n, m);
         SinkConst2 k2;
         k2.norm2 = (float)(-log2((double)(n + m)));
         k2.log_a_m2 = k2.norm2 + (float)log2((double)(n - m));
+        const size_t guard = sinkfast_fwd_floats<64>(n) * sizeof(float);
+        size_t fs = sinkscaled_fwd_floats(n) * sizeof(float);
+        if (fs < guard) fs = guard;
+        if (fs <= 227 * 1024) {          // scaled tile (one exp2 per element), log-domain body as its range guard
+            if (p_dtype == VPR_BF16) {
+                VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_scaled<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+                sinkhorn_fwd_scaled<bf16><<<B, SS_NT, fs, st>>>(S, dust_bin, (bf16*)P, U, V, n, iters, k2);
+            } else {
+                VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_scaled<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+                sinkhorn_fwd_scaled<float><<<B, SS_NT, fs, st>>>(S, dust_bin, (float*)P, U, V, n, iters, k2);
+            }
+            return launch_ok("sinkhorn_fwd_scaled");
+        }
+        VPR_REQUIRE(guard <= 227 * 1024, "score tile [%d,%d] does not fit in shared memory", n, m);
         if (p_dtype == VPR_BF16) {
-            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_fast<bf16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
-            sinkhorn_fwd_fast<bf16, 64><<<B, SK_NT, fs, st>>>(S, dust_bin, (bf16*)P, U, V, n, iters, k2);
+            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_fast<bf16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)guard));
+            sinkhorn_fwd_fast<bf16, 64><<<B, SK_NT, guard, st>>>(S, dust_bin, (bf16*)P, U, V, n, iters, k2);
         } else {
-            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_fast<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
-            sinkhorn_fwd_fast<float, 64><<<B, SK_NT, fs, st>>>(S, dust_bin, (float*)P, U, V, n, iters, k2);
+            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_fast<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)guard));
+            sinkhorn_fwd_fast<float, 64><<<B, SK_NT, guard, st>>>(S, dust_bin, (float*)P, U, V, n, iters, k2);
         }
         return launch_ok("sinkhorn_fwd_fast");
     }
@@ -332,17 +344,31 @@ static int sinkhorn_bwd(const float* S, const float* dust_bin, const float* U, c
     VPR_REQUIRE(m == 16 || m == 32 || m == 64 || m == 128, "num_clusters must be 16/32/64/128 (got %d)", m);
     VPR_REQUIRE(n > m, "Sinkhorn needs n > m");
     if (m == 64) {
-        const size_t fs = sinkfast_bwd_floats<64>(n, iters) * sizeof(float);
-        VPR_REQUIRE(fs <= 227 * 1024, "score tile [%d,%d] does not fit in shared memory", n, m);
         SinkConst2 k2;
         k2.norm2 = (float)(-log2((double)(n + m)));
         k2.log_a_m2 = k2.norm2 + (float)log2((double)(n - m));
+        const size_t guard = sinkfast_bwd_floats<64>(n, iters) * sizeof(float);
+        size_t fs = sinkscaled_bwd_floats(n, iters) * sizeof(float);
+        if (fs < guard) fs = guard;
+        if (fs <= 227 * 1024) {
+#define VPR_SS_BWD(TD, KIT)                                                                                            \
+    do {                                                                                                               \
+        VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_bwd_scaled<TD, KIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                         (int)fs));                                                                    \
+        sinkhorn_bwd_scaled<TD, KIT><<<B, SS_NT, fs, st>>>(S, dust_bin, U, V, dP, (TD*)dS, d_bias, n, iters, k2);      \
+    } while (0)
+            if (ds_dtype == VPR_BF16) { if (iters == 3) VPR_SS_BWD(bf16, 3); else VPR_SS_BWD(bf16, 0); }
+            else                      { if (iters == 3) VPR_SS_BWD(float, 3); else VPR_SS_BWD(float, 0); }
+#undef VPR_SS_BWD
+            return launch_ok("sinkhorn_bwd_scaled");
+        }
+        VPR_REQUIRE(guard <= 227 * 1024, "score tile [%d,%d] does not fit in shared memory", n, m);
         if (ds_dtype == VPR_BF16) {
-            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_bwd_fast<bf16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
-            sinkhorn_bwd_fast<bf16, 64><<<B, SK_NT, fs, st>>>(S, dust_bin, U, V, dP, (bf16*)dS, d_bias, n, iters, k2);
+            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_bwd_fast<bf16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)guard));
+            sinkhorn_bwd_fast<bf16, 64><<<B, SK_NT, guard, st>>>(S, dust_bin, U, V, dP, (bf16*)dS, d_bias, n, iters, k2);
         } else {
-            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_bwd_fast<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
-            sinkhorn_bwd_fast<float, 64><<<B, SK_NT, fs, st>>>(S, dust_bin, U, V, dP, (float*)dS, d_bias, n, iters, k2);
+            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_bwd_fast<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)guard));
+            sinkhorn_bwd_fast<float, 64><<<B, SK_NT, guard, st>>>(S, dust_bin, U, V, dP, (float*)dS, d_bias, n, iters, k2);
         }
         return launch_ok("sinkhorn_bwd_fast");
     }

@@ -1,6 +1,9 @@
-// Sinkhorn forward/backward specialised for a compile-time cluster count (m = 64 upstream).
-// Same algorithm as the generic kernels in salad.cu, restructured for
-// issue-slot efficiency:
+// Element-wise log-domain Sinkhorn forward/backward for a compile-time cluster count (m = 64
+// upstream): one exp2 per tile element per pass, nothing exponentiated outside a max-subtracted
+// logsumexp, so it is safe for any score range.  These bodies are the guard path of the
+// scaled-tile kernels in sinkhorn_scaled.cuh (and the only path when their larger tile pitch
+// does not fit in shared memory).  Same algorithm as the generic kernels in salad.cu
+// (SURVEY.md A-2 / A-3), restructured for issue-slot efficiency:
 //   * 512 threads per image, everything in the base-2 log domain so that every exp / log is a
 //     single MUFU (ex2.approx / lg2.approx) with fp32 range (max-subtracted logsumexp kept);
 //   * row reductions (over tokens j): thread = (cluster c, 1/8 of the tokens), partials via smem;
@@ -69,12 +72,12 @@ __host__ __device__ constexpr size_t sinkfast_bwd_floats(int n, int iters) {
 }
 
 template <typename TP, int M_>
-__global__ void __launch_bounds__(SK_NT) sinkhorn_fwd_fast(const float* __restrict__ S, const float* __restrict__ dust_bin,
-                                                           TP* __restrict__ P, float* __restrict__ U,
-                                                           float* __restrict__ V, int n, int iters, SinkConst2 k) {
+__device__ __noinline__ void sinkhorn_fwd_logdomain(float* sm, const float* __restrict__ S,
+                                                    const float* __restrict__ dust_bin, TP* __restrict__ P,
+                                                    float* __restrict__ U, float* __restrict__ V, int n, int iters,
+                                                    SinkConst2 k) {
     static_assert(M_ == 64, "column-pass register tiling assumes 64 clusters");
     constexpr int PITCH = M_ + 1, NT = SK_NT, PARTS = NT / M_;
-    extern __shared__ float sm[];
     float* Ms = sm;
     float* vs = Ms + (size_t)n * PITCH;
     float* us = vs + n;
@@ -156,13 +159,13 @@ __global__ void __launch_bounds__(SK_NT) sinkhorn_fwd_fast(const float* __restri
 }
 
 template <typename TD, int M_>
-__global__ void __launch_bounds__(SK_NT) sinkhorn_bwd_fast(const float* __restrict__ S, const float* __restrict__ dust_bin,
-                                                           const float* __restrict__ U, const float* __restrict__ V,
-                                                           const float* __restrict__ dP, TD* __restrict__ dS,
-                                                           float* __restrict__ d_bias, int n, int iters, SinkConst2 k) {
+__device__ __noinline__ void sinkhorn_bwd_logdomain(float* sm, const float* __restrict__ S,
+                                                    const float* __restrict__ dust_bin, const float* __restrict__ U,
+                                                    const float* __restrict__ V, const float* __restrict__ dP,
+                                                    TD* __restrict__ dS, float* __restrict__ d_bias, int n, int iters,
+                                                    SinkConst2 k) {
     static_assert(M_ == 64, "column-pass register tiling assumes 64 clusters");
     constexpr int PITCH = M_ + 1, NT = SK_NT, PARTS = NT / M_;
-    extern __shared__ float sm[];
     float* Ms = sm;                                   // [n][PITCH]        scores * log2(e)
     float* vs = Ms + (size_t)n * PITCH;               // [iters+1][n]      v^0..v^K (log2 units)
     float* us = vs + (size_t)(iters + 1) * n;         // [iters][M_+1]     u^1..u^K (log2 units)
@@ -287,6 +290,23 @@ __global__ void __launch_bounds__(SK_NT) sinkhorn_bwd_fast(const float* __restri
             atomicAdd(d_bias + c, tot);
         }
     }
+}
+
+// stand-alone launches of the log-domain bodies (tiles too large for the scaled kernels' pitch)
+template <typename TP, int M_>
+__global__ void __launch_bounds__(SK_NT) sinkhorn_fwd_fast(const float* __restrict__ S, const float* __restrict__ dust_bin,
+                                                           TP* __restrict__ P, float* __restrict__ U,
+                                                           float* __restrict__ V, int n, int iters, SinkConst2 k) {
+    extern __shared__ __align__(16) float sk_smem[];
+    sinkhorn_fwd_logdomain<TP, M_>(sk_smem, S, dust_bin, P, U, V, n, iters, k);
+}
+template <typename TD, int M_>
+__global__ void __launch_bounds__(SK_NT) sinkhorn_bwd_fast(const float* __restrict__ S, const float* __restrict__ dust_bin,
+                                                           const float* __restrict__ U, const float* __restrict__ V,
+                                                           const float* __restrict__ dP, TD* __restrict__ dS,
+                                                           float* __restrict__ d_bias, int n, int iters, SinkConst2 k) {
+    extern __shared__ __align__(16) float sk_smem[];
+    sinkhorn_bwd_logdomain<TD, M_>(sk_smem, S, dust_bin, U, V, dP, dS, d_bias, n, iters, k);
 }
 
 }  // namespace vpr
