@@ -27,7 +27,21 @@ def timeit(fn, iters=10, warm=3):
 
 
 def main():
-    B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("B", nargs="?", type=int, default=256)
+    ap.add_argument("--only", default="")          # comma list of: h,hdrop,dx,dw0,dh,f
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--warm", type=int, default=3)
+    a = ap.parse_args()
+    B = a.B
+    only = set(x for x in a.only.split(",") if x)
+    global timeit
+    _t = timeit
+    timeit = lambda fn: _t(fn, a.iters, a.warm)  # noqa: E731
+
+    def want(k):
+        return not only or k in only
     T = B * 256
     dev = "cuda"
     bf = torch.bfloat16
@@ -48,22 +62,28 @@ def main():
         print(f"{name:44s} {ms*1e3:8.1f} us  {flops/ms/1e9:8.1f} TFLOP/s  {bytes_/ms/1e6:8.1f} GB/s", flush=True)
 
     f_h = 2.0 * T * 1024 * 768
-    ms = timeit(lambda: ops.gemm(X, W0, T, 1024, 768, out_kind=L.OUT_BF16, bias=b0, relu=True, out=H, ldo=1024, out_bs=0))
-    rec("H = relu(X W0^T + b)            KK  N=1024 K=768", ms, f_h, (T * 768 + T * 1024) * 2)
-    ms = timeit(lambda: ops.gemm(X, W0, T, 1024, 768, out_kind=L.OUT_BF16, bias=b0, relu=True, out=H, ldo=1024, out_bs=0,
-                                 dropout_p=0.3, dropout_seed=7))
-    rec("H with fused dropout", ms, f_h, (T * 768 + T * 1024) * 2)
-    ms = timeit(lambda: ops.gemm(dH, W0, T, 768, 1024, b_mn=True, out_kind=L.OUT_BF16, out=dX, ldo=768, out_bs=0))
-    rec("dX = dH W0                      K.MN N=768 K=1024", ms, 2.0 * T * 768 * 1024, (T * 1024 + T * 768) * 2)
-    ms = timeit(lambda: ops.gemm(dH, X, 512, 768, T, a_mn=True, b_mn=True, out_kind=L.OUT_ATOMIC_F32, out=gW0, ldo=768,
-                                 out_bs=0, k_splits=12))
-    rec("dW0 = dH[:, :512]^T X           MN.MN split-K 12", ms, 2.0 * 512 * 768 * T, (T * 512 + T * 768) * 2)
-    ms = timeit(lambda: ops.gemm(dF, W1c, T, 512, 128, b_mn=True, out_kind=L.OUT_BF16, out=dH, ldo=1024, out_bs=0, mask=H,
-                                 mask_scale=1.0 / 0.7, colsum=cs))
-    rec("dH half = (dF W1c)*(H>0)        K.MN N=512 K=128", ms, 2.0 * T * 512 * 128, (T * 128 + 2 * T * 512) * 2)
-    F = torch.empty(T, 128, device=dev, dtype=bf)
-    ms = timeit(lambda: ops.gemm(H, W1c, T, 128, 512, out_kind=L.OUT_BF16, out=F, ldo=128, out_bs=0))
-    rec("F = H[:, :512] W1c^T            KK  N=128 K=512", ms, 2.0 * T * 128 * 512, (T * 512 + T * 128) * 2)
+    if want("h"):
+        ms = timeit(lambda: ops.gemm(X, W0, T, 1024, 768, out_kind=L.OUT_BF16, bias=b0, relu=True, out=H, ldo=1024, out_bs=0))
+        rec("H = relu(X W0^T + b)            KK  N=1024 K=768", ms, f_h, (T * 768 + T * 1024) * 2)
+    if want("hdrop"):
+        ms = timeit(lambda: ops.gemm(X, W0, T, 1024, 768, out_kind=L.OUT_BF16, bias=b0, relu=True, out=H, ldo=1024, out_bs=0,
+                                     dropout_p=0.3, dropout_seed=7))
+        rec("H with fused dropout", ms, f_h, (T * 768 + T * 1024) * 2)
+    if want("dx"):
+        ms = timeit(lambda: ops.gemm(dH, W0, T, 768, 1024, b_mn=True, out_kind=L.OUT_BF16, out=dX, ldo=768, out_bs=0))
+        rec("dX = dH W0                      K.MN N=768 K=1024", ms, 2.0 * T * 768 * 1024, (T * 1024 + T * 768) * 2)
+    if want("dw0"):
+        ms = timeit(lambda: ops.gemm(dH, X, 512, 768, T, a_mn=True, b_mn=True, out_kind=L.OUT_ATOMIC_F32, out=gW0, ldo=768,
+                                     out_bs=0, k_splits=12))
+        rec("dW0 = dH[:, :512]^T X           MN.MN split-K 12", ms, 2.0 * 512 * 768 * T, (T * 512 + T * 768) * 2)
+    if want("dh"):
+        ms = timeit(lambda: ops.gemm(dF, W1c, T, 512, 128, b_mn=True, out_kind=L.OUT_BF16, out=dH, ldo=1024, out_bs=0, mask=H,
+                                     mask_scale=1.0 / 0.7, colsum=cs))
+        rec("dH half = (dF W1c)*(H>0)        K.MN N=512 K=128", ms, 2.0 * T * 512 * 128, (T * 128 + 2 * T * 512) * 2)
+    if want("f"):
+        F = torch.empty(T, 128, device=dev, dtype=bf)
+        ms = timeit(lambda: ops.gemm(H, W1c, T, 128, 512, out_kind=L.OUT_BF16, out=F, ldo=128, out_bs=0))
+        rec("F = H[:, :512] W1c^T            KK  N=128 K=512", ms, 2.0 * T * 128 * 512, (T * 512 + T * 128) * 2)
 
 
 if __name__ == "__main__":

@@ -59,21 +59,40 @@ static inline size_t carve_size(size_t& off, size_t bytes) {
     return r;
 }
 
-// Counter-based dropout: one splitmix64 of (seed, element index / 4) yields four 16-bit lanes;
-// element e is kept iff lane (e & 3) >= p * 65536.
-__host__ __device__ inline uint64_t dropout_hash64(uint64_t seed, uint64_t group) {
-    uint64_t z = group + (seed + 1) * 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
+// Counter-based dropout.  Element indices are grouped in runs of 32; a 32-bit avalanche mix of
+// (seed, run) seeds the full-period LCG x -> A x + C (mod 2^32) and element i of the run is kept iff
+// the LCG's i-th state is >= p * 2^32.  State i is the affine map A^i x0 + C_i of the run's seed, so
+// a thread that owns a whole run pays one multiply-add per element (the GEMM epilogue), while
+// anything else can evaluate single elements.
+static constexpr uint32_t DROP_LCG_A = 1664525u, DROP_LCG_C = 1013904223u;
+__host__ __device__ constexpr uint32_t drop_lcg_mul(int i) {
+    uint32_t a = 1u;
+    for (int k = 0; k < i; ++k) a *= DROP_LCG_A;
+    return a;
 }
-__host__ __device__ inline bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t thr16) {
-    return (uint32_t)((dropout_hash64(seed, idx >> 2) >> (16 * (idx & 3))) & 0xFFFFu) >= thr16;
+__host__ __device__ constexpr uint32_t drop_lcg_add(int i) {
+    uint32_t c = 0u;
+    for (int k = 0; k < i; ++k) c = c * DROP_LCG_A + DROP_LCG_C;
+    return c;
+}
+__host__ __device__ inline uint32_t dropout_mix(uint64_t seed, uint64_t run) {
+    uint32_t h = (uint32_t)run * 0x9E3779B1u + (uint32_t)seed;
+    h ^= h >> 16; h *= 0x85EBCA6Bu;
+    h ^= (uint32_t)(run >> 32) * 0xC2B2AE35u + (uint32_t)(seed >> 32);
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+__host__ __device__ inline bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t thr32) {
+    uint32_t w = dropout_mix(seed, idx >> 5);
+    const int i = (int)(idx & 31);
+    for (int k = 0; k < i; ++k) w = w * DROP_LCG_A + DROP_LCG_C;
+    return w >= thr32;
 }
 static inline uint32_t dropout_threshold(float p) {
-    double t = (double)p * 65536.0 + 0.5;
-    if (t < 0) t = 0;
-    if (t > 65535.0) t = 65535.0;
+    double t = (double)p * 4294967296.0;
+    if (t < 1.0) t = 1.0;                    // 0 is reserved for "no dropout"
+    if (t > 4294967295.0) t = 4294967295.0;
     return (uint32_t)t;
 }
 
@@ -157,6 +176,26 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
         " [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+
+// smem -> global tile store; completion is tracked by the issuing thread's bulk async-groups
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {      // at most N groups still reading shared memory
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (TMA store)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 // ---------------------------------------------------------------------------

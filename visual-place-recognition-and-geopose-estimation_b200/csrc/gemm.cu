@@ -1,10 +1,13 @@
 // Persistent, warp-specialised, grouped bf16 GEMM for sm_100a.
-//   warp 0      : TMA producer (cp.async.bulk.tensor, SWIZZLE_128B boxes into an mbarrier ring)
+//   warp 0      : TMA producer (cp.async.bulk.tensor, SWIZZLE_128B boxes into an mbarrier ring; in
+//                 mask mode also the relu-mask tile of every output tile, double buffered)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (fp32 accumulators in TMEM,
 //                 double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 2..9  : epilogue: tcgen05.ld -> bias / relu / dropout -> swizzled smem staging tile ->
-//                 coalesced 16-byte global stores (relu-mask applied and column sums taken on the
-//                 way out), or vector fp32 reductions for split-K
+//   warps 2..9  : epilogue, two groups of four warps (one warp per TMEM lane quarter) that take
+//                 alternate 128-byte-wide output boxes: tcgen05.ld -> bias / relu / dropout / relu-mask
+//                 / column sums in registers -> SWIZZLE_128B staging box -> one elected thread issues
+//                 the TMA tile store (edges are clipped by the tensor map), or vector fp32
+//                 reductions straight from registers for split-K
 // Operands may be K-major or MN-major in global memory (all four combinations), batched through
 // the third tensor-map dimension and split along K.  One launch runs up to MAX_GROUP independent
 // problems of the same operand layout / tile shape (the token-MLP GEMMs ride along with the
@@ -24,29 +27,30 @@ static constexpr int BK = 64;                   // 64 bf16 = 128 B = one swizzle
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
 static constexpr int GEMM_THREADS = 320;        // TMA warp, MMA warp, 8 epilogue warps
 static constexpr int EPI_WARPS = 8;
-static constexpr int SMEM_BUDGET = 196608;      // operand ring
-static constexpr int STAGING_BYTES = 128 * 256; // epilogue staging: 128 rows x 256 B
+static constexpr int BOX_BYTES = 128 * 128;     // 128 rows x 128 B: one swizzled TMA box
 static constexpr int MAX_GROUP = 4;
+static constexpr int SMEM_LIMIT = 227 * 1024;
+
+enum : uint32_t { F_BIAS = 1u, F_RELU = 2u, F_DROP = 4u, F_MASK = 8u, F_ALPHA = 16u, F_COLSUM = 32u };
 
 struct TcArgs {
     int M, N, K, batch;
     int tiles_m, tiles_n, k_splits, kb_total;
     int b_batched;
     int work_begin;            // first work item of this problem inside the group
-    void* out;
     int out_kind;
+    uint32_t flags;
+    void* out;                 // split-K (atomic) epilogue only; stored outputs go through tmO
     long long ldo, out_bs;
     const float* bias;
-    int relu;
-    const bf16* mask;
-    long long ld_mask, mask_bs;
-    float mask_scale, alpha;
-    uint32_t drop_thr; float drop_scale; unsigned long long drop_seed;
     float* colsum;             // [N] fp32 += column sums of the stored (masked, rounded) output
+    float mask_scale, alpha;
+    uint32_t drop_thr; float drop_scale;
+    unsigned long long drop_seed;
 };
 
 struct TcProblem {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmO, tmM;     // operands, output tile store, relu-mask tile load
     TcArgs args;
 };
 struct TcGroup {
@@ -56,27 +60,39 @@ struct TcGroup {
 };
 static_assert(sizeof(TcArgs) % 8 == 0, "TcArgs is copied to shared memory in 4-byte words");
 static constexpr int ARGS_SMEM_BYTES = ((MAX_GROUP * (int)sizeof(TcArgs) + 127) / 128) * 128;
+static constexpr int MISC_SMEM_BYTES = 256 + ARGS_SMEM_BYTES;        // barriers + tmem slot, arguments
 
-template <int BN>
+template <int BN, bool MASK>
 struct TcCfg {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
+    static constexpr int MASK_BOXES = BN / 64;                          // bf16 mask tile, 64 columns per box
+    static constexpr int MASK_BYTES = MASK ? 2 * MASK_BOXES * BOX_BYTES : 0;
+    static constexpr int SBUF = (BN >= 256) ? 1 : 2;                    // staging boxes per epilogue group
+    static constexpr int STAGING_BYTES = 2 * SBUF * BOX_BYTES;
+    static constexpr int RING_BUDGET = SMEM_LIMIT - 1024 - MISC_SMEM_BYTES - MASK_BYTES - STAGING_BYTES;
+    static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                      : (2 * BN <= 256) ? 256 : 512;
-    // ring + staging + barriers/tmem slot (256) + column-sum scratch (512) + alignment slack
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 512 + ARGS_SMEM_BYTES + 1024;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + MASK_BYTES + STAGING_BYTES + MISC_SMEM_BYTES;
+    static_assert(STAGES >= 2, "operand ring too small");
+    static_assert(2 * STAGES + 8 <= 31, "barrier area overflow");
+    static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget");
 };
 
-// Per-thread epilogue math on one 32-column chunk of one output row.
-__device__ __forceinline__ void epilogue_math32(const TcArgs& a, const uint32_t (&r)[32], float (&v)[32], int b,
-                                                int m, int n0) {
+// Per-thread epilogue math on one 32-column chunk of one output row: alpha, bias, relu, dropout.
+__device__ __forceinline__ void epilogue_math32(const TcArgs& a, uint32_t flags, const uint32_t (&r)[32], float (&v)[32],
+                                                int b, int m, int n0) {
     const int N = a.N;
-    const bool full = (n0 + 32 <= N);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * a.alpha;
-    if (a.bias != nullptr) {
-        if (full) {
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (flags & F_ALPHA) {
+        const float al = a.alpha;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= al;
+    }
+    if (flags & F_BIAS) {
+        if (n0 + 32 <= N) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n0) + j);
@@ -88,29 +104,32 @@ __device__ __forceinline__ void epilogue_math32(const TcArgs& a, const uint32_t 
                 if (n0 + i < N) v[i] += __ldg(a.bias + n0 + i);
         }
     }
-    if (a.relu) {
+    if (flags & F_RELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
     }
-    if (a.drop_thr != 0u) {
+    if (flags & F_DROP) {
         const unsigned long long base = ((unsigned long long)b * a.M + m) * (unsigned long long)N + n0;
-        if ((base & 3ull) == 0ull) {
+        const uint32_t thr = a.drop_thr;
+        const float sc = a.drop_scale;
+        const int off = (int)(base & 31ull);
+        uint32_t w0 = dropout_mix(a.drop_seed, base >> 5);
+        if (off == 0) {                          // this thread owns a whole run: one multiply-add per element
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const unsigned long long h = dropout_hash64(a.drop_seed, (base >> 2) + j);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    v[4 * j + i] = ((uint32_t)(h >> (16 * i)) & 0xFFFFu) >= a.drop_thr ? v[4 * j + i] * a.drop_scale : 0.f;
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t w = w0 * drop_lcg_mul(i) + drop_lcg_add(i);
+                v[i] = (w >= thr) ? v[i] * sc : 0.f;
             }
-        } else {
+        } else {                                 // the chunk straddles two runs: step the generator
+            const uint32_t w1 = dropout_mix(a.drop_seed, (base >> 5) + 1);
+            for (int k = 0; k < off; ++k) w0 = w0 * DROP_LCG_A + DROP_LCG_C;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                v[i] = dropout_keep(a.drop_seed, base + i, a.drop_thr) ? v[i] * a.drop_scale : 0.f;
+            for (int i = 0; i < 32; ++i) {
+                if (off + i == 32) w0 = w1;
+                v[i] = (w0 >= thr) ? v[i] * sc : 0.f;
+                w0 = w0 * DROP_LCG_A + DROP_LCG_C;
+            }
         }
-    }
-    if (a.mask != nullptr) {       // the mask's scale; its zeroing happens in the coalesced flush
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= a.mask_scale;
     }
 }
 
@@ -130,119 +149,48 @@ __device__ __forceinline__ void epilogue_atomic32(const TcArgs& a, const float (
     }
 }
 
-// Staging tile: 128 rows x 256 B, 16-byte slots XOR-swizzled with (row & 7) inside each 128 B line so
-// that both the row-per-thread writes and the row-per-half-warp reads are bank-conflict free.
-__device__ __forceinline__ uint32_t stage_addr(uint32_t base, int row, int i16) {
-    return base + (uint32_t)row * 256u + (uint32_t)(i16 >> 3) * 128u + (uint32_t)(((i16 & 7) ^ (row & 7)) << 4);
+// Column sums of a 32-row x 32-column register tile (lane = row, v[i] = column i): a butterfly
+// reduce-scatter over the warp leaves the total of column `lane` in lane `lane`.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float send = up ? v[i] : v[i + o];
+            const float keep = up ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
 }
 
-// Phase B of the epilogue for one staged round: every warp owns 16 rows of the tile, a row segment
-// (<= 256 B) is spread over LPR consecutive lanes -> fully coalesced global traffic.
-template <int ESIZE, int LPR>
-__device__ __forceinline__ void flush_round(const TcArgs& a, uint32_t staging, float* cs, int ew, int lane, int b,
-                                            int mt, int col0, int seg_n) {
-    constexpr int RPS = 32 / LPR;            // rows per warp step
-    constexpr int STEPS = 16 / RPS;
-    constexpr int EPL = 16 / ESIZE;          // elements per lane (8 bf16 / 4 fp32)
-    const int i16 = lane % LPR;
-    const int ncol = i16 * EPL;
-    const int rsub = lane / LPR;
-    const bool col_ok = ncol < seg_n;
-    const bool vec_ok = (ncol + EPL <= seg_n);
-    const bool use_mask = (ESIZE == 2) && a.mask != nullptr;
-    uint4 mq[STEPS];
-    if (use_mask) {                          // all mask loads in flight before anything depends on them
-        const bool mvec = vec_ok && ((a.ld_mask & 7) == 0);
-#pragma unroll
-        for (int s = 0; s < STEPS; ++s) {
-            const int mm = mt * BM + ew * 16 + s * RPS + rsub;
-            mq[s] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);   // bf16 1.0
-            if (mm < a.M && col_ok) {
-                const bf16* mp = a.mask + (long long)b * a.mask_bs + (long long)mm * a.ld_mask + col0 + ncol;
-                if (mvec) {
-                    mq[s] = __ldg(reinterpret_cast<const uint4*>(mp));
-                } else {
-                    bf16* mh = reinterpret_cast<bf16*>(&mq[s]);
-                    for (int i = 0; i < 8; ++i)
-                        if (ncol + i < seg_n) mh[i] = mp[i];
-                }
-            }
-        }
-    }
-    float csum[EPL];
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) csum[i] = 0.f;
-#pragma unroll
-    for (int s = 0; s < STEPS; ++s) {
-        const int rr = ew * 16 + s * RPS + rsub;
-        const int mm = mt * BM + rr;
-        if (mm >= a.M || !col_ok) continue;
-        uint4 d;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w)
-                     : "r"(stage_addr(staging, rr, i16)) : "memory");
-        const long long goff = (long long)b * a.out_bs + (long long)mm * a.ldo + col0 + ncol;
-        if (ESIZE == 2) {
-            bf16* dv = reinterpret_cast<bf16*>(&d);
-            if (use_mask) {
-                const bf16* mh = reinterpret_cast<const bf16*>(&mq[s]);
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (!(__bfloat162float(mh[i]) > 0.f)) dv[i] = __float2bfloat16_rn(0.f);
-            }
-            if (a.colsum != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) csum[i] += __bfloat162float(dv[i]);
-            }
-            bf16* op = reinterpret_cast<bf16*>(a.out) + goff;
-            if (vec_ok && ((a.ldo & 7) == 0)) {
-                *reinterpret_cast<uint4*>(op) = d;
-            } else {
-                for (int i = 0; i < 8; ++i)
-                    if (ncol + i < seg_n) op[i] = dv[i];
-            }
-        } else {
-            float* op = reinterpret_cast<float*>(a.out) + goff;
-            if (vec_ok && ((a.ldo & 3) == 0)) {
-                *reinterpret_cast<uint4*>(op) = d;
-            } else {
-                const float* dv = reinterpret_cast<const float*>(&d);
-                for (int i = 0; i < 4; ++i)
-                    if (ncol + i < seg_n) op[i] = dv[i];
-            }
-        }
-    }
-    if (ESIZE == 2 && a.colsum != nullptr) {
-        // lanes that share a column group (same i16) first, then one shared-memory add per column
-#pragma unroll
-        for (int o = LPR; o < 32; o <<= 1)
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) csum[i] += __shfl_xor_sync(0xffffffffu, csum[i], o);
-        if (rsub == 0 && col_ok) {
-#pragma unroll
-            for (int i = 0; i < EPL; ++i)
-                if (ncol + i < seg_n) atomicAdd(cs + ncol + i, csum[i]);
-        }
-    }
+// 16-byte slot `c16` of row `row` inside a 128-row x 128-byte SWIZZLE_128B box
+__device__ __forceinline__ uint32_t box_addr(uint32_t box, int row, int c16) {
+    return box + (uint32_t)row * 128u + (uint32_t)((c16 ^ (row & 7)) << 4);
 }
 
-template <bool A_MN, bool B_MN, int BN>
+template <bool A_MN, bool B_MN, int BN, bool MASK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcGroup grp) {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, MASK>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int SBUF = Cfg::SBUF;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t staging = smem_base + STAGES * Cfg::STAGE_BYTES;
-    const uint32_t bar_base = staging + STAGING_BYTES;
+    const uint32_t mask_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    const uint32_t staging = mask_base + Cfg::MASK_BYTES;
+    const uint32_t bar_base = staging + Cfg::STAGING_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    auto mfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };
+    auto mempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 6 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 8);
     uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
-    float* cs = reinterpret_cast<float*>(smem_al + (bar_base + 256 - smem_base));      // [128] column-sum scratch
     // per-problem arguments in shared memory: dynamically indexed by every role without touching param space
-    TcArgs* sargs = reinterpret_cast<TcArgs*>(smem_al + (bar_base + 256 + 512 - smem_base));
+    TcArgs* sargs = reinterpret_cast<TcArgs*>(smem_al + (bar_base + 256 - smem_base));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -251,6 +199,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         for (int g = 0; g < grp.count; ++g) {
             tma_prefetch_desc(&grp.p[g].tmA);
             tma_prefetch_desc(&grp.p[g].tmB);
+            if (grp.p[g].args.out_kind != OUT_ATOMIC_F32) tma_prefetch_desc(&grp.p[g].tmO);
+            if (MASK && (grp.p[g].args.flags & F_MASK)) tma_prefetch_desc(&grp.p[g].tmM);
         }
     }
     if (warp == 1) {
@@ -262,6 +212,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             for (int s = 0; s < 2; ++s) {
                 mbar_init(tfull_bar(s), 1);
                 mbar_init(tempty_bar(s), EPI_WARPS);
+                mbar_init(mfull_bar(s), 1);
+                mbar_init(mempty_bar(s), EPI_WARPS);
             }
             mbar_fence_init();
         }
@@ -269,7 +221,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
         tmem_relinquish();
     }
-    if (warp >= 2 && threadIdx.x - 64 < 128) cs[threadIdx.x - 64] = 0.f;
     for (int i = threadIdx.x; i < grp.count * (int)(sizeof(TcArgs) / 4); i += GEMM_THREADS) {
         const int gi = i / (int)(sizeof(TcArgs) / 4), wi = i % (int)(sizeof(TcArgs) / 4);
         reinterpret_cast<uint32_t*>(sargs + gi)[wi] = reinterpret_cast<const uint32_t*>(&grp.p[gi].args)[wi];
@@ -303,12 +254,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int mit = 0;                                  // masked tiles so far (mask buffer = mit & 1)
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
                 int g, b, mt, nt, kb0, kb1;
                 decode(w, g, b, mt, nt, kb0, kb1);
                 const CUtensorMap* tmA = &grp.p[g].tmA;
                 const CUtensorMap* tmB = &grp.p[g].tmB;
                 const int bb = sargs[g].b_batched ? b : 0;
+                if (MASK && (sargs[g].flags & F_MASK)) {
+                    const int mb = mit & 1;
+                    mbar_wait(mempty_bar(mb), ((uint32_t)(mit >> 1) & 1u) ^ 1u);
+                    int nbox = (sargs[g].N - nt * BN + 63) / 64;
+                    if (nbox > Cfg::MASK_BOXES) nbox = Cfg::MASK_BOXES;
+                    mbar_expect_tx(mfull_bar(mb), (uint32_t)nbox * BOX_BYTES);
+                    for (int bx = 0; bx < nbox; ++bx)
+                        tma_load_3d(mask_base + (uint32_t)(mb * Cfg::MASK_BOXES + bx) * BOX_BYTES, &grp.p[g].tmM,
+                                    mfull_bar(mb), nt * BN + bx * 64, mt * BM, b);
+                    ++mit;
+                }
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -372,23 +335,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         // ------------------------------ epilogue ------------------------------
         const int ew = warp - 2;           // 0..7
         const int q = warp & 3;            // TMEM lane quarter this warp may touch
-        const int chalf = ew >> 2;         // two warps share a quarter: even / odd 32-column chunks
-        const int et = threadIdx.x - 64;   // 0..255
-        int it = 0;
+        const int eg = ew >> 2;            // epilogue group: alternate output boxes / 32-column chunks
+        const bool issuer = ((ew & 3) == 0) && lane == 0;
+        const uint32_t my_staging = staging + (uint32_t)(eg * SBUF) * BOX_BYTES;
+        const int row = q * 32 + lane;
+        int nstore = 0;                    // boxes this group has stored so far
+        int it = 0, mit = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
             int g, b, mt, nt, kb0, kb1;
             decode(w, g, b, mt, nt, kb0, kb1);
             const TcArgs& args = sargs[g];
+            const uint32_t flags = args.flags;
             const int as = it & 1;
             const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-            mbar_wait(tfull_bar(as), aphase);
-            tc_fence_after();
-            const int row = q * 32 + lane;
             const int m = mt * BM + row;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+            const bool masked = MASK && (flags & F_MASK);
+            const int mb = mit & 1;
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
             if (args.out_kind == OUT_ATOMIC_F32) {
 #pragma unroll 1
-                for (int c = chalf; c < BN / 32; c += 2) {
+                for (int c = eg; c < BN / 32; c += 2) {
                     const int n0 = nt * BN + c * 32;
                     if (n0 >= args.N) break;
                     uint32_t r[32];
@@ -396,81 +364,98 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     tmem_ld32(taddr + c * 32, r);
                     tmem_ld_wait();
                     if (m < args.M) {
-                        epilogue_math32(args, r, v, b, m, n0);
+                        epilogue_math32(args, flags, r, v, b, m, n0);
                         epilogue_atomic32(args, v, b, m, n0);
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(as));
-                continue;
-            }
-            const int esize = args.out_kind == OUT_BF16 ? 2 : 4;
-            const int seg_cols = 256 / esize;                                // columns staged per round
-            const int rounds = (BN + seg_cols - 1) / seg_cols;
-            const int round_chunks = (BN < seg_cols ? BN : seg_cols) / 32;    // 32-column chunks per round
-            int valid_rounds = (args.N - nt * BN + seg_cols - 1) / seg_cols;      // rounds that hold real columns
-            if (valid_rounds > rounds) valid_rounds = rounds;
+            } else {
+                const bool bf = args.out_kind == OUT_BF16;
+                const int box_cols = bf ? 64 : 32;                     // 128 bytes of output per box row
+                int nbox = (args.N - nt * BN + box_cols - 1) / box_cols;
+                if (nbox > BN / box_cols) nbox = BN / box_cols;
+                if (masked) mbar_wait(mfull_bar(mb), (uint32_t)(mit >> 1) & 1u);
 #pragma unroll 1
-            for (int rd = 0; rd < valid_rounds; ++rd) {
-                const int col0 = nt * BN + rd * seg_cols;
-                // ---- phase A: TMEM -> registers -> epilogue math -> swizzled staging tile ----
+                for (int bx = eg; bx < nbox; bx += 2) {
+                    const uint32_t sbuf = my_staging + (uint32_t)(nstore % SBUF) * BOX_BYTES;
+                    ++nstore;
+                    if (issuer) bulk_wait_read<SBUF - 1>();            // the box we are about to overwrite has been read
+                    named_bar_sync(1 + eg, 128);
+                    const int cpb = bf ? 2 : 1;
 #pragma unroll 1
-                for (int c = chalf; c < round_chunks; c += 2) {
-                    const int n0 = col0 + c * 32;
-                    if (n0 >= args.N) break;
-                    uint32_t r[32];
-                    float v[32];
-                    tmem_ld32(taddr + rd * seg_cols + c * 32, r);
-                    tmem_ld_wait();
-                    epilogue_math32(args, r, v, b, m, n0);
-                    if (esize == 2) {
+                    for (int c = 0; c < cpb; ++c) {
+                        const int n0 = nt * BN + bx * box_cols + c * 32;
+                        if (n0 >= args.N) break;
+                        uint32_t r[32];
+                        float v[32];
+                        tmem_ld32(taddr + bx * box_cols + c * 32, r);
+                        tmem_ld_wait();
+                        epilogue_math32(args, flags, r, v, b, m, n0);
+                        if (bf) {
+                            if (masked) {
+                                const float ms = args.mask_scale;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint32_t pk[4];
+                                for (int i = 0; i < 32; ++i) v[i] *= ms;
+                            }
+                            uint32_t pk[16];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j * 8 + 2 * i], v[j * 8 + 2 * i + 1]);
+                            for (int i = 0; i < 16; ++i) {
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
                                 pk[i] = *reinterpret_cast<uint32_t*>(&h2);
                             }
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(staging, row, c * 4 + j)),
-                                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-                        }
-                    } else {
+                            if (MASK && masked) {                          // keep where the saved activation is > 0
+                                const uint32_t mbox = mask_base + (uint32_t)(mb * Cfg::MASK_BOXES + bx) * BOX_BYTES;
+                                const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(staging, row, c * 8 + j)),
-                                         "r"(__float_as_uint(v[4 * j])), "r"(__float_as_uint(v[4 * j + 1])),
-                                         "r"(__float_as_uint(v[4 * j + 2])), "r"(__float_as_uint(v[4 * j + 3])) : "memory");
+                                for (int j = 0; j < 4; ++j) {
+                                    uint32_t mw[4];
+                                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                                 : "=r"(mw[0]), "=r"(mw[1]), "=r"(mw[2]), "=r"(mw[3])
+                                                 : "r"(box_addr(mbox, row, c * 4 + j)) : "memory");
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t)
+                                        pk[4 * j + t] &= __hgt2_mask(*reinterpret_cast<__nv_bfloat162*>(&mw[t]), zero2);
+                                }
+                            }
+                            if (flags & F_COLSUM) {
+                                const bool live = m < args.M;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    v[2 * i] = live ? __uint_as_float(pk[i] << 16) : 0.f;
+                                    v[2 * i + 1] = live ? __uint_as_float(pk[i] & 0xFFFF0000u) : 0.f;
+                                }
+                                const float tot = warp_colsum32(v, lane);
+                                if (n0 + lane < args.N) atomicAdd(args.colsum + n0 + lane, tot);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box_addr(sbuf, row, c * 4 + j)),
+                                             "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box_addr(sbuf, row, j)),
+                                             "r"(__float_as_uint(v[4 * j])), "r"(__float_as_uint(v[4 * j + 1])),
+                                             "r"(__float_as_uint(v[4 * j + 2])), "r"(__float_as_uint(v[4 * j + 3])) : "memory");
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1 + eg, 128);
+                    if (issuer) {
+                        tma_store_3d(&grp.p[g].tmO, sbuf, nt * BN + bx * box_cols, mt * BM, b);
+                        bulk_commit();
                     }
                 }
-                if (rd == valid_rounds - 1) {
-                    // every tcgen05.ld of this tile has completed: hand the accumulator back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(as));
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                // ---- phase B: coalesced flush ----
-                int seg_n = args.N - col0;                                       // valid columns of this round
-                if (seg_n > round_chunks * 32) seg_n = round_chunks * 32;
-                const int lpr = (round_chunks * 32 * esize) >> 4;                 // 16-byte lanes per row
-                if (esize == 2) {
-                    if (lpr == 16) flush_round<2, 16>(args, staging, cs, ew, lane, b, mt, col0, seg_n);
-                    else if (lpr == 8) flush_round<2, 8>(args, staging, cs, ew, lane, b, mt, col0, seg_n);
-                    else flush_round<2, 4>(args, staging, cs, ew, lane, b, mt, col0, seg_n);
-                } else {
-                    if (lpr == 16) flush_round<4, 16>(args, staging, cs, ew, lane, b, mt, col0, seg_n);
-                    else flush_round<4, 8>(args, staging, cs, ew, lane, b, mt, col0, seg_n);
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");   // staging tile reusable, column sums complete
-                if (args.colsum != nullptr && et < seg_n) {
-                    const float sv = cs[et];
-                    cs[et] = 0.f;
-                    if (sv != 0.f) atomicAdd(args.colsum + col0 + et, sv);
-                }
             }
+            // every tcgen05.ld / mask read of this tile by this warp has completed: release both buffers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(tempty_bar(as));
+                if (masked) mbar_arrive(mempty_bar(mb));
+            }
+            if (masked) ++mit;
         }
+        if (issuer) bulk_wait_read<0>();   // staging must outlive the last tile stores
     }
 
     tc_fence_before();
@@ -605,47 +590,56 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 3-D bf16 tensor map over a row-major [batch][rows][inner] operand, 128B swizzle.
-static int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t rows, int64_t batch, int64_t ld,
-                    int64_t bs, int box_inner, int box_rows) {
+// 3-D tensor map over a row-major [batch][rows][inner] array of 2-byte (bf16) or 4-byte (fp32)
+// elements, 128B swizzle; ld / bs in elements.
+static int make_map(CUtensorMap* map, const void* ptr, int esize, int64_t inner, int64_t rows, int64_t batch, int64_t ld,
+                    int64_t bs, int box_inner, int box_rows, const char* what) {
     EncodeTiledFn enc = get_encode();
     VPR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
-    VPR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand pointer must be 16-byte aligned");
-    VPR_REQUIRE((ld % 8) == 0, "TMA operand row stride must be a multiple of 8 bf16 (got %lld)", (long long)ld);
-    VPR_REQUIRE(inner > 0 && rows > 0 && batch > 0, "empty TMA operand");
+    VPR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "%s: pointer must be 16-byte aligned", what);
+    VPR_REQUIRE((ld * esize) % 16 == 0, "%s: row stride must be a multiple of 16 bytes (got %lld elements of %d bytes)",
+                what, (long long)ld, esize);
+    VPR_REQUIRE(inner > 0 && rows > 0 && batch > 0, "%s: empty tensor", what);
     if (batch == 1 || bs == 0) { batch = 1; bs = rows * ld; }
-    VPR_REQUIRE((bs % 8) == 0, "TMA operand batch stride must be a multiple of 8 bf16 (got %lld)", (long long)bs);
+    VPR_REQUIRE((bs * esize) % 16 == 0, "%s: batch stride must be a multiple of 16 bytes (got %lld elements)", what,
+                (long long)bs);
     cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch};
-    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bs * 2};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * esize, (cuuint64_t)bs * esize};
     cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    VPR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): inner=%lld rows=%lld batch=%lld ld=%lld bs=%lld",
-                (int)r, (long long)inner, (long long)rows, (long long)batch, (long long)ld, (long long)bs);
+    CUresult r = enc(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                     const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VPR_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed (%d): inner=%lld rows=%lld batch=%lld ld=%lld bs=%lld",
+                what, (int)r, (long long)inner, (long long)rows, (long long)batch, (long long)ld, (long long)bs);
     return 0;
 }
 
-template <bool A_MN, bool B_MN, int BN>
+template <bool A_MN, bool B_MN, int BN, bool MASK>
 static int launch_tc(const TcGroup& grp, int grid, cudaStream_t st) {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, MASK>;
     static bool attr_set = false;
     if (!attr_set) {
-        VPR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VPR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, BN, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    gemm_tc_kernel<A_MN, B_MN, BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(grp);
+    gemm_tc_kernel<A_MN, B_MN, BN, MASK><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(grp);
     return launch_ok("gemm_tc_kernel");
 }
 
 template <int BN>
-static int dispatch_major(int a_mn, int b_mn, const TcGroup& grp, int grid, cudaStream_t st) {
-    if (!a_mn && !b_mn) return launch_tc<false, false, BN>(grp, grid, st);
-    if (!a_mn && b_mn) return launch_tc<false, true, BN>(grp, grid, st);
-    if (a_mn && !b_mn) return launch_tc<true, false, BN>(grp, grid, st);
-    return launch_tc<true, true, BN>(grp, grid, st);
+static int dispatch_major(int a_mn, int b_mn, bool mask, const TcGroup& grp, int grid, cudaStream_t st) {
+    if constexpr (BN <= 128) {
+        if (mask) {
+            VPR_REQUIRE(!a_mn, "the relu-mask epilogue needs a K-major A operand");
+            return b_mn ? launch_tc<false, true, BN, true>(grp, grid, st) : launch_tc<false, false, BN, true>(grp, grid, st);
+        }
+    }
+    if (!a_mn && !b_mn) return launch_tc<false, false, BN, false>(grp, grid, st);
+    if (!a_mn && b_mn) return launch_tc<false, true, BN, false>(grp, grid, st);
+    if (a_mn && !b_mn) return launch_tc<true, false, BN, false>(grp, grid, st);
+    return launch_tc<true, true, BN, false>(grp, grid, st);
 }
 
 static int auto_bn(int N) { return (N > 128) ? 256 : (N > 64) ? 128 : 64; }
@@ -653,11 +647,14 @@ static int auto_bn(int N) { return (N > 128) ? 256 : (N > 64) ? 128 : 64; }
 static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
     VPR_REQUIRE(count >= 1 && count <= MAX_GROUP, "a GEMM group holds 1..%d problems", MAX_GROUP);
     int bn = 0;
+    bool any_mask = false;
     for (int i = 0; i < count; ++i) {
         VPR_REQUIRE(gs[i].a_mn == gs[0].a_mn && gs[i].b_mn == gs[0].b_mn, "grouped GEMMs must share the operand layout");
         const int want = gs[i].bn ? gs[i].bn : auto_bn(gs[i].N);
         if (want > bn) bn = want;
+        any_mask = any_mask || gs[i].mask != nullptr;
     }
+    if (any_mask && bn > 128) bn = 128;          // the mask tile shares shared memory with the operand ring
     VPR_REQUIRE(bn == 64 || bn == 128 || bn == 256, "bad tile N %d", bn);
     TcGroup grp;
     grp.count = count;
@@ -665,10 +662,16 @@ static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
     for (int i = 0; i < count; ++i) {
         const GemmDesc& g = gs[i];
         TcProblem& p = grp.p[i];
-        if (g.a_mn) VPR_TRY(make_map(&p.tmA, g.A, g.M, g.K, g.batch, g.lda, g.a_bs, 64, 64));
-        else        VPR_TRY(make_map(&p.tmA, g.A, g.K, g.M, g.batch, g.lda, g.a_bs, 64, BM));
-        if (g.b_mn) VPR_TRY(make_map(&p.tmB, g.B, g.N, g.K, g.batch, g.ldb, g.b_bs, 64, 64));
-        else        VPR_TRY(make_map(&p.tmB, g.B, g.K, g.N, g.batch, g.ldb, g.b_bs, 64, bn));
+        if (g.a_mn) VPR_TRY(make_map(&p.tmA, g.A, 2, g.M, g.K, g.batch, g.lda, g.a_bs, 64, 64, "GEMM operand A"));
+        else        VPR_TRY(make_map(&p.tmA, g.A, 2, g.K, g.M, g.batch, g.lda, g.a_bs, 64, BM, "GEMM operand A"));
+        if (g.b_mn) VPR_TRY(make_map(&p.tmB, g.B, 2, g.N, g.K, g.batch, g.ldb, g.b_bs, 64, 64, "GEMM operand B"));
+        else        VPR_TRY(make_map(&p.tmB, g.B, 2, g.K, g.N, g.batch, g.ldb, g.b_bs, 64, bn, "GEMM operand B"));
+        if (g.out_kind == OUT_BF16)
+            VPR_TRY(make_map(&p.tmO, g.out, 2, g.N, g.M, g.batch, g.ldo, g.out_bs, 64, BM, "GEMM output"));
+        else if (g.out_kind == OUT_F32)
+            VPR_TRY(make_map(&p.tmO, g.out, 4, g.N, g.M, g.batch, g.ldo, g.out_bs, 32, BM, "GEMM output"));
+        if (g.mask != nullptr)
+            VPR_TRY(make_map(&p.tmM, g.mask, 2, g.N, g.M, g.batch, g.ld_mask, g.mask_bs, 64, BM, "GEMM relu-mask"));
         TcArgs& a = p.args;
         a.M = g.M; a.N = g.N; a.K = g.K; a.batch = g.batch;
         a.tiles_m = (g.M + BM - 1) / BM;
@@ -678,12 +681,12 @@ static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
         if (a.k_splits > a.kb_total) a.k_splits = a.kb_total;
         a.b_batched = (g.batch > 1 && g.b_bs != 0) ? 1 : 0;
         a.out = g.out; a.out_kind = g.out_kind; a.ldo = g.ldo; a.out_bs = g.out_bs;
-        a.bias = g.bias; a.relu = g.relu;
-        a.mask = reinterpret_cast<const bf16*>(g.mask); a.ld_mask = g.ld_mask; a.mask_bs = g.mask_bs;
+        a.bias = g.bias; a.colsum = g.colsum;
         a.mask_scale = g.mask_scale; a.alpha = g.alpha;
         a.drop_thr = g.dropout_p > 0.f ? dropout_threshold(g.dropout_p) : 0u;
         a.drop_scale = g.dropout_p > 0.f ? 1.f / (1.f - g.dropout_p) : 1.f; a.drop_seed = g.dropout_seed;
-        a.colsum = g.colsum;
+        a.flags = (g.bias ? F_BIAS : 0u) | (g.relu ? F_RELU : 0u) | (a.drop_thr ? F_DROP : 0u) | (g.mask ? F_MASK : 0u) |
+                  (g.alpha != 1.f ? F_ALPHA : 0u) | (g.colsum ? F_COLSUM : 0u);
         VPR_REQUIRE(g.colsum == nullptr || g.out_kind == OUT_BF16, "fused column sums need a bf16 output");
         VPR_REQUIRE(g.mask == nullptr || g.out_kind == OUT_BF16, "the relu-mask epilogue needs a bf16 output");
         a.work_begin = (int)total;
@@ -692,9 +695,9 @@ static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
     }
     grp.total_work = (int)total;
     int grid = (int)(total < num_sms() ? total : num_sms());
-    if (bn == 256) return dispatch_major<256>(gs[0].a_mn, gs[0].b_mn, grp, grid, st);
-    if (bn == 128) return dispatch_major<128>(gs[0].a_mn, gs[0].b_mn, grp, grid, st);
-    return dispatch_major<64>(gs[0].a_mn, gs[0].b_mn, grp, grid, st);
+    if (bn == 256) return dispatch_major<256>(gs[0].a_mn, gs[0].b_mn, any_mask, grp, grid, st);
+    if (bn == 128) return dispatch_major<128>(gs[0].a_mn, gs[0].b_mn, any_mask, grp, grid, st);
+    return dispatch_major<64>(gs[0].a_mn, gs[0].b_mn, any_mask, grp, grid, st);
 }
 
 static int gemm_simt(const GemmDesc& g, cudaStream_t st) {
