@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "gemm.h"
 #include "sinkhorn_scaled.cuh"
+#include "finalize_fast.cuh"
 #include "../../include/vpr_b200.h"
 
 #include <math.h>
@@ -50,27 +51,29 @@ __device__ __forceinline__ float block_max256(float v, float* red) {
 // ---------------------------------------------------------------------------
 // parameter packing: fp32 master weights -> run dtype, first layers concatenated
 // ---------------------------------------------------------------------------
+struct PackSeg { const float* src; void* dst; long long n4; };      // n4 = number of 4-element groups
+struct PackPlan { PackSeg seg[8]; long long total4; };
+
+// fp32 master weights -> run dtype, four elements per thread (all tensor sizes are multiples of 8)
 template <typename T>
-__global__ void pack_params_kernel(const VprSaladParams p, int d, int h, int l, int m, int g, T* w0cat, T* w1c,
-                                   T* w1s, T* wt0, T* wt1, float* b0cat) {
-    const long long n0 = (long long)h * d, n1 = (long long)l * h, n2 = (long long)m * h, n3 = (long long)g * h;
-    const long long total = 2 * n0 + n1 + n2 + n0 + n3 + 2 * h;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+__global__ void __launch_bounds__(256) pack_params_kernel(const PackPlan plan) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plan.total4;
          i += (long long)gridDim.x * blockDim.x) {
         long long e = i;
-        if (e < n0) { stf(w0cat + e, p.cluster_w0[e]); continue; }
-        e -= n0;
-        if (e < n0) { stf(w0cat + n0 + e, p.score_w0[e]); continue; }
-        e -= n0;
-        if (e < n1) { stf(w1c + e, p.cluster_w1[e]); continue; }
-        e -= n1;
-        if (e < n2) { stf(w1s + e, p.score_w1[e]); continue; }
-        e -= n2;
-        if (e < n0) { stf(wt0 + e, p.token_w0[e]); continue; }
-        e -= n0;
-        if (e < n3) { stf(wt1 + e, p.token_w1[e]); continue; }
-        e -= n3;
-        b0cat[e] = e < h ? p.cluster_b0[e] : p.score_b0[e - h];
+        int sidx = 0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k)
+            if (sidx == k && e >= plan.seg[k].n4) { e -= plan.seg[k].n4; sidx = k + 1; }
+        const float4 v = __ldg(reinterpret_cast<const float4*>(plan.seg[sidx].src) + e);
+        if (sizeof(T) == 2 && sidx < 6) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(plan.seg[sidx].dst)[e] = pk;
+        } else {
+            reinterpret_cast<float4*>(plan.seg[sidx].dst)[e] = v;      // fp32 mode, and the bias concat
+        }
     }
 }
 
@@ -516,7 +519,7 @@ struct SavePlan {
     size_t w0cat, w1c, w1s, wt0, wt1, b0cat, H, F, S, P, U, V, AGG, HT, TF, total;
 };
 struct WorkPlan {
-    size_t dAGG, dTF, dF, dP, dS, dH, dHT, total;
+    size_t dAGG, dAGGT, dTF, dF, dP, dS, dH, dHT, total;
 };
 
 static SavePlan save_plan(const VprSaladShape& s, int dtype) {
@@ -549,6 +552,7 @@ static WorkPlan work_plan(const VprSaladShape& s, int dtype) {
     WorkPlan p;
     size_t off = 0;
     p.dAGG = carve_size(off, (size_t)s.B * s.l * s.m * e);
+    p.dAGGT = carve_size(off, (size_t)s.B * s.l * s.m * e);
     p.dTF = carve_size(off, (size_t)s.B * s.g * e);
     p.dF = carve_size(off, T * s.l * e);
     p.dP = carve_size(off, T * s.m * 4);
@@ -583,8 +587,27 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
     T* HT = (T*)(save + sp.HT); float* TF = (float*)(save + sp.TF);
     const int okT = dtype == VPR_BF16 ? OUT_BF16 : OUT_F32;
 
-    pack_params_kernel<T><<<num_sms() * 2, 256, 0, st>>>(p, s.d, h, s.l, s.m, s.g, w0cat, w1c, w1s, wt0, wt1, b0cat);
-    VPR_TRY(launch_ok("pack_params_kernel"));
+    {
+        const long long n0 = (long long)h * s.d;
+        PackPlan plan;
+        plan.seg[0] = {p.cluster_w0, w0cat, n0 / 4};
+        plan.seg[1] = {p.score_w0, w0cat + n0, n0 / 4};
+        plan.seg[2] = {p.cluster_w1, w1c, (long long)s.l * h / 4};
+        plan.seg[3] = {p.score_w1, w1s, (long long)s.m * h / 4};
+        plan.seg[4] = {p.token_w0, wt0, n0 / 4};
+        plan.seg[5] = {p.token_w1, wt1, (long long)s.g * h / 4};
+        plan.seg[6] = {p.cluster_b0, b0cat, h / 4};
+        plan.seg[7] = {p.score_b0, b0cat + h, h / 4};
+        plan.total4 = 0;
+        for (int k = 0; k < 8; ++k) {
+            VPR_REQUIRE((reinterpret_cast<uintptr_t>(plan.seg[k].src) & 15) == 0, "parameter tensors must be 16-byte aligned");
+            plan.total4 += plan.seg[k].n4;
+        }
+        int blocks = (int)((plan.total4 + 255) / 256);
+        if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+        pack_params_kernel<T><<<blocks, 256, 0, st>>>(plan);
+        VPR_TRY(launch_ok("pack_params_kernel"));
+    }
 
     VPR_REQUIRE(Tk < (1ll << 31), "too many tokens");
     GemmDesc g[3];
@@ -617,6 +640,10 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
     g[0].M = s.l; g[0].N = s.m; g[0].K = s.n; g[0].batch = s.B;
     g[0].out = AGG; g[0].out_kind = OUT_F32; g[0].ldo = s.m; g[0].out_bs = (int64_t)s.l * s.m;
     VPR_TRY(gemm_run(g[0], st));
+    if (finalize_fast_ok(s.l, s.m, s.g)) {
+        finalize_fwd_fast<T><<<s.B, 256, 0, st>>>(AGG, TF, out, s.l, s.m, s.g);
+        return launch_ok("finalize_fwd_fast");
+    }
     finalize_fwd_kernel<T><<<s.B, 256, 0, st>>>(AGG, TF, out, s.l, s.m, s.g);
     return launch_ok("finalize_fwd_kernel");
 }
@@ -661,31 +688,46 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         }
     }
 
-    // norms backward: d_out -> dAGG [B,l,m], dTF [B,g] (+ token_features.2.bias gradient)
-    finalize_bwd_kernel<T><<<s.B, 256, 0, st>>>(AGG, TF, d_out, dAGG, dTF, gr.token_b1, s.l, s.m, s.g);
-    VPR_TRY(launch_ok("finalize_bwd_kernel"));
+    // norms backward: d_out -> dAGG [B,l,m] (and its transpose [B,m,l]), dTF [B,g] (+ token_features.2.bias gradient)
+    T* dAGGT = (T*)(ws + wp.dAGGT);
+    const bool fin_fast = finalize_fast_ok(s.l, s.m, s.g);
+    if (fin_fast) {
+        const size_t fsm = finalize_bwd_fast_smem<T>(s.l, s.m);
+        VPR_CUDA_OK(cudaFuncSetAttribute(finalize_bwd_fast<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+        finalize_bwd_fast<T><<<s.B, 256, fsm, st>>>(AGG, TF, d_out, dAGG, dAGGT, dTF, gr.token_b1, s.l, s.m, s.g);
+        VPR_TRY(launch_ok("finalize_bwd_fast"));
+    } else {
+        finalize_bwd_kernel<T><<<s.B, 256, 0, st>>>(AGG, TF, d_out, dAGG, dTF, gr.token_b1, s.l, s.m, s.g);
+        VPR_TRY(launch_ok("finalize_bwd_kernel"));
+    }
 
     GemmDesc g[3];
     const int kb_tok = (int)((Tk + 63) / 64);
-    // ---- aggregation backward ----
+    // ---- aggregation backward (one launch when the transposed dAGG is available) ----
     g[0] = GemmDesc(); g[0].dtype = dtype;    // dF[b][j][l] = sum_c P[b][j][c] dAGG[b][l][c]   (+ cluster bias gradient)
     g[0].A = P; g[0].lda = s.m; g[0].a_bs = (int64_t)s.n * s.m; g[0].B = dAGG; g[0].ldb = s.m; g[0].b_bs = (int64_t)s.l * s.m;
     g[0].M = s.n; g[0].N = s.l; g[0].K = s.m; g[0].batch = s.B;
     g[0].out = dF; g[0].out_kind = okT; g[0].ldo = s.l; g[0].out_bs = (int64_t)s.n * s.l; g[0].colsum = gr.cluster_b1;
-    VPR_TRY(gemm_run(g[0], st));
-    g[0] = GemmDesc(); g[0].dtype = dtype;    // dP[b][j][c] = sum_l F[b][j][l] dAGG[b][l][c]
-    g[0].A = F; g[0].lda = s.l; g[0].a_bs = (int64_t)s.n * s.l; g[0].B = dAGG; g[0].b_mn = 1; g[0].ldb = s.m;
-    g[0].b_bs = (int64_t)s.l * s.m; g[0].M = s.n; g[0].N = s.m; g[0].K = s.l; g[0].batch = s.B;
-    g[0].out = dP; g[0].out_kind = OUT_F32; g[0].ldo = s.m; g[0].out_bs = (int64_t)s.n * s.m;
-    VPR_TRY(gemm_run(g[0], st));
+    g[1] = GemmDesc(); g[1].dtype = dtype;    // dP[b][j][c] = sum_l F[b][j][l] dAGG[b][l][c]
+    g[1].A = F; g[1].lda = s.l; g[1].a_bs = (int64_t)s.n * s.l;
+    g[1].M = s.n; g[1].N = s.m; g[1].K = s.l; g[1].batch = s.B;
+    g[1].out = dP; g[1].out_kind = OUT_F32; g[1].ldo = s.m; g[1].out_bs = (int64_t)s.n * s.m;
+    if (fin_fast) {
+        g[1].B = dAGGT; g[1].ldb = s.l; g[1].b_bs = (int64_t)s.l * s.m;
+        VPR_TRY(gemm_run_group(g, 2, st));
+    } else {
+        g[1].B = dAGG; g[1].b_mn = 1; g[1].ldb = s.m; g[1].b_bs = (int64_t)s.l * s.m;
+        VPR_TRY(gemm_run(g[0], st));
+        VPR_TRY(gemm_run(g[1], st));
+    }
     // ---- Sinkhorn backward: dP -> dS (+ score bias gradient) ----
     VPR_TRY(sinkhorn_bwd(S, p.dust_bin, U, V, dP, dS, dtype, gr.score_b1, s.B, s.n, s.m, s.iters, st));
 
     // ---- second-layer weight gradients (split-K + fp32 reductions), one launch ----
     {
-        const int small = ((s.g + 127) / 128) * ((h + 255) / 256);
+        // the token problem's few short work items come last and are absorbed by the CTAs that finish first
         const int tiles = ((s.l + 127) / 128 + (s.m + 127) / 128) * ((h + 255) / 256);
-        int ks = (nsm - small) / tiles; if (ks < 1) ks = 1; if (ks > kb_tok) ks = kb_tok;
+        int ks = nsm / tiles; if (ks < 1) ks = 1; if (ks > kb_tok) ks = kb_tok;
         g[0] = GemmDesc(); g[0].dtype = dtype;    // dW1c[l,h] = dF^T H[:, :h]
         g[0].A = dF; g[0].a_mn = 1; g[0].lda = s.l; g[0].B = H; g[0].b_mn = 1; g[0].ldb = 2 * h; g[0].M = s.l; g[0].N = h;
         g[0].K = (int)Tk; g[0].out = gr.cluster_w1; g[0].out_kind = OUT_ATOMIC_F32; g[0].ldo = h; g[0].k_splits = ks;
@@ -712,9 +754,8 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
     VPR_TRY(gemm_run_group(g, 3, st));
     // ---- first-layer weight gradients: dW0[h,d] = dH^T X (two parameter tensors) and dWt0 = dHT^T t ----
     {
-        const int small = ((h + 127) / 128) * ((s.d + 255) / 256);
-        const int tiles = 2 * small;
-        int ks = (nsm - small) / tiles; if (ks < 1) ks = 1; if (ks > kb_tok) ks = kb_tok;
+        const int tiles = 2 * ((h + 127) / 128) * ((s.d + 255) / 256);
+        int ks = nsm / tiles; if (ks < 1) ks = 1; if (ks > kb_tok) ks = kb_tok;
         for (int half = 0; half < 2; ++half) {
             g[half] = GemmDesc(); g[half].dtype = dtype;
             g[half].A = dH + half * h; g[half].a_mn = 1; g[half].lda = 2 * h; g[half].B = x; g[half].b_mn = 1; g[half].ldb = s.d;
