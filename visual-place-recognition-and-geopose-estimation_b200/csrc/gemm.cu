@@ -16,6 +16,7 @@
 #include "gemm.h"
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace vpr {
 
@@ -62,9 +63,13 @@ static_assert(sizeof(TcArgs) % 8 == 0, "TcArgs is copied to shared memory in 4-b
 static constexpr int ARGS_SMEM_BYTES = ((MAX_GROUP * (int)sizeof(TcArgs) + 127) / 128) * 128;
 static constexpr int MISC_SMEM_BYTES = 256 + ARGS_SMEM_BYTES;        // barriers + tmem slot, arguments
 
-template <int BN, bool MASK>
+template <int BN, bool MASK, bool CTA2>
 struct TcCfg {
-    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    // CTA2: a CTA pair (cta_group::2) owns a 256 x BN tile; each CTA stages its own 128 rows of A and
+    // half of the B tile, so a k-block costs 32 KB per SM instead of 48 KB at BN = 256
+    static constexpr int TILE_M = CTA2 ? 2 * BM : BM;
+    static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;                   // B-tile rows (n) staged by one CTA
+    static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int MASK_BOXES = BN / 64;                          // bf16 mask tile, 64 columns per box
     static constexpr int MASK_BYTES = MASK ? 2 * MASK_BOXES * BOX_BYTES : 0;
@@ -75,6 +80,7 @@ struct TcCfg {
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                      : (2 * BN <= 256) ? 256 : 512;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + MASK_BYTES + STAGING_BYTES + MISC_SMEM_BYTES;
+    static_assert(!(MASK && CTA2), "the relu-mask epilogue runs single-CTA tiles");
     static_assert(STAGES >= 2, "operand ring too small");
     static_assert(2 * STAGES + 8 <= 31, "barrier area overflow");
     static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget");
@@ -170,9 +176,9 @@ __device__ __forceinline__ uint32_t box_addr(uint32_t box, int row, int c16) {
     return box + (uint32_t)row * 128u + (uint32_t)((c16 ^ (row & 7)) << 4);
 }
 
-template <bool A_MN, bool B_MN, int BN, bool MASK>
+template <bool A_MN, bool B_MN, int BN, bool MASK, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcGroup grp) {
-    using Cfg = TcCfg<BN, MASK>;
+    using Cfg = TcCfg<BN, MASK, CTA2>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int SBUF = Cfg::SBUF;
     extern __shared__ uint8_t smem_raw[];
@@ -194,6 +200,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;     // 0 = leader of the pair (issues the MMAs)
+    const int w_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int w_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         for (int g = 0; g < grp.count; ++g) {
@@ -211,22 +220,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(tfull_bar(s), 1);
-                mbar_init(tempty_bar(s), EPI_WARPS);
+                mbar_init(tempty_bar(s), CTA2 ? 2 * EPI_WARPS : EPI_WARPS);     // the leader's is the one waited on
                 mbar_init(mfull_bar(s), 1);
                 mbar_init(mempty_bar(s), EPI_WARPS);
             }
             mbar_fence_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if (CTA2) { tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_2sm(); }
+        else      { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
     }
     for (int i = threadIdx.x; i < grp.count * (int)(sizeof(TcArgs) / 4); i += GEMM_THREADS) {
         const int gi = i / (int)(sizeof(TcArgs) / 4), wi = i % (int)(sizeof(TcArgs) / 4);
         reinterpret_cast<uint32_t*>(sargs + gi)[wi] = reinterpret_cast<const uint32_t*>(&grp.p[gi].args)[wi];
     }
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all();          // the peer's barriers must exist before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const int total_work = grp.total_work;
@@ -255,12 +265,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             int stage = 0;
             uint32_t phase = 0;
             int mit = 0;                                  // masked tiles so far (mask buffer = mit & 1)
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            // CTA pair: both producers credit the leader's full barrier, which expects both CTAs' bytes
+            const uint32_t full0 = CTA2 ? mapa_shared(full_bar(0), 0u) : full_bar(0);
+            for (int w = w_first; w < total_work; w += w_step) {
                 int g, b, mt, nt, kb0, kb1;
                 decode(w, g, b, mt, nt, kb0, kb1);
                 const CUtensorMap* tmA = &grp.p[g].tmA;
                 const CUtensorMap* tmB = &grp.p[g].tmB;
                 const int bb = sargs[g].b_batched ? b : 0;
+                const int m0 = mt * Cfg::TILE_M + (int)cta_rank * BM;
+                const int n0 = nt * BN + (int)cta_rank * (CTA2 ? Cfg::B_ROWS : 0);
                 if (MASK && (sargs[g].flags & F_MASK)) {
                     const int mb = mit & 1;
                     mbar_wait(mempty_bar(mb), ((uint32_t)(mit >> 1) & 1u) ^ 1u);
@@ -276,20 +290,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + A_STAGE_BYTES;
-                    mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                    const uint32_t fb = full0 + 8u * stage;
+                    if (!CTA2 || cta_rank == 0) mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * (CTA2 ? 2 : 1));
+                    auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2) {
+                        if (CTA2) tma_load_3d_2sm(dst, tm, fb, c0, c1, c2);
+                        else tma_load_3d(dst, tm, fb, c0, c1, c2);
+                    };
                     if (A_MN) {
 #pragma unroll
-                        for (int i = 0; i < BM / 64; ++i)
-                            tma_load_3d(sa + i * 8192, tmA, full_bar(stage), mt * BM + i * 64, kb * BK, b);
+                        for (int i = 0; i < BM / 64; ++i) load(sa + i * 8192, tmA, m0 + i * 64, kb * BK, b);
                     } else {
-                        tma_load_3d(sa, tmA, full_bar(stage), kb * BK, mt * BM, b);
+                        load(sa, tmA, kb * BK, m0, b);
                     }
                     if (B_MN) {
 #pragma unroll
-                        for (int i = 0; i < BN / 64; ++i)
-                            tma_load_3d(sb + i * 8192, tmB, full_bar(stage), nt * BN + i * 64, kb * BK, bb);
+                        for (int i = 0; i < Cfg::B_ROWS / 64; ++i) load(sb + i * 8192, tmB, n0 + i * 64, kb * BK, bb);
                     } else {
-                        tma_load_3d(sb, tmB, full_bar(stage), kb * BK, nt * BN, bb);
+                        load(sb, tmB, kb * BK, n0, bb);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -297,8 +314,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(Cfg::TILE_M, BN, A_MN, B_MN);
             constexpr uint32_t A_LBO = A_MN ? 8192u : 16u;
             constexpr uint32_t B_LBO = B_MN ? 8192u : 16u;
             constexpr uint32_t A_KSTEP = A_MN ? 2048u : 32u;   // bytes per UMMA_K = 16 elements
@@ -306,7 +323,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+            for (int w = w_first; w < total_work; w += w_step, ++it) {
                 int g, b, mt, nt, kb0, kb1;
                 decode(w, g, b, mt, nt, kb0, kb1);
                 const int as = it & 1;
@@ -323,12 +340,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t ad = make_smem_desc(sa + k * A_KSTEP, A_LBO, 1024u);
                         const uint64_t bd = make_smem_desc(sb + k * B_KSTEP, B_LBO, 1024u);
-                        tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (CTA2) tc_mma_bf16_2sm(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        else tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    tc_commit(empty_bar(stage));
+                    if (CTA2) tc_commit_2sm(empty_bar(stage), 3);     // frees the stage in both CTAs
+                    else tc_commit(empty_bar(stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(tfull_bar(as));
+                if (CTA2) tc_commit_2sm(tfull_bar(as), 3);
+                else tc_commit(tfull_bar(as));
             }
         }
     } else {
@@ -341,14 +361,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const int row = q * 32 + lane;
         int nstore = 0;                    // boxes this group has stored so far
         int it = 0, mit = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+        const uint32_t tempty0 = CTA2 ? mapa_shared(tempty_bar(0), 0u) : tempty_bar(0);   // the MMA issuer's barrier
+        for (int w = w_first; w < total_work; w += w_step, ++it) {
             int g, b, mt, nt, kb0, kb1;
             decode(w, g, b, mt, nt, kb0, kb1);
             const TcArgs& args = sargs[g];
             const uint32_t flags = args.flags;
             const int as = it & 1;
             const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-            const int m = mt * BM + row;
+            const int m_base = mt * Cfg::TILE_M + (int)cta_rank * BM;
+            const int m = m_base + row;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
             const bool masked = MASK && (flags & F_MASK);
             const int mb = mit & 1;
@@ -441,7 +463,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     fence_proxy_async_smem();
                     named_bar_sync(1 + eg, 128);
                     if (issuer) {
-                        tma_store_3d(&grp.p[g].tmO, sbuf, nt * BN + bx * box_cols, mt * BM, b);
+                        tma_store_3d(&grp.p[g].tmO, sbuf, nt * BN + bx * box_cols, m_base, b);
                         bulk_commit();
                     }
                 }
@@ -450,7 +472,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(tempty_bar(as));
+                if (CTA2) mbar_arrive_cluster(tempty0 + 8u * as);
+                else mbar_arrive(tempty_bar(as));
                 if (masked) mbar_arrive(mempty_bar(mb));
             }
             if (masked) ++mit;
@@ -459,10 +482,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all();          // the leader's MMAs read the peer's shared memory and write its TMEM
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (CTA2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -615,39 +640,72 @@ static int make_map(CUtensorMap* map, const void* ptr, int esize, int64_t inner,
     return 0;
 }
 
-template <bool A_MN, bool B_MN, int BN, bool MASK>
+template <bool A_MN, bool B_MN, int BN, bool MASK, bool CTA2>
 static int launch_tc(const TcGroup& grp, int grid, cudaStream_t st) {
-    using Cfg = TcCfg<BN, MASK>;
+    using Cfg = TcCfg<BN, MASK, CTA2>;
     static bool attr_set = false;
     if (!attr_set) {
-        VPR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, BN, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES));
+        VPR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, BN, MASK, CTA2>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    gemm_tc_kernel<A_MN, B_MN, BN, MASK><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(grp);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VPR_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A_MN, B_MN, BN, MASK, CTA2>, grp));
     return launch_ok("gemm_tc_kernel");
 }
 
 template <int BN>
-static int dispatch_major(int a_mn, int b_mn, bool mask, const TcGroup& grp, int grid, cudaStream_t st) {
+static int dispatch_major(int a_mn, int b_mn, bool mask, bool cta2, const TcGroup& grp, int grid, cudaStream_t st) {
     if constexpr (BN <= 128) {
         if (mask) {
             VPR_REQUIRE(!a_mn, "the relu-mask epilogue needs a K-major A operand");
-            return b_mn ? launch_tc<false, true, BN, true>(grp, grid, st) : launch_tc<false, false, BN, true>(grp, grid, st);
+            return b_mn ? launch_tc<false, true, BN, true, false>(grp, grid, st)
+                        : launch_tc<false, false, BN, true, false>(grp, grid, st);
         }
     }
-    if (!a_mn && !b_mn) return launch_tc<false, false, BN, false>(grp, grid, st);
-    if (!a_mn && b_mn) return launch_tc<false, true, BN, false>(grp, grid, st);
-    if (a_mn && !b_mn) return launch_tc<true, false, BN, false>(grp, grid, st);
-    return launch_tc<true, true, BN, false>(grp, grid, st);
+    if constexpr (BN == 256) {
+        if (cta2) {
+            if (!a_mn && !b_mn) return launch_tc<false, false, BN, false, true>(grp, grid, st);
+            if (!a_mn && b_mn) return launch_tc<false, true, BN, false, true>(grp, grid, st);
+            if (a_mn && !b_mn) return launch_tc<true, false, BN, false, true>(grp, grid, st);
+            return launch_tc<true, true, BN, false, true>(grp, grid, st);
+        }
+    }
+    if (!a_mn && !b_mn) return launch_tc<false, false, BN, false, false>(grp, grid, st);
+    if (!a_mn && b_mn) return launch_tc<false, true, BN, false, false>(grp, grid, st);
+    if (a_mn && !b_mn) return launch_tc<true, false, BN, false, false>(grp, grid, st);
+    return launch_tc<true, true, BN, false, false>(grp, grid, st);
+}
+
+// VPR_GEMM_2CTA=0 forces single-CTA tiles (A/B measurements)
+static bool cta_pairs_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VPR_GEMM_2CTA");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 static int auto_bn(int N) { return (N > 128) ? 256 : (N > 64) ? 128 : 64; }
 
-static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
+// Tile shape for a group of bf16 problems: the widest N any problem wants; 256 x 256 CTA-pair tiles
+// when that does not inflate the MMA work (short-M problems would leave the peer CTA's rows empty).
+static int plan_group(const GemmDesc* gs, int count, int& bn, bool& any_mask, bool& cta2) {
     VPR_REQUIRE(count >= 1 && count <= MAX_GROUP, "a GEMM group holds 1..%d problems", MAX_GROUP);
-    int bn = 0;
-    bool any_mask = false;
+    bn = 0;
+    any_mask = false;
     for (int i = 0; i < count; ++i) {
         VPR_REQUIRE(gs[i].a_mn == gs[0].a_mn && gs[i].b_mn == gs[0].b_mn, "grouped GEMMs must share the operand layout");
         const int want = gs[i].bn ? gs[i].bn : auto_bn(gs[i].N);
@@ -656,6 +714,37 @@ static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
     }
     if (any_mask && bn > 128) bn = 128;          // the mask tile shares shared memory with the operand ring
     VPR_REQUIRE(bn == 64 || bn == 128 || bn == 256, "bad tile N %d", bn);
+    cta2 = false;
+    bool single = false;
+    for (int i = 0; i < count; ++i) single = single || gs[i].cta_pair == 2;
+    if (bn == 256 && !any_mask && !single && cta_pairs_enabled()) {
+        double c1 = 0, c2 = 0;
+        for (int i = 0; i < count; ++i) {
+            const double w = (double)gs[i].batch * ((gs[i].N + bn - 1) / bn) * gs[i].K;
+            c1 += w * ((gs[i].M + BM - 1) / BM) * BM;
+            c2 += w * ((gs[i].M + 2 * BM - 1) / (2 * BM)) * (2 * BM);
+        }
+        cta2 = c2 <= 1.05 * c1;
+    }
+    return 0;
+}
+
+GemmTilePlan gemm_tile_plan(const GemmDesc* gs, int count) {
+    GemmTilePlan p = {BM, 256, num_sms()};
+    if (gs[0].dtype != DT_BF16) return p;
+    int bn; bool any_mask, cta2;
+    if (plan_group(gs, count, bn, any_mask, cta2) != 0) return p;
+    p.tile_m = cta2 ? 2 * BM : BM;
+    p.tile_n = bn;
+    p.slots = cta2 ? num_sms() / 2 : num_sms();
+    return p;
+}
+
+static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
+    int bn;
+    bool any_mask, cta2;
+    VPR_TRY(plan_group(gs, count, bn, any_mask, cta2));
+    const int tile_m = cta2 ? 2 * BM : BM;
     TcGroup grp;
     grp.count = count;
     long long total = 0;
@@ -665,7 +754,7 @@ static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
         if (g.a_mn) VPR_TRY(make_map(&p.tmA, g.A, 2, g.M, g.K, g.batch, g.lda, g.a_bs, 64, 64, "GEMM operand A"));
         else        VPR_TRY(make_map(&p.tmA, g.A, 2, g.K, g.M, g.batch, g.lda, g.a_bs, 64, BM, "GEMM operand A"));
         if (g.b_mn) VPR_TRY(make_map(&p.tmB, g.B, 2, g.N, g.K, g.batch, g.ldb, g.b_bs, 64, 64, "GEMM operand B"));
-        else        VPR_TRY(make_map(&p.tmB, g.B, 2, g.K, g.N, g.batch, g.ldb, g.b_bs, 64, bn, "GEMM operand B"));
+        else        VPR_TRY(make_map(&p.tmB, g.B, 2, g.K, g.N, g.batch, g.ldb, g.b_bs, 64, cta2 ? bn / 2 : bn, "GEMM operand B"));
         if (g.out_kind == OUT_BF16)
             VPR_TRY(make_map(&p.tmO, g.out, 2, g.N, g.M, g.batch, g.ldo, g.out_bs, 64, BM, "GEMM output"));
         else if (g.out_kind == OUT_F32)
@@ -674,7 +763,7 @@ static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
             VPR_TRY(make_map(&p.tmM, g.mask, 2, g.N, g.M, g.batch, g.ld_mask, g.mask_bs, 64, BM, "GEMM relu-mask"));
         TcArgs& a = p.args;
         a.M = g.M; a.N = g.N; a.K = g.K; a.batch = g.batch;
-        a.tiles_m = (g.M + BM - 1) / BM;
+        a.tiles_m = (g.M + tile_m - 1) / tile_m;
         a.tiles_n = (g.N + bn - 1) / bn;
         a.kb_total = (g.K + BK - 1) / BK;
         a.k_splits = g.k_splits < 1 ? 1 : g.k_splits;
@@ -694,10 +783,16 @@ static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
         VPR_REQUIRE(total < (1ll << 31), "too many tiles");
     }
     grp.total_work = (int)total;
-    int grid = (int)(total < num_sms() ? total : num_sms());
-    if (bn == 256) return dispatch_major<256>(gs[0].a_mn, gs[0].b_mn, any_mask, grp, grid, st);
-    if (bn == 128) return dispatch_major<128>(gs[0].a_mn, gs[0].b_mn, any_mask, grp, grid, st);
-    return dispatch_major<64>(gs[0].a_mn, gs[0].b_mn, any_mask, grp, grid, st);
+    int grid;
+    if (cta2) {
+        const int pairs = num_sms() / 2;
+        grid = 2 * (int)(total < pairs ? total : pairs);
+    } else {
+        grid = (int)(total < num_sms() ? total : num_sms());
+    }
+    if (bn == 256) return dispatch_major<256>(gs[0].a_mn, gs[0].b_mn, any_mask, cta2, grp, grid, st);
+    if (bn == 128) return dispatch_major<128>(gs[0].a_mn, gs[0].b_mn, any_mask, cta2, grp, grid, st);
+    return dispatch_major<64>(gs[0].a_mn, gs[0].b_mn, any_mask, cta2, grp, grid, st);
 }
 
 static int gemm_simt(const GemmDesc& g, cudaStream_t st) {

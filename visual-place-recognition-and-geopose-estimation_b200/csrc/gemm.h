@@ -33,7 +33,13 @@ struct GemmDesc {
     float* colsum = nullptr;
     int k_splits = 1;              // > 1 requires OUT_ATOMIC_F32 (caller zeroes out)
     int bn = 0;                    // tcgen05 tile N (64/128/256); 0 = auto
+    int cta_pair = 0;              // 0 = auto (256 x 256 CTA-pair tiles when N > 128), 2 = single-CTA tiles
 };
+
+// How a group will be tiled: tile shape and the number of tiles that run concurrently (SMs, or SM
+// pairs for 256 x 256 CTA-pair tiles).  Callers size split-K with it.
+struct GemmTilePlan { int tile_m, tile_n, slots; };
+GemmTilePlan gemm_tile_plan(const GemmDesc* gs, int count);
 
 int gemm_run(const GemmDesc& g, cudaStream_t stream);
 // Up to 4 independent problems with the same dtype and operand layout in ONE launch.

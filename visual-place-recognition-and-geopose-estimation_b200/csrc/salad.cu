@@ -616,6 +616,9 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
     g[0].A = x; g[0].lda = s.d; g[0].B = w0cat; g[0].ldb = s.d; g[0].M = (int)Tk; g[0].N = 2 * h; g[0].K = s.d;
     g[0].out = H; g[0].out_kind = okT; g[0].ldo = 2 * h; g[0].bias = b0cat; g[0].relu = 1;
     g[0].dropout_p = drop_p; g[0].dropout_seed = seed;
+    // measured (tools/gemm_bench.py, B200): with the dropout epilogue, pair tiles make the leader's MMA wait for
+    // the slower of two epilogues (100 us vs 90 us single-CTA); the weight/input-gradient GEMMs gain 8-12 % from pairs
+    if (drop_p > 0.f) g[0].cta_pair = 2;
     g[1] = GemmDesc(); g[1].dtype = dtype;
     g[1].A = t; g[1].lda = s.d; g[1].B = wt0; g[1].ldb = s.d; g[1].M = s.B; g[1].N = h; g[1].K = s.d;
     g[1].out = HT; g[1].out_kind = okT; g[1].ldo = h; g[1].bias = p.token_b0; g[1].relu = 1;
@@ -725,18 +728,21 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
 
     // ---- second-layer weight gradients (split-K + fp32 reductions), one launch ----
     {
-        // the token problem's few short work items come last and are absorbed by the CTAs that finish first
-        const int tiles = ((s.l + 127) / 128 + (s.m + 127) / 128) * ((h + 255) / 256);
-        int ks = nsm / tiles; if (ks < 1) ks = 1; if (ks > kb_tok) ks = kb_tok;
         g[0] = GemmDesc(); g[0].dtype = dtype;    // dW1c[l,h] = dF^T H[:, :h]
         g[0].A = dF; g[0].a_mn = 1; g[0].lda = s.l; g[0].B = H; g[0].b_mn = 1; g[0].ldb = 2 * h; g[0].M = s.l; g[0].N = h;
-        g[0].K = (int)Tk; g[0].out = gr.cluster_w1; g[0].out_kind = OUT_ATOMIC_F32; g[0].ldo = h; g[0].k_splits = ks;
+        g[0].K = (int)Tk; g[0].out = gr.cluster_w1; g[0].out_kind = OUT_ATOMIC_F32; g[0].ldo = h;
         g[1] = GemmDesc(); g[1].dtype = dtype;    // dW1s[m,h] = dS^T H[:, h:]
         g[1].A = dS; g[1].a_mn = 1; g[1].lda = s.m; g[1].B = H + h; g[1].b_mn = 1; g[1].ldb = 2 * h; g[1].M = s.m; g[1].N = h;
-        g[1].K = (int)Tk; g[1].out = gr.score_w1; g[1].out_kind = OUT_ATOMIC_F32; g[1].ldo = h; g[1].k_splits = ks;
+        g[1].K = (int)Tk; g[1].out = gr.score_w1; g[1].out_kind = OUT_ATOMIC_F32; g[1].ldo = h;
         g[2] = GemmDesc(); g[2].dtype = dtype;    // dWt1[g,h] = dTF^T HT
         g[2].A = dTF; g[2].a_mn = 1; g[2].lda = s.g; g[2].B = HT; g[2].b_mn = 1; g[2].ldb = h; g[2].M = s.g; g[2].N = h;
         g[2].K = s.B; g[2].out = gr.token_w1; g[2].out_kind = OUT_ATOMIC_F32; g[2].ldo = h;
+        // split K so that the two token-long problems fill the machine; the token-MLP problem's few short
+        // work items come last and are absorbed by the CTAs that finish first
+        const GemmTilePlan tp = gemm_tile_plan(g, 3);
+        const int tiles = ((s.l + tp.tile_m - 1) / tp.tile_m + (s.m + tp.tile_m - 1) / tp.tile_m) * ((h + tp.tile_n - 1) / tp.tile_n);
+        int ks = tp.slots / tiles; if (ks < 1) ks = 1; if (ks > kb_tok) ks = kb_tok;
+        g[0].k_splits = ks; g[1].k_splits = ks;
         VPR_TRY(gemm_run_group(g, 3, st));
     }
     // ---- dH = [dF W1c | dS W1s] * (H > 0) * keep_scale,  dHT = (dTF Wt1) * (HT > 0); first-layer bias gradients ----
@@ -754,18 +760,19 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
     VPR_TRY(gemm_run_group(g, 3, st));
     // ---- first-layer weight gradients: dW0[h,d] = dH^T X (two parameter tensors) and dWt0 = dHT^T t ----
     {
-        const int tiles = 2 * ((h + 127) / 128) * ((s.d + 255) / 256);
-        int ks = nsm / tiles; if (ks < 1) ks = 1; if (ks > kb_tok) ks = kb_tok;
         for (int half = 0; half < 2; ++half) {
             g[half] = GemmDesc(); g[half].dtype = dtype;
             g[half].A = dH + half * h; g[half].a_mn = 1; g[half].lda = 2 * h; g[half].B = x; g[half].b_mn = 1; g[half].ldb = s.d;
             g[half].M = h; g[half].N = s.d; g[half].K = (int)Tk;
             g[half].out = half == 0 ? gr.cluster_w0 : gr.score_w0; g[half].out_kind = OUT_ATOMIC_F32; g[half].ldo = s.d;
-            g[half].k_splits = ks;
         }
         g[2] = GemmDesc(); g[2].dtype = dtype;
         g[2].A = dHT; g[2].a_mn = 1; g[2].lda = h; g[2].B = t; g[2].b_mn = 1; g[2].ldb = s.d; g[2].M = h; g[2].N = s.d; g[2].K = s.B;
         g[2].out = gr.token_w0; g[2].out_kind = OUT_ATOMIC_F32; g[2].ldo = s.d;
+        const GemmTilePlan tp = gemm_tile_plan(g, 3);
+        const int tiles = 2 * ((h + tp.tile_m - 1) / tp.tile_m) * ((s.d + tp.tile_n - 1) / tp.tile_n);
+        int ks = tp.slots / tiles; if (ks < 1) ks = 1; if (ks > kb_tok) ks = kb_tok;
+        g[0].k_splits = ks; g[1].k_splits = ks;
         VPR_TRY(gemm_run_group(g, 3, st));
     }
     // ---- input gradients: dX = dH W0cat, dt = dHT Wt0 ----
