@@ -135,6 +135,20 @@ def _gloo_worker(rank, world, port, q):
     fin = vpr_b200.allreduce_grads(lin.parameters(), bucket_bytes=64 << 10, async_op=True)   # several buckets
     fin()
     ok = all(torch.allclose(p.grad, torch.full_like(p, 3.0 * (i + 1))) for i, p in enumerate(lin.parameters()))
+    # gradients that are back-to-back views of one buffer (what SaladHead's backward produces) are reduced in
+    # place by a single collective: same storage afterwards, summed values
+    ps = list(lin.parameters())
+    flat = torch.full((sum(p.numel() for p in ps),), float(rank + 1))
+    off = 0
+    for p in ps:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    from vpr_b200.parallel import _shared_flat_view
+    fv = _shared_flat_view([p.grad for p in ps])
+    ok = ok and fv is not None and fv.data_ptr() == flat.data_ptr() and fv.numel() == flat.numel()
+    vpr_b200.allreduce_grads(ps)
+    ok = ok and bool((flat == 3.0).all()) and all(p.grad.data_ptr() >= flat.data_ptr() for p in ps)
+    ok = ok and _shared_flat_view([ps[0].grad, ps[2].grad]) is None          # a gap -> bucketed path
     # sharded top-k merge: allgather of per-rank lists, merged with the oracle's merge on CPU
     from oracle.salad_ref import knn_topk_ref, merge_topk
     g = torch.Generator().manual_seed(1)

@@ -14,18 +14,24 @@
 
 namespace vpr {
 
+// A CTA pair (cta_group::2) owns a 256-query x 256-gallery-row tile: each CTA stages its own 128
+// query rows and half of the gallery tile (32 KB per k-block per SM instead of 48 KB), the leader
+// issues the 256 x 256 x 16 MMAs, and each CTA runs the top-k epilogue for its own 128 queries.
 static constexpr int KBM = 128, KBN = 256, KBK = 64;
-static constexpr int K_A_BYTES = KBM * KBK * 2, K_B_BYTES = KBN * KBK * 2;
+static constexpr int K_TILE_M = 2 * KBM;                         // query rows per CTA pair
+static constexpr int K_A_BYTES = KBM * KBK * 2, K_B_BYTES = (KBN / 2) * KBK * 2;
 static constexpr int K_STAGE_BYTES = K_A_BYTES + K_B_BYTES;
-static constexpr int K_STAGES = 4;
+static constexpr int K_STAGES = 6;
 static constexpr int KMAX = 32;   // list capacity per row
 static constexpr int K_LIST_BYTES = KMAX * KBM * 8;
 static constexpr int K_SMEM_BYTES = K_STAGES * K_STAGE_BYTES + K_LIST_BYTES + 1024 + 256;
+static_assert(K_SMEM_BYTES <= 227 * 1024, "kNN shared memory budget");
 static constexpr int K_THREADS = 192;
 
 struct KnnArgs {
     int Q, G, D, k;
     int tiles_m, chunks, tiles_per_chunk, tiles_n, kb_total;
+    int q_group;           // query tiles that walk the same gallery chunk at the same time (L2 reuse)
     float* ws_score;       // [Q, chunks, k]
     int* ws_idx;           // [Q, chunks, k] local gallery row, -1 = empty
 };
@@ -46,26 +52,37 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();                 // 0 = leader of the pair
+    const int w_first = (int)(blockIdx.x >> 1), w_step = (int)(gridDim.x >> 1);
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmG); }
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < K_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-            for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+            for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }   // both CTAs' warps
             mbar_fence_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
+        tmem_alloc_2sm(tmem_slot, 512);
+        tmem_relinquish_2sm();
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const int total_work = args.tiles_m * args.chunks;
 
+    // Work order: groups of q_group query tiles; inside a group chunk-major, so the CTAs that run
+    // concurrently are (q_group query tiles) x (a few gallery chunks) walking their gallery tiles in
+    // lock step: every gallery tile is fetched from HBM once per group and shared through L2, and the
+    // group's query tiles (q_group * 128 * D * 2 bytes) stay L2-resident.
     auto tile_range = [&](int w, int& mt, int& ch, int& nt0, int& nt1) {
-        ch = w % args.chunks;
-        mt = w / args.chunks;
+        const int per_group = args.q_group * args.chunks;
+        const int qg = w / per_group;
+        const int r = w - qg * per_group;
+        int qt = args.tiles_m - qg * args.q_group;
+        if (qt > args.q_group) qt = args.q_group;
+        ch = r / qt;
+        mt = qg * args.q_group + (r - ch * qt);
         nt0 = ch * args.tiles_per_chunk;
         nt1 = nt0 + args.tiles_per_chunk;
         if (nt1 > args.tiles_n) nt1 = args.tiles_n;
@@ -74,25 +91,27 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const uint32_t full0 = mapa_shared(full_bar(0), 0u);     // both producers credit the leader's barrier
+            for (int w = w_first; w < total_work; w += w_step) {
                 int mt, ch, nt0, nt1;
                 tile_range(w, mt, ch, nt0, nt1);
+                const int q0 = mt * K_TILE_M + (int)cta_rank * KBM;
                 for (int nt = nt0; nt < nt1; ++nt)
                     for (int kb = 0; kb < args.kb_total; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         const uint32_t sa = smem_base + stage * K_STAGE_BYTES, sb = sa + K_A_BYTES;
-                        mbar_expect_tx(full_bar(stage), K_STAGE_BYTES);
-                        tma_load_3d(sa, &tmQ, full_bar(stage), kb * KBK, mt * KBM, 0);
-                        tma_load_3d(sb, &tmG, full_bar(stage), kb * KBK, nt * KBN, 0);
+                        if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * K_STAGE_BYTES);
+                        tma_load_3d_2sm(sa, &tmQ, full0 + 8u * stage, kb * KBK, q0, 0);
+                        tma_load_3d_2sm(sb, &tmG, full0 + 8u * stage, kb * KBK, nt * KBN + (int)cta_rank * (KBN / 2), 0);
                         if (++stage == K_STAGES) { stage = 0; phase ^= 1u; }
                     }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(KBM, KBN, false, false);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(K_TILE_M, KBN, false, false);
             int stage = 0; uint32_t phase = 0; int it = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            for (int w = w_first; w < total_work; w += w_step) {
                 int mt, ch, nt0, nt1;
                 tile_range(w, mt, ch, nt0, nt1);
                 for (int nt = nt0; nt < nt1; ++nt, ++it) {
@@ -107,12 +126,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                         const uint32_t sa = smem_base + stage * K_STAGE_BYTES, sb = sa + K_A_BYTES;
 #pragma unroll
                         for (int k = 0; k < KBK / 16; ++k)
-                            tc_mma_bf16(d_tmem, make_smem_desc(sa + k * 32, 16u, 1024u),
-                                        make_smem_desc(sb + k * 32, 16u, 1024u), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        tc_commit(empty_bar(stage));
+                            tc_mma_bf16_2sm(d_tmem, make_smem_desc(sa + k * 32, 16u, 1024u),
+                                            make_smem_desc(sb + k * 32, 16u, 1024u), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        tc_commit_2sm(empty_bar(stage), 3);
                         if (++stage == K_STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    tc_commit(tfull_bar(as));
+                    tc_commit_2sm(tfull_bar(as), 3);
                 }
             }
         }
@@ -121,7 +140,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int row = q * 32 + lane;              // this thread's query row within the tile
         const int kk = args.k;
         int it = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const uint32_t tempty0 = mapa_shared(tempty_bar(0), 0u);     // the MMA issuer's barrier
+        for (int w = w_first; w < total_work; w += w_step) {
             int mt, ch, nt0, nt1;
             tile_range(w, mt, ch, nt0, nt1);
             for (int s = 0; s < kk; ++s) { lscore[s * KBM + row] = -INFINITY; lidx[s * KBM + row] = -1; }
@@ -158,9 +178,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(as));
+                if (lane == 0) mbar_arrive_cluster(tempty0 + 8u * as);
             }
-            const int qrow = mt * KBM + row;
+            const int qrow = mt * K_TILE_M + (int)cta_rank * KBM + row;
             if (qrow < args.Q) {
                 float* os = args.ws_score + ((size_t)qrow * args.chunks + ch) * kk;
                 int* oi = args.ws_idx + ((size_t)qrow * args.chunks + ch) * kk;
@@ -169,8 +189,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    cluster_sync_all();          // the leader's MMAs read the peer's shared memory and write its TMEM
+    if (warp == 1) { tc_fence_after(); tmem_dealloc_2sm(tmem_base, 512); }
 }
 
 // Merge R sorted-or-not candidate lists of k entries per query into the global top-k
@@ -245,10 +265,10 @@ static int knn_map(CUtensorMap* map, const void* ptr, int64_t rows, int D, int b
 }
 
 static void knn_plan(int64_t Q, int64_t G, int& tiles_m, int& tiles_n, int& chunks, int& tiles_per_chunk) {
-    tiles_m = (int)((Q + KBM - 1) / KBM);
+    tiles_m = (int)((Q + K_TILE_M - 1) / K_TILE_M);
     tiles_n = (int)((G + KBN - 1) / KBN);
-    // aim for >= 8 work items per SM so the last wave is short, but keep >= 8 gallery tiles per chunk
-    int want = (8 * num_sms() + tiles_m - 1) / tiles_m;
+    // aim for >= 8 work items per CTA pair so the last wave is short, but keep >= 8 gallery tiles per chunk
+    int want = (8 * (num_sms() / 2) + tiles_m - 1) / tiles_m;
     if (want < 1) want = 1;
     int max_chunks = (tiles_n + 7) / 8;
     if (max_chunks < 1) max_chunks = 1;
@@ -286,20 +306,40 @@ int vpr_knn_topk(const void* q, const void* g, int64_t Q, int64_t G, int D, int 
     a.Q = (int)Q; a.G = (int)G; a.D = D; a.k = k;
     knn_plan(Q, G, a.tiles_m, a.tiles_n, a.chunks, a.tiles_per_chunk);
     a.kb_total = (D + KBK - 1) / KBK;
+    {   // query tiles per group: their operands must fit in about 80 MB of the 126 MB L2
+        const int pairs = num_sms() / 2;
+        long long qt = (80ll << 20) / ((long long)K_TILE_M * D * 2);
+        if (qt < 1) qt = 1;
+        if (qt > pairs) qt = pairs;
+        const int waves = (pairs + (int)qt - 1) / (int)qt;           // gallery chunks in flight
+        qt = pairs / waves;
+        if (qt > a.tiles_m) qt = a.tiles_m;
+        a.q_group = (int)qt;
+    }
     size_t off = 0;
     a.ws_score = (float*)((char*)workspace + carve_size(off, (size_t)Q * a.chunks * k * 4));
     a.ws_idx = (int*)((char*)workspace + carve_size(off, (size_t)Q * a.chunks * k * 4));
     CUtensorMap tq, tg;
     VPR_TRY(knn_map(&tq, q, Q, D, KBM));
-    VPR_TRY(knn_map(&tg, g, G, D, KBN));
+    VPR_TRY(knn_map(&tg, g, G, D, KBN / 2));
     static bool attr = false;
     if (!attr) {
         VPR_CUDA_OK(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K_SMEM_BYTES));
         attr = true;
     }
     long long total = (long long)a.tiles_m * a.chunks;
-    int grid = (int)(total < num_sms() ? total : num_sms());
-    knn_tc_kernel<<<grid, K_THREADS, K_SMEM_BYTES, stream>>>(tq, tg, a);
+    const int pairs = num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * (total < pairs ? total : pairs)));
+    cfg.blockDim = dim3(K_THREADS);
+    cfg.dynamicSmemBytes = K_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    VPR_CUDA_OK(cudaLaunchKernelEx(&cfg, knn_tc_kernel, tq, tg, a));
     VPR_TRY(launch_ok("knn_tc_kernel"));
     const long long warps = Q;
     knn_merge_kernel<int><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(

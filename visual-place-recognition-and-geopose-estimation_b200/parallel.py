@@ -44,14 +44,53 @@ def _flatten(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
     return torch.cat([t.reshape(-1) for t in tensors])
 
 
+def _shared_flat_view(grads: Sequence[torch.Tensor]):
+    """If the gradients are back-to-back views of ONE buffer (SaladHead's backward writes all its
+    parameter gradients into a single flat fp32 buffer), return that buffer as a 1-D tensor so it
+    can be reduced in place; otherwise None."""
+    if len(grads) < 2:
+        return None
+    g0 = grads[0]
+    base = g0.untyped_storage().data_ptr()
+    dt, dev = g0.dtype, g0.device
+    spans = []
+    for g in grads:
+        if g.dtype != dt or g.device != dev or not g.is_contiguous() or g.untyped_storage().data_ptr() != base:
+            return None
+        spans.append((g.storage_offset(), g.numel()))
+    spans.sort()
+    off = spans[0][0]
+    for o, n in spans:
+        if o != off:
+            return None
+        off += n
+    total = off - spans[0][0]
+    return torch.empty(0, dtype=dt, device=dev).set_(g0.untyped_storage(), spans[0][0], (total,))
+
+
 def allreduce_grads(params: Iterable[torch.nn.Parameter], group=None, bucket_bytes: int = 32 << 20,
                     average: bool = False, async_op: bool = False):
-    """Sum-allreduce ``p.grad`` of every parameter that has one, in flat buckets of about
-    ``bucket_bytes``.  Returns a finaliser that waits and scatters the reduced values back."""
+    """Sum-allreduce ``p.grad`` of every parameter that has one.  Gradients that already live
+    back-to-back in one buffer are reduced in place with a single collective and no copies;
+    anything else goes through flat buckets of about ``bucket_bytes``.  Returns a finaliser
+    that waits (and scatters bucketed values back)."""
     ps = [p for p in params if p.grad is not None]
     if not ps or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return lambda: None
     world = dist.get_world_size(group)
+    flat_view = _shared_flat_view([p.grad for p in ps])
+    if flat_view is not None:
+        work = dist.all_reduce(flat_view, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+        def finish_inplace():
+            work.wait()
+            if average:
+                flat_view.div_(world)
+
+        if async_op:
+            return finish_inplace
+        finish_inplace()
+        return lambda: None
     buckets: List[List[torch.nn.Parameter]] = [[]]
     size = 0
     for p in ps:
