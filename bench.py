@@ -107,6 +107,8 @@ def make_inputs(B, n, device, seed):
 # ------------------------------------------------------------------------------------------
 def cpu_oracle_rate(n: int, sample_B: int, steps: int, warmup: int):
     from oracle import salad_ref as O
+    # torchrun pins OMP_NUM_THREADS=1 in every rank; the CPU arm runs on rank 0 alone and may use the host
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     torch.manual_seed(0)
     mod = O.SaladRef(dropout=0.3)
     mod.train()
@@ -150,6 +152,51 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# kNN leg (the second quantity BASELINE.json's metric names): queries/s of the fused GEMM + top-25
+# kernel over ONE GPU's gallery shard of configs[4] (10 M x 8448 bf16 sharded over 8 GPUs = 1.25 M
+# rows = 21 GB per GPU).  Every rank of the sharded job scans all queries against its own shard, so
+# the job's queries/s equals the per-shard rate (the [Q,25] allgather + merge is < 1 % of it).
+# ------------------------------------------------------------------------------------------
+def knn_leg(dev, peaks, Q, G, D=8448, k=25):
+    import vpr_b200
+
+    def rows(nrows, seed):
+        out = torch.empty(nrows, D, dtype=torch.bfloat16, device=dev)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        for r0 in range(0, nrows, 65536):
+            r1 = min(nrows, r0 + 65536)
+            out[r0:r1] = torch.nn.functional.normalize(torch.randn(r1 - r0, D, device=dev, generator=g), dim=1).bfloat16()
+        return out
+
+    q, g = rows(Q, 555), rows(G, 777)
+    for _ in range(2):
+        vpr_b200.knn_topk(q, g, k)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s, i = vpr_b200.knn_topk(q, g, k)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sum(ts) / len(ts)
+    # bounded exactness probe against a direct product (64 queries x the first 200k gallery rows)
+    sub = min(G, 200_000)
+    ss, si = vpr_b200.knn_topk(q[:64], g[:sub], k)
+    ref = (q[:64].float() @ g[:sub].float().T).topk(k, dim=1).indices
+    match = sum(set(a.tolist()) == set(b.tolist()) for a, b in zip(si.cpu(), ref.cpu())) / 64
+    tflops = 2.0 * Q * G * D / (ms * 1e-3) / 1e12
+    return {"metric": "kNN queries/s (top-25, one GPU's 1/8 gallery shard of configs[4])", "value": Q / (ms * 1e-3),
+            "unit": "queries/s", "ms": ms, "queries": Q, "gallery_rows": G, "dim": D, "k": k, "dtype": "bf16",
+            "roofline": {"bound": "tensor", "kernel": "knn_tc_kernel (CTA-pair 256x256 tiles, fused top-k)",
+                         "achieved": tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": tflops / peaks["bf16_tflops_sustained"],
+                         "peak_source": peaks["source"] + " sustained (the launch runs for > 100 ms)"},
+            "topk_set_match_vs_direct_product": match}
 
 
 # ------------------------------------------------------------------------------------------
@@ -281,7 +328,8 @@ def run_own(args, rank, local, world):
         flush.zero_()                                   # evict L2 (126 MB) between launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.gemm(X2, Wc, T, 2 * HID, D, out_kind=L.OUT_BF16, bias=bias, relu=True, out=Hbuf, ldo=2 * HID, out_bs=0)
+        ops.gemm(X2, Wc, T, 2 * HID, D, out_kind=L.OUT_BF16, bias=bias, relu=True, out=Hbuf, ldo=2 * HID, out_bs=0,
+                 dropout_p=0.3, dropout_seed=1234 + i)
         e1.record()
         torch.cuda.synchronize()
         if i >= 3:
@@ -296,16 +344,23 @@ def run_own(args, rank, local, world):
             traffic = json.load(open(tp_path)).get("gemm_tc_kernel_H_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<A K-major,B K-major,BN=256> (H = relu(X W0^T + b), "
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<A K-major,B K-major,BN=256> (H = dropout(relu(X W0cat^T + b)), "
                 f"M={T} N=1024 K=768)", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peaks["source"] + " burst",
                 "kernel_ms": k_ms,
                 "step_tflops": flops_per_image(n) * B / (ms_step * 1e-3) / 1e12,
                 "step_frac_of_sustained": flops_per_image(n) * B / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]}
 
+    # ---------------- descriptor kNN (BASELINE configs[4], this GPU's gallery shard) ----------------
+    knn = None
+    if not args.no_knn:
+        del Wc, Hbuf, flush
+        torch.cuda.empty_cache()
+        knn = knn_leg(dev, peaks, args.knn_queries, args.knn_gallery)
+
     # ---------------- CPU baseline (bounded sample) ----------------
-    threads = torch.get_num_threads()
     cpu_rate, cpu_sec = cpu_oracle_rate(n, 16, 4, 1)
+    threads = torch.get_num_threads()
     cpu_baseline = {"value": cpu_rate, "unit": "img/s", "cores": threads, "kind": "port",
                     "sample": f"oracle SaladRef fwd+bwd fp32 eager, 4 steps of 16 images (n={n}) after 1 warm-up, "
                               f"{threads} host threads ({os.cpu_count()} logical CPUs)"}
@@ -323,6 +378,8 @@ def run_own(args, rank, local, world):
         "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
+    if knn is not None:
+        line["knn"] = knn
     print(json.dumps(line), flush=True)
 
 
@@ -334,6 +391,9 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--no-knn", action="store_true", help="skip the kNN leg")
+    ap.add_argument("--knn-queries", type=int, default=8192)
+    ap.add_argument("--knn-gallery", type=int, default=1_250_000)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -32,6 +32,14 @@ def main():
     for _ in range(5):
         step()
     torch.cuda.synchronize()
+    import time
+    t0 = time.perf_counter()
+    for _ in range(50):
+        step()
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"host issue time {1e6 * (t1 - t0) / 50:.0f} us/step, wall incl. drain {1e6 * (t2 - t0) / 50:.0f} us/step")
     steps = 10
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(steps):

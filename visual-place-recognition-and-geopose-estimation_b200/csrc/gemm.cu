@@ -716,7 +716,9 @@ static int plan_group(const GemmDesc* gs, int count, int& bn, bool& any_mask, bo
     VPR_REQUIRE(bn == 64 || bn == 128 || bn == 256, "bad tile N %d", bn);
     cta2 = false;
     bool single = false;
-    for (int i = 0; i < count; ++i) single = single || gs[i].cta_pair == 2;
+    // measured (tools/gemm_bench.py, B200): with the dropout epilogue the leader's MMA ends up waiting for the
+    // slower of two CTAs' epilogues (100 us vs 90 us for H); the gradient GEMMs gain 8-12 % from pair tiles
+    for (int i = 0; i < count; ++i) single = single || gs[i].cta_pair == 2 || gs[i].dropout_p > 0.f;
     if (bn == 256 && !any_mask && !single && cta_pairs_enabled()) {
         double c1 = 0, c2 = 0;
         for (int i = 0; i < count; ++i) {

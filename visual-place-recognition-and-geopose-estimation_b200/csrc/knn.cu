@@ -1,7 +1,8 @@
 // Descriptor kNN: scores = Q G^T on tcgen05 with a fused per-row top-k epilogue (SURVEY.md
 // section 8 row a10).  The [Q, G] score matrix is never written: each epilogue thread owns one
 // query row of the 128-row tile, keeps that row's current k-th best score in a register as a
-// threshold and inserts the (rare) survivors into a sorted list in shared memory.
+// threshold, and the warp inserts the (rare) survivors cooperatively into sorted lists in shared
+// memory (lane = list slot).
 //
 // Work decomposition: one work item = (128-query tile, gallery chunk); a CTA streams every
 // 256-row gallery tile of its chunk through the TMA/MMA pipeline, then writes the chunk-local
@@ -41,8 +42,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-    float* lscore = reinterpret_cast<float*>(smem_al + K_STAGES * K_STAGE_BYTES);      // [KMAX][128]
-    int* lidx = reinterpret_cast<int*>(lscore + KMAX * KBM);                             // [KMAX][128]
+    float* lscore = reinterpret_cast<float*>(smem_al + K_STAGES * K_STAGE_BYTES);      // [128][KMAX] sorted, descending
+    int* lidx = reinterpret_cast<int*>(lscore + KMAX * KBM);                             // [128][KMAX]
     const uint32_t bar_base = smem_base + K_STAGES * K_STAGE_BYTES + K_LIST_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (K_STAGES + s); };
@@ -136,15 +137,23 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             }
         }
     } else {
+        // Top-k epilogue.  Lane = one query row: it keeps the row's current k-th best score in a register and
+        // tests its 32 scores of a chunk against it (2-3 instructions per score).  Survivors are rare
+        // (k ln(G/k) per row), but a lane-private insertion loop would stall the other 31 lanes for the whole
+        // shift, so insertion is warp-cooperative: the warp takes the candidates one at a time, lane s holds
+        // slot s of that row's sorted list, one ballot finds the position and one shuffle does the shift.
         const int q = warp & 3;
-        const int row = q * 32 + lane;              // this thread's query row within the tile
+        const int row = q * 32 + lane;              // this thread's query row within the CTA's 128
         const int kk = args.k;
+        float* wl_s = lscore + (size_t)(q * 32) * KMAX;      // this warp's 32 lists: [row][KMAX]
+        int* wl_i = lidx + (size_t)(q * 32) * KMAX;
         int it = 0;
         const uint32_t tempty0 = mapa_shared(tempty_bar(0), 0u);     // the MMA issuer's barrier
         for (int w = w_first; w < total_work; w += w_step) {
             int mt, ch, nt0, nt1;
             tile_range(w, mt, ch, nt0, nt1);
-            for (int s = 0; s < kk; ++s) { lscore[s * KBM + row] = -INFINITY; lidx[s * KBM + row] = -1; }
+            for (int s = 0; s < KMAX; ++s) { wl_s[lane * KMAX + s] = -INFINITY; wl_i[lane * KMAX + s] = -1; }
+            __syncwarp();
             float thr = -INFINITY;                   // current k-th best of this row
             for (int nt = nt0; nt < nt1; ++nt, ++it) {
                 const int as = it & 1;
@@ -162,17 +171,24 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const float v = __uint_as_float(r[i]);
-                        if (v > thr && n0 + i < args.G) {
-                            // insert (v, n0+i) into the descending list; equal scores keep the earlier index first
-                            int pos = kk - 1;
-                            while (pos > 0 && lscore[(pos - 1) * KBM + row] < v) {
-                                lscore[pos * KBM + row] = lscore[(pos - 1) * KBM + row];
-                                lidx[pos * KBM + row] = lidx[(pos - 1) * KBM + row];
-                                --pos;
-                            }
-                            lscore[pos * KBM + row] = v;
-                            lidx[pos * KBM + row] = n0 + i;
-                            thr = lscore[(kk - 1) * KBM + row];
+                        unsigned cand = __ballot_sync(0xffffffffu, v > thr && n0 + i < args.G);
+                        while (cand) {
+                            const int src = __ffs(cand) - 1;
+                            cand &= cand - 1;
+                            const float cv = __shfl_sync(0xffffffffu, v, src);
+                            float* ls = wl_s + src * KMAX;
+                            int* li = wl_i + src * KMAX;
+                            const float cur = ls[lane];
+                            const int curi = li[lane];
+                            // entries that stay ahead: score >= cv (equal scores keep the earlier gallery row first)
+                            const int pos = __popc(__ballot_sync(0xffffffffu, lane < kk && cur >= cv));
+                            const float up = __shfl_up_sync(0xffffffffu, cur, 1);
+                            const int upi = __shfl_up_sync(0xffffffffu, curi, 1);
+                            const float nv = lane > pos ? up : (lane == pos ? cv : cur);
+                            if (lane < kk && lane >= pos) { ls[lane] = nv; li[lane] = lane == pos ? n0 + i : upi; }
+                            const float nthr = __shfl_sync(0xffffffffu, nv, kk - 1);
+                            if (lane == src) thr = nthr;
+                            __syncwarp();
                         }
                     }
                 }
@@ -184,8 +200,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             if (qrow < args.Q) {
                 float* os = args.ws_score + ((size_t)qrow * args.chunks + ch) * kk;
                 int* oi = args.ws_idx + ((size_t)qrow * args.chunks + ch) * kk;
-                for (int s = 0; s < kk; ++s) { os[s] = lscore[s * KBM + row]; oi[s] = lidx[s * KBM + row]; }
+                for (int s = 0; s < kk; ++s) { os[s] = wl_s[lane * KMAX + s]; oi[s] = wl_i[lane * KMAX + s]; }
             }
+            __syncwarp();
         }
     }
     tc_fence_before();

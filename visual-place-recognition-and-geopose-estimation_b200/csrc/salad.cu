@@ -616,9 +616,6 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
     g[0].A = x; g[0].lda = s.d; g[0].B = w0cat; g[0].ldb = s.d; g[0].M = (int)Tk; g[0].N = 2 * h; g[0].K = s.d;
     g[0].out = H; g[0].out_kind = okT; g[0].ldo = 2 * h; g[0].bias = b0cat; g[0].relu = 1;
     g[0].dropout_p = drop_p; g[0].dropout_seed = seed;
-    // measured (tools/gemm_bench.py, B200): with the dropout epilogue, pair tiles make the leader's MMA wait for
-    // the slower of two epilogues (100 us vs 90 us single-CTA); the weight/input-gradient GEMMs gain 8-12 % from pairs
-    if (drop_p > 0.f) g[0].cta_pair = 2;
     g[1] = GemmDesc(); g[1].dtype = dtype;
     g[1].A = t; g[1].lda = s.d; g[1].B = wt0; g[1].ldb = s.d; g[1].M = s.B; g[1].N = h; g[1].K = s.d;
     g[1].out = HT; g[1].out_kind = okT; g[1].ldo = h; g[1].bias = p.token_b0; g[1].relu = 1;
