@@ -221,17 +221,27 @@ def run_own(args, rank, local, world):
     x_d, t_d, w_d = x_h.to(dev), t_h.to(dev), w_h.to(dev)
     params = list(head.parameters())
 
+    graphed = None if args.eager else vpr_b200.GraphedSaladStep(head, B, n)
+
     def fwd_bwd(x_tok, t, w):
-        for p in params:
-            p.grad = None
-        xg = x_tok.requires_grad_(True)
-        tg = t.requires_grad_(True)
-        f_map = xg.view(B, hw, hw, D).permute(0, 3, 1, 2)     # upstream's [B,C,h,w] view, no copy
-        out = head((f_map, tg))
-        out.backward(w)
+        """One step through the public API.  Default: vpr_b200.GraphedSaladStep (fwd+bwd of SaladHead captured in
+        one CUDA graph; inputs are copied into its static buffers unless they already are those buffers).
+        --eager: SaladHead + torch autograd, one Python call per kernel group."""
+        if graphed is not None:
+            out, dx, _ = graphed(None if x_tok is graphed.x else x_tok, None if t is graphed.t else t,
+                                 None if w is graphed.d_out else w)
+        else:
+            for p in params:
+                p.grad = None
+            xg = x_tok.requires_grad_(True)
+            tg = t.requires_grad_(True)
+            f_map = xg.view(B, hw, hw, D).permute(0, 3, 1, 2)     # upstream's [B,C,h,w] view, no copy
+            out = head((f_map, tg))
+            out.backward(w)
+            dx = xg.grad
         fin = vpr_b200.allreduce_grads(params, async_op=True) if world > 1 else (lambda: None)
         fin()
-        return out, xg.grad
+        return out, dx
 
     def barrier():
         if world > 1:
@@ -239,8 +249,15 @@ def run_own(args, rank, local, world):
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing (value) ----------------
+    if graphed is not None:                       # inputs resident in the step's own buffers
+        graphed.x.data.copy_(x_d)
+        graphed.t.data.copy_(t_d)
+        graphed.d_out.copy_(w_d)
+        dev_in = (graphed.x, graphed.t, graphed.d_out)
+    else:
+        dev_in = None
     for _ in range(max(args.warmup, 3)):
-        fwd_bwd(x_d.detach(), t_d.detach(), w_d)
+        fwd_bwd(*(dev_in or (x_d.detach(), t_d.detach(), w_d)))
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -250,11 +267,13 @@ def run_own(args, rank, local, world):
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        fwd_bwd(x_d.detach(), t_d.detach(), w_d)
+        fwd_bwd(*(dev_in or (x_d.detach(), t_d.detach(), w_d)))
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = lib.vpr_launch_count() - l0
+    if graphed is not None:
+        launches = graphed.launches_per_replay * args.steps      # replays do not go through the launch counter
     clocks = sampler.stop() if rank == 0 else None
     tmax = torch.tensor([ms_total], device=dev)
     if world > 1:
@@ -291,7 +310,7 @@ def run_own(args, rank, local, world):
             if i + 1 < steps:
                 issue_copy(i + 1)
             torch.cuda.current_stream().wait_event(ready[s])
-            out, _ = fwd_bwd(xb[s].detach(), tb[s].detach(), w_d)
+            out, _ = fwd_bwd(xb[s].detach(), tb[s].detach(), w_d if graphed is None else graphed.d_out)
             res = (out.float() * w_d.float()).sum().reshape(1)
             freed[s].record(torch.cuda.current_stream())
             res_host.copy_(res, non_blocking=True)
@@ -370,7 +389,9 @@ def run_own(args, rank, local, world):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"SALAD head fwd+bwd (all parameter grads + dX), ViT-B/14 tokens n={n} d=768, m=64 l=128 "
-                               f"g=256, 3 Sinkhorn iters, dropout 0.3 (train mode), batch {B} per GPU"
+                               f"g=256, 3 Sinkhorn iters, dropout 0.3 (train mode), batch {B} per GPU, "
+                               + ("SaladHead + torch autograd (eager)" if graphed is None else
+                                  "fwd+bwd replayed from one CUDA graph (vpr_b200.GraphedSaladStep)")
                                + (", + NCCL allreduce of 1,411,009 head grads" if world > 1 else ""),
                    "per_gpu_batch": B, "global_batch": B * world, "n": n,
                    "l2": "working set per step (X 100 MB + H 134 MB + dH 134 MB ...) exceeds the 126 MB L2; "
@@ -391,6 +412,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--eager", action="store_true", help="SaladHead + autograd per step instead of the CUDA-graph step")
     ap.add_argument("--no-knn", action="store_true", help="skip the kNN leg")
     ap.add_argument("--knn-queries", type=int, default=8192)
     ap.add_argument("--knn-gallery", type=int, default=1_250_000)

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define VPR_ABI_VERSION 1
+#define VPR_ABI_VERSION 2
 #if defined(__GNUC__)
 #define VPR_API __attribute__((visibility("default")))
 #else
@@ -95,10 +95,15 @@ VPR_API size_t vpr_salad_workspace_bytes(const VprSaladShape* s, int dtype);
 /* x: [B, n, d] token-major contiguous (the memory of upstream's permuted [B,d,h,w] view),
  * t: [B, d], out: [B, g + l*m] L2-normalised rows; all of `dtype`.
  * dropout_p > 0 applies the two Dropout(p) layers of cluster_features / score with a
- * counter-based mask keyed on `seed` (see vpr_dropout_mask). */
+ * counter-based mask keyed on `seed` + *seed_offset_dev (see vpr_dropout_mask). */
 VPR_API int vpr_salad_fwd(const VprSaladParams* p, const void* x, const void* t, void* out, void* save,
                   void* workspace, size_t workspace_bytes, const VprSaladShape* s, int dtype,
-                  float dropout_p, uint64_t seed, cudaStream_t stream);
+                  float dropout_p, uint64_t seed, const uint64_t* seed_offset_dev, cudaStream_t stream);
+
+/* *counter += 1 on the stream.  seed_offset_dev (a device counter, may be NULL) is added to `seed` by the
+ * kernels themselves, so a forward captured in a CUDA graph draws a fresh dropout mask on every replay:
+ * capture a vpr_counter_advance after the forward. */
+VPR_API int vpr_counter_advance(uint64_t* counter, cudaStream_t stream);
 
 /* d_out: [B, g + l*m]; dx: [B, n, d] or NULL; dt: [B, d] or NULL (all `dtype`). */
 VPR_API int vpr_salad_bwd(const VprSaladParams* p, const void* x, const void* t, const void* d_out,

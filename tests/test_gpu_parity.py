@@ -265,6 +265,47 @@ def test_salad_no_grad_and_frozen_use(vpr):
     assert out.shape == (2, 8448) and not out.requires_grad
 
 
+def test_graphed_step_matches_eager_and_redraws_dropout(vpr):
+    """One CUDA-graph replay == one eager fwd+bwd (dropout off); with dropout on, every replay draws a new mask
+    because the step counter lives on the device."""
+    torch.manual_seed(0)
+    mod = vpr.SaladHead(dropout=0.0).cuda().train()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, n = 4, 256
+    x = torch.randn(B, n, 768, device="cuda", generator=g).bfloat16()
+    t = torch.randn(B, 768, device="cuda", generator=g).bfloat16()
+    w = torch.randn(B, 8448, device="cuda", generator=g).bfloat16()
+    xe, te = x.clone().requires_grad_(True), t.clone().requires_grad_(True)
+    mod((xe, te)).backward(w)
+    eager = {n_: p.grad.clone() for n_, p in mod.named_parameters()}
+    out_e = mod((x, t)).detach().clone()
+    for p in mod.parameters():
+        p.grad = None
+    step = vpr.GraphedSaladStep(mod, B, n)
+    assert step.launches_per_replay >= 10
+    for _ in range(2):                                    # replays are repeatable
+        out, dx, dt = step(x, t, w)
+        assert rel(out, out_e) < 1e-6 and rel(dx, xe.grad) < 1e-6 and rel(dt, te.grad) < 1e-6
+        for n_, p in mod.named_parameters():
+            if eager[n_].norm() > 1e-6:
+                assert rel(p.grad, eager[n_]) < 1e-5, n_       # split-K reductions: summation order only
+    drop = vpr.SaladHead(dropout=0.3).cuda().train()
+    dstep = vpr.GraphedSaladStep(drop, B, n)
+    s0 = drop.current_seed()
+    o1 = dstep(x, t, w)[0].clone()
+    s1 = drop.current_seed()
+    o2 = dstep(x, t, w)[0].clone()
+    assert s1 == s0 + 1 and rel(o1, o2) > 1e-3              # fresh mask per replay
+    # the replay's mask is the exported one for that seed: eager forward with the same seed reproduces it
+    drop.use_device_step_counter(False)
+    drop._step = 0
+    drop.seed, saved = 0, drop.seed
+    drop._step = s1                                         # eager seed = seed*1000003 + _step
+    o2e = drop((x, t)).detach()
+    drop.seed = saved
+    assert rel(o2, o2e) < 1e-6
+
+
 def test_salad_error_behaviour(vpr):
     mod = vpr.SaladHead().cuda()
     with pytest.raises(ValueError, match="more patch tokens"):

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(built):
         assert hasattr(handle, name), f"{name} declared in include/vpr_b200.h but not exported"
     from vpr_b200 import _lib
     assert sorted(_lib.EXPORTS) == declared, "ctypes binding and header disagree"
-    assert built.lib().vpr_abi_version() == 1
+    assert built.lib().vpr_abi_version() == _lib.ABI_VERSION
 
 
 def test_buffer_size_queries_need_no_gpu(built):

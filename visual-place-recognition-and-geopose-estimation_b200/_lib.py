@@ -16,7 +16,7 @@ VPR_F32, VPR_BF16 = 0, 1
 OUT_F32, OUT_BF16, OUT_ATOMIC_F32 = 0, 1, 2
 LATLON_MSE, LATLON_HUBER = 0, 1
 ANGLE_NONE, ANGLE_ATAN2_MAAE, ANGLE_ACOS, ANGLE_MSE = 0, 1, 2, 3
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _fp = C.c_void_p
 
@@ -56,7 +56,8 @@ EXPORTS = {
     "vpr_salad_save_bytes": (C.c_size_t, [C.POINTER(SaladShape), C.c_int]),
     "vpr_salad_workspace_bytes": (C.c_size_t, [C.POINTER(SaladShape), C.c_int]),
     "vpr_salad_fwd": (C.c_int, [C.POINTER(SaladParams), _fp, _fp, _fp, _fp, _fp, C.c_size_t,
-                                C.POINTER(SaladShape), C.c_int, C.c_float, C.c_uint64, _fp]),
+                                C.POINTER(SaladShape), C.c_int, C.c_float, C.c_uint64, _fp, _fp]),
+    "vpr_counter_advance": (C.c_int, [_fp, _fp]),
     "vpr_salad_bwd": (C.c_int, [C.POINTER(SaladParams), _fp, _fp, _fp, _fp, _fp, C.c_size_t,
                                 C.POINTER(SaladGrads), _fp, _fp, C.POINTER(SaladShape), C.c_int, C.c_float, _fp]),
     "vpr_dropout_mask": (C.c_int, [C.c_uint64, C.c_float, C.c_int64, C.c_int64, _fp, _fp]),

@@ -4,6 +4,7 @@
 #include "../../include/vpr_b200.h"
 
 #include <atomic>
+#include <mutex>
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -30,6 +31,22 @@ int num_sms() {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     }
     return n;
+}
+
+int ensure_dynamic_smem(const void* kernel, size_t bytes) {
+    struct Slot { const void* fn; size_t bytes; };
+    static Slot slots[128];
+    static int used = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    Slot* sl = nullptr;
+    for (int i = 0; i < used; ++i)
+        if (slots[i].fn == kernel) { sl = &slots[i]; break; }
+    if (sl != nullptr && sl->bytes >= bytes) return 0;
+    VPR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (sl == nullptr && used < 128) { sl = &slots[used++]; sl->fn = kernel; sl->bytes = 0; }
+    if (sl != nullptr) sl->bytes = bytes;
+    return 0;
 }
 
 }  // namespace vpr

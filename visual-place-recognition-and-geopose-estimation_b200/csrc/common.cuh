@@ -38,6 +38,11 @@ void note_launch();   // counts kernel launches (vpr_launch_count)
         if (!(cond)) return ::vpr::fail(1, __VA_ARGS__);         \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize only has to grow: remember the largest value set per kernel
+// so that steady-state launches skip the driver call (api.cu)
+int ensure_dynamic_smem(const void* kernel, size_t bytes);
+#define VPR_SMEM_OK(kernel, bytes) VPR_TRY(::vpr::ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), (bytes)))
+
 static inline int launch_ok(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(3, "launch %s: %s", what, cudaGetErrorString(e));

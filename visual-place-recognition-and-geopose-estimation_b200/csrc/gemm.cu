@@ -17,6 +17,7 @@
 
 #include <mutex>
 #include <stdlib.h>
+#include <string.h>
 
 namespace vpr {
 
@@ -48,6 +49,7 @@ struct TcArgs {
     float mask_scale, alpha;
     uint32_t drop_thr; float drop_scale;
     unsigned long long drop_seed;
+    const unsigned long long* drop_seed_dev;   // optional device-side offset of the seed
 };
 
 struct TcProblem {
@@ -119,7 +121,8 @@ __device__ __forceinline__ void epilogue_math32(const TcArgs& a, uint32_t flags,
         const uint32_t thr = a.drop_thr;
         const float sc = a.drop_scale;
         const int off = (int)(base & 31ull);
-        uint32_t w0 = dropout_mix(a.drop_seed, base >> 5);
+        const unsigned long long seed = a.drop_seed + (a.drop_seed_dev != nullptr ? __ldg(a.drop_seed_dev) : 0ull);
+        uint32_t w0 = dropout_mix(seed, base >> 5);
         if (off == 0) {                          // this thread owns a whole run: one multiply-add per element
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -127,7 +130,7 @@ __device__ __forceinline__ void epilogue_math32(const TcArgs& a, uint32_t flags,
                 v[i] = (w >= thr) ? v[i] * sc : 0.f;
             }
         } else {                                 // the chunk straddles two runs: step the generator
-            const uint32_t w1 = dropout_mix(a.drop_seed, (base >> 5) + 1);
+            const uint32_t w1 = dropout_mix(seed, (base >> 5) + 1);
             for (int k = 0; k < off; ++k) w0 = w0 * DROP_LCG_A + DROP_LCG_C;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -501,7 +504,7 @@ struct SimtArgs {
     float* out; int out_kind; long long ldo, out_bs;
     const float* bias; int relu;
     const float* mask; long long ld_mask, mask_bs; float mask_scale, alpha;
-    uint32_t drop_thr; float drop_scale; unsigned long long drop_seed;
+    uint32_t drop_thr; float drop_scale; unsigned long long drop_seed; const unsigned long long* drop_seed_dev;
 };
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs a) {
@@ -558,7 +561,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs a) {
             if (a.bias) v += a.bias[n];
             if (a.relu) v = fmaxf(v, 0.f);
             if (a.drop_thr != 0u)
-                v = dropout_keep(a.drop_seed, ((unsigned long long)b * a.M + m) * (unsigned long long)a.N + n, a.drop_thr)
+                v = dropout_keep(a.drop_seed + (a.drop_seed_dev != nullptr ? __ldg(a.drop_seed_dev) : 0ull),
+                                 ((unsigned long long)b * a.M + m) * (unsigned long long)a.N + n, a.drop_thr)
                         ? v * a.drop_scale : 0.f;
             if (a.mask) {
                 float mk = a.mask[(long long)b * a.mask_bs + (long long)m * a.ld_mask + n];
@@ -628,6 +632,19 @@ static int make_map(CUtensorMap* map, const void* ptr, int esize, int64_t inner,
     if (batch == 1 || bs == 0) { batch = 1; bs = rows * ld; }
     VPR_REQUIRE((bs * esize) % 16 == 0, "%s: batch stride must be a multiple of 16 bytes (got %lld elements)", what,
                 (long long)bs);
+    // Encoding a map is a ~2 us driver call and a training step needs ~50 of them over the same buffers
+    // (the caller's allocator hands back the same pointers step after step): keep them in a small cache.
+    struct Key { const void* ptr; int64_t inner, rows, batch, ld, bs; int esize, box_inner, box_rows; };
+    struct Entry { Key key; CUtensorMap map; bool valid; };
+    static thread_local Entry cache[512];
+    Key key;
+    memset(&key, 0, sizeof(key));
+    key.ptr = ptr; key.inner = inner; key.rows = rows; key.batch = batch; key.ld = ld; key.bs = bs;
+    key.esize = esize; key.box_inner = box_inner; key.box_rows = box_rows;
+    uint64_t hsh = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(Key); ++i) hsh = (hsh ^ reinterpret_cast<const unsigned char*>(&key)[i]) * 1099511628211ull;
+    Entry& ce = cache[(hsh >> 20) & 511];
+    if (ce.valid && memcmp(&ce.key, &key, sizeof(Key)) == 0) { *map = ce.map; return 0; }
     cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch};
     cuuint64_t strides[2] = {(cuuint64_t)ld * esize, (cuuint64_t)bs * esize};
     cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
@@ -637,6 +654,7 @@ static int make_map(CUtensorMap* map, const void* ptr, int esize, int64_t inner,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VPR_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed (%d): inner=%lld rows=%lld batch=%lld ld=%lld bs=%lld",
                 what, (int)r, (long long)inner, (long long)rows, (long long)batch, (long long)ld, (long long)bs);
+    ce.key = key; ce.map = *map; ce.valid = true;
     return 0;
 }
 
@@ -645,8 +663,7 @@ static int launch_tc(const TcGroup& grp, int grid, cudaStream_t st) {
     using Cfg = TcCfg<BN, MASK, CTA2>;
     static bool attr_set = false;
     if (!attr_set) {
-        VPR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, BN, MASK, CTA2>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        VPR_SMEM_OK((gemm_tc_kernel<A_MN, B_MN, BN, MASK, CTA2>), Cfg::SMEM_BYTES);
         attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -776,6 +793,7 @@ static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
         a.mask_scale = g.mask_scale; a.alpha = g.alpha;
         a.drop_thr = g.dropout_p > 0.f ? dropout_threshold(g.dropout_p) : 0u;
         a.drop_scale = g.dropout_p > 0.f ? 1.f / (1.f - g.dropout_p) : 1.f; a.drop_seed = g.dropout_seed;
+        a.drop_seed_dev = reinterpret_cast<const unsigned long long*>(g.dropout_seed_dev);
         a.flags = (g.bias ? F_BIAS : 0u) | (g.relu ? F_RELU : 0u) | (a.drop_thr ? F_DROP : 0u) | (g.mask ? F_MASK : 0u) |
                   (g.alpha != 1.f ? F_ALPHA : 0u) | (g.colsum ? F_COLSUM : 0u);
         VPR_REQUIRE(g.colsum == nullptr || g.out_kind == OUT_BF16, "fused column sums need a bf16 output");
@@ -813,6 +831,7 @@ static int gemm_simt(const GemmDesc& g, cudaStream_t st) {
     a.mask_scale = g.mask_scale; a.alpha = g.alpha;
     a.drop_thr = g.dropout_p > 0.f ? dropout_threshold(g.dropout_p) : 0u;
     a.drop_scale = g.dropout_p > 0.f ? 1.f / (1.f - g.dropout_p) : 1.f; a.drop_seed = g.dropout_seed;
+    a.drop_seed_dev = reinterpret_cast<const unsigned long long*>(g.dropout_seed_dev);
     dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, g.batch * a.k_splits);
     VPR_REQUIRE(grid.y < 65536 && grid.z < 65536, "fp32 GEMM grid too large");
     gemm_simt_kernel<<<grid, 256, 0, st>>>(a);

@@ -29,6 +29,7 @@ struct GemmDesc {
     float alpha = 1.f;
     // inverted dropout on the output (after relu): keep iff dropout_hash(seed, (b*M+m)*N+n) >= p*2^32
     float dropout_p = 0.f; uint64_t dropout_seed = 0;
+    const uint64_t* dropout_seed_dev = nullptr;   // optional device counter added to dropout_seed (CUDA-graph replays)
     // colsum[n] += sum over (b, m) of the stored output (after mask / rounding); caller zeroes it
     float* colsum = nullptr;
     int k_splits = 1;              // > 1 requires OUT_ATOMIC_F32 (caller zeroes out)

@@ -341,7 +341,7 @@ int vpr_knn_topk(const void* q, const void* g, int64_t Q, int64_t G, int D, int 
     VPR_TRY(knn_map(&tg, g, G, D, KBN / 2));
     static bool attr = false;
     if (!attr) {
-        VPR_CUDA_OK(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K_SMEM_BYTES));
+        VPR_SMEM_OK(knn_tc_kernel, K_SMEM_BYTES);
         attr = true;
     }
     long long total = (long long)a.tiles_m * a.chunks;

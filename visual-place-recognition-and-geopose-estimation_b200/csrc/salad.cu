@@ -311,20 +311,20 @@ static int sinkhorn_fwd(const float* S, const float* dust_bin, void* P, int p_dt
         if (fs < guard) fs = guard;
         if (fs <= 227 * 1024) {          // scaled tile (one exp2 per element), log-domain body as its range guard
             if (p_dtype == VPR_BF16) {
-                VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_scaled<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+                VPR_SMEM_OK(sinkhorn_fwd_scaled<bf16>, fs);
                 sinkhorn_fwd_scaled<bf16><<<B, SS_NT, fs, st>>>(S, dust_bin, (bf16*)P, U, V, n, iters, k2);
             } else {
-                VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_scaled<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+                VPR_SMEM_OK(sinkhorn_fwd_scaled<float>, fs);
                 sinkhorn_fwd_scaled<float><<<B, SS_NT, fs, st>>>(S, dust_bin, (float*)P, U, V, n, iters, k2);
             }
             return launch_ok("sinkhorn_fwd_scaled");
         }
         VPR_REQUIRE(guard <= 227 * 1024, "score tile [%d,%d] does not fit in shared memory", n, m);
         if (p_dtype == VPR_BF16) {
-            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_fast<bf16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)guard));
+            VPR_SMEM_OK((sinkhorn_fwd_fast<bf16, 64>), guard);
             sinkhorn_fwd_fast<bf16, 64><<<B, SK_NT, guard, st>>>(S, dust_bin, (bf16*)P, U, V, n, iters, k2);
         } else {
-            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_fast<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)guard));
+            VPR_SMEM_OK((sinkhorn_fwd_fast<float, 64>), guard);
             sinkhorn_fwd_fast<float, 64><<<B, SK_NT, guard, st>>>(S, dust_bin, (float*)P, U, V, n, iters, k2);
         }
         return launch_ok("sinkhorn_fwd_fast");
@@ -333,10 +333,10 @@ static int sinkhorn_fwd(const float* S, const float* dust_bin, void* P, int p_dt
     VPR_REQUIRE(smem <= 227 * 1024, "score tile [%d,%d] does not fit in shared memory", n, m);
     const SinkConst k = sink_consts(n, m);
     if (p_dtype == VPR_BF16) {
-        VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VPR_SMEM_OK(sinkhorn_fwd_kernel<bf16>, smem);
         sinkhorn_fwd_kernel<bf16><<<B, 256, smem, st>>>(S, dust_bin, (bf16*)P, U, V, n, m, iters, k);
     } else {
-        VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VPR_SMEM_OK(sinkhorn_fwd_kernel<float>, smem);
         sinkhorn_fwd_kernel<float><<<B, 256, smem, st>>>(S, dust_bin, (float*)P, U, V, n, m, iters, k);
     }
     return launch_ok("sinkhorn_fwd_kernel");
@@ -356,8 +356,8 @@ static int sinkhorn_bwd(const float* S, const float* dust_bin, const float* U, c
         if (fs <= 227 * 1024) {
 #define VPR_SS_BWD(TD, KIT)                                                                                            \
     do {                                                                                                               \
-        VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_bwd_scaled<TD, KIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                         (int)fs));                                                                    \
+        VPR_SMEM_OK((sinkhorn_bwd_scaled<TD, KIT>), \
+                                         (int)fs);                                                                    \
         sinkhorn_bwd_scaled<TD, KIT><<<B, SS_NT, fs, st>>>(S, dust_bin, U, V, dP, (TD*)dS, d_bias, n, iters, k2);      \
     } while (0)
             if (ds_dtype == VPR_BF16) { if (iters == 3) VPR_SS_BWD(bf16, 3); else VPR_SS_BWD(bf16, 0); }
@@ -367,10 +367,10 @@ static int sinkhorn_bwd(const float* S, const float* dust_bin, const float* U, c
         }
         VPR_REQUIRE(guard <= 227 * 1024, "score tile [%d,%d] does not fit in shared memory", n, m);
         if (ds_dtype == VPR_BF16) {
-            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_bwd_fast<bf16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)guard));
+            VPR_SMEM_OK((sinkhorn_bwd_fast<bf16, 64>), guard);
             sinkhorn_bwd_fast<bf16, 64><<<B, SK_NT, guard, st>>>(S, dust_bin, U, V, dP, (bf16*)dS, d_bias, n, iters, k2);
         } else {
-            VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_bwd_fast<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)guard));
+            VPR_SMEM_OK((sinkhorn_bwd_fast<float, 64>), guard);
             sinkhorn_bwd_fast<float, 64><<<B, SK_NT, guard, st>>>(S, dust_bin, U, V, dP, (float*)dS, d_bias, n, iters, k2);
         }
         return launch_ok("sinkhorn_bwd_fast");
@@ -379,10 +379,10 @@ static int sinkhorn_bwd(const float* S, const float* dust_bin, const float* U, c
     VPR_REQUIRE(smem <= 227 * 1024, "score tile [%d,%d] does not fit in shared memory", n, m);
     const SinkConst k = sink_consts(n, m);
     if (ds_dtype == VPR_BF16) {
-        VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VPR_SMEM_OK(sinkhorn_bwd_kernel<bf16>, smem);
         sinkhorn_bwd_kernel<bf16><<<B, 256, smem, st>>>(S, dust_bin, U, V, dP, (bf16*)dS, d_bias, n, m, iters, k);
     } else {
-        VPR_CUDA_OK(cudaFuncSetAttribute(sinkhorn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VPR_SMEM_OK(sinkhorn_bwd_kernel<float>, smem);
         sinkhorn_bwd_kernel<float><<<B, 256, smem, st>>>(S, dust_bin, U, V, dP, (float*)dS, d_bias, n, m, iters, k);
     }
     return launch_ok("sinkhorn_bwd_kernel");
@@ -507,6 +507,8 @@ __global__ void __launch_bounds__(256) finalize_bwd_kernel(const float* __restri
     }
 }
 
+__global__ void counter_advance_kernel(unsigned long long* c) { *c += 1ull; }
+
 __global__ void dropout_mask_kernel(unsigned long long seed, uint32_t thr, long long total, uint8_t* out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
         out[i] = dropout_keep(seed, (unsigned long long)i, thr) ? 1 : 0;
@@ -576,7 +578,7 @@ static int check_shape(const VprSaladShape& s, int dtype) {
 
 template <typename T>
 static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, char* save, const VprSaladShape& s,
-                       int dtype, float drop_p, uint64_t seed, cudaStream_t st) {
+                       int dtype, float drop_p, uint64_t seed, const uint64_t* seed_dev, cudaStream_t st) {
     const SavePlan sp = save_plan(s, dtype);
     const int h = s.hidden;
     const long long Tk = (long long)s.B * s.n;
@@ -615,7 +617,7 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
     g[0] = GemmDesc(); g[0].dtype = dtype;
     g[0].A = x; g[0].lda = s.d; g[0].B = w0cat; g[0].ldb = s.d; g[0].M = (int)Tk; g[0].N = 2 * h; g[0].K = s.d;
     g[0].out = H; g[0].out_kind = okT; g[0].ldo = 2 * h; g[0].bias = b0cat; g[0].relu = 1;
-    g[0].dropout_p = drop_p; g[0].dropout_seed = seed;
+    g[0].dropout_p = drop_p; g[0].dropout_seed = seed; g[0].dropout_seed_dev = seed_dev;
     g[1] = GemmDesc(); g[1].dtype = dtype;
     g[1].A = t; g[1].lda = s.d; g[1].B = wt0; g[1].ldb = s.d; g[1].M = s.B; g[1].N = h; g[1].K = s.d;
     g[1].out = HT; g[1].out_kind = okT; g[1].ldo = h; g[1].bias = p.token_b0; g[1].relu = 1;
@@ -693,7 +695,7 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
     const bool fin_fast = finalize_fast_ok(s.l, s.m, s.g);
     if (fin_fast) {
         const size_t fsm = finalize_bwd_fast_smem<T>(s.l, s.m);
-        VPR_CUDA_OK(cudaFuncSetAttribute(finalize_bwd_fast<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+        VPR_SMEM_OK(finalize_bwd_fast<T>, fsm);
         finalize_bwd_fast<T><<<s.B, 256, fsm, st>>>(AGG, TF, d_out, dAGG, dAGGT, dTF, gr.token_b1, s.l, s.m, s.g);
         VPR_TRY(launch_ok("finalize_bwd_fast"));
     } else {
@@ -803,14 +805,14 @@ size_t vpr_salad_workspace_bytes(const VprSaladShape* s, int dtype) { return wor
 
 int vpr_salad_fwd(const VprSaladParams* p, const void* x, const void* t, void* out, void* save, void* workspace,
                   size_t workspace_bytes, const VprSaladShape* s, int dtype, float dropout_p, uint64_t seed,
-                  cudaStream_t stream) {
+                  const uint64_t* seed_offset_dev, cudaStream_t stream) {
     (void)workspace; (void)workspace_bytes;
     VPR_REQUIRE(p && x && t && out && save && s, "null argument");
     VPR_TRY(check_shape(*s, dtype));
     VPR_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout_p out of range");
     if (dtype == VPR_BF16)
-        return salad_fwd_t<bf16>(*p, (const bf16*)x, (const bf16*)t, (bf16*)out, (char*)save, *s, dtype, dropout_p, seed, stream);
-    return salad_fwd_t<float>(*p, (const float*)x, (const float*)t, (float*)out, (char*)save, *s, dtype, dropout_p, seed, stream);
+        return salad_fwd_t<bf16>(*p, (const bf16*)x, (const bf16*)t, (bf16*)out, (char*)save, *s, dtype, dropout_p, seed, seed_offset_dev, stream);
+    return salad_fwd_t<float>(*p, (const float*)x, (const float*)t, (float*)out, (char*)save, *s, dtype, dropout_p, seed, seed_offset_dev, stream);
 }
 
 int vpr_salad_bwd(const VprSaladParams* p, const void* x, const void* t, const void* d_out, const void* save,
@@ -825,6 +827,12 @@ int vpr_salad_bwd(const VprSaladParams* p, const void* x, const void* t, const v
                                  (char*)workspace, *grads, (bf16*)dx, (bf16*)dt, *s, dtype, dropout_p, stream);
     return salad_bwd_t<float>(*p, (const float*)x, (const float*)t, (const float*)d_out, (const char*)save,
                               (char*)workspace, *grads, (float*)dx, (float*)dt, *s, dtype, dropout_p, stream);
+}
+
+int vpr_counter_advance(uint64_t* counter, cudaStream_t stream) {
+    VPR_REQUIRE(counter != nullptr, "null counter");
+    counter_advance_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<unsigned long long*>(counter));
+    return launch_ok("counter_advance_kernel");
 }
 
 int vpr_dropout_mask(uint64_t seed, float p, int64_t rows, int64_t cols, uint8_t* out, cudaStream_t stream) {
