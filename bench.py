@@ -425,6 +425,8 @@ def main():
         return
     if world > 1:
         import vpr_b200
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner out of the one-JSON-line stdout
         vpr_b200.init_distributed("nccl")
     run_own(args, rank, local, world)
     if world > 1:

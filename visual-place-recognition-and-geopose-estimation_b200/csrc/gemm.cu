@@ -621,8 +621,8 @@ static EncodeTiledFn get_encode() {
 
 // 3-D tensor map over a row-major [batch][rows][inner] array of 2-byte (bf16) or 4-byte (fp32)
 // elements, 128B swizzle; ld / bs in elements.
-static int make_map(CUtensorMap* map, const void* ptr, int esize, int64_t inner, int64_t rows, int64_t batch, int64_t ld,
-                    int64_t bs, int box_inner, int box_rows, const char* what) {
+int make_map(CUtensorMap* map, const void* ptr, int esize, int64_t inner, int64_t rows, int64_t batch, int64_t ld,
+             int64_t bs, int box_inner, int box_rows, const char* what) {
     EncodeTiledFn enc = get_encode();
     VPR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     VPR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "%s: pointer must be 16-byte aligned", what);

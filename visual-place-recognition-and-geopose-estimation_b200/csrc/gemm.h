@@ -43,6 +43,21 @@ struct GemmTilePlan { int tile_m, tile_n, slots; };
 GemmTilePlan gemm_tile_plan(const GemmDesc* gs, int count);
 
 int gemm_run(const GemmDesc& g, cudaStream_t stream);
+
+// SALAD backward, fused: dH = [dF W1c | dS W1s] * relu/dropout mask, and -- from the tiles that launch already has
+// in shared memory -- the second-layer weight gradients dW1 = [dF^T H_c ; dS^T H_s] and the first-layer bias
+// gradients (column sums of dH), all on the tensor core.  dtype bf16, l == 128, m == 64, hidden % 128 == 0.
+struct DhFusedDesc {
+    const void* dF; const void* dS;          // [T, 128], [T, 64] bf16
+    const void* W1c; const void* W1s;        // [128, hidden], [64, hidden] bf16
+    const void* H;                           // [T, 2*hidden] bf16 saved activation (mask and dW1 operand)
+    void* dH;                                // [T, 2*hidden] bf16
+    float* dW1c; float* dW1s;                // [128, hidden], [64, hidden] fp32, accumulated (caller zeroes)
+    float* db0c; float* db0s;                // [hidden] fp32 each, accumulated (caller zeroes)
+    long long T; int hidden; float mask_scale;
+};
+bool dh_fused_supported(int dtype, int l, int m, int hidden);
+int dh_fused_run(const DhFusedDesc& d, cudaStream_t stream);
 // Up to 4 independent problems with the same dtype and operand layout in ONE launch.
 int gemm_run_group(const GemmDesc* gs, int count, cudaStream_t stream);
 

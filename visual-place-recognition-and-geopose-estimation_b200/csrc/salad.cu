@@ -725,17 +725,32 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
     // ---- Sinkhorn backward: dP -> dS (+ score bias gradient) ----
     VPR_TRY(sinkhorn_bwd(S, p.dust_bin, U, V, dP, dS, dtype, gr.score_b1, s.B, s.n, s.m, s.iters, st));
 
-    // ---- second-layer weight gradients (split-K + fp32 reductions), one launch ----
-    {
+    const bool fused = dh_fused_supported(dtype, s.l, s.m, h);
+    // dWt1[g,h] = dTF^T HT (token MLP, K = B): rides along with whichever split-K launch comes next
+    GemmDesc gtok1 = GemmDesc(); gtok1.dtype = dtype;
+    gtok1.A = dTF; gtok1.a_mn = 1; gtok1.lda = s.g; gtok1.B = HT; gtok1.b_mn = 1; gtok1.ldb = h; gtok1.M = s.g; gtok1.N = h;
+    gtok1.K = s.B; gtok1.out = gr.token_w1; gtok1.out_kind = OUT_ATOMIC_F32; gtok1.ldo = h;
+    // dHT = (dTF Wt1) * (HT > 0)  (+ token_features.0.bias gradient)
+    GemmDesc gtokh = GemmDesc(); gtokh.dtype = dtype;
+    gtokh.A = dTF; gtokh.lda = s.g; gtokh.B = wt1; gtokh.b_mn = 1; gtokh.ldb = h; gtokh.M = s.B; gtokh.N = h; gtokh.K = s.g;
+    gtokh.out = dHT; gtokh.out_kind = okT; gtokh.ldo = h; gtokh.mask = HT; gtokh.ld_mask = h; gtokh.colsum = gr.token_b0;
+    if (fused) {
+        // ---- one pass over H: dH, the second-layer weight gradients and the first-layer bias gradients ----
+        DhFusedDesc fd;
+        fd.dF = dF; fd.dS = dS; fd.W1c = w1c; fd.W1s = w1s; fd.H = H; fd.dH = dH;
+        fd.dW1c = gr.cluster_w1; fd.dW1s = gr.score_w1; fd.db0c = gr.cluster_b0; fd.db0s = gr.score_b0;
+        fd.T = Tk; fd.hidden = h; fd.mask_scale = keep_scale;
+        VPR_TRY(dh_fused_run(fd, st));
+        VPR_TRY(gemm_run(gtokh, st));
+    } else {
+        // ---- second-layer weight gradients (split-K + fp32 reductions), one launch ----
         g[0] = GemmDesc(); g[0].dtype = dtype;    // dW1c[l,h] = dF^T H[:, :h]
         g[0].A = dF; g[0].a_mn = 1; g[0].lda = s.l; g[0].B = H; g[0].b_mn = 1; g[0].ldb = 2 * h; g[0].M = s.l; g[0].N = h;
         g[0].K = (int)Tk; g[0].out = gr.cluster_w1; g[0].out_kind = OUT_ATOMIC_F32; g[0].ldo = h;
         g[1] = GemmDesc(); g[1].dtype = dtype;    // dW1s[m,h] = dS^T H[:, h:]
         g[1].A = dS; g[1].a_mn = 1; g[1].lda = s.m; g[1].B = H + h; g[1].b_mn = 1; g[1].ldb = 2 * h; g[1].M = s.m; g[1].N = h;
         g[1].K = (int)Tk; g[1].out = gr.score_w1; g[1].out_kind = OUT_ATOMIC_F32; g[1].ldo = h;
-        g[2] = GemmDesc(); g[2].dtype = dtype;    // dWt1[g,h] = dTF^T HT
-        g[2].A = dTF; g[2].a_mn = 1; g[2].lda = s.g; g[2].B = HT; g[2].b_mn = 1; g[2].ldb = h; g[2].M = s.g; g[2].N = h;
-        g[2].K = s.B; g[2].out = gr.token_w1; g[2].out_kind = OUT_ATOMIC_F32; g[2].ldo = h;
+        g[2] = gtok1;
         // split K so that the two token-long problems fill the machine; the token-MLP problem's few short
         // work items come last and are absorbed by the CTAs that finish first
         const GemmTilePlan tp = gemm_tile_plan(g, 3);
@@ -743,36 +758,37 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         int ks = tp.slots / tiles; if (ks < 1) ks = 1; if (ks > kb_tok) ks = kb_tok;
         g[0].k_splits = ks; g[1].k_splits = ks;
         VPR_TRY(gemm_run_group(g, 3, st));
+        // ---- dH = [dF W1c | dS W1s] * (H > 0) * keep_scale,  dHT; first-layer bias gradients ----
+        g[0] = GemmDesc(); g[0].dtype = dtype;
+        g[0].A = dF; g[0].lda = s.l; g[0].B = w1c; g[0].b_mn = 1; g[0].ldb = h; g[0].M = (int)Tk; g[0].N = h; g[0].K = s.l;
+        g[0].out = dH; g[0].out_kind = okT; g[0].ldo = 2 * h; g[0].mask = H; g[0].ld_mask = 2 * h; g[0].mask_scale = keep_scale;
+        g[0].colsum = gr.cluster_b0;
+        g[1] = GemmDesc(); g[1].dtype = dtype;
+        g[1].A = dS; g[1].lda = s.m; g[1].B = w1s; g[1].b_mn = 1; g[1].ldb = h; g[1].M = (int)Tk; g[1].N = h; g[1].K = s.m;
+        g[1].out = dH + h; g[1].out_kind = okT; g[1].ldo = 2 * h; g[1].mask = H + h; g[1].ld_mask = 2 * h; g[1].mask_scale = keep_scale;
+        g[1].colsum = gr.score_b0;
+        g[2] = gtokh;
+        VPR_TRY(gemm_run_group(g, 3, st));
     }
-    // ---- dH = [dF W1c | dS W1s] * (H > 0) * keep_scale,  dHT = (dTF Wt1) * (HT > 0); first-layer bias gradients ----
-    g[0] = GemmDesc(); g[0].dtype = dtype;
-    g[0].A = dF; g[0].lda = s.l; g[0].B = w1c; g[0].b_mn = 1; g[0].ldb = h; g[0].M = (int)Tk; g[0].N = h; g[0].K = s.l;
-    g[0].out = dH; g[0].out_kind = okT; g[0].ldo = 2 * h; g[0].mask = H; g[0].ld_mask = 2 * h; g[0].mask_scale = keep_scale;
-    g[0].colsum = gr.cluster_b0;
-    g[1] = GemmDesc(); g[1].dtype = dtype;
-    g[1].A = dS; g[1].lda = s.m; g[1].B = w1s; g[1].b_mn = 1; g[1].ldb = h; g[1].M = (int)Tk; g[1].N = h; g[1].K = s.m;
-    g[1].out = dH + h; g[1].out_kind = okT; g[1].ldo = 2 * h; g[1].mask = H + h; g[1].ld_mask = 2 * h; g[1].mask_scale = keep_scale;
-    g[1].colsum = gr.score_b0;
-    g[2] = GemmDesc(); g[2].dtype = dtype;
-    g[2].A = dTF; g[2].lda = s.g; g[2].B = wt1; g[2].b_mn = 1; g[2].ldb = h; g[2].M = s.B; g[2].N = h; g[2].K = s.g;
-    g[2].out = dHT; g[2].out_kind = okT; g[2].ldo = h; g[2].mask = HT; g[2].ld_mask = h; g[2].colsum = gr.token_b0;
-    VPR_TRY(gemm_run_group(g, 3, st));
     // ---- first-layer weight gradients: dW0[h,d] = dH^T X (two parameter tensors) and dWt0 = dHT^T t ----
     {
+        GemmDesc g4[4];
         for (int half = 0; half < 2; ++half) {
-            g[half] = GemmDesc(); g[half].dtype = dtype;
-            g[half].A = dH + half * h; g[half].a_mn = 1; g[half].lda = 2 * h; g[half].B = x; g[half].b_mn = 1; g[half].ldb = s.d;
-            g[half].M = h; g[half].N = s.d; g[half].K = (int)Tk;
-            g[half].out = half == 0 ? gr.cluster_w0 : gr.score_w0; g[half].out_kind = OUT_ATOMIC_F32; g[half].ldo = s.d;
+            g4[half] = GemmDesc(); g4[half].dtype = dtype;
+            g4[half].A = dH + half * h; g4[half].a_mn = 1; g4[half].lda = 2 * h; g4[half].B = x; g4[half].b_mn = 1; g4[half].ldb = s.d;
+            g4[half].M = h; g4[half].N = s.d; g4[half].K = (int)Tk;
+            g4[half].out = half == 0 ? gr.cluster_w0 : gr.score_w0; g4[half].out_kind = OUT_ATOMIC_F32; g4[half].ldo = s.d;
         }
-        g[2] = GemmDesc(); g[2].dtype = dtype;
-        g[2].A = dHT; g[2].a_mn = 1; g[2].lda = h; g[2].B = t; g[2].b_mn = 1; g[2].ldb = s.d; g[2].M = h; g[2].N = s.d; g[2].K = s.B;
-        g[2].out = gr.token_w0; g[2].out_kind = OUT_ATOMIC_F32; g[2].ldo = s.d;
-        const GemmTilePlan tp = gemm_tile_plan(g, 3);
+        g4[2] = GemmDesc(); g4[2].dtype = dtype;
+        g4[2].A = dHT; g4[2].a_mn = 1; g4[2].lda = h; g4[2].B = t; g4[2].b_mn = 1; g4[2].ldb = s.d; g4[2].M = h; g4[2].N = s.d; g4[2].K = s.B;
+        g4[2].out = gr.token_w0; g4[2].out_kind = OUT_ATOMIC_F32; g4[2].ldo = s.d;
+        int cnt = 3;
+        if (fused) g4[cnt++] = gtok1;
+        const GemmTilePlan tp = gemm_tile_plan(g4, cnt);
         const int tiles = 2 * ((h + tp.tile_m - 1) / tp.tile_m) * ((s.d + tp.tile_n - 1) / tp.tile_n);
         int ks = tp.slots / tiles; if (ks < 1) ks = 1; if (ks > kb_tok) ks = kb_tok;
-        g[0].k_splits = ks; g[1].k_splits = ks;
-        VPR_TRY(gemm_run_group(g, 3, st));
+        g4[0].k_splits = ks; g4[1].k_splits = ks;
+        VPR_TRY(gemm_run_group(g4, cnt, st));
     }
     // ---- input gradients: dX = dH W0cat, dt = dHT Wt0 ----
     {
