@@ -3,6 +3,7 @@
 //   dH  = [dF W1c | dS W1s] * (H > 0) * keep_scale                 (128 x 128 tiles, written by TMA)
 //   dW1 = [dF^T H_c ; dS^T H_s]            second-layer weight gradients   (tensor core, TMEM-resident)
 //   db0 = column sums of dH                first-layer bias gradients      (tensor core, TMEM-resident)
+//   db1 = column sums of dF                cluster_features.3.bias gradient (same trick, first column slice only)
 //
 // The generic path needs two launches for this (a split-K GEMM that streams H as an operand and a
 // masked GEMM that streams H again as the ReLU/dropout mask, with a register butterfly for the column
@@ -37,8 +38,8 @@ static constexpr int DH_ONES_BYTES = 4096;               // [16 n][128 k] bf16, 
 static constexpr int DH_SMEM = 1024 + DH_B_BYTES + DH_A_STAGES * DH_A_STAGE + 2 * DH_MASK_BYTES + 2 * DH_BOX +
                                DH_ONES_BYTES + 256;
 static_assert(DH_SMEM <= 227 * 1024, "dh_fused shared memory budget");
-// TMEM columns: dH accumulators 2 x 128, dW1 128, column sums 16
-static constexpr uint32_t DH_TM_D2 = 256, DH_TM_D3 = 384, DH_TM_COLS = 512;
+// TMEM columns: dH accumulators 2 x 128, dW1 128, column sums of dH 16, column sums of dF 16
+static constexpr uint32_t DH_TM_D2 = 256, DH_TM_D3 = 384, DH_TM_D4 = 400, DH_TM_COLS = 512;
 
 struct DhArgs {
     int tiles_m;             // token tiles (128 tokens each)
@@ -46,7 +47,7 @@ struct DhArgs {
     int hidden;
     int T;
     float mask_scale;
-    float* dW1c; float* dW1s; float* db0c; float* db0s;
+    float* dW1c; float* dW1s; float* db0c; float* db0s; float* db1c;
 };
 
 __global__ void __launch_bounds__(DH_THREADS, 1)
@@ -140,6 +141,7 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
             constexpr uint32_t idesc1 = make_idesc_bf16(128, 128, false, true);    // dH: A K-major, B MN-major
             constexpr uint32_t idesc2 = make_idesc_bf16(128, 128, true, true);     // dW1: both MN-major views
             constexpr uint32_t idesc3 = make_idesc_bf16(128, 16, true, false);     // column sums: A MN-major, ones K-major
+            const bool do_db1 = half == 0 && cn == 0 && args.db1c != nullptr;
             mbar_wait(bfull, 0);
             tc_fence_after();
             int it = 0;
@@ -179,6 +181,14 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
                     const uint64_t ad = make_smem_desc(a_s + ks * 2048, DH_BOX, 1024u);
                     const uint64_t bd = make_smem_desc(m_s + ks * 2048, DH_BOX, 1024u);
                     tc_mma_bf16(tmem_base + DH_TM_D2, ad, bd, idesc2, (it > 0 || ks > 0) ? 1u : 0u);
+                }
+                if (do_db1) {                              // D4[l, .] += sum_token dF[token, l]
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint64_t ad = make_smem_desc(a_s + ks * 2048, DH_BOX, 1024u);
+                        const uint64_t bd = make_smem_desc(sOnes + (ks >> 2) * 2048 + (ks & 3) * 32, 16u, 1024u);
+                        tc_mma_bf16(tmem_base + DH_TM_D4, ad, bd, idesc3, (it > 0 || ks > 0) ? 1u : 0u);
+                    }
                 }
                 tc_commit(aempty(s));
                 tc_commit(mempty(s));
@@ -275,6 +285,12 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
                 tmem_ld_wait();
                 float* db = half == 0 ? args.db0c : args.db0s;
                 atomicAdd(db + cn * 128 + row, __uint_as_float(cs));
+            } else if (half == 0 && cn == 0 && args.db1c != nullptr) {      // TMEM lane = cluster feature l
+                uint32_t cs;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];"
+                             : "=r"(cs) : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + DH_TM_D4) : "memory");
+                tmem_ld_wait();
+                atomicAdd(args.db1c + row, __uint_as_float(cs));
             }
         }
         if (issuer) bulk_wait_read<0>();
@@ -312,7 +328,7 @@ int dh_fused_run(const DhFusedDesc& d, cudaStream_t st) {
     a.hidden = h;
     a.T = (int)d.T;
     a.mask_scale = d.mask_scale;
-    a.dW1c = d.dW1c; a.dW1s = d.dW1s; a.db0c = d.db0c; a.db0s = d.db0s;
+    a.dW1c = d.dW1c; a.dW1s = d.dW1s; a.db0c = d.db0c; a.db0s = d.db0s; a.db1c = d.db1c;
     const int nct = 2 * a.ct_per_half;
     long long want = (long long)a.tiles_m * nct;
     int grid = (int)(want < num_sms() ? want : num_sms());

@@ -26,6 +26,17 @@ __device__ __forceinline__ void st4(bf16* p, float4 v) {
     u.y = *reinterpret_cast<uint32_t*>(&hi);
     *reinterpret_cast<uint2*>(p) = u;
 }
+__device__ __forceinline__ void ld8(const float* p, float (&w)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const bf16* p, float (&w)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    w[0] = __uint_as_float(u.x << 16); w[1] = __uint_as_float(u.x & 0xFFFF0000u);
+    w[2] = __uint_as_float(u.y << 16); w[3] = __uint_as_float(u.y & 0xFFFF0000u);
+    w[4] = __uint_as_float(u.z << 16); w[5] = __uint_as_float(u.z & 0xFFFF0000u);
+    w[6] = __uint_as_float(u.w << 16); w[7] = __uint_as_float(u.w & 0xFFFF0000u);
+}
 __device__ __forceinline__ float ldf1(const float* p) { return *p; }
 __device__ __forceinline__ float ldf1(const bf16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void stf1(float* p, float v) { *p = v; }
@@ -35,7 +46,8 @@ static constexpr int FIN_MAXV = 8;      // 16-byte vectors of the aggregate per 
 
 static inline bool finalize_fast_ok(int l, int m, int g) {
     const long long e = (long long)l * m;
-    return (m == 16 || m == 32 || m == 64 || m == 128) && e % 1024 == 0 && e / 1024 <= FIN_MAXV && g % 4 == 0 && l % 4 == 0;
+    return (m == 16 || m == 32 || m == 64 || m == 128) && e % 1024 == 0 && e / 1024 <= FIN_MAXV && g % 4 == 0 && l % 4 == 0 &&
+           g <= 1024;
 }
 template <typename T>
 static inline size_t finalize_bwd_fast_smem(int l, int m) { return (size_t)m * (l + 4) * sizeof(T); }
@@ -109,7 +121,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) finalize_bwd_fast(const float* __restrict__ AGG, const float* __restrict__ TF,
                                                          const T* __restrict__ d_out, T* __restrict__ dAGG,
                                                          T* __restrict__ dAGGT, T* __restrict__ dTF,
-                                                         float* __restrict__ g_bias_tok, int l, int m, int g) {
+                                                         float* __restrict__ g_bias_tok, int l, int m, int g,
+                                                         const T* __restrict__ wt1, const T* __restrict__ HT,
+                                                         T* __restrict__ dHT, float* __restrict__ g_bias_tok0, int hid) {
     extern __shared__ __align__(16) uint8_t fin_smem[];
     T* tileT = reinterpret_cast<T*>(fin_smem);                 // [m][l + 4]
     __shared__ __align__(16) float red_s[8][128];
@@ -118,6 +132,8 @@ __global__ void __launch_bounds__(256) finalize_bwd_fast(const float* __restrict
     __shared__ __align__(16) float dot_c[128];
     __shared__ float wred[2][8];
     __shared__ float sc[4];
+    __shared__ float sdt[1024];                                // this image's dTF row (g <= 1024)
+    __shared__ float spart[4][512];                            // partial dHT rows of the four k-quarters
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* A = AGG + (size_t)b * l * m;
     const float* t = TF + (size_t)b * g;
@@ -211,6 +227,7 @@ __global__ void __launch_bounds__(256) finalize_bwd_fast(const float* __restrict
         const float dz = (ldf1(dy + i) - th * ns) * invN;
         const float dti = (dz - th * dt_dot) * invt;
         stf1(dT + i, dti);
+        sdt[i] = dti;
         if (g_bias_tok != nullptr) atomicAdd(g_bias_tok + i, dti);
     }
     __syncthreads();
@@ -221,6 +238,39 @@ __global__ void __launch_bounds__(256) finalize_bwd_fast(const float* __restrict
         const T* src = tileT + (size_t)c * lp + l4;
         if constexpr (sizeof(T) == 2) *reinterpret_cast<uint2*>(dAT + (size_t)c * l + l4) = *reinterpret_cast<const uint2*>(src);
         else *reinterpret_cast<float4*>(dAT + (size_t)c * l + l4) = *reinterpret_cast<const float4*>(src);
+    }
+    // token MLP, hidden-layer gradient of this image: dHT[b, :] = (dTF[b, :] Wt1) * (HT[b, :] > 0), and its
+    // contribution to token_features.0.bias -- 2 * g * hid MACs, not worth a launch of its own.  Thread =
+    // (8 adjacent hidden units, one quarter of the g rows): 16-byte weight loads, 16 in flight per thread.
+    if (dHT != nullptr) {                                      // requires hid == 512 (host checks)
+        const int c8 = (tid & 63) * 8, ksl = tid >> 6;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 16
+        for (int k = ksl; k < g; k += 4) {
+            const float dk = sdt[k];
+            float w[8];
+            ld8(wt1 + (size_t)k * hid + c8, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(dk, w[i], acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) spart[ksl][c8 + i] = acc[i];
+        __syncthreads();
+        const int c2 = tid * 2;
+        float a0 = spart[0][c2] + spart[1][c2] + spart[2][c2] + spart[3][c2];
+        float a1 = spart[0][c2 + 1] + spart[1][c2 + 1] + spart[2][c2 + 1] + spart[3][c2 + 1];
+        const T* hp = HT + (size_t)b * hid + c2;
+        a0 = ldf1(hp) > 0.f ? a0 : 0.f;
+        a1 = ldf1(hp + 1) > 0.f ? a1 : 0.f;
+        T* op = dHT + (size_t)b * hid + c2;
+        stf1(op, a0);
+        stf1(op + 1, a1);
+        if (g_bias_tok0 != nullptr) {                          // column sums of the stored (rounded) values
+            atomicAdd(g_bias_tok0 + c2, ldf1(op));
+            atomicAdd(g_bias_tok0 + c2 + 1, ldf1(op + 1));
+        }
     }
 }
 

@@ -54,6 +54,7 @@ struct DhFusedDesc {
     void* dH;                                // [T, 2*hidden] bf16
     float* dW1c; float* dW1s;                // [128, hidden], [64, hidden] fp32, accumulated (caller zeroes)
     float* db0c; float* db0s;                // [hidden] fp32 each, accumulated (caller zeroes)
+    float* db1c;                             // [128] fp32 column sums of dF (cluster_features.3.bias), or NULL
     long long T; int hidden; float mask_scale;
 };
 bool dh_fused_supported(int dtype, int l, int m, int hidden);

@@ -693,10 +693,13 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
     // norms backward: d_out -> dAGG [B,l,m] (and its transpose [B,m,l]), dTF [B,g] (+ token_features.2.bias gradient)
     T* dAGGT = (T*)(ws + wp.dAGGT);
     const bool fin_fast = finalize_fast_ok(s.l, s.m, s.g);
+    bool fin_dht = false;                                  // dHT already produced by finalize_bwd_fast
     if (fin_fast) {
         const size_t fsm = finalize_bwd_fast_smem<T>(s.l, s.m);
         VPR_SMEM_OK(finalize_bwd_fast<T>, fsm);
-        finalize_bwd_fast<T><<<s.B, 256, fsm, st>>>(AGG, TF, d_out, dAGG, dAGGT, dTF, gr.token_b1, s.l, s.m, s.g);
+        fin_dht = h == 512;                                // the in-kernel token-MLP gradient is laid out for 512 hidden units
+        finalize_bwd_fast<T><<<s.B, 256, fsm, st>>>(AGG, TF, d_out, dAGG, dAGGT, dTF, gr.token_b1, s.l, s.m, s.g,
+                                                    wt1, HT, fin_dht ? dHT : (T*)nullptr, gr.token_b0, h);
         VPR_TRY(launch_ok("finalize_bwd_fast"));
     } else {
         finalize_bwd_kernel<T><<<s.B, 256, 0, st>>>(AGG, TF, d_out, dAGG, dTF, gr.token_b1, s.l, s.m, s.g);
@@ -705,11 +708,13 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
 
     GemmDesc g[3];
     const int kb_tok = (int)((Tk + 63) / 64);
+    const bool fused = dh_fused_supported(dtype, s.l, s.m, h);
     // ---- aggregation backward (one launch when the transposed dAGG is available) ----
     g[0] = GemmDesc(); g[0].dtype = dtype;    // dF[b][j][l] = sum_c P[b][j][c] dAGG[b][l][c]   (+ cluster bias gradient)
     g[0].A = P; g[0].lda = s.m; g[0].a_bs = (int64_t)s.n * s.m; g[0].B = dAGG; g[0].ldb = s.m; g[0].b_bs = (int64_t)s.l * s.m;
     g[0].M = s.n; g[0].N = s.l; g[0].K = s.m; g[0].batch = s.B;
-    g[0].out = dF; g[0].out_kind = okT; g[0].ldo = s.l; g[0].out_bs = (int64_t)s.n * s.l; g[0].colsum = gr.cluster_b1;
+    g[0].out = dF; g[0].out_kind = okT; g[0].ldo = s.l; g[0].out_bs = (int64_t)s.n * s.l;
+    g[0].colsum = fused ? nullptr : gr.cluster_b1;       // the fused dH launch sums dF's columns on the tensor core
     g[1] = GemmDesc(); g[1].dtype = dtype;    // dP[b][j][c] = sum_l F[b][j][l] dAGG[b][l][c]
     g[1].A = F; g[1].lda = s.l; g[1].a_bs = (int64_t)s.n * s.l;
     g[1].M = s.n; g[1].N = s.m; g[1].K = s.l; g[1].batch = s.B;
@@ -725,7 +730,6 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
     // ---- Sinkhorn backward: dP -> dS (+ score bias gradient) ----
     VPR_TRY(sinkhorn_bwd(S, p.dust_bin, U, V, dP, dS, dtype, gr.score_b1, s.B, s.n, s.m, s.iters, st));
 
-    const bool fused = dh_fused_supported(dtype, s.l, s.m, h);
     // dWt1[g,h] = dTF^T HT (token MLP, K = B): rides along with whichever split-K launch comes next
     GemmDesc gtok1 = GemmDesc(); gtok1.dtype = dtype;
     gtok1.A = dTF; gtok1.a_mn = 1; gtok1.lda = s.g; gtok1.B = HT; gtok1.b_mn = 1; gtok1.ldb = h; gtok1.M = s.g; gtok1.N = h;
@@ -739,9 +743,10 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         DhFusedDesc fd;
         fd.dF = dF; fd.dS = dS; fd.W1c = w1c; fd.W1s = w1s; fd.H = H; fd.dH = dH;
         fd.dW1c = gr.cluster_w1; fd.dW1s = gr.score_w1; fd.db0c = gr.cluster_b0; fd.db0s = gr.score_b0;
+        fd.db1c = gr.cluster_b1;
         fd.T = Tk; fd.hidden = h; fd.mask_scale = keep_scale;
         VPR_TRY(dh_fused_run(fd, st));
-        VPR_TRY(gemm_run(gtokh, st));
+        if (!fin_dht) VPR_TRY(gemm_run(gtokh, st));       // otherwise finalize_bwd_fast already produced dHT
     } else {
         // ---- second-layer weight gradients (split-K + fp32 reductions), one launch ----
         g[0] = GemmDesc(); g[0].dtype = dtype;    // dW1c[l,h] = dF^T H[:, :h]
@@ -768,7 +773,7 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         g[1].out = dH + h; g[1].out_kind = okT; g[1].ldo = 2 * h; g[1].mask = H + h; g[1].ld_mask = 2 * h; g[1].mask_scale = keep_scale;
         g[1].colsum = gr.score_b0;
         g[2] = gtokh;
-        VPR_TRY(gemm_run_group(g, 3, st));
+        VPR_TRY(gemm_run_group(g, fin_dht ? 2 : 3, st));      // finalize_bwd_fast already produced dHT
     }
     // ---- first-layer weight gradients: dW0[h,d] = dH^T X (two parameter tensors) and dWt0 = dHT^T t ----
     {

@@ -27,6 +27,7 @@ namespace vpr {
 
 static constexpr int SS_NT = SK_NT;       // 512 threads
 static constexpr int SS_PITCH = 80;       // floats per token row of the tile (64 used)
+static constexpr int SS_LDB = 8;          // 16-byte global loads in flight per thread
 static constexpr int SS_RED = 68;         // pitch of the cross-warp partial-sum rows (64 clusters + dustbin)
 static constexpr float SS_LO = 1e-20f, SS_HI = 1e20f;   // flushed-to-zero tile entries then cost < 1e-18 absolute
 
@@ -46,23 +47,36 @@ __device__ __forceinline__ float ss_load_tile(const float* __restrict__ Sb, floa
     const int tid = threadIdx.x;
     float bmax = -INFINITY;
     const int total = n * 16;
-    for (int i0 = 0; i0 < total; i0 += SS_NT) {
-        const int idx = i0 + tid;
-        const bool valid = idx < total;
-        const int j = valid ? (idx >> 4) : (n - 1);
-        const int cg = idx & 15;
-        float4 s4 = __ldg(reinterpret_cast<const float4*>(Sb + (size_t)j * 64) + cg);
-        s4.x *= VPR_L2E; s4.y *= VPR_L2E; s4.z *= VPR_L2E; s4.w *= VPR_L2E;
-        float mx = fmaxf(fmaxf(s4.x, s4.y), fmaxf(s4.z, s4.w));
+    // all global loads of a batch are issued before any of them is consumed: the tile arrives in one
+    // memory round trip instead of one per 512 x 16 bytes
+    for (int b0 = 0; b0 < total; b0 += SS_LDB * SS_NT) {
+        float4 buf[SS_LDB];
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        mx = fmaxf(mx, z2);
-        if (valid) {
-            float4 e4;
-            e4.x = fex2(s4.x - mx); e4.y = fex2(s4.y - mx); e4.z = fex2(s4.z - mx); e4.w = fex2(s4.w - mx);
-            *reinterpret_cast<float4*>(E + (size_t)j * SS_PITCH + cg * 4) = e4;
-            if (cg == 0) { mxs[j] = mx; dst[j] = fex2(z2 - mx); }
-            bmax = fmaxf(bmax, mx);
+        for (int u = 0; u < SS_LDB; ++u) {
+            const int idx = b0 + u * SS_NT + tid;
+            const int j = idx < total ? (idx >> 4) : (n - 1);
+            buf[u] = __ldg(reinterpret_cast<const float4*>(Sb + (size_t)j * 64) + (idx & 15));
+        }
+#pragma unroll
+        for (int u = 0; u < SS_LDB; ++u) {
+            const int idx = b0 + u * SS_NT + tid;
+            if (b0 + u * SS_NT >= total) break;                      // block-uniform
+            const bool valid = idx < total;
+            const int j = valid ? (idx >> 4) : (n - 1);
+            const int cg = idx & 15;
+            float4 s4 = buf[u];
+            s4.x *= VPR_L2E; s4.y *= VPR_L2E; s4.z *= VPR_L2E; s4.w *= VPR_L2E;
+            float mx = fmaxf(fmaxf(s4.x, s4.y), fmaxf(s4.z, s4.w));
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mx = fmaxf(mx, z2);
+            if (valid) {
+                float4 e4;
+                e4.x = fex2(s4.x - mx); e4.y = fex2(s4.y - mx); e4.z = fex2(s4.z - mx); e4.w = fex2(s4.w - mx);
+                *reinterpret_cast<float4*>(E + (size_t)j * SS_PITCH + cg * 4) = e4;
+                if (cg == 0) { mxs[j] = mx; dst[j] = fex2(z2 - mx); }
+                bmax = fmaxf(bmax, mx);
+            }
         }
     }
     return bmax;
@@ -305,21 +319,32 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
         const float4 a4 = *reinterpret_cast<const float4*>(aLast + cg * 4);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const int total = n * 16;
-        for (int i0 = 0; i0 < total; i0 += NT) {
-            const int idx = i0 + tid;
-            const bool valid = idx < total;
-            const int j = valid ? (idx >> 4) : (n - 1);
-            const float4 d4 = __ldg(reinterpret_cast<const float4*>(dPb + (size_t)j * 64) + cg);
-            const float4 e4 = *reinterpret_cast<const float4*>(E + (size_t)j * SS_PITCH + cg * 4);
-            const float bj = bvLast[j];
-            const float t0 = d4.x * e4.x, t1 = d4.y * e4.y, t2 = d4.z * e4.z, t3 = d4.w * e4.w;
-            float rs = t0 * a4.x + t1 * a4.y + t2 * a4.z + t3 * a4.w;
+        for (int b0 = 0; b0 < total; b0 += SS_LDB * NT) {
+            float4 dbuf[SS_LDB];
 #pragma unroll
-            for (int o = 1; o < 16; o <<= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-            if (valid) {
-                acc.x = fmaf(t0, bj, acc.x); acc.y = fmaf(t1, bj, acc.y);
-                acc.z = fmaf(t2, bj, acc.z); acc.w = fmaf(t3, bj, acc.w);
-                if (cg == 0) X[(size_t)(iters - 1) * np + j] = rs * bj * bj;      // dv^K_j * bv^K_j
+            for (int u = 0; u < SS_LDB; ++u) {
+                const int idx = b0 + u * NT + tid;
+                const int j = idx < total ? (idx >> 4) : (n - 1);
+                dbuf[u] = __ldg(reinterpret_cast<const float4*>(dPb + (size_t)j * 64) + cg);
+            }
+#pragma unroll
+            for (int u = 0; u < SS_LDB; ++u) {
+                const int idx = b0 + u * NT + tid;
+                if (b0 + u * NT >= total) break;                     // block-uniform
+                const bool valid = idx < total;
+                const int j = valid ? (idx >> 4) : (n - 1);
+                const float4 d4 = dbuf[u];
+                const float4 e4 = *reinterpret_cast<const float4*>(E + (size_t)j * SS_PITCH + cg * 4);
+                const float bj = bvLast[j];
+                const float t0 = d4.x * e4.x, t1 = d4.y * e4.y, t2 = d4.z * e4.z, t3 = d4.w * e4.w;
+                float rs = t0 * a4.x + t1 * a4.y + t2 * a4.z + t3 * a4.w;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+                if (valid) {
+                    acc.x = fmaf(t0, bj, acc.x); acc.y = fmaf(t1, bj, acc.y);
+                    acc.z = fmaf(t2, bj, acc.z); acc.w = fmaf(t3, bj, acc.w);
+                    if (cg == 0) X[(size_t)(iters - 1) * np + j] = rs * bj * bj;      // dv^K_j * bv^K_j
+                }
             }
         }
         acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
@@ -376,9 +401,20 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
             }
         }
         const float4 a4 = *reinterpret_cast<const float4*>(aLast + cg * 4);
-        for (int idx = tid; idx < n * 16; idx += NT) {
+        const int total = n * 16;
+        for (int b0 = 0; b0 < total; b0 += SS_LDB * NT) {
+          float4 dbuf[SS_LDB];                                   // dP again (L2-resident by now), batched
+#pragma unroll
+          for (int u = 0; u < SS_LDB; ++u) {
+              const int idx = b0 + u * NT + tid;
+              dbuf[u] = __ldg(reinterpret_cast<const float4*>(dPb + (size_t)(idx < total ? (idx >> 4) : (n - 1)) * 64) + cg);
+          }
+#pragma unroll
+          for (int u = 0; u < SS_LDB; ++u) {
+            const int idx = b0 + u * NT + tid;
+            if (idx >= total) break;
             const int j = idx >> 4;
-            const float4 d4 = __ldg(reinterpret_cast<const float4*>(dPb + (size_t)j * 64) + cg);
+            const float4 d4 = dbuf[u];
             const float4 e4 = *reinterpret_cast<const float4*>(E + (size_t)j * SS_PITCH + cg * 4);
             const float bj = bvLast[j];
             float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
@@ -410,6 +446,7 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
                 *reinterpret_cast<float4*>(dSb + (size_t)idx * 4) = make_float4(g0, g1, g2, g3);
             }
             bacc.x += g0; bacc.y += g1; bacc.z += g2; bacc.w += g3;
+          }
         }
     }
     if (d_bias != nullptr) {
