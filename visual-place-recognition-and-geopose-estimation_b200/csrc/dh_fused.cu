@@ -15,9 +15,9 @@
 // of a third MMA against a constant all-ones B (N = 16) that accumulates the column sums.  dW1 and db0
 // live in TMEM for the whole launch and are flushed once with fp32 reductions.
 //
-//   warp 0   : TMA producer (resident W1 slice once; per tile dF/dS rows into a 2-stage ring, H tile x2)
-//   warp 1   : tcgen05.mma issuer: dH MMA -> dW1 MMA (same stage) -> column-sum MMA of the previous tile
-//   warps 2-9: epilogue: tcgen05.ld -> scale -> bf16 -> mask (H tile in smem) -> swizzled staging -> TMA store
+//   warp 8   : TMA producer (resident W1 slice once; per tile dF/dS rows into a 2-stage ring, H tile x2)
+//   warp 9   : tcgen05.mma issuer: dH MMA -> dW1 MMA (same stage) -> column-sum MMA of the previous tile
+//   warps 0-7: epilogue: tcgen05.ld -> scale -> bf16 -> mask (H tile in smem) -> swizzled staging -> TMA store
 #include "common.cuh"
 #include "gemm.h"
 
@@ -29,6 +29,7 @@ int make_map(CUtensorMap* map, const void* ptr, int esize, int64_t inner, int64_
              int64_t bs, int box_inner, int box_rows, const char* what);
 
 static constexpr int DH_THREADS = 320;
+static constexpr int DH_W_PROD = 8, DH_W_MMA = 9;     // above the epilogue warps: the arbiter favours high warp ids
 static constexpr int DH_BOX = 128 * 128;                 // 128 rows x 128 B swizzled box (16 KB)
 static constexpr int DH_A_STAGE = 2 * DH_BOX;            // [128 tokens x 128 l] bf16 (score half uses one box)
 static constexpr int DH_A_STAGES = 2;
@@ -84,11 +85,11 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
     const int nj = ((int)gridDim.x - ct + nct - 1) / nct;    // CTAs that share this column slice
     const int kboxes = half == 0 ? 2 : 1;                    // K = 128 (l) or 64 (m)
 
-    if (warp == 0 && lane == 0) {
+    if (warp == DH_W_PROD && lane == 0) {
         tma_prefetch_desc(&tmF); tma_prefetch_desc(&tmS); tma_prefetch_desc(&tmW1c); tma_prefetch_desc(&tmW1s);
         tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmO);
     }
-    if (warp == 1) {
+    if (warp == DH_W_MMA) {
         if (lane == 0) {
             for (int s = 0; s < 2; ++s) {
                 mbar_init(afull(s), 1); mbar_init(aempty(s), 1);
@@ -111,7 +112,7 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp == 0) {
+    if (warp == DH_W_PROD) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             const CUtensorMap* tmA = half == 0 ? &tmF : &tmS;
@@ -135,7 +136,7 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
                     tma_load_3d(sM + (uint32_t)s * DH_MASK_BYTES + (uint32_t)i * DH_BOX, &tmH, mfull(s), col0 + i * 64, mt * 128, 0);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == DH_W_MMA) {
         // ------------------------------ MMA issuer ------------------------------
         if (lane == 0) {
             constexpr uint32_t idesc1 = make_idesc_bf16(128, 128, false, true);    // dH: A K-major, B MN-major
@@ -199,7 +200,7 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
         }
     } else {
         // ------------------------------ epilogue ------------------------------
-        const int ew = warp - 2;
+        const int ew = warp;
         const int q = warp & 3;
         const int eg = ew >> 2;                      // group 0: columns 0-63, group 1: columns 64-127 of the tile
         const bool issuer = ((ew & 3) == 0) && lane == 0;
@@ -297,7 +298,7 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == DH_W_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, DH_TM_COLS);
     }

@@ -1,13 +1,14 @@
 // Persistent, warp-specialised, grouped bf16 GEMM for sm_100a.
-//   warp 0      : TMA producer (cp.async.bulk.tensor, SWIZZLE_128B boxes into an mbarrier ring; in
+//   warp 8      : TMA producer (cp.async.bulk.tensor, SWIZZLE_128B boxes into an mbarrier ring; in
 //                 mask mode also the relu-mask tile of every output tile, double buffered)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (fp32 accumulators in TMEM,
+//   warp 9      : TMEM allocator + single-thread tcgen05.mma issuer (fp32 accumulators in TMEM,
 //                 double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 2..9  : epilogue, two groups of four warps (one warp per TMEM lane quarter) that take
+//   warps 0..7  : epilogue, two groups of four warps (one warp per TMEM lane quarter) that take
 //                 alternate 128-byte-wide output boxes: tcgen05.ld -> bias / relu / dropout / relu-mask
-//                 / column sums in registers -> SWIZZLE_128B staging box -> one elected thread issues
-//                 the TMA tile store (edges are clipped by the tensor map), or vector fp32
-//                 reductions straight from registers for split-K
+//                 / column sums in registers -> the warp's own 32-row SWIZZLE_128B staging box -> its
+//                 lane 0 issues the TMA tile store (edges are clipped by the tensor map); no
+//                 cross-warp barrier anywhere in the epilogue.  Split-K uses vector fp32 reductions
+//                 straight from registers
 // Operands may be K-major or MN-major in global memory (all four combinations), batched through
 // the third tensor-map dimension and split along K.  One launch runs up to MAX_GROUP independent
 // problems of the same operand layout / tile shape (the token-MLP GEMMs ride along with the
@@ -29,7 +30,11 @@ static constexpr int BK = 64;                   // 64 bf16 = 128 B = one swizzle
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
 static constexpr int GEMM_THREADS = 320;        // TMA warp, MMA warp, 8 epilogue warps
 static constexpr int EPI_WARPS = 8;
+// Roles by warp index.  The SM's warp arbiter favours the highest warp id of a scheduler, so the two
+// latency-critical single-thread roles sit ABOVE the epilogue warps they share schedulers with.
+static constexpr int W_PROD = 8, W_MMA = 9;
 static constexpr int BOX_BYTES = 128 * 128;     // 128 rows x 128 B: one swizzled TMA box
+static constexpr int WBOX_BYTES = 32 * 128;     // one epilogue warp's 32 rows of an output box
 static constexpr int MAX_GROUP = 4;
 static constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -75,8 +80,8 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int MASK_BOXES = BN / 64;                          // bf16 mask tile, 64 columns per box
     static constexpr int MASK_BYTES = MASK ? 2 * MASK_BOXES * BOX_BYTES : 0;
-    static constexpr int SBUF = (BN >= 256) ? 1 : 2;                    // staging boxes per epilogue group
-    static constexpr int STAGING_BYTES = 2 * SBUF * BOX_BYTES;
+    static constexpr int SBUF = (BN >= 256) ? 1 : 2;                    // staging boxes per epilogue warp
+    static constexpr int STAGING_BYTES = EPI_WARPS * SBUF * WBOX_BYTES;
     static constexpr int RING_BUDGET = SMEM_LIMIT - 1024 - MISC_SMEM_BYTES - MASK_BYTES - STAGING_BYTES;
     static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
@@ -89,8 +94,24 @@ struct TcCfg {
 };
 
 // Per-thread epilogue math on one 32-column chunk of one output row: alpha, bias, relu, dropout.
-__device__ __forceinline__ void epilogue_math32(const TcArgs& a, uint32_t flags, const uint32_t (&r)[32], float (&v)[32],
-                                                int b, int m, int n0) {
+// The 32 bias values of a chunk, fetched while the accumulator chunk is still on its way from TMEM.
+__device__ __forceinline__ void epilogue_bias32(const TcArgs& a, uint32_t flags, float (&bv)[32], int n0) {
+    if (flags & F_BIAS) {
+        if (n0 + 32 <= a.N) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n0) + j);
+                bv[4 * j] = bq.x; bv[4 * j + 1] = bq.y; bv[4 * j + 2] = bq.z; bv[4 * j + 3] = bq.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bv[i] = (n0 + i < a.N) ? __ldg(a.bias + n0 + i) : 0.f;
+        }
+    }
+}
+
+__device__ __forceinline__ void epilogue_math32(const TcArgs& a, uint32_t flags, const uint32_t (&r)[32], const float (&bv)[32],
+                                                float (&v)[32], int b, int m, int n0) {
     const int N = a.N;
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -100,17 +121,8 @@ __device__ __forceinline__ void epilogue_math32(const TcArgs& a, uint32_t flags,
         for (int i = 0; i < 32; ++i) v[i] *= al;
     }
     if (flags & F_BIAS) {
-        if (n0 + 32 <= N) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n0) + j);
-                v[4 * j] += bq.x; v[4 * j + 1] += bq.y; v[4 * j + 2] += bq.z; v[4 * j + 3] += bq.w;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (n0 + i < N) v[i] += __ldg(a.bias + n0 + i);
-        }
+        for (int i = 0; i < 32; ++i) v[i] += bv[i];
     }
     if (flags & F_RELU) {
 #pragma unroll
@@ -207,7 +219,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int w_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int w_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == W_PROD && lane == 0) {
         for (int g = 0; g < grp.count; ++g) {
             tma_prefetch_desc(&grp.p[g].tmA);
             tma_prefetch_desc(&grp.p[g].tmB);
@@ -215,7 +227,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             if (MASK && (grp.p[g].args.flags & F_MASK)) tma_prefetch_desc(&grp.p[g].tmM);
         }
     }
-    if (warp == 1) {
+    if (warp == W_MMA) {
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) {
                 mbar_init(full_bar(s), 1);
@@ -262,7 +274,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         kb1 = ((ks + 1) * a.kb_total) / a.k_splits;
     };
 
-    if (warp == 0) {
+    if (warp == W_PROD) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             int stage = 0;
@@ -315,7 +327,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
         // ------------------------------ MMA issuer ------------------------------
         if (lane == 0 && cta_rank == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(Cfg::TILE_M, BN, A_MN, B_MN);
@@ -356,11 +368,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
     } else {
         // ------------------------------ epilogue ------------------------------
-        const int ew = warp - 2;           // 0..7
+        const int ew = warp;               // 0..7
         const int q = warp & 3;            // TMEM lane quarter this warp may touch
         const int eg = ew >> 2;            // epilogue group: alternate output boxes / 32-column chunks
-        const bool issuer = ((ew & 3) == 0) && lane == 0;
-        const uint32_t my_staging = staging + (uint32_t)(eg * SBUF) * BOX_BYTES;
+        const uint32_t my_staging = staging + (uint32_t)(ew * SBUF) * WBOX_BYTES;      // 32 rows x 128 B, private
         const int row = q * 32 + lane;
         int nstore = 0;                    // boxes this group has stored so far
         int it = 0, mit = 0;
@@ -385,11 +396,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     const int n0 = nt * BN + c * 32;
                     if (n0 >= args.N) break;
                     uint32_t r[32];
-                    float v[32];
+                    float v[32], bv[32];
                     tmem_ld32(taddr + c * 32, r);
+                    epilogue_bias32(args, flags, bv, n0);
                     tmem_ld_wait();
                     if (m < args.M) {
-                        epilogue_math32(args, flags, r, v, b, m, n0);
+                        epilogue_math32(args, flags, r, bv, v, b, m, n0);
                         epilogue_atomic32(args, v, b, m, n0);
                     }
                 }
@@ -401,20 +413,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 if (masked) mbar_wait(mfull_bar(mb), (uint32_t)(mit >> 1) & 1u);
 #pragma unroll 1
                 for (int bx = eg; bx < nbox; bx += 2) {
-                    const uint32_t sbuf = my_staging + (uint32_t)(nstore % SBUF) * BOX_BYTES;
+                    const uint32_t sbuf = my_staging + (uint32_t)(nstore % SBUF) * WBOX_BYTES;
                     ++nstore;
-                    if (issuer) bulk_wait_read<SBUF - 1>();            // the box we are about to overwrite has been read
-                    named_bar_sync(1 + eg, 128);
+                    if (lane == 0) bulk_wait_read<SBUF - 1>();         // the box we are about to overwrite has been read
+                    __syncwarp();
                     const int cpb = bf ? 2 : 1;
 #pragma unroll 1
                     for (int c = 0; c < cpb; ++c) {
                         const int n0 = nt * BN + bx * box_cols + c * 32;
                         if (n0 >= args.N) break;
                         uint32_t r[32];
-                        float v[32];
+                        float v[32], bv[32];
                         tmem_ld32(taddr + bx * box_cols + c * 32, r);
+                        epilogue_bias32(args, flags, bv, n0);
                         tmem_ld_wait();
-                        epilogue_math32(args, flags, r, v, b, m, n0);
+                        epilogue_math32(args, flags, r, bv, v, b, m, n0);
                         if (bf) {
                             if (masked) {
                                 const float ms = args.mask_scale;
@@ -453,20 +466,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                             }
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box_addr(sbuf, row, c * 4 + j)),
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box_addr(sbuf, lane, c * 4 + j)),
                                              "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
                         } else {
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box_addr(sbuf, row, j)),
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box_addr(sbuf, lane, j)),
                                              "r"(__float_as_uint(v[4 * j])), "r"(__float_as_uint(v[4 * j + 1])),
                                              "r"(__float_as_uint(v[4 * j + 2])), "r"(__float_as_uint(v[4 * j + 3])) : "memory");
                         }
                     }
                     fence_proxy_async_smem();
-                    named_bar_sync(1 + eg, 128);
-                    if (issuer) {
-                        tma_store_3d(&grp.p[g].tmO, sbuf, nt * BN + bx * box_cols, m_base, b);
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&grp.p[g].tmO, sbuf, nt * BN + bx * box_cols, m_base + q * 32, b);
                         bulk_commit();
                     }
                 }
@@ -481,13 +494,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             }
             if (masked) ++mit;
         }
-        if (issuer) bulk_wait_read<0>();   // staging must outlive the last tile stores
+        if (lane == 0) bulk_wait_read<0>();   // staging must outlive the last tile stores
     }
 
     tc_fence_before();
     if (CTA2) cluster_sync_all();          // the leader's MMAs read the peer's shared memory and write its TMEM
     else __syncthreads();
-    if (warp == 1) {
+    if (warp == W_MMA) {
         tc_fence_after();
         if (CTA2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
         else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -775,9 +788,9 @@ static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
         if (g.b_mn) VPR_TRY(make_map(&p.tmB, g.B, 2, g.N, g.K, g.batch, g.ldb, g.b_bs, 64, 64, "GEMM operand B"));
         else        VPR_TRY(make_map(&p.tmB, g.B, 2, g.K, g.N, g.batch, g.ldb, g.b_bs, 64, cta2 ? bn / 2 : bn, "GEMM operand B"));
         if (g.out_kind == OUT_BF16)
-            VPR_TRY(make_map(&p.tmO, g.out, 2, g.N, g.M, g.batch, g.ldo, g.out_bs, 64, BM, "GEMM output"));
+            VPR_TRY(make_map(&p.tmO, g.out, 2, g.N, g.M, g.batch, g.ldo, g.out_bs, 64, 32, "GEMM output"));
         else if (g.out_kind == OUT_F32)
-            VPR_TRY(make_map(&p.tmO, g.out, 4, g.N, g.M, g.batch, g.ldo, g.out_bs, 32, BM, "GEMM output"));
+            VPR_TRY(make_map(&p.tmO, g.out, 4, g.N, g.M, g.batch, g.ldo, g.out_bs, 32, 32, "GEMM output"));
         if (g.mask != nullptr)
             VPR_TRY(make_map(&p.tmM, g.mask, 2, g.N, g.M, g.batch, g.ld_mask, g.mask_bs, 64, BM, "GEMM relu-mask"));
         TcArgs& a = p.args;

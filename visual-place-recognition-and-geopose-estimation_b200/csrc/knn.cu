@@ -28,6 +28,7 @@ static constexpr int K_LIST_BYTES = KMAX * KBM * 8;
 static constexpr int K_SMEM_BYTES = K_STAGES * K_STAGE_BYTES + K_LIST_BYTES + 1024 + 256;
 static_assert(K_SMEM_BYTES <= 227 * 1024, "kNN shared memory budget");
 static constexpr int K_THREADS = 192;
+static constexpr int K_W_PROD = 4, K_W_MMA = 5;        // above the 4 epilogue warps: the arbiter favours high warp ids
 
 struct KnnArgs {
     int Q, G, D, k;
@@ -55,8 +56,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = cluster_ctarank();                 // 0 = leader of the pair
     const int w_first = (int)(blockIdx.x >> 1), w_step = (int)(gridDim.x >> 1);
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmG); }
-    if (warp == 1) {
+    if (warp == K_W_PROD && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmG); }
+    if (warp == K_W_MMA) {
         if (lane == 0) {
             for (int s = 0; s < K_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
             for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }   // both CTAs' warps
@@ -89,7 +90,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if (nt1 > args.tiles_n) nt1 = args.tiles_n;
     };
 
-    if (warp == 0) {
+    if (warp == K_W_PROD) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             const uint32_t full0 = mapa_shared(full_bar(0), 0u);     // both producers credit the leader's barrier
@@ -108,7 +109,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                     }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == K_W_MMA) {
         if (lane == 0 && cta_rank == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(K_TILE_M, KBN, false, false);
             int stage = 0; uint32_t phase = 0; int it = 0;
@@ -207,7 +208,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
     tc_fence_before();
     cluster_sync_all();          // the leader's MMAs read the peer's shared memory and write its TMEM
-    if (warp == 1) { tc_fence_after(); tmem_dealloc_2sm(tmem_base, 512); }
+    if (warp == K_W_MMA) { tc_fence_after(); tmem_dealloc_2sm(tmem_base, 512); }
 }
 
 // Merge R sorted-or-not candidate lists of k entries per query into the global top-k
