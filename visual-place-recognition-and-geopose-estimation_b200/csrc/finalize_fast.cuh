@@ -60,16 +60,43 @@ __device__ __forceinline__ void fin_share(float4& x, int cpr) {
     }
 }
 
+// wt1 != nullptr: the token MLP's second layer TF[b, :] = HT[b, :] Wt1^T + bt1 is computed here (one image per
+// CTA, g dot products of length hid: a warp per output, lanes along k) and written to TF for the backward.
 template <typename T>
-__global__ void __launch_bounds__(256) finalize_fwd_fast(const float* __restrict__ AGG, const float* __restrict__ TF,
-                                                         T* __restrict__ out, int l, int m, int g) {
+__global__ void __launch_bounds__(256) finalize_fwd_fast(const float* __restrict__ AGG, float* __restrict__ TF,
+                                                         T* __restrict__ out, int l, int m, int g,
+                                                         const T* __restrict__ HT, const T* __restrict__ wt1,
+                                                         const float* __restrict__ bt1, int hid) {
     __shared__ __align__(16) float red[8][128];
     __shared__ __align__(16) float inv_c[128];
     __shared__ float wred[8];
     __shared__ float sc[4];
+    __shared__ __align__(16) float sht[1024];                  // HT row (hid <= 1024)
+    __shared__ float stf[1024];                                // TF row (g <= 1024)
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* A = AGG + (size_t)b * l * m;
     const float* t = TF + (size_t)b * g;
+    if (wt1 != nullptr) {
+        for (int i = tid; i < hid; i += 256) sht[i] = ldf1(HT + (size_t)b * hid + i);
+        __syncthreads();
+        for (int o = warp; o < g; o += 8) {
+            float acc = 0.f;
+            for (int k8 = lane * 8; k8 < hid; k8 += 256) {
+                float w[8];
+                ld8(wt1 + (size_t)o * hid + k8, w);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc = fmaf(w[i], sht[k8 + i], acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                const float v = acc + __ldg(bt1 + o);
+                stf[o] = v;
+                TF[(size_t)b * g + o] = v;
+            }
+        }
+        __syncthreads();
+        t = stf;
+    }
     T* o = out + (size_t)b * (g + l * m);
     const int nv = (l * m) >> 10, cpr = m >> 2, c0 = (tid % cpr) * 4;
     float4 a[FIN_MAXV];

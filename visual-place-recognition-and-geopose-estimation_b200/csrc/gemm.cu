@@ -723,10 +723,11 @@ static bool cta_pairs_enabled() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("VPR_GEMM_2CTA");
-        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+        v = (e != nullptr && e[0] == '0') ? 0 : (e != nullptr && e[0] == '2') ? 2 : 1;
     }
-    return v == 1;
+    return v >= 1;
 }
+static bool cta_pairs_forced() { cta_pairs_enabled(); const char* e = getenv("VPR_GEMM_2CTA"); return e != nullptr && e[0] == '2'; }
 
 static int auto_bn(int N) { return (N > 128) ? 256 : (N > 64) ? 128 : 64; }
 
@@ -748,7 +749,7 @@ static int plan_group(const GemmDesc* gs, int count, int& bn, bool& any_mask, bo
     bool single = false;
     // measured (tools/gemm_bench.py, B200): with the dropout epilogue the leader's MMA ends up waiting for the
     // slower of two CTAs' epilogues (100 us vs 90 us for H); the gradient GEMMs gain 8-12 % from pair tiles
-    for (int i = 0; i < count; ++i) single = single || gs[i].cta_pair == 2 || gs[i].dropout_p > 0.f;
+    for (int i = 0; i < count; ++i) single = single || gs[i].cta_pair == 2 || (gs[i].dropout_p > 0.f && !cta_pairs_forced());
     if (bn == 256 && !any_mask && !single && cta_pairs_enabled()) {
         double c1 = 0, c2 = 0;
         for (int i = 0; i < count; ++i) {

@@ -57,6 +57,19 @@ struct DhFusedDesc {
     float* db1c;                             // [128] fp32 column sums of dF (cluster_features.3.bias), or NULL
     long long T; int hidden; float mask_scale;
 };
+// SALAD forward, second layer: F = H[:, :h] W1c^T + b1c (bf16), S = H[:, h:] W1s^T + b1s (fp32), weights resident
+// in shared memory, H streamed once.  dtype bf16, l == 128, m == 64, hidden == 512.
+struct FsFwdDesc {
+    const void* H; const void* W1c; const void* W1s;     // [T, 2*hidden], [128, hidden], [64, hidden] bf16
+    const float* bias_f; const float* bias_s;            // [128], [64]
+    void* F; float* S;                                   // [T, 128] bf16, [T, 64] fp32
+    long long T; int hidden;
+    // token MLP second layer on two extra CTAs: TF[B, g] = HT[B, hidden] Wt1[g, hidden]^T + bias_t (g == 256)
+    const void* HT; const void* Wt1; const float* bias_t; float* TF; int B; int g;
+};
+bool fs_fwd_supported(int dtype, int l, int m, int hidden);
+int fs_fwd_run(const FsFwdDesc& d, cudaStream_t stream);
+
 bool dh_fused_supported(int dtype, int l, int m, int hidden);
 int dh_fused_run(const DhFusedDesc& d, cudaStream_t stream);
 // Up to 4 independent problems with the same dtype and operand layout in ONE launch.

@@ -623,16 +623,28 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
     g[1].out = HT; g[1].out_kind = okT; g[1].ldo = h; g[1].bias = p.token_b0; g[1].relu = 1;
     VPR_TRY(gemm_run_group(g, 2, st));
     // launch 2: F = H[:, :h] W1c^T + b1c [T, l]   S = H[:, h:] W1s^T + b1s [T, m] fp32   TF = HT Wt1^T + bt1 [B, g] fp32
-    g[0] = GemmDesc(); g[0].dtype = dtype;
-    g[0].A = H; g[0].lda = 2 * h; g[0].B = w1c; g[0].ldb = h; g[0].M = (int)Tk; g[0].N = s.l; g[0].K = h;
-    g[0].out = F; g[0].out_kind = okT; g[0].ldo = s.l; g[0].bias = p.cluster_b1;
-    g[1] = GemmDesc(); g[1].dtype = dtype;
-    g[1].A = H + h; g[1].lda = 2 * h; g[1].B = w1s; g[1].ldb = h; g[1].M = (int)Tk; g[1].N = s.m; g[1].K = h;
-    g[1].out = S; g[1].out_kind = OUT_F32; g[1].ldo = s.m; g[1].bias = p.score_b1;
-    g[2] = GemmDesc(); g[2].dtype = dtype;
-    g[2].A = HT; g[2].lda = h; g[2].B = wt1; g[2].ldb = h; g[2].M = s.B; g[2].N = s.g; g[2].K = h;
-    g[2].out = TF; g[2].out_kind = OUT_F32; g[2].ldo = s.g; g[2].bias = p.token_b1; g[2].bn = 128;
-    VPR_TRY(gemm_run_group(g, 3, st));
+    const bool fin_fast = finalize_fast_ok(s.l, s.m, s.g);
+    const bool fs_fused = s.g == 256 && fs_fwd_supported(dtype, s.l, s.m, h);
+    if (fs_fused) {
+        if constexpr (sizeof(T) == 2) {
+            FsFwdDesc fd;
+            fd.H = H; fd.W1c = w1c; fd.W1s = w1s; fd.bias_f = p.cluster_b1; fd.bias_s = p.score_b1;
+            fd.F = F; fd.S = S; fd.T = Tk; fd.hidden = h;
+            fd.HT = HT; fd.Wt1 = wt1; fd.bias_t = p.token_b1; fd.TF = TF; fd.B = s.B; fd.g = s.g;
+            VPR_TRY(fs_fwd_run(fd, st));
+        }
+    } else {
+        g[0] = GemmDesc(); g[0].dtype = dtype;
+        g[0].A = H; g[0].lda = 2 * h; g[0].B = w1c; g[0].ldb = h; g[0].M = (int)Tk; g[0].N = s.l; g[0].K = h;
+        g[0].out = F; g[0].out_kind = okT; g[0].ldo = s.l; g[0].bias = p.cluster_b1;
+        g[1] = GemmDesc(); g[1].dtype = dtype;
+        g[1].A = H + h; g[1].lda = 2 * h; g[1].B = w1s; g[1].ldb = h; g[1].M = (int)Tk; g[1].N = s.m; g[1].K = h;
+        g[1].out = S; g[1].out_kind = OUT_F32; g[1].ldo = s.m; g[1].bias = p.score_b1;
+        g[2] = GemmDesc(); g[2].dtype = dtype;
+        g[2].A = HT; g[2].lda = h; g[2].B = wt1; g[2].ldb = h; g[2].M = s.B; g[2].N = s.g; g[2].K = h;
+        g[2].out = TF; g[2].out_kind = OUT_F32; g[2].ldo = s.g; g[2].bias = p.token_b1; g[2].bn = 128;
+        VPR_TRY(gemm_run_group(g, 3, st));
+    }
     // P = sinkhorn(S)
     VPR_TRY(sinkhorn_fwd(S, p.dust_bin, P, dtype, U, V, s.B, s.n, s.m, s.iters, st));
     // AGG[b][l][c] = sum_j F[b][j][l] P[b][j][c]      both operands MN-major, K = tokens of image b
@@ -642,8 +654,8 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
     g[0].M = s.l; g[0].N = s.m; g[0].K = s.n; g[0].batch = s.B;
     g[0].out = AGG; g[0].out_kind = OUT_F32; g[0].ldo = s.m; g[0].out_bs = (int64_t)s.l * s.m;
     VPR_TRY(gemm_run(g[0], st));
-    if (finalize_fast_ok(s.l, s.m, s.g)) {
-        finalize_fwd_fast<T><<<s.B, 256, 0, st>>>(AGG, TF, out, s.l, s.m, s.g);
+    if (fin_fast) {
+        finalize_fwd_fast<T><<<s.B, 256, 0, st>>>(AGG, TF, out, s.l, s.m, s.g, HT, (const T*)nullptr, p.token_b1, h);
         return launch_ok("finalize_fwd_fast");
     }
     finalize_fwd_kernel<T><<<s.B, 256, 0, st>>>(AGG, TF, out, s.l, s.m, s.g);
