@@ -155,6 +155,53 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------
+# HBM-bound kernels (north_star: "achieved HBM GB/s for the Sinkhorn and norm kernels"): algorithmic bytes
+# (forward reads S fp32 and writes P, backward reads S and dP and writes dS, plus the
+# saved potentials) divided by the CUDA-event time of the launch alone, against the measured copy bandwidth.
+# ------------------------------------------------------------------------------------------
+def hbm_kernel_leg(dev, lib, L, B, n, peaks, flush, m=64, iters=3):
+    S = torch.randn(B, n, m, device=dev) * 2
+    dP = torch.randn(B, n, m, device=dev)
+    db = torch.ones(1, device=dev)
+    P = torch.empty(B, n, m, dtype=torch.bfloat16, device=dev)
+    dS = torch.empty(B, n, m, dtype=torch.bfloat16, device=dev)
+    U = torch.empty(B, iters, m + 1, device=dev)
+    V = torch.empty(B, iters, n, device=dev)
+    dbias = torch.zeros(m, device=dev)
+    st = L.stream_ptr(dev)
+
+    def fwd():
+        L.check(lib.vpr_sinkhorn_fwd(L.ptr(S), L.ptr(db), L.ptr(P), L.VPR_BF16, L.ptr(U), L.ptr(V), B, n, m, iters, st), "sinkhorn_fwd")
+
+    def bwd():
+        L.check(lib.vpr_sinkhorn_bwd(L.ptr(S), L.ptr(db), L.ptr(U), L.ptr(V), L.ptr(dP), L.ptr(dS), L.VPR_BF16, L.ptr(dbias),
+                                     B, n, m, iters, st), "sinkhorn_bwd")
+
+    def timed(fn):
+        ts = []
+        for i in range(3 + 8):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1))
+        return sum(ts) / len(ts)
+
+    pot = B * iters * (m + 1 + n) * 4
+    out = {}
+    for name, fn, nbytes in (("sinkhorn_fwd_scaled", fwd, B * n * m * (4 + 2) + pot),
+                             ("sinkhorn_bwd_scaled", bwd, B * n * m * (4 + 4 + 2) + pot)):
+        ms = timed(fn)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"bound": "hbm", "ms": ms, "bytes": nbytes, "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": gbs / peaks["hbm_gbs"]}
+    return out
+
+
+# ------------------------------------------------------------------------------------------
 # kNN leg (the second quantity BASELINE.json's metric names): queries/s of the fused GEMM + top-25
 # kernel over ONE GPU's gallery shard of configs[4] (10 M x 8448 bf16 sharded over 8 GPUs = 1.25 M
 # rows = 21 GB per GPU).  Every rank of the sharded job scans all queries against its own shard, so
@@ -370,6 +417,9 @@ def run_own(args, rank, local, world):
                 "step_tflops": flops_per_image(n) * B / (ms_step * 1e-3) / 1e12,
                 "step_frac_of_sustained": flops_per_image(n) * B / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]}
 
+    # ---------------- the HBM-bound kernels of the step, timed alone (L2 flushed) ----------------
+    hbm_kernels = hbm_kernel_leg(dev, lib, L, B, n, peaks, flush)
+
     # ---------------- descriptor kNN (BASELINE configs[4], this GPU's gallery shard) ----------------
     knn = None
     if not args.no_knn:
@@ -399,6 +449,7 @@ def run_own(args, rank, local, world):
         "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
+    line["hbm_kernels"] = hbm_kernels
     if knn is not None:
         line["knn"] = knn
     print(json.dumps(line), flush=True)
