@@ -151,7 +151,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": rate, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -452,10 +452,24 @@ def run_own(args, rank, local, world):
     line["hbm_kernels"] = hbm_kernels
     if knn is not None:
         line["knn"] = knn
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else this process (or NCCL's C code, which
+    prints its version banner to fd 1) writes during the run has been pointed at stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -476,8 +490,6 @@ def main():
         return
     if world > 1:
         import vpr_b200
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner out of the one-JSON-line stdout
         vpr_b200.init_distributed("nccl")
     run_own(args, rank, local, world)
     if world > 1:
