@@ -70,6 +70,18 @@ struct FsFwdDesc {
 bool fs_fwd_supported(int dtype, int l, int m, int hidden);
 int fs_fwd_run(const FsFwdDesc& d, cudaStream_t stream);
 
+// SALAD forward, last step, one CTA per image: AGG = F^T P on the tensor core fused with the descriptor assembly
+// (per-cluster L2 norm over l, token L2 norm, concat, global L2 norm).  dtype bf16, l == 128, m == 64.
+struct AggFwdDesc {
+    const void* F; const void* P;            // [B, n, 128], [B, n, 64] bf16
+    const float* TF;                         // [B, g] fp32
+    float* AGG;                              // [B, 128, 64] fp32 (kept for the backward)
+    void* out;                               // [B, g + 8192] bf16
+    int B, n, g;
+};
+bool agg_fwd_supported(int dtype, int l, int m, int g, int n);
+int agg_fwd_run(const AggFwdDesc& d, cudaStream_t stream);
+
 bool dh_fused_supported(int dtype, int l, int m, int hidden);
 int dh_fused_run(const DhFusedDesc& d, cudaStream_t stream);
 // Up to 4 independent problems with the same dtype and operand layout in ONE launch.

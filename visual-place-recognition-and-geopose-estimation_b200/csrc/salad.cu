@@ -647,6 +647,13 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
     }
     // P = sinkhorn(S)
     VPR_TRY(sinkhorn_fwd(S, p.dust_bin, P, dtype, U, V, s.B, s.n, s.m, s.iters, st));
+    if (agg_fwd_supported(dtype, s.l, s.m, s.g, s.n)) {
+        if constexpr (sizeof(T) == 2) {          // aggregation + descriptor assembly in one launch, one CTA per image
+            AggFwdDesc ad;
+            ad.F = F; ad.P = P; ad.TF = TF; ad.AGG = AGG; ad.out = out; ad.B = s.B; ad.n = s.n; ad.g = s.g;
+            return agg_fwd_run(ad, st);
+        }
+    }
     // AGG[b][l][c] = sum_j F[b][j][l] P[b][j][c]      both operands MN-major, K = tokens of image b
     g[0] = GemmDesc(); g[0].dtype = dtype;
     g[0].A = F; g[0].a_mn = 1; g[0].lda = s.l; g[0].a_bs = (int64_t)s.n * s.l;
