@@ -306,6 +306,22 @@ def test_graphed_step_matches_eager_and_redraws_dropout(vpr):
     assert rel(o2, o2e) < 1e-6
 
 
+@pytest.mark.parametrize("env", [{"VPR_DH_FUSED": "0", "VPR_FS_FUSED": "0", "VPR_AGG_FUSED": "0"},
+                                 {"VPR_GEMM_2CTA": "0"}])
+def test_generic_paths_still_match_when_the_fused_kernels_are_switched_off(vpr, env):
+    """The default head shape runs the column-owner / per-image fused kernels and CTA-pair tiles; other shapes fall
+    back to the generic grouped GEMMs.  Switch the fused kernels off (environment knobs read once per process, hence
+    a child process) and re-run the bf16 parity tests on the fallback path."""
+    import subprocess
+    import sys
+    child_env = dict(os.environ, **env)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "bf16_matches_oracle or full_size or graphed or gemm_epilogues"],
+                       cwd=root, env=child_env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_salad_error_behaviour(vpr):
     mod = vpr.SaladHead().cuda()
     with pytest.raises(ValueError, match="more patch tokens"):

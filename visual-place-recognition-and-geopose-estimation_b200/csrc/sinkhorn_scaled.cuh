@@ -55,7 +55,7 @@ __device__ __forceinline__ float ss_load_tile(const float* __restrict__ Sb, floa
         for (int u = 0; u < SS_LDB; ++u) {
             const int idx = b0 + u * SS_NT + tid;
             const int j = idx < total ? (idx >> 4) : (n - 1);
-            buf[u] = __ldg(reinterpret_cast<const float4*>(Sb + (size_t)j * 64) + (idx & 15));
+            buf[u] = __ldg(reinterpret_cast<const float4*>(Sb + j * 64) + (idx & 15));
         }
 #pragma unroll
         for (int u = 0; u < SS_LDB; ++u) {
@@ -73,7 +73,7 @@ __device__ __forceinline__ float ss_load_tile(const float* __restrict__ Sb, floa
             if (valid) {
                 float4 e4;
                 e4.x = fex2(s4.x - mx); e4.y = fex2(s4.y - mx); e4.z = fex2(s4.z - mx); e4.w = fex2(s4.w - mx);
-                *reinterpret_cast<float4*>(E + (size_t)j * SS_PITCH + cg * 4) = e4;
+                *reinterpret_cast<float4*>(E + j * SS_PITCH + cg * 4) = e4;
                 if (cg == 0) { mxs[j] = mx; dst[j] = fex2(z2 - mx); }
                 bmax = fmaxf(bmax, mx);
             }
@@ -93,7 +93,7 @@ __device__ __forceinline__ void ss_row_pass(const float* E, const float* dst, co
 #pragma unroll 4
     for (int j = part; j < n; j += SS_NT / 16) {
         const float xj = x[j];
-        const float4 e4 = *reinterpret_cast<const float4*>(E + (size_t)j * SS_PITCH + cg * 4);
+        const float4 e4 = *reinterpret_cast<const float4*>(E + j * SS_PITCH + cg * 4);
         acc.x = fmaf(e4.x, xj, acc.x); acc.y = fmaf(e4.y, xj, acc.y);
         acc.z = fmaf(e4.z, xj, acc.z); acc.w = fmaf(e4.w, xj, acc.w);
         if (cg == 0) accd = fmaf(dst[j], xj, accd);
@@ -132,7 +132,7 @@ __device__ __forceinline__ void ss_col_pass(const float* E, const float* dst, co
         const int j = j0 + jt;
         const bool valid = j < n;
         const int jj = valid ? j : n - 1;
-        const float* row = E + (size_t)jj * SS_PITCH;
+        const float* row = E + jj * SS_PITCH;
         float s = (q == 0) ? dst[jj] * ym : 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_fwd_scaled(const float* __r
     constexpr int NT = SS_NT, NW = SS_NT / 32;
     extern __shared__ __align__(16) float sk_smem[];
     float* E = sk_smem;                          // [n][SS_PITCH]
-    float* mxs = E + (size_t)n * SS_PITCH;       // [n]  per-token shift
+    float* mxs = E + n * SS_PITCH;       // [n]  per-token shift
     const int np = (n + 3) & ~3;                 // vectors padded so that everything stays 16-byte aligned
     float* dst = mxs + np;                       // [n]  dustbin column of E
     float* binv = dst + np;                      // [n]  2^(mx_j - B0) before the first pass, 1/s_j afterwards
@@ -230,16 +230,16 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_fwd_scaled(const float* __r
     for (int idx = tid; idx < n * 16; idx += NT) {
         const int j = idx >> 4;
         const float bj = binv[j];
-        const float4 e4 = *reinterpret_cast<const float4*>(E + (size_t)j * SS_PITCH + cg * 4);
+        const float4 e4 = *reinterpret_cast<const float4*>(E + j * SS_PITCH + cg * 4);
         const float p0 = e4.x * a4.x * bj, p1 = e4.y * a4.y * bj, p2 = e4.z * a4.z * bj, p3 = e4.w * a4.w * bj;
         if constexpr (sizeof(TP) == 2) {
             __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
             uint2 pk;
             pk.x = *reinterpret_cast<uint32_t*>(&lo);
             pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(Pb + (size_t)idx * 4) = pk;
+            *reinterpret_cast<uint2*>(Pb + idx * 4) = pk;
         } else {
-            *reinterpret_cast<float4*>(Pb + (size_t)idx * 4) = make_float4(p0, p1, p2, p3);
+            *reinterpret_cast<float4*>(Pb + idx * 4) = make_float4(p0, p1, p2, p3);
         }
     }
 }
@@ -256,15 +256,15 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
     const int iters = KIT > 0 ? KIT : iters_rt;
     extern __shared__ __align__(16) float sk_smem[];
     float* E = sk_smem;                                  // [n][SS_PITCH]
-    float* mxs = E + (size_t)n * SS_PITCH;               // [n]
+    float* mxs = E + n * SS_PITCH;               // [n]
     const int np = (n + 3) & ~3;
     float* dst = mxs + np;                               // [n]
     float* bv = dst + np;                                // [iters][np]  Wv^k = E * a^k_c * bv^k_j
-    float* bu = bv + (size_t)iters * np;                 // [iters][np]  Wu^k = E * a'^k_c * bu^k_j
-    float* X = bu + (size_t)iters * np;                  // [iters][np]  dv^k_j * bv^k_j
-    float* aK = X + (size_t)iters * np;                  // [iters][SS_RED]  a^k_c ; [64] dustbin of Wv ; [65] dustbin of Wu
-    float* Y = aK + (size_t)iters * SS_RED;              // [iters][SS_RED]  du^k_c * a'^k_c ; [64] dustbin
-    float* Ak = Y + (size_t)iters * SS_RED;              // [16]
+    float* bu = bv + iters * np;                 // [iters][np]  Wu^k = E * a'^k_c * bu^k_j
+    float* X = bu + iters * np;                  // [iters][np]  dv^k_j * bv^k_j
+    float* aK = X + iters * np;                  // [iters][SS_RED]  a^k_c ; [64] dustbin of Wv ; [65] dustbin of Wu
+    float* Y = aK + iters * SS_RED;              // [iters][SS_RED]  du^k_c * a'^k_c ; [64] dustbin
+    float* Ak = Y + iters * SS_RED;              // [16]
     float* red = Ak + 16;                                // [NW][SS_RED]
     float* wred = red + NW * SS_RED;                     // [32]
     float* scal = wred + 32;                             // [8]  7: guard flag
@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
                 const float vk = __ldg(V + ((size_t)b * iters + kk) * n + j) * VPR_L2E;
                 const float fv = fex2(vk + mj + Ak[kk]), fu = fex2(vprev + mj + Ak[kk]);
                 bad |= !(fv < SS_HI && fu < SS_HI);
-                bv[(size_t)kk * np + j] = fv;
-                bu[(size_t)kk * np + j] = fu;
+                bv[kk * np + j] = fv;
+                bu[kk * np + j] = fu;
                 vprev = vk;
             }
         }
@@ -311,8 +311,8 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
         return;
     }
     const int cg = tid & 15;
-    const float* aLast = aK + (size_t)(iters - 1) * SS_RED;
-    const float* bvLast = bv + (size_t)(iters - 1) * np;
+    const float* aLast = aK + (iters - 1) * SS_RED;
+    const float* bvLast = bv + (iters - 1) * np;
     // ---- G = dP * P (P = Wv^K):  dv^K_j = sum_c G_jc,  du^K_c = sum_j G_jc ----
     float du0 = 0.f, du1 = 0.f;       // warp 0: du of clusters lane, lane + 32 for the current iteration
     {
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
             for (int u = 0; u < SS_LDB; ++u) {
                 const int idx = b0 + u * NT + tid;
                 const int j = idx < total ? (idx >> 4) : (n - 1);
-                dbuf[u] = __ldg(reinterpret_cast<const float4*>(dPb + (size_t)j * 64) + cg);
+                dbuf[u] = __ldg(reinterpret_cast<const float4*>(dPb + j * 64) + cg);
             }
 #pragma unroll
             for (int u = 0; u < SS_LDB; ++u) {
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
                 const bool valid = idx < total;
                 const int j = valid ? (idx >> 4) : (n - 1);
                 const float4 d4 = dbuf[u];
-                const float4 e4 = *reinterpret_cast<const float4*>(E + (size_t)j * SS_PITCH + cg * 4);
+                const float4 e4 = *reinterpret_cast<const float4*>(E + j * SS_PITCH + cg * 4);
                 const float bj = bvLast[j];
                 const float t0 = d4.x * e4.x, t1 = d4.y * e4.y, t2 = d4.z * e4.z, t3 = d4.w * e4.w;
                 float rs = t0 * a4.x + t1 * a4.y + t2 * a4.z + t3 * a4.w;
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
                 if (valid) {
                     acc.x = fmaf(t0, bj, acc.x); acc.y = fmaf(t1, bj, acc.y);
                     acc.z = fmaf(t2, bj, acc.z); acc.w = fmaf(t3, bj, acc.w);
-                    if (cg == 0) X[(size_t)(iters - 1) * np + j] = rs * bj * bj;      // dv^K_j * bv^K_j
+                    if (cg == 0) X[(iters - 1) * np + j] = rs * bj * bj;      // dv^K_j * bv^K_j
                 }
             }
         }
@@ -361,9 +361,9 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
         __syncthreads();
     }
     for (int kk = iters - 1; kk >= 0; --kk) {
-        const float* ak = aK + (size_t)kk * SS_RED;
+        const float* ak = aK + kk * SS_RED;
         // du^k_c -= sum_j dv^k_j Wv^k_jc = a^k_c * sum_j E_jc x^k_j
-        ss_row_pass(E, dst, X + (size_t)kk * np, 1.f, n, red);
+        ss_row_pass(E, dst, X + kk * np, 1.f, n, red);
         __syncthreads();
         if (warp == 0) {
             float t0, t1, tm;
@@ -379,10 +379,10 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
         __syncthreads();
         // dv^{k-1}_j = - sum_c du^k_c Wu^k_jc = - bu^k_j * sum_c E_jc y^k_c
         if (kk > 0) {
-            const float* buk = bu + (size_t)kk * np;
-            const float* bvp = bv + (size_t)(kk - 1) * np;
-            float* Xp = X + (size_t)(kk - 1) * np;
-            ss_col_pass(E, dst, Y + (size_t)kk * SS_RED, n, [&](int j, float s) { Xp[j] = -buk[j] * s * bvp[j]; });
+            const float* buk = bu + kk * np;
+            const float* bvp = bv + (kk - 1) * np;
+            float* Xp = X + (kk - 1) * np;
+            ss_col_pass(E, dst, Y + kk * SS_RED, n, [&](int j, float s) { Xp[j] = -buk[j] * s * bvp[j]; });
             __syncthreads();
         }
     }
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
 #pragma unroll
           for (int u = 0; u < SS_LDB; ++u) {
               const int idx = b0 + u * NT + tid;
-              dbuf[u] = __ldg(reinterpret_cast<const float4*>(dPb + (size_t)(idx < total ? (idx >> 4) : (n - 1)) * 64) + cg);
+              dbuf[u] = __ldg(reinterpret_cast<const float4*>(dPb + (idx < total ? (idx >> 4) : (n - 1)) * 64) + cg);
           }
 #pragma unroll
           for (int u = 0; u < SS_LDB; ++u) {
@@ -415,13 +415,13 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
             if (idx >= total) break;
             const int j = idx >> 4;
             const float4 d4 = dbuf[u];
-            const float4 e4 = *reinterpret_cast<const float4*>(E + (size_t)j * SS_PITCH + cg * 4);
+            const float4 e4 = *reinterpret_cast<const float4*>(E + j * SS_PITCH + cg * 4);
             const float bj = bvLast[j];
             float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
             if (KIT > 0) {
 #pragma unroll
                 for (int kk = 0; kk < KR; ++kk) {
-                    const float xj = X[(size_t)kk * np + j], uj = bu[(size_t)kk * np + j];
+                    const float xj = X[kk * np + j], uj = bu[kk * np + j];
                     c0 = fmaf(ar[kk].x, xj, fmaf(yr[kk].x, uj, c0)); c1 = fmaf(ar[kk].y, xj, fmaf(yr[kk].y, uj, c1));
                     c2 = fmaf(ar[kk].z, xj, fmaf(yr[kk].z, uj, c2)); c3 = fmaf(ar[kk].w, xj, fmaf(yr[kk].w, uj, c3));
                 }
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
                 for (int kk = 0; kk < iters; ++kk) {
                     const float4 aa = *reinterpret_cast<const float4*>(aK + kk * SS_RED + cg * 4);
                     const float4 yy = *reinterpret_cast<const float4*>(Y + kk * SS_RED + cg * 4);
-                    const float xj = X[(size_t)kk * np + j], uj = bu[(size_t)kk * np + j];
+                    const float xj = X[kk * np + j], uj = bu[kk * np + j];
                     c0 = fmaf(aa.x, xj, fmaf(yy.x, uj, c0)); c1 = fmaf(aa.y, xj, fmaf(yy.y, uj, c1));
                     c2 = fmaf(aa.z, xj, fmaf(yy.z, uj, c2)); c3 = fmaf(aa.w, xj, fmaf(yy.w, uj, c3));
                 }
@@ -441,9 +441,9 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
                 uint2 pk;
                 pk.x = *reinterpret_cast<uint32_t*>(&lo);
                 pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                *reinterpret_cast<uint2*>(dSb + (size_t)idx * 4) = pk;
+                *reinterpret_cast<uint2*>(dSb + idx * 4) = pk;
             } else {
-                *reinterpret_cast<float4*>(dSb + (size_t)idx * 4) = make_float4(g0, g1, g2, g3);
+                *reinterpret_cast<float4*>(dSb + idx * 4) = make_float4(g0, g1, g2, g3);
             }
             bacc.x += g0; bacc.y += g1; bacc.z += g2; bacc.w += g3;
           }
