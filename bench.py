@@ -268,6 +268,9 @@ def run_own(args, rank, local, world):
     x_d, t_d, w_d = x_h.to(dev), t_h.to(dev), w_h.to(dev)
     params = list(head.parameters())
 
+    if world > 1 and not args.no_overlap:
+        # the head all-reduces its flat gradient buffer from inside backward, overlapped with the dX GEMM
+        vpr_b200.overlap_grad_allreduce(head, reserve_sms=args.reserve_sms)
     graphed = None if args.eager else vpr_b200.GraphedSaladStep(head, B, n)
 
     def fwd_bwd(x_tok, t, w):
@@ -286,8 +289,8 @@ def run_own(args, rank, local, world):
             out = head((f_map, tg))
             out.backward(w)
             dx = xg.grad
-        fin = vpr_b200.allreduce_grads(params, async_op=True) if world > 1 else (lambda: None)
-        fin()
+        if world > 1 and args.no_overlap:
+            vpr_b200.allreduce_grads(params, async_op=True)()
         return out, dx
 
     def barrier():
@@ -442,7 +445,8 @@ def run_own(args, rank, local, world):
                                f"g=256, 3 Sinkhorn iters, dropout 0.3 (train mode), batch {B} per GPU, "
                                + ("SaladHead + torch autograd (eager)" if graphed is None else
                                   "fwd+bwd replayed from one CUDA graph (vpr_b200.GraphedSaladStep)")
-                               + (", + NCCL allreduce of 1,411,009 head grads" if world > 1 else ""),
+                               + (", + NCCL allreduce of 1,411,009 head grads" + ("" if args.no_overlap else " overlapped with the dX GEMM")
+                                  if world > 1 else ""),
                    "per_gpu_batch": B, "global_batch": B * world, "n": n,
                    "l2": "working set per step (X 100 MB + H 134 MB + dH 134 MB ...) exceeds the 126 MB L2; "
                          "the isolated-kernel roofline timing flushes L2 with a 256 MB write between launches"},
@@ -478,6 +482,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--n", type=int, default=256)
     ap.add_argument("--eager", action="store_true", help="SaladHead + autograd per step instead of the CUDA-graph step")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: all-reduce after backward instead of inside it")
+    ap.add_argument("--reserve-sms", type=int, default=32, help="N>1: SMs the dX GEMM leaves to the collective")
     ap.add_argument("--no-knn", action="store_true", help="skip the kNN leg")
     ap.add_argument("--knn-queries", type=int, default=8192)
     ap.add_argument("--knn-gallery", type=int, default=1_250_000)

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define VPR_ABI_VERSION 2
+#define VPR_ABI_VERSION 3
 #if defined(__GNUC__)
 #define VPR_API __attribute__((visibility("default")))
 #else
@@ -109,7 +109,13 @@ VPR_API int vpr_counter_advance(uint64_t* counter, cudaStream_t stream);
 VPR_API int vpr_salad_bwd(const VprSaladParams* p, const void* x, const void* t, const void* d_out,
                   const void* save, void* workspace, size_t workspace_bytes, VprSaladGrads* grads,
                   void* dx, void* dt, const VprSaladShape* s, int dtype, float dropout_p,
-                  cudaStream_t stream);
+                  int phase, int reserve_sms, cudaStream_t stream);
+/* phase: VPR_BWD_ALL, or the same work in two calls -- VPR_BWD_PARAMS (every parameter gradient) then
+ * VPR_BWD_INPUTS (dx, dt) -- so that a data-parallel caller can start the gradient all-reduce between them;
+ * reserve_sms > 0 keeps that many SMs free of the input-gradient GEMM's persistent CTAs for the collective. */
+#define VPR_BWD_ALL 0
+#define VPR_BWD_PARAMS 1
+#define VPR_BWD_INPUTS 2
 
 /* The keep-mask ({0,1} bytes, [rows, cols]) the dropout epilogue uses for (seed). */
 VPR_API int vpr_dropout_mask(uint64_t seed, float p, int64_t rows, int64_t cols, uint8_t* out, cudaStream_t stream);

@@ -5,9 +5,10 @@ the directory name carries the reference's hyphenated name)."""
 from ._lib import LIB_PATH, lib  # noqa: F401
 from .heads import GeoposeHeads, sincos_to_degrees  # noqa: F401
 from .knn import knn_topk, knn_topk_sharded, merge_topk  # noqa: F401
-from .parallel import DataParallelStep, allreduce_grads, init_distributed, shard_range  # noqa: F401
+from .parallel import (DataParallelStep, allreduce_grads, init_distributed, overlap_grad_allreduce,  # noqa: F401
+                       shard_range)
 from .salad import GraphedSaladStep, SaladHead, dropout_keep_mask, sinkhorn, sinkhorn_backward  # noqa: F401
 
 __all__ = ["SaladHead", "GraphedSaladStep", "GeoposeHeads", "knn_topk", "knn_topk_sharded", "merge_topk", "sinkhorn",
-           "sinkhorn_backward", "dropout_keep_mask", "DataParallelStep", "allreduce_grads", "init_distributed",
+           "sinkhorn_backward", "dropout_keep_mask", "DataParallelStep", "allreduce_grads", "overlap_grad_allreduce", "init_distributed",
            "shard_range", "sincos_to_degrees", "lib", "LIB_PATH"]

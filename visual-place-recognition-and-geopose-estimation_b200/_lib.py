@@ -13,10 +13,11 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libvpr_b200.so")
 
 VPR_F32, VPR_BF16 = 0, 1
+BWD_ALL, BWD_PARAMS, BWD_INPUTS = 0, 1, 2
 OUT_F32, OUT_BF16, OUT_ATOMIC_F32 = 0, 1, 2
 LATLON_MSE, LATLON_HUBER = 0, 1
 ANGLE_NONE, ANGLE_ATAN2_MAAE, ANGLE_ACOS, ANGLE_MSE = 0, 1, 2, 3
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _fp = C.c_void_p
 
@@ -59,7 +60,8 @@ EXPORTS = {
                                 C.POINTER(SaladShape), C.c_int, C.c_float, C.c_uint64, _fp, _fp]),
     "vpr_counter_advance": (C.c_int, [_fp, _fp]),
     "vpr_salad_bwd": (C.c_int, [C.POINTER(SaladParams), _fp, _fp, _fp, _fp, _fp, C.c_size_t,
-                                C.POINTER(SaladGrads), _fp, _fp, C.POINTER(SaladShape), C.c_int, C.c_float, _fp]),
+                                C.POINTER(SaladGrads), _fp, _fp, C.POINTER(SaladShape), C.c_int, C.c_float,
+                                C.c_int, C.c_int, _fp]),
     "vpr_dropout_mask": (C.c_int, [C.c_uint64, C.c_float, C.c_int64, C.c_int64, _fp, _fp]),
     "vpr_sinkhorn_fwd": (C.c_int, [_fp, _fp, _fp, C.c_int, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     "vpr_sinkhorn_bwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, _fp, C.c_int, C.c_int, C.c_int,

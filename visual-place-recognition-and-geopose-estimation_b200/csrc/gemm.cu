@@ -817,12 +817,15 @@ static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
         VPR_REQUIRE(total < (1ll << 31), "too many tiles");
     }
     grp.total_work = (int)total;
+    int reserve = 0;
+    for (int i = 0; i < count; ++i) if (gs[i].reserve_sms > reserve) reserve = gs[i].reserve_sms;
+    if (reserve > num_sms() / 2) reserve = num_sms() / 2;
     int grid;
     if (cta2) {
-        const int pairs = num_sms() / 2;
+        const int pairs = (num_sms() - reserve) / 2;
         grid = 2 * (int)(total < pairs ? total : pairs);
     } else {
-        grid = (int)(total < num_sms() ? total : num_sms());
+        grid = (int)(total < num_sms() - reserve ? total : num_sms() - reserve);
     }
     if (bn == 256) return dispatch_major<256>(gs[0].a_mn, gs[0].b_mn, any_mask, cta2, grp, grid, st);
     if (bn == 128) return dispatch_major<128>(gs[0].a_mn, gs[0].b_mn, any_mask, cta2, grp, grid, st);

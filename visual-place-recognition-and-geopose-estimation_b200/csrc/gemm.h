@@ -35,6 +35,7 @@ struct GemmDesc {
     int k_splits = 1;              // > 1 requires OUT_ATOMIC_F32 (caller zeroes out)
     int bn = 0;                    // tcgen05 tile N (64/128/256); 0 = auto
     int cta_pair = 0;              // 0 = auto (256 x 256 CTA-pair tiles when N > 128), 2 = single-CTA tiles
+    int reserve_sms = 0;           // leave this many SMs without a persistent CTA (room for a concurrent collective)
 };
 
 // How a group will be tiled: tile shape and the number of tiles that run concurrently (SMs, or SM

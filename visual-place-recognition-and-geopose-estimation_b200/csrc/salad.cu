@@ -672,7 +672,7 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
 template <typename T>
 static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T* d_out, const char* save, char* ws,
                        VprSaladGrads& gr, T* dx, T* dt, const VprSaladShape& s, int dtype, float drop_p,
-                       cudaStream_t st) {
+                       int phase, int reserve_sms, cudaStream_t st) {
     const SavePlan sp = save_plan(s, dtype);
     const WorkPlan wp = work_plan(s, dtype);
     const int h = s.hidden;
@@ -690,6 +690,7 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
     const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     const int nsm = num_sms();
 
+    if (phase != VPR_BWD_INPUTS) {
     // zero every gradient buffer that is accumulated with atomics (adjacent buffers -> one memset)
     {
         struct Rng { float* p; size_t n; };
@@ -814,13 +815,17 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         g4[0].k_splits = ks; g4[1].k_splits = ks;
         VPR_TRY(gemm_run_group(g4, cnt, st));
     }
+    }   // phase != VPR_BWD_INPUTS
+    if (phase == VPR_BWD_PARAMS) return 0;
     // ---- input gradients: dX = dH W0cat, dt = dHT Wt0 ----
     {
+        GemmDesc g[2];
         int cnt = 0;
         if (dx != nullptr) {
             g[cnt] = GemmDesc(); g[cnt].dtype = dtype;
             g[cnt].A = dH; g[cnt].lda = 2 * h; g[cnt].B = w0cat; g[cnt].b_mn = 1; g[cnt].ldb = s.d; g[cnt].M = (int)Tk; g[cnt].N = s.d;
             g[cnt].K = 2 * h; g[cnt].out = dx; g[cnt].out_kind = okT; g[cnt].ldo = s.d;
+            g[cnt].reserve_sms = reserve_sms;
             ++cnt;
         }
         if (dt != nullptr) {
@@ -857,16 +862,17 @@ int vpr_salad_fwd(const VprSaladParams* p, const void* x, const void* t, void* o
 
 int vpr_salad_bwd(const VprSaladParams* p, const void* x, const void* t, const void* d_out, const void* save,
                   void* workspace, size_t workspace_bytes, VprSaladGrads* grads, void* dx, void* dt,
-                  const VprSaladShape* s, int dtype, float dropout_p, cudaStream_t stream) {
+                  const VprSaladShape* s, int dtype, float dropout_p, int phase, int reserve_sms, cudaStream_t stream) {
     VPR_REQUIRE(p && x && t && d_out && save && workspace && grads && s, "null argument");
+    VPR_REQUIRE(phase >= VPR_BWD_ALL && phase <= VPR_BWD_INPUTS && reserve_sms >= 0, "bad phase / reserve_sms");
     VPR_TRY(check_shape(*s, dtype));
     VPR_REQUIRE(workspace_bytes >= work_plan(*s, dtype).total, "workspace too small: %zu < %zu", workspace_bytes,
                 work_plan(*s, dtype).total);
     if (dtype == VPR_BF16)
         return salad_bwd_t<bf16>(*p, (const bf16*)x, (const bf16*)t, (const bf16*)d_out, (const char*)save,
-                                 (char*)workspace, *grads, (bf16*)dx, (bf16*)dt, *s, dtype, dropout_p, stream);
+                                 (char*)workspace, *grads, (bf16*)dx, (bf16*)dt, *s, dtype, dropout_p, phase, reserve_sms, stream);
     return salad_bwd_t<float>(*p, (const float*)x, (const float*)t, (const float*)d_out, (const char*)save,
-                              (char*)workspace, *grads, (float*)dx, (float*)dt, *s, dtype, dropout_p, stream);
+                              (char*)workspace, *grads, (float*)dx, (float*)dt, *s, dtype, dropout_p, phase, reserve_sms, stream);
 }
 
 int vpr_counter_advance(uint64_t* counter, cudaStream_t stream) {

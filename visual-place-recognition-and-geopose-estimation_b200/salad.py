@@ -39,7 +39,7 @@ class _SaladFn(torch.autograd.Function):
     """x_tok: [B, n, d] contiguous, t: [B, d]; params in _PARAM_ORDER (fp32, contiguous)."""
 
     @staticmethod
-    def forward(ctx, x_tok, t, shape_tuple, dropout_p, seed, seed_dev, *params):
+    def forward(ctx, x_tok, t, shape_tuple, dropout_p, seed, seed_dev, grad_hook, *params):
         lib = L.lib()
         B, n, d, hidden, m, l, g, iters = shape_tuple
         dt = L.dtype_code(x_tok.dtype)
@@ -55,6 +55,7 @@ class _SaladFn(torch.autograd.Function):
             L.check(lib.vpr_counter_advance(L.ptr(seed_dev), L.stream_ptr(dev)), "vpr_counter_advance")
         ctx.shape_tuple = shape_tuple
         ctx.dropout_p = float(dropout_p)
+        ctx.grad_hook = grad_hook
         ctx.save_for_backward(x_tok, t, save, *params)
         return out
 
@@ -78,13 +79,29 @@ class _SaladFn(torch.autograd.Function):
         ps = _params_struct(L.SaladParams, params)
         dx = torch.empty_like(x_tok) if ctx.needs_input_grad[0] else None
         dtok = torch.empty_like(t) if ctx.needs_input_grad[1] else None
-        L.check(lib.vpr_salad_bwd(C.byref(ps), L.ptr(x_tok), L.ptr(t), L.ptr(d_out), L.ptr(save), L.ptr(ws),
-                                  ws_bytes, C.byref(gs), L.ptr(dx), L.ptr(dtok), C.byref(shape), dt,
-                                  ctx.dropout_p, L.stream_ptr(dev)),
-                "vpr_salad_bwd")
-        pg = [gr.view_as(p) if ctx.needs_input_grad[6 + i] else None
+        def bwd(phase, reserve):
+            L.check(lib.vpr_salad_bwd(C.byref(ps), L.ptr(x_tok), L.ptr(t), L.ptr(d_out), L.ptr(save), L.ptr(ws),
+                                      ws_bytes, C.byref(gs), L.ptr(dx), L.ptr(dtok), C.byref(shape), dt,
+                                      ctx.dropout_p, phase, reserve, L.stream_ptr(dev)),
+                    "vpr_salad_bwd")
+
+        hook = ctx.grad_hook
+        if hook is None:
+            bwd(L.BWD_ALL, 0)
+        else:
+            # data parallel: every parameter gradient first, hand the flat buffer to the hook (it starts the
+            # all-reduce on the collective's stream), then the input-gradient GEMM on a few SMs less so that the
+            # collective's kernel finds room and the two overlap; finally order later work after the collective
+            fn, reserve = hook
+            bwd(L.BWD_PARAMS, 0)
+            work = fn(flat)
+            if dx is not None or dtok is not None:
+                bwd(L.BWD_INPUTS, int(reserve))
+            if work is not None:
+                work.wait()
+        pg = [gr.view_as(p) if ctx.needs_input_grad[7 + i] else None
               for i, (gr, p) in enumerate(zip(grads, params))]
-        return (dx, dtok, None, None, None, None, *pg)
+        return (dx, dtok, None, None, None, None, None, *pg)
 
 
 class SaladHead(nn.Module):
@@ -116,12 +133,21 @@ class SaladHead(nn.Module):
         self._step = 0
         self.seed = 0x5A1AD
         self._seed_dev = None          # device-side step counter (use_device_step_counter)
+        self._grad_hook = None         # (callable(flat_grads) -> work | None, reserve_sms); see set_grad_ready_hook
 
     def use_device_step_counter(self, enabled: bool = True) -> None:
         """Keep the dropout step counter on the device: the kernels add it to the seed and a one-thread kernel
         advances it after every training forward.  Needed when the forward is captured in a CUDA graph (a host
         counter would be frozen into the graph and every replay would draw the same mask)."""
         self._seed_dev = torch.zeros(1, dtype=torch.int64, device=self.dust_bin.device) if enabled else None
+
+    def set_grad_ready_hook(self, fn, reserve_sms: int = 32) -> None:
+        """``fn(flat)`` is called inside backward as soon as ALL parameter gradients (one flat fp32 buffer, the
+        ``p.grad`` views point into it) have been enqueued and before the input-gradient GEMM is launched; it may
+        start an asynchronous collective on ``flat`` and return its work handle (``.wait()`` is called after the
+        remaining launches).  ``reserve_sms`` SMs are kept free of the input-gradient GEMM for the collective's
+        kernel.  ``fn=None`` removes the hook.  See ``parallel.overlap_grad_allreduce``."""
+        self._grad_hook = None if fn is None else (fn, int(reserve_sms))
 
     def current_seed(self) -> int:
         """Seed the NEXT training forward will use (synchronises when the counter lives on the device)."""
@@ -175,7 +201,7 @@ class SaladHead(nn.Module):
             self._step += 1
         shape = (B, n, d, 512, self.num_clusters, self.cluster_dim, self.token_dim, self.sinkhorn_iters)
         self.last_seed = seed if seed_dev is None else None      # device counter: ask current_seed() before the call
-        return _SaladFn.apply(x_tok, t, shape, p_drop, seed, seed_dev, *[p.contiguous() for p in params])
+        return _SaladFn.apply(x_tok, t, shape, p_drop, seed, seed_dev, self._grad_hook, *[p.contiguous() for p in params])
 
 
 class GraphedSaladStep:
