@@ -282,11 +282,29 @@ static int knn_map(CUtensorMap* map, const void* ptr, int64_t rows, int D, int b
     return 0;
 }
 
-static void knn_plan(int64_t Q, int64_t G, int& tiles_m, int& tiles_n, int& chunks, int& tiles_per_chunk) {
+// query tiles per group: their operands must fit in about 80 MB of the 126 MB L2
+static int knn_q_group(int D, int tiles_m) {
+    const int pairs = num_sms() / 2;
+    long long qt = (80ll << 20) / ((long long)K_TILE_M * D * 2);
+    if (qt < 1) qt = 1;
+    if (qt > pairs) qt = pairs;
+    const int waves = (pairs + (int)qt - 1) / (int)qt;           // gallery chunks in flight
+    qt = pairs / waves;
+    if (qt > tiles_m) qt = tiles_m;
+    return (int)qt;
+}
+
+static void knn_plan(int64_t Q, int64_t G, int D, int& tiles_m, int& tiles_n, int& chunks, int& tiles_per_chunk) {
     tiles_m = (int)((Q + K_TILE_M - 1) / K_TILE_M);
     tiles_n = (int)((G + KBN - 1) / KBN);
-    // aim for >= 8 work items per CTA pair so the last wave is short, but keep >= 8 gallery tiles per chunk
-    int want = (8 * (num_sms() / 2) + tiles_m - 1) / tiles_m;
+    const int pairs = num_sms() / 2;
+    // aim for >= 8 work items per CTA pair so the last wave is short, and for enough chunks that ONE query group
+    // (q_group tiles x chunks work items) fills the machine -- otherwise two groups run side by side and their
+    // query tiles no longer fit in L2; but keep >= 8 gallery tiles per chunk
+    int want = (8 * pairs + tiles_m - 1) / tiles_m;
+    const int qg = knn_q_group(D, tiles_m);
+    const int fill = (pairs + qg - 1) / qg;
+    if (want < fill) want = fill;
     if (want < 1) want = 1;
     int max_chunks = (tiles_n + 7) / 8;
     if (max_chunks < 1) max_chunks = 1;
@@ -303,9 +321,8 @@ using namespace vpr;
 extern "C" {
 
 size_t vpr_knn_workspace_bytes(int64_t Q, int64_t G, int D, int k) {
-    (void)D;
     int tm, tn, ch, tpc;
-    knn_plan(Q, G, tm, tn, ch, tpc);
+    knn_plan(Q, G, D, tm, tn, ch, tpc);
     size_t off = 0;
     carve_size(off, (size_t)Q * ch * k * 4);
     carve_size(off, (size_t)Q * ch * k * 4);
@@ -322,18 +339,9 @@ int vpr_knn_topk(const void* q, const void* g, int64_t Q, int64_t G, int D, int 
     VPR_REQUIRE(workspace_bytes >= vpr_knn_workspace_bytes(Q, G, D, k), "workspace too small");
     KnnArgs a;
     a.Q = (int)Q; a.G = (int)G; a.D = D; a.k = k;
-    knn_plan(Q, G, a.tiles_m, a.tiles_n, a.chunks, a.tiles_per_chunk);
+    knn_plan(Q, G, D, a.tiles_m, a.tiles_n, a.chunks, a.tiles_per_chunk);
     a.kb_total = (D + KBK - 1) / KBK;
-    {   // query tiles per group: their operands must fit in about 80 MB of the 126 MB L2
-        const int pairs = num_sms() / 2;
-        long long qt = (80ll << 20) / ((long long)K_TILE_M * D * 2);
-        if (qt < 1) qt = 1;
-        if (qt > pairs) qt = pairs;
-        const int waves = (pairs + (int)qt - 1) / (int)qt;           // gallery chunks in flight
-        qt = pairs / waves;
-        if (qt > a.tiles_m) qt = a.tiles_m;
-        a.q_group = (int)qt;
-    }
+    a.q_group = knn_q_group(D, a.tiles_m);
     size_t off = 0;
     a.ws_score = (float*)((char*)workspace + carve_size(off, (size_t)Q * a.chunks * k * 4));
     a.ws_idx = (int*)((char*)workspace + carve_size(off, (size_t)Q * a.chunks * k * 4));
