@@ -49,6 +49,17 @@ int ensure_dynamic_smem(const void* kernel, size_t bytes) {
     return 0;
 }
 
+int side_branch(SideBranch** out) {
+    static thread_local SideBranch sb = {nullptr, nullptr, nullptr};
+    if (sb.stream == nullptr) {
+        VPR_CUDA_OK(cudaStreamCreateWithFlags(&sb.stream, cudaStreamNonBlocking));
+        VPR_CUDA_OK(cudaEventCreateWithFlags(&sb.fork, cudaEventDisableTiming));
+        VPR_CUDA_OK(cudaEventCreateWithFlags(&sb.join, cudaEventDisableTiming));
+    }
+    *out = &sb;
+    return 0;
+}
+
 }  // namespace vpr
 
 extern "C" {

@@ -43,6 +43,12 @@ void note_launch();   // counts kernel launches (vpr_launch_count)
 int ensure_dynamic_smem(const void* kernel, size_t bytes);
 #define VPR_SMEM_OK(kernel, bytes) VPR_TRY(::vpr::ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), (bytes)))
 
+// A side stream + fork/join events (thread-local, created on first use) for small launches that are off the
+// critical path of a call: fork after the producer on the caller's stream, join before the consumer.  Works
+// under stream capture (the side stream joins the capture and becomes a parallel branch of the graph).
+struct SideBranch { cudaStream_t stream; cudaEvent_t fork, join; };
+int side_branch(SideBranch** out);
+
 static inline int launch_ok(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(3, "launch %s: %s", what, cudaGetErrorString(e));

@@ -83,6 +83,18 @@ struct AggFwdDesc {
 bool agg_fwd_supported(int dtype, int l, int m, int g, int n);
 int agg_fwd_run(const AggFwdDesc& d, cudaStream_t stream);
 
+// SALAD backward, first step, one CTA per image: cluster part of the descriptor-assembly backward fused with
+// dF = P dAGG^T and dP = F dAGG (dAGG never leaves shared memory).  dtype bf16, l == 128, m == 64.
+struct AggBwdDesc {
+    const float* AGG; const float* TF; const void* d_out;    // [B,128,64] fp32, [B,g] fp32, [B, g+8192] bf16
+    const void* P; const void* F;                            // [B, n, 64], [B, n, 128] bf16
+    void* dF; float* dP;                                     // [B, n, 128] bf16, [B, n, 64] fp32
+    float* scal;                                             // [B, 4] norm scalars for the token-MLP backward
+    int B, n, g;
+};
+bool agg_bwd_supported(int dtype, int l, int m, int g);
+int agg_bwd_run(const AggBwdDesc& d, cudaStream_t stream);
+
 bool dh_fused_supported(int dtype, int l, int m, int hidden);
 int dh_fused_run(const DhFusedDesc& d, cudaStream_t stream);
 // Up to 4 independent problems with the same dtype and operand layout in ONE launch.

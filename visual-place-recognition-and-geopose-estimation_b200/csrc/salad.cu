@@ -521,7 +521,7 @@ struct SavePlan {
     size_t w0cat, w1c, w1s, wt0, wt1, b0cat, H, F, S, P, U, V, AGG, HT, TF, total;
 };
 struct WorkPlan {
-    size_t dAGG, dAGGT, dTF, dF, dP, dS, dH, dHT, total;
+    size_t dAGG, dAGGT, dTF, dF, dP, dS, dH, dHT, scal, total;
 };
 
 static SavePlan save_plan(const VprSaladShape& s, int dtype) {
@@ -561,6 +561,7 @@ static WorkPlan work_plan(const VprSaladShape& s, int dtype) {
     p.dS = carve_size(off, T * s.m * e);
     p.dH = carve_size(off, T * 2 * h * e);
     p.dHT = carve_size(off, (size_t)s.B * h * e);
+    p.scal = carve_size(off, (size_t)s.B * 4 * sizeof(float));
     p.total = (off + 255) & ~size_t(255);
     return p;
 }
@@ -710,10 +711,31 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         }
     }
 
+    GemmDesc g[3];
+    const int kb_tok = (int)((Tk + 63) / 64);
+    const bool fused = dh_fused_supported(dtype, s.l, s.m, h);
+    const bool fin_fast = finalize_fast_ok(s.l, s.m, s.g);
+    bool fin_dht = false;                                  // dHT already produced (finalize_bwd_fast / token_bwd_kernel)
+    SideBranch* side = nullptr;                            // token-MLP backward running beside the main chain
+    if (fused && h == 512 && s.g <= 1024 && sizeof(T) == 2 && agg_bwd_supported(dtype, s.l, s.m, s.g)) {
+        // ---- one CTA per image: cluster part of the norm backward + dF + dP (dAGG stays in shared memory) ----
+        float* scal = (float*)(ws + wp.scal);
+        AggBwdDesc ad;
+        ad.AGG = AGG; ad.TF = TF; ad.d_out = d_out; ad.P = P; ad.F = F; ad.dF = dF; ad.dP = dP; ad.scal = scal;
+        ad.B = s.B; ad.n = s.n; ad.g = s.g;
+        VPR_TRY(agg_bwd_run(ad, st));
+        // token-MLP part (dTF, dHT, two bias gradients): a small per-image kernel off the critical path
+        VPR_TRY(side_branch(&side));
+        VPR_CUDA_OK(cudaEventRecord(side->fork, st));
+        VPR_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        token_bwd_kernel<T><<<s.B, 256, 0, side->stream>>>(scal, TF, d_out, dTF, gr.token_b1, wt1, HT, dHT, gr.token_b0, s.g,
+                                                         s.l * s.m, h);
+        VPR_TRY(launch_ok("token_bwd_kernel"));
+        VPR_CUDA_OK(cudaEventRecord(side->join, side->stream));
+        fin_dht = true;
+    } else {
     // norms backward: d_out -> dAGG [B,l,m] (and its transpose [B,m,l]), dTF [B,g] (+ token_features.2.bias gradient)
     T* dAGGT = (T*)(ws + wp.dAGGT);
-    const bool fin_fast = finalize_fast_ok(s.l, s.m, s.g);
-    bool fin_dht = false;                                  // dHT already produced by finalize_bwd_fast
     if (fin_fast) {
         const size_t fsm = finalize_bwd_fast_smem<T>(s.l, s.m);
         VPR_SMEM_OK(finalize_bwd_fast<T>, fsm);
@@ -726,9 +748,6 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         VPR_TRY(launch_ok("finalize_bwd_kernel"));
     }
 
-    GemmDesc g[3];
-    const int kb_tok = (int)((Tk + 63) / 64);
-    const bool fused = dh_fused_supported(dtype, s.l, s.m, h);
     // ---- aggregation backward (one launch when the transposed dAGG is available) ----
     g[0] = GemmDesc(); g[0].dtype = dtype;    // dF[b][j][l] = sum_c P[b][j][c] dAGG[b][l][c]   (+ cluster bias gradient)
     g[0].A = P; g[0].lda = s.m; g[0].a_bs = (int64_t)s.n * s.m; g[0].B = dAGG; g[0].ldb = s.m; g[0].b_bs = (int64_t)s.l * s.m;
@@ -746,6 +765,7 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         g[1].B = dAGG; g[1].b_mn = 1; g[1].ldb = s.m; g[1].b_bs = (int64_t)s.l * s.m;
         VPR_TRY(gemm_run(g[0], st));
         VPR_TRY(gemm_run(g[1], st));
+    }
     }
     // ---- Sinkhorn backward: dP -> dS (+ score bias gradient) ----
     VPR_TRY(sinkhorn_bwd(S, p.dust_bin, U, V, dP, dS, dtype, gr.score_b1, s.B, s.n, s.m, s.iters, st));
@@ -795,6 +815,7 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         g[2] = gtokh;
         VPR_TRY(gemm_run_group(g, fin_dht ? 2 : 3, st));      // finalize_bwd_fast already produced dHT
     }
+    if (side != nullptr) VPR_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));      // dTF / dHT / token bias gradients are in
     // ---- first-layer weight gradients: dW0[h,d] = dH^T X (two parameter tensors) and dWt0 = dHT^T t ----
     {
         GemmDesc g4[4];
