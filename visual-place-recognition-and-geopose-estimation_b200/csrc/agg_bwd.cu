@@ -11,8 +11,8 @@
 // neither dAGG nor a transposed copy of it ever goes to HBM.  P[b] / F[b] arrive by TMA as 128-token
 // chunks (A operands, K-major); the same threads then drain the accumulators: dF as bf16, dP as fp32,
 // staged per warp and written with TMA tile stores.
-// The token-MLP part of the assembly backward (token_bwd_kernel, finalize_fast.cuh) needs only four scalars per
-// image from here; the caller runs it on a side branch next to the main chain.
+// The token part of the norm backward (dTF and its column sums) is done by the same threads while the first
+// chunk's MMAs run; the caller follows with the small masked dHT GEMM on a side branch.
 //
 //   warps 0-3: norm backward, then epilogue (one TMEM lane quarter each)   warp 4: TMA producer   warp 5: MMA issuer
 #include "common.cuh"
@@ -41,7 +41,8 @@ struct GbArgs {
     const float* AGG;        // [B, 128, 64] fp32
     const float* TF;         // [B, g] fp32
     const bf16* d_out;       // [B, g + 8192]
-    float* scal;             // [B, 4]: invN, invt, invN * (y . dy), that . dz_t   (for the token-MLP part)
+    bf16* dTF;               // [B, g]: gradient of the token-MLP output
+    float* g_bias_tok;       // [g] += column sums of dTF (token_features.2.bias gradient), or null
 };
 
 __device__ __forceinline__ float gb_colsum32(float (&v)[32], int lane) {
@@ -65,7 +66,7 @@ agg_bwd_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
     __shared__ float part[2][4][64];         // per-warp partial sums (sum a^2, sum a*dy) per cluster
     __shared__ float s_ic[64], s_dot[64];
     __shared__ float wred[2][4];
-    __shared__ float sc[2];
+    __shared__ float sc[5];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sDA = base + GB_STAGES * GB_STAGE;        // dAGG tile: [128 l rows][64 c] bf16, SWIZZLE_128B
     const uint32_t sStage = sDA + GB_BOX;
@@ -209,10 +210,8 @@ agg_bwd_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
             for (int k = 0; k < 2; ++k)
                 s_dot[lane + 32 * k] = invN * (icv[k] * qc[k] - ssc[k] * icv[k] * icv[k] * invN * s);
             if (lane == 0) {
-                sc[0] = invN; sc[1] = s;
-                float* so = args.scal + (size_t)b * 4;
-                so[0] = invN; so[1] = invt; so[2] = invN * s;
-                so[3] = invN * (psum * invt - tsum * invt * invt * invN * s);
+                sc[0] = invN; sc[1] = s; sc[2] = invt;
+                sc[3] = invN * (psum * invt - tsum * invt * invt * invN * s);      // that . dz_t
             }
         }
         named_bar_sync(1, 128);
@@ -240,6 +239,17 @@ agg_bwd_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(daready);
+        {   // token part of the norm backward (the MMAs of the first chunk run meanwhile)
+            const float invN = sc[0], ns = sc[0] * sc[1], invt = sc[2], dt_dot = sc[3];
+            bf16* dT = args.dTF + (size_t)b * args.g;
+            for (int i = tid; i < args.g; i += 128) {
+                const float th = __ldg(t + i) * invt;
+                const float dz = (__bfloat162float(dy[i]) - th * ns) * invN;
+                const float dti = (dz - th * dt_dot) * invt;
+                dT[i] = __float2bfloat16_rn(dti);
+                if (args.g_bias_tok != nullptr) atomicAdd(args.g_bias_tok + i, dti);
+            }
+        }
         // ------------------------------ epilogue: thread = token row of the chunk ------------------------------
         const uint32_t sbuf = sStage + (uint32_t)warp * GB_WBOX;
         for (int ch = 0; ch < chunks; ++ch) {
@@ -307,7 +317,8 @@ bool agg_bwd_supported(int dtype, int l, int m, int g) {
     static int enabled = -1;
     if (enabled < 0) {
         const char* e = getenv("VPR_AGG_FUSED");
-        enabled = (e != nullptr && e[0] == '0') ? 0 : 1;
+        const char* e2 = getenv("VPR_AGG_BWD_FUSED");
+        enabled = ((e != nullptr && e[0] == '0') || (e2 != nullptr && e2[0] == '0')) ? 0 : 1;
     }
     return enabled == 1 && dtype == DT_BF16 && l == 128 && m == 64 && g % 8 == 0;
 }
@@ -320,7 +331,7 @@ int agg_bwd_run(const AggBwdDesc& d, cudaStream_t st) {
     VPR_TRY(make_map(&tmDP, d.dP, 4, 64, d.n, d.B, 64, (int64_t)d.n * 64, 32, 32, "dP"));
     GbArgs a;
     a.n = d.n; a.g = d.g; a.AGG = d.AGG; a.TF = d.TF; a.d_out = reinterpret_cast<const bf16*>(d.d_out);
-    a.scal = d.scal;
+    a.dTF = reinterpret_cast<bf16*>(d.dTF); a.g_bias_tok = d.g_bias_tok;
     VPR_SMEM_OK(agg_bwd_kernel, GB_SMEM);
     agg_bwd_kernel<<<d.B, GB_THREADS, GB_SMEM, st>>>(tmP, tmF, tmDF, tmDP, a);
     return launch_ok("agg_bwd_kernel");

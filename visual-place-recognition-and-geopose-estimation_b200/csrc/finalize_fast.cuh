@@ -301,59 +301,4 @@ __global__ void __launch_bounds__(256) finalize_bwd_fast(const float* __restrict
     }
 }
 
-// Token-MLP part of the descriptor-assembly backward when the cluster part runs in agg_bwd_kernel: dTF from the
-// four per-image norm scalars that kernel exports, then the hidden-layer gradient dHT = (dTF Wt1) * (HT > 0) and
-// the two token bias gradients.  One CTA (256 threads) per image; hid == 512.
-template <typename T>
-__global__ void __launch_bounds__(256) token_bwd_kernel(const float* __restrict__ scal, const float* __restrict__ TF,
-                                                        const T* __restrict__ d_out, T* __restrict__ dTF,
-                                                        float* __restrict__ g_bias_tok, const T* __restrict__ wt1,
-                                                        const T* __restrict__ HT, T* __restrict__ dHT,
-                                                        float* __restrict__ g_bias_tok0, int g, int lm, int hid) {
-    __shared__ float sdt[1024];
-    __shared__ float spart[4][512];
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const float invN = scal[b * 4 + 0], invt = scal[b * 4 + 1], ns = scal[b * 4 + 2], dt_dot = scal[b * 4 + 3];
-    const float* t = TF + (size_t)b * g;
-    const T* dy = d_out + (size_t)b * (g + lm);
-    T* dT = dTF + (size_t)b * g;
-    for (int i = tid; i < g; i += 256) {
-        const float th = t[i] * invt;
-        const float dz = (ldf1(dy + i) - th * ns) * invN;
-        const float dti = (dz - th * dt_dot) * invt;
-        stf1(dT + i, dti);
-        sdt[i] = dti;
-        if (g_bias_tok != nullptr) atomicAdd(g_bias_tok + i, dti);
-    }
-    __syncthreads();
-    const int c8 = (tid & 63) * 8, ksl = tid >> 6;
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll 16
-    for (int k = ksl; k < g; k += 4) {
-        const float dk = sdt[k];
-        float w[8];
-        ld8(wt1 + (size_t)k * hid + c8, w);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(dk, w[i], acc[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) spart[ksl][c8 + i] = acc[i];
-    __syncthreads();
-    const int c2 = tid * 2;
-    float a0 = spart[0][c2] + spart[1][c2] + spart[2][c2] + spart[3][c2];
-    float a1 = spart[0][c2 + 1] + spart[1][c2 + 1] + spart[2][c2 + 1] + spart[3][c2 + 1];
-    const T* hp = HT + (size_t)b * hid + c2;
-    a0 = ldf1(hp) > 0.f ? a0 : 0.f;
-    a1 = ldf1(hp + 1) > 0.f ? a1 : 0.f;
-    T* op = dHT + (size_t)b * hid + c2;
-    stf1(op, a0);
-    stf1(op + 1, a1);
-    if (g_bias_tok0 != nullptr) {
-        atomicAdd(g_bias_tok0 + c2, ldf1(op));
-        atomicAdd(g_bias_tok0 + c2 + 1, ldf1(op + 1));
-    }
-}
-
 }  // namespace vpr

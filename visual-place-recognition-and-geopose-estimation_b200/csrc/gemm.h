@@ -89,7 +89,7 @@ struct AggBwdDesc {
     const float* AGG; const float* TF; const void* d_out;    // [B,128,64] fp32, [B,g] fp32, [B, g+8192] bf16
     const void* P; const void* F;                            // [B, n, 64], [B, n, 128] bf16
     void* dF; float* dP;                                     // [B, n, 128] bf16, [B, n, 64] fp32
-    float* scal;                                             // [B, 4] norm scalars for the token-MLP backward
+    void* dTF; float* g_bias_tok;                            // [B, g] bf16; [g] += column sums of dTF (or null)
     int B, n, g;
 };
 bool agg_bwd_supported(int dtype, int l, int m, int g);

@@ -521,7 +521,7 @@ struct SavePlan {
     size_t w0cat, w1c, w1s, wt0, wt1, b0cat, H, F, S, P, U, V, AGG, HT, TF, total;
 };
 struct WorkPlan {
-    size_t dAGG, dAGGT, dTF, dF, dP, dS, dH, dHT, scal, total;
+    size_t dAGG, dAGGT, dTF, dF, dP, dS, dH, dHT, total;
 };
 
 static SavePlan save_plan(const VprSaladShape& s, int dtype) {
@@ -561,7 +561,6 @@ static WorkPlan work_plan(const VprSaladShape& s, int dtype) {
     p.dS = carve_size(off, T * s.m * e);
     p.dH = carve_size(off, T * 2 * h * e);
     p.dHT = carve_size(off, (size_t)s.B * h * e);
-    p.scal = carve_size(off, (size_t)s.B * 4 * sizeof(float));
     p.total = (off + 255) & ~size_t(255);
     return p;
 }
@@ -716,23 +715,16 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
     const bool fused = dh_fused_supported(dtype, s.l, s.m, h);
     const bool fin_fast = finalize_fast_ok(s.l, s.m, s.g);
     bool fin_dht = false;                                  // dHT already produced (finalize_bwd_fast / token_bwd_kernel)
-    SideBranch* side = nullptr;                            // token-MLP backward running beside the main chain
+    SideBranch* side = nullptr;                            // token-MLP hidden gradient running beside the main chain
+    bool tok_side = false;
     if (fused && h == 512 && s.g <= 1024 && sizeof(T) == 2 && agg_bwd_supported(dtype, s.l, s.m, s.g)) {
         // ---- one CTA per image: cluster part of the norm backward + dF + dP (dAGG stays in shared memory) ----
-        float* scal = (float*)(ws + wp.scal);
         AggBwdDesc ad;
-        ad.AGG = AGG; ad.TF = TF; ad.d_out = d_out; ad.P = P; ad.F = F; ad.dF = dF; ad.dP = dP; ad.scal = scal;
+        ad.AGG = AGG; ad.TF = TF; ad.d_out = d_out; ad.P = P; ad.F = F; ad.dF = dF; ad.dP = dP;
+        ad.dTF = dTF; ad.g_bias_tok = gr.token_b1;
         ad.B = s.B; ad.n = s.n; ad.g = s.g;
         VPR_TRY(agg_bwd_run(ad, st));
-        // token-MLP part (dTF, dHT, two bias gradients): a small per-image kernel off the critical path
-        VPR_TRY(side_branch(&side));
-        VPR_CUDA_OK(cudaEventRecord(side->fork, st));
-        VPR_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
-        token_bwd_kernel<T><<<s.B, 256, 0, side->stream>>>(scal, TF, d_out, dTF, gr.token_b1, wt1, HT, dHT, gr.token_b0, s.g,
-                                                         s.l * s.m, h);
-        VPR_TRY(launch_ok("token_bwd_kernel"));
-        VPR_CUDA_OK(cudaEventRecord(side->join, side->stream));
-        fin_dht = true;
+        tok_side = true;
     } else {
     // norms backward: d_out -> dAGG [B,l,m] (and its transpose [B,m,l]), dTF [B,g] (+ token_features.2.bias gradient)
     T* dAGGT = (T*)(ws + wp.dAGGT);
@@ -767,9 +759,6 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         VPR_TRY(gemm_run(g[1], st));
     }
     }
-    // ---- Sinkhorn backward: dP -> dS (+ score bias gradient) ----
-    VPR_TRY(sinkhorn_bwd(S, p.dust_bin, U, V, dP, dS, dtype, gr.score_b1, s.B, s.n, s.m, s.iters, st));
-
     // dWt1[g,h] = dTF^T HT (token MLP, K = B): rides along with whichever split-K launch comes next
     GemmDesc gtok1 = GemmDesc(); gtok1.dtype = dtype;
     gtok1.A = dTF; gtok1.a_mn = 1; gtok1.lda = s.g; gtok1.B = HT; gtok1.b_mn = 1; gtok1.ldb = h; gtok1.M = s.g; gtok1.N = h;
@@ -778,6 +767,24 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
     GemmDesc gtokh = GemmDesc(); gtokh.dtype = dtype;
     gtokh.A = dTF; gtokh.lda = s.g; gtokh.B = wt1; gtokh.b_mn = 1; gtokh.ldb = h; gtokh.M = s.B; gtokh.N = h; gtokh.K = s.g;
     gtokh.out = dHT; gtokh.out_kind = okT; gtokh.ldo = h; gtokh.mask = HT; gtokh.ld_mask = h; gtokh.colsum = gr.token_b0;
+    if (tok_side) {
+        // dHT depends only on dTF: a few tiles on a side branch next to the Sinkhorn backward / fused dH launch
+        static int use_side = -1;
+        if (use_side < 0) { const char* e = getenv("VPR_TOKEN_SIDE"); use_side = (e != nullptr && e[0] == '0') ? 0 : 1; }
+        if (use_side) {
+            VPR_TRY(side_branch(&side));
+            VPR_CUDA_OK(cudaEventRecord(side->fork, st));
+            VPR_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+            VPR_TRY(gemm_run(gtokh, side->stream));
+            VPR_CUDA_OK(cudaEventRecord(side->join, side->stream));
+        } else {
+            VPR_TRY(gemm_run(gtokh, st));
+        }
+        fin_dht = true;
+    }
+    // ---- Sinkhorn backward: dP -> dS (+ score bias gradient) ----
+    VPR_TRY(sinkhorn_bwd(S, p.dust_bin, U, V, dP, dS, dtype, gr.score_b1, s.B, s.n, s.m, s.iters, st));
+
     if (fused) {
         // ---- one pass over H: dH, the second-layer weight gradients and the first-layer bias gradients ----
         DhFusedDesc fd;
