@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define VPR_ABI_VERSION 3
+#define VPR_ABI_VERSION 4
 #if defined(__GNUC__)
 #define VPR_API __attribute__((visibility("default")))
 #else
@@ -169,6 +169,40 @@ VPR_API int vpr_heads_loss_fwd_bwd(const VprHeadsParams* p, const void* desc, co
                            const float* angle_target_deg, float* latlon_pred, float* sincos_pred,
                            float* losses, VprHeadsGrads* grads, void* d_desc, void* workspace,
                            size_t workspace_bytes, const VprHeadsShape* s, int dtype, cudaStream_t stream);
+
+/* ---- backbone -> head seam: final LayerNorm + CLS/patch split + cast ----------
+ * Replaces, in one pass, [UPSTREAM] DINOv2 forward_features' `x_norm = self.norm(x)`,
+ * `x_norm[:, 0]` / `x_norm[:, 1 + registers:]` and the reshape/permute the reference's hub model does
+ * before its aggregator (reached from dinov2salad/dinov2salad_finetuning.py:36).
+ * hidden: [B, 1 + skip + n, d] (`dtype_in`, pre-LayerNorm); x_tok: [B, n, d], t: [B, d] (`dtype_out`);
+ * stats: [B * (1 + n), 2] fp32 (mean, rstd) or NULL when no backward will follow. */
+VPR_API int vpr_seam_ln_split_fwd(const void* hidden, const float* ln_weight, const float* ln_bias, float eps, void* x_tok,
+                          void* t, float* stats, int B, int n, int skip, int d, int dtype_in, int dtype_out,
+                          cudaStream_t stream);
+/* d_x_tok / d_t may be NULL (zero). d_hidden: [B, 1 + skip + n, d] (`dtype_in`), fully written.
+ * d_ln_weight / d_ln_bias: [d] fp32, overwritten (or NULL). */
+VPR_API int vpr_seam_ln_split_bwd(const void* hidden, const float* ln_weight, const float* stats, const void* d_x_tok,
+                          const void* d_t, void* d_hidden, float* d_ln_weight, float* d_ln_bias, int B, int n, int skip,
+                          int d, int dtype_in, int dtype_out, cudaStream_t stream);
+
+/* ---- validation metrics on the device ------------------------------------------
+ * vpr_metrics_latlon: pred/target [N,2] fp32; scaler_mean/scale [2] fp64 device pointers (StandardScaler mean_,
+ * scale_; NULL = identity), predictions are always de-normalised, targets only when `targets_scaled`
+ * (dinov2salad_validation.py:84-85 keeps them in original units, dinov2salad_finetuning_2.py:202-203 does not).
+ * out_sums [4] fp64 = sum dlat^2, sum dlon^2, sum |dlat|, sum |dlon|  ->  final_loss = 0.5*(s0+s1)/N
+ * (dinov2salad_validation.py:101), MSE = (s0+s1)/(2N), MAE = (s2+s3)/(2N) (dinov2salad_finetuning_2.py:211-215).
+ * vpr_metrics_angle: sincos_pred [N,2] fp32, true_deg [N] fp32, pred_deg [N] fp32 or NULL, out_sum [1] fp64 =
+ * sum of angular errors (MAAE = out_sum / N). cos_first = 0: [sin,cos], `% 360` on both
+ * (angle_prediction/dinov2salad/dino_v2_gemini.py:117-141); 1: [cos,sin], `(deg+360) % 360`
+ * (angle_prediction/efficient_net/validation_script.py:180-189).
+ * vpr_recall_at_k: idx [Q,k] int64 (vpr_knn_topk output), labels int64; ks [nk] int32 device pointer, nk <= 16;
+ * hits [nk] uint64 = queries with a same-label neighbour among their first ks[j]. No reference code. */
+VPR_API int vpr_metrics_latlon(const float* pred, const float* target, const double* scaler_mean, const double* scaler_scale,
+                       int targets_scaled, int64_t N, double* out_sums, cudaStream_t stream);
+VPR_API int vpr_metrics_angle(const float* sincos_pred, const float* true_deg, int cos_first, int64_t N, float* pred_deg,
+                      double* out_sum, cudaStream_t stream);
+VPR_API int vpr_recall_at_k(const int64_t* idx, const int64_t* gallery_label, const int64_t* query_label, int64_t Q, int k,
+                    int64_t G, const int* ks, int nk, unsigned long long* hits, cudaStream_t stream);
 
 /* ---- descriptor kNN ------------------------------------------------------------------- */
 VPR_API size_t vpr_knn_workspace_bytes(int64_t Q, int64_t G, int D, int k);

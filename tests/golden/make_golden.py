@@ -136,7 +136,76 @@ def make_salad():
     print("salad_golden.npz:", sorted(out))
 
 
+def metrics_inputs():
+    g = torch.Generator().manual_seed(77)
+    N = 203
+    train = torch.stack([17.44 + 0.01 * torch.randn(500, generator=g), 78.35 + 0.02 * torch.randn(500, generator=g)], 1)
+    tgt = torch.stack([17.44 + 0.01 * torch.randn(N, generator=g), 78.35 + 0.02 * torch.randn(N, generator=g)], 1)
+    pred_scaled = torch.randn(N, 2, generator=g)
+    cs = torch.randn(N, 2, generator=g)
+    cs[0] = torch.tensor([-1.0, 0.0])
+    cs[1] = torch.tensor([-2.0, -1e-5])
+    true_deg = torch.rand(N, generator=g) * 360.0
+    return train.double().numpy(), tgt.double().numpy(), pred_scaled.numpy(), cs, true_deg
+
+
+def make_metrics():
+    """dinov2salad_finetuning_2.py:202-215 (sklearn, targets scaled) and dinov2salad_validation.py:84-101 (targets in
+    original units), and the MAAE loop body of angle_prediction/efficient_net/validation_script.py:180-202."""
+    import math
+    from sklearn.metrics import mean_absolute_error, mean_squared_error
+    from sklearn.preprocessing import StandardScaler
+    train, tgt, pred_scaled, cs, true_deg = metrics_inputs()
+    scaler = StandardScaler()
+    scaler.fit(train)
+    out = {"scaler_mean": scaler.mean_, "scaler_scale": scaler.scale_}
+    tgt_scaled = scaler.transform(tgt).astype(np.float32)
+    preds_original = scaler.inverse_transform(pred_scaled)
+    targets_original = scaler.inverse_transform(tgt_scaled)
+    val_mse = mean_squared_error(targets_original, preds_original)
+    out["f2_mse"] = np.asarray(val_mse)
+    out["f2_rmse"] = np.asarray(math.sqrt(val_mse))
+    out["f2_mae"] = np.asarray(mean_absolute_error(targets_original, preds_original))
+    out["f2_mae_lat"] = np.asarray(mean_absolute_error(targets_original[:, 0], preds_original[:, 0]))
+    out["f2_mae_lon"] = np.asarray(mean_absolute_error(targets_original[:, 1], preds_original[:, 1]))
+    all_preds = np.vstack([scaler.inverse_transform(pred_scaled)])
+    all_targets = np.vstack([tgt.astype(np.float32)])
+    out["val_final_loss"] = np.asarray(
+        0.5 * (np.sum((all_preds[:, 0] - all_targets[:, 0]) ** 2) + np.sum((all_preds[:, 1] - all_targets[:, 1]) ** 2))
+        / len(all_preds))
+    preds_cos_sin = cs
+    pred_angle_rad = torch.atan2(preds_cos_sin[:, 1], preds_cos_sin[:, 0])
+    pred_angle_deg = torch.rad2deg(pred_angle_rad)
+    pred_angle_deg = (pred_angle_deg + 360.0) % 360.0
+    diff = torch.abs(pred_angle_deg - true_deg)
+    batch_angular_errors = torch.minimum(diff, 360.0 - diff)
+    out["maae_cos_sin"] = np.asarray(torch.sum(batch_angular_errors).item() / cs.size(0))
+    out["deg_cos_sin"] = pred_angle_deg.numpy()
+    np.savez(os.path.join(HERE, "metrics_golden.npz"), **out)
+    print("metrics_golden.npz:", sorted(out))
+
+
+def make_seam():
+    """HuggingFace Dinov2Model (random init): hidden_states[-1] is the input of its final LayerNorm and
+    last_hidden_state the output (the backbone for config 1)."""
+    from transformers import Dinov2Config, Dinov2Model
+    torch.manual_seed(5)
+    cfg = Dinov2Config(hidden_size=768, num_hidden_layers=2, num_attention_heads=12, mlp_ratio=4, patch_size=14,
+                       image_size=56)
+    model = Dinov2Model(cfg).eval()
+    with torch.no_grad():
+        model.layernorm.weight.copy_(1.0 + 0.1 * torch.randn(768))
+        model.layernorm.bias.copy_(0.1 * torch.randn(768))
+        o = model(pixel_values=torch.randn(2, 3, 56, 56), output_hidden_states=True)
+    np.savez_compressed(os.path.join(HERE, "seam_golden.npz"), hidden=o.hidden_states[-1].numpy(),
+                        out=o.last_hidden_state.numpy(), ln_w=model.layernorm.weight.detach().numpy(),
+                        ln_b=model.layernorm.bias.detach().numpy(), eps=np.asarray(cfg.layer_norm_eps))
+    print("seam_golden.npz:", tuple(o.last_hidden_state.shape), "eps", cfg.layer_norm_eps)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     make_heads()
     make_salad()
+    make_metrics()
+    make_seam()

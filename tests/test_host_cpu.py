@@ -6,6 +6,7 @@ import os
 import re
 import sys
 
+import numpy as np
 import pytest
 import torch
 import torch.multiprocessing as mp
@@ -90,6 +91,82 @@ def test_no_cpu_fallback(built):
         built.knn_topk(torch.randn(4, 64).bfloat16(), torch.randn(9, 64).bfloat16(), 3)
     with pytest.raises(RuntimeError, match="CUDA"):
         built.GeoposeHeads()(torch.randn(2, 8448), torch.randn(2, 2), torch.rand(2))
+
+
+def test_next_rows_have_no_cpu_fallback_either(built):
+    with pytest.raises(RuntimeError, match="CUDA"):
+        built.BackboneSeam()(torch.randn(2, 17, 768))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        built.latlon_metrics(torch.randn(4, 2), torch.randn(4, 2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        built.maae(torch.randn(4, 2), torch.rand(4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        built.recall_at_k(torch.zeros(4, 3, dtype=torch.int64), torch.zeros(4), torch.zeros(9))
+    model = built.DINOv2RegressionModel(torch.nn.Identity()).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(torch.randn(2, 8448))
+
+
+def test_scaler_mirrors_sklearn_and_joblib(built, tmp_path):
+    import joblib
+    from sklearn.preprocessing import StandardScaler
+    rng = np.random.default_rng(0)
+    latlon = np.stack([17.44 + 0.01 * rng.standard_normal(400), 78.35 + 0.02 * rng.standard_normal(400)], 1)
+    sk = StandardScaler().fit(latlon)                      # dinov2salad_finetuning.py:79-81
+    mine = built.LatLonScaler.fit(latlon)
+    np.testing.assert_allclose(mine.mean_, sk.mean_, rtol=1e-13)
+    np.testing.assert_allclose(mine.scale_, sk.scale_, rtol=1e-13)
+    z = rng.standard_normal((5, 2))
+    np.testing.assert_allclose(mine.inverse_transform(z), sk.inverse_transform(z), rtol=1e-13)
+    np.testing.assert_allclose(mine.transform(latlon[:5]), sk.transform(latlon[:5]), rtol=1e-9, atol=1e-9)
+    path = tmp_path / "latlon_scaler_x.pkl"
+    joblib.dump(sk, path)                                  # dinov2salad_finetuning.py:110-111
+    loaded = built.LatLonScaler.from_joblib(str(path))     # dinov2salad_validation.py:73
+    np.testing.assert_array_equal(loaded.mean_, sk.mean_)
+    np.testing.assert_allclose(loaded.to_sklearn().inverse_transform(z), sk.inverse_transform(z), rtol=1e-13)
+    t = torch.from_numpy(z)
+    np.testing.assert_allclose(mine.inverse_transform(t).numpy(), sk.inverse_transform(z), rtol=1e-13)
+
+
+def test_reference_model_wrapper_and_checkpoint_layout(built, tmp_path):
+    """dinov2salad_finetuning.py:21-37,130-135 / dinov2salad_validation.py:68-69 key layout, on CPU."""
+    from oracle.salad_ref import LatLonRegressorRef, SaladRef
+    torch.manual_seed(2)
+    ref, reg = SaladRef(), LatLonRegressorRef(8448, 512)
+    model = built.DINOv2RegressionModel(built.VPRModel(torch.nn.Identity(), built.SaladHead()))
+    assert all(not p.requires_grad for p in model.feature_extractor.parameters())
+    assert all(p.requires_grad for p in model.regressor.parameters())
+    keys = set(model.state_dict())
+    assert {"regressor.0.weight", "regressor.0.bias", "regressor.2.weight", "regressor.2.bias",
+            "feature_extractor.aggregator.dust_bin", "feature_extractor.aggregator.score.3.weight"} <= keys
+    assert {"regressor.0.weight", "regressor.3.weight"} <= set(
+        built.DINOv2RegressionModel(torch.nn.Identity(), dropout_prob=0.3).state_dict())   # finetuning_2.py:118-123
+    sd = {f"feature_extractor.aggregator.{k}": v.clone() for k, v in ref.state_dict().items()}
+    sd["feature_extractor.backbone.model.cls_token"] = torch.zeros(1, 1, 768)
+    sd.update({f"regressor.{k}": v.clone() for k, v in reg.regressor.state_dict().items()})
+    path = tmp_path / "checkpoint_7_.pth"
+    torch.save({"epoch": 7, "model_state_dict": sd, "optimizer_state_dict": {}, "loss": torch.tensor(0.5)}, path)
+    info = built.load_reference_checkpoint(model, str(path))
+    assert info["epoch"] == 7 and info["skipped"] == ["feature_extractor.backbone.model.cls_token"]
+    for k, v in ref.state_dict().items():
+        assert torch.equal(model.feature_extractor.aggregator.state_dict()[k], v)
+    assert torch.equal(model.regressor[2].bias, reg.regressor[2].bias)
+    bad = dict(sd)
+    del bad["regressor.2.bias"]
+    with pytest.raises(RuntimeError):
+        built.load_reference_checkpoint(model, {"model_state_dict": bad})
+    out = tmp_path / "checkpoint_8_.pth"
+    built.save_reference_checkpoint(str(out), model, None, 8, 0.25)
+    back = torch.load(out, weights_only=False)
+    assert set(back) == {"epoch", "model_state_dict", "optimizer_state_dict", "loss"} and back["epoch"] == 8
+    SaladRef().load_state_dict({k[len("feature_extractor.aggregator."):]: v for k, v in back["model_state_dict"].items()
+                                if k.startswith("feature_extractor.aggregator.")})
+    head = built.SaladHead()
+    flat = {f"aggregator.{k}": (v.flatten(1) if v.dim() == 4 else v) for k, v in ref.state_dict().items()}
+    built.load_upstream_salad_weights(head, {"state_dict": flat})      # Linear-shaped conv weights are accepted too
+    assert torch.equal(head.state_dict()["score.3.weight"], ref.state_dict()["score.3.weight"])
+    with pytest.raises(KeyError):
+        built.load_upstream_salad_weights(head, {"state_dict": {"backbone.x": torch.zeros(1)}})
 
 
 def test_product_never_imports_the_oracle():

@@ -188,3 +188,39 @@ def test_knn_ref_ties_and_merge():
     s2, i2 = O.knn_topk_ref(Q, G[250:], 25, g_offset=250)
     ms, mi = O.merge_topk(torch.cat([s1, s2], 1), torch.cat([i1, i2], 1), 25)
     assert torch.equal(mi, i) and torch.equal(ms, s)
+
+
+# ------------------------------------------------------------------ rows next to the path
+def test_seam_oracle_matches_huggingface_dinov2(golden_dir):
+    from oracle import extras_ref as X
+    z = np.load(os.path.join(golden_dir, "seam_golden.npz"))
+    x_tok, t = X.seam_ref(torch.from_numpy(z["hidden"]), torch.from_numpy(z["ln_w"]), torch.from_numpy(z["ln_b"]),
+                          float(z["eps"]))
+    out = torch.from_numpy(z["out"])
+    assert torch.allclose(x_tok, out[:, 1:], atol=1e-5) and torch.allclose(t, out[:, 0], atol=1e-5)
+
+
+def test_metric_oracles_match_reference_expressions(golden_dir):
+    from oracle import extras_ref as X
+    from tests.golden.make_golden import heads_inputs, metrics_inputs
+    z = np.load(os.path.join(golden_dir, "metrics_golden.npz"))
+    hg = np.load(os.path.join(golden_dir, "heads_golden.npz"))
+    train, tgt, pred_scaled, cs, true_deg = metrics_inputs()
+    mean, scale = z["scaler_mean"], z["scaler_scale"]
+    tgt_scaled = ((tgt - mean) / scale).astype(np.float32)
+    m = X.latlon_metrics_ref(pred_scaled, tgt_scaled, mean, scale, targets_scaled=True)
+    # the reference de-normalises in float32 (sklearn keeps the dtype of the float32 predictions) at magnitudes of
+    # 17.4 / 78.4 degrees, so its own numbers carry ~1e-5 relative rounding noise; the oracle works in float64
+    for key in ("mse", "rmse", "mae", "mae_lat", "mae_lon"):
+        np.testing.assert_allclose(m[key], float(z["f2_" + key]), rtol=1e-4)
+    m2 = X.latlon_metrics_ref(pred_scaled, tgt.astype(np.float32), mean, scale)
+    np.testing.assert_allclose(m2["final_loss"], float(z["val_final_loss"]), rtol=1e-4)
+    val, deg = X.maae_ref(cs, true_deg, "cos_sin")
+    np.testing.assert_allclose(val, float(z["maae_cos_sin"]), rtol=1e-6)
+    np.testing.assert_allclose(deg.numpy(), z["deg_cos_sin"], rtol=1e-6)
+    sc, tgt_deg, *_ = heads_inputs()
+    val2, _ = X.maae_ref(sc, tgt_deg, "sin_cos")
+    np.testing.assert_allclose(val2, float(hg["maae_atan2"]), rtol=1e-6)
+    idx = torch.tensor([[3, 1, 2], [0, 0, 0], [2, 3, 1]])
+    got = X.recall_at_k_ref(idx, torch.tensor([7, 9, 5]), torch.tensor([1, 7, 5, 8]), (1, 2, 3))
+    assert got == {1: 1 / 3, 2: 2 / 3, 3: 2 / 3}

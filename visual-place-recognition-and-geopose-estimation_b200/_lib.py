@@ -17,7 +17,7 @@ BWD_ALL, BWD_PARAMS, BWD_INPUTS = 0, 1, 2
 OUT_F32, OUT_BF16, OUT_ATOMIC_F32 = 0, 1, 2
 LATLON_MSE, LATLON_HUBER = 0, 1
 ANGLE_NONE, ANGLE_ATAN2_MAAE, ANGLE_ACOS, ANGLE_MSE = 0, 1, 2, 3
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _fp = C.c_void_p
 
@@ -70,6 +70,13 @@ EXPORTS = {
     "vpr_heads_loss_fwd_bwd": (C.c_int, [C.POINTER(HeadsParams), _fp, _fp, _fp, _fp, _fp, _fp,
                                          C.POINTER(HeadsGrads), _fp, _fp, C.c_size_t, C.POINTER(HeadsShape),
                                          C.c_int, _fp]),
+    "vpr_seam_ln_split_fwd": (C.c_int, [_fp, _fp, _fp, C.c_float, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, _fp]),
+    "vpr_seam_ln_split_bwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, _fp]),
+    "vpr_metrics_latlon": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int64, _fp, _fp]),
+    "vpr_metrics_angle": (C.c_int, [_fp, _fp, C.c_int, C.c_int64, _fp, _fp, _fp]),
+    "vpr_recall_at_k": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int, C.c_int64, _fp, C.c_int, _fp, _fp]),
     "vpr_knn_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int, C.c_int]),
     "vpr_knn_topk": (C.c_int, [_fp, _fp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int64, _fp, _fp, _fp,
                                C.c_size_t, _fp]),

@@ -33,12 +33,11 @@ def _run(desc, params, latlon_target, angle_target, cfg, want_d_desc):
                          cfg["global_B"] or B, cfg["reg_dropout_p"], cfg["seed"])
     ws_bytes = lib.vpr_heads_workspace_bytes(C.byref(shape), dt)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    w0, b0, w1, b1, wa, ba = params
-    sizes = [p.numel() for p in params]
+    sizes = [p.numel() if p is not None else 0 for p in params]      # the angle head may be absent (None, None)
     flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
     grads = list(torch.split(flat, sizes))
-    ps = L.HeadsParams(*[p.data_ptr() for p in params])
-    gs = L.HeadsGrads(*[g.data_ptr() for g in grads])
+    ps = L.HeadsParams(*[p.data_ptr() if p is not None else None for p in params])
+    gs = L.HeadsGrads(*[g.data_ptr() if p is not None else None for g, p in zip(grads, params)])
     latlon_pred = torch.empty(B, 2, dtype=torch.float32, device=dev)
     sincos_pred = torch.zeros(B, 2, dtype=torch.float32, device=dev)
     losses = torch.empty(2, dtype=torch.float32, device=dev)
@@ -47,7 +46,8 @@ def _run(desc, params, latlon_target, angle_target, cfg, want_d_desc):
                                        L.ptr(latlon_pred), L.ptr(sincos_pred), L.ptr(losses), C.byref(gs),
                                        L.ptr(d_desc), L.ptr(ws), ws_bytes, C.byref(shape), dt, L.stream_ptr(dev)),
             "vpr_heads_loss_fwd_bwd")
-    return latlon_pred, sincos_pred, losses, [g.view_as(p) for g, p in zip(grads, params)], d_desc, flat
+    return (latlon_pred, sincos_pred, losses, [g.view_as(p) if p is not None else None for g, p in zip(grads, params)],
+            d_desc, flat)
 
 
 class _HeadsLossFn(torch.autograd.Function):
@@ -55,7 +55,8 @@ class _HeadsLossFn(torch.autograd.Function):
     def forward(ctx, desc, latlon_target, angle_target, cfg, *params):
         latlon_pred, sincos_pred, losses, grads, d_desc, _ = _run(
             desc, params, latlon_target, angle_target, cfg, ctx.needs_input_grad[0])
-        ctx.save_for_backward(*( [d_desc] if d_desc is not None else [] ), *grads)
+        ctx.present = [g is not None for g in grads]
+        ctx.save_for_backward(*( [d_desc] if d_desc is not None else [] ), *[g for g in grads if g is not None])
         ctx.has_d_desc = d_desc is not None
         ctx.mark_non_differentiable(latlon_pred, sincos_pred, losses)
         total = losses[0] + losses[1] if cfg["angle"] != L.ANGLE_NONE else losses[0].clone()
@@ -67,7 +68,8 @@ class _HeadsLossFn(torch.autograd.Function):
         d_desc = saved.pop(0) if ctx.has_d_desc else None
         scale = g_total
         out_d = (d_desc * scale.to(d_desc.dtype)) if d_desc is not None else None
-        pg = [g * scale for g in saved]
+        it = iter(saved)
+        pg = [next(it) * scale if present else None for present in ctx.present]
         return (out_d, None, None, None, *pg)
 
 
