@@ -198,6 +198,34 @@ def hbm_kernel_leg(dev, lib, L, B, n, peaks, flush, m=64, iters=3):
         gbs = nbytes / (ms * 1e-3) / 1e9
         out[name] = {"bound": "hbm", "ms": ms, "bytes": nbytes, "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": gbs / peaks["hbm_gbs"]}
+    del S, dP, P, dS
+    # backbone->head seam (final LayerNorm + CLS/patch split + cast): 24 back-to-back launches over 4 rotating
+    # working sets (800 MB, so no launch finds its operands in L2), bf16 in / bf16 out
+    d, sets = 768, []
+    rows = B * (1 + n)
+    for _ in range(4):
+        sets.append((torch.randn(B, 1 + n, d, device=dev).bfloat16(), torch.empty(B, n, d, dtype=torch.bfloat16, device=dev),
+                     torch.empty(B, d, dtype=torch.bfloat16, device=dev)))
+    w, b = torch.ones(d, device=dev), torch.zeros(d, device=dev)
+
+    def seam(i):
+        h, x, t = sets[i % 4]
+        L.check(lib.vpr_seam_ln_split_fwd(L.ptr(h), L.ptr(w), L.ptr(b), 1e-6, L.ptr(x), L.ptr(t), None, B, n, 0, d, L.VPR_BF16,
+                                          L.VPR_BF16, st), "seam_fwd")
+    for i in range(4):
+        seam(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(24):
+        seam(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 24
+    nbytes = rows * d * 4
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    out["seam_fwd_kernel"] = {"bound": "hbm", "ms": ms, "bytes": nbytes, "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                              "frac": gbs / peaks["hbm_gbs"]}
     return out
 
 

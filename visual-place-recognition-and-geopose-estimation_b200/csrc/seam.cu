@@ -151,10 +151,12 @@ seam_fwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, 
     }
 }
 
-// d_hidden = LN backward of (d_x_tok, d_t); register-token rows get zero.  dgamma / dbeta accumulate with atomics
-// (the caller zeroes them).  Grid-stride over rows so that each CTA issues its atomics once.
+// d_hidden = LN backward of (d_x_tok, d_t); register-token rows get zero.  dgamma / dbeta accumulate in registers over
+// the rows a warp walks, are combined per CTA in shared memory and leave with one atomic per element per CTA
+// (the caller zeroes them).  A row's x and dy slices stay packed in registers and are unpacked twice (once for the
+// two row sums, once for the output) so the next row's loads can already be in flight.
 template <typename TI, typename TO, int NCH>
-__global__ void __launch_bounds__(SEAM_WARPS * 32)
+__global__ void __launch_bounds__(SEAM_WARPS * 32, NCH <= 4 ? 2 : 1)
 seam_bwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, const float* __restrict__ stats,
                 const TO* __restrict__ d_x_tok, const TO* __restrict__ d_t, TI* __restrict__ d_hidden,
                 float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int n, int skip, int d) {
@@ -167,22 +169,50 @@ seam_bwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, 
     for (int c = 0; c < NCH; ++c)
 #pragma unroll
         for (int i = 0; i < 8; ++i) { ag[c][i] = 0.f; ab[c][i] = 0.f; }
-    for (long long r = (long long)blockIdx.x * SEAM_WARPS + warp; r < rows; r += (long long)gridDim.x * SEAM_WARPS) {
-        const SeamRow rw = seam_row(r, n, skip);
+    typedef typename RawOf<TI>::type RawI;
+    typedef typename RawOf<TO>::type RawO;
+    RawI nxx[NCH];
+    RawO nxd[NCH];
+    bool nx_has_dy = false;
+    float nx_mean = 0.f, nx_rstd = 0.f;
+    const long long stride = (long long)gridDim.x * SEAM_WARPS;
+    long long r = (long long)blockIdx.x * SEAM_WARPS + warp;
+    auto issue = [&](long long rr) {
+        const SeamRow rw = seam_row(rr, n, skip);
         const TI* x = hidden + rw.in_row * d;
-        TI* dx = d_hidden + rw.in_row * d;
         const TO* dy = rw.tok_row < 0 ? (d_t != nullptr ? d_t + (long long)rw.b * d : nullptr)
                                       : (d_x_tok != nullptr ? d_x_tok + rw.tok_row * d : nullptr);
-        const float mean = stats[2 * r], rstd = stats[2 * r + 1];
-        float xh[NCH][8], g[NCH][8];
+        nx_has_dy = dy != nullptr;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int e = c * 256 + lane * 8;
+            if (e < d) {
+                seam_ldraw(x + e, nxx[c]);
+                if (nx_has_dy) seam_ldraw(dy + e, nxd[c]);
+            }
+        }
+        nx_mean = __ldg(stats + 2 * rr);
+        nx_rstd = __ldg(stats + 2 * rr + 1);
+    };
+    if (r < rows) issue(r);
+    for (; r < rows; r += stride) {
+        RawI cx[NCH];
+        RawO cd[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) { cx[c] = nxx[c]; cd[c] = nxd[c]; }
+        const bool has_dy = nx_has_dy;
+        const float mean = nx_mean, rstd = nx_rstd;
+        if (r + stride < rows) issue(r + stride);
+        const SeamRow rw = seam_row(r, n, skip);
+        TI* dx = d_hidden + rw.in_row * d;
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int e = c * 256 + lane * 8;
             if (e < d) {
                 float xv[8], dv[8], gm[8];
-                seam_ld8(x + e, xv);
-                if (dy != nullptr) seam_ld8(dy + e, dv);
+                seam_unpack(cx[c], xv);
+                if (has_dy) seam_unpack(cd[c], dv);
                 else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dv[i] = 0.f;
@@ -190,11 +220,10 @@ seam_bwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, 
                 seam_ldg8(gamma + e, gm);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    xh[c][i] = (xv[i] - mean) * rstd;
-                    g[c][i] = dv[i] * gm[i];
-                    s1 += g[c][i];
-                    s2 = fmaf(g[c][i], xh[c][i], s2);
-                    ag[c][i] = fmaf(dv[i], xh[c][i], ag[c][i]);
+                    const float xh = (xv[i] - mean) * rstd, g = dv[i] * gm[i];
+                    s1 += g;
+                    s2 = fmaf(g, xh, s2);
+                    ag[c][i] = fmaf(dv[i], xh, ag[c][i]);
                     ab[c][i] += dv[i];
                 }
             }
@@ -204,9 +233,16 @@ seam_bwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, 
         for (int c = 0; c < NCH; ++c) {
             const int e = c * 256 + lane * 8;
             if (e < d) {
-                float o[8];
+                float xv[8], dv[8], gm[8], o[8];
+                seam_unpack(cx[c], xv);
+                if (has_dy) seam_unpack(cd[c], dv);
+                else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = rstd * (g[c][i] - m1 - xh[c][i] * m2);
+                    for (int i = 0; i < 8; ++i) dv[i] = 0.f;
+                }
+                seam_ldg8(gamma + e, gm);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = rstd * (dv[i] * gm[i] - m1 - (xv[i] - mean) * rstd * m2);
                 seam_st8(dx + e, o);
             }
         }
@@ -243,8 +279,7 @@ static int seam_fwd_launch(const void* hidden, const float* g, const float* b, f
 template <typename TI, typename TO, int NCH>
 static int seam_bwd_launch(const void* hidden, const float* g, const float* stats, const void* dx_tok, const void* dt,
                            void* d_hidden, float* dg, float* db, long long rows, int n, int skip, int d, cudaStream_t st) {
-    long long want = (rows + SEAM_WARPS - 1) / SEAM_WARPS;
-    const long long cap = (long long)num_sms() * 8;
+    const long long want = (rows + SEAM_WARPS - 1) / SEAM_WARPS, cap = (long long)num_sms() * (NCH <= 4 ? 2 : 1);
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     seam_bwd_kernel<TI, TO, NCH><<<grid, SEAM_WARPS * 32, 0, st>>>((const TI*)hidden, g, stats, (const TO*)dx_tok, (const TO*)dt,
                                                                    (TI*)d_hidden, dg, db, rows, n, skip, d);
