@@ -204,6 +204,17 @@ VPR_API int vpr_metrics_angle(const float* sincos_pred, const float* true_deg, i
 VPR_API int vpr_recall_at_k(const int64_t* idx, const int64_t* gallery_label, const int64_t* query_label, int64_t Q, int k,
                     int64_t G, const int* ks, int nk, unsigned long long* hits, cudaStream_t stream);
 
+/* ---- image preprocessing in front of the backbone ------------------------------
+ * `transforms.Resize((h, w))` on a PIL image + `ToTensor()` + `Normalize(mean, std)`,
+ * dinov2salad/dinov2salad_finetuning.py:45-50.  The resize is Pillow's 8-bit bilinear resampler (antialiased
+ * separable triangle filter, 22-bit fixed-point coefficients, uint8 between the two passes) restated bit-exactly.
+ * rgb_hwc: [H, W, 3] uint8 (device); mean3 / std3: HOST pointers to 3 floats; out_chw: [3, out_h, out_w] (`dtype_out`);
+ * out_u8_hwc: optional [out_h, out_w, 3] uint8 copy of the resized image (NULL to skip). */
+VPR_API size_t vpr_preprocess_workspace_bytes(int H, int W, int out_h, int out_w);
+VPR_API int vpr_preprocess_image(const uint8_t* rgb_hwc, int H, int W, int out_h, int out_w, const float* mean3,
+                         const float* std3, void* out_chw, int dtype_out, uint8_t* out_u8_hwc, void* workspace,
+                         size_t workspace_bytes, cudaStream_t stream);
+
 /* ---- descriptor kNN ------------------------------------------------------------------- */
 VPR_API size_t vpr_knn_workspace_bytes(int64_t Q, int64_t G, int D, int k);
 /* q: [Q, D] bf16, g: [G, D] bf16 (this rank's gallery shard), scores = q . g (fp32 accumulate).

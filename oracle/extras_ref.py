@@ -65,3 +65,66 @@ def recall_at_k_ref(idx: torch.Tensor, query_labels: torch.Tensor, gallery_label
     """Fraction of queries with at least one same-label gallery row among their first k neighbours."""
     hit = gallery_labels[idx] == query_labels[:, None]            # [Q, k]
     return {int(k): float(hit[:, :k].any(dim=1).double().mean()) for k in ks}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# preprocessing (SURVEY 8f-4): transforms.Resize((224,224)) -> ToTensor() -> Normalize(mean, std) on a PIL image,
+# dinov2salad/dinov2salad_finetuning.py:45-50.  torchvision delegates the resize to Pillow; what follows restates
+# [THIRD-PARTY] Pillow src/libImaging/Resample.c (8-bit path, bilinear filter).  **Pinned**: tests/golden/
+# preprocess_golden.npz holds the outputs of the reference's own torchvision/Pillow pipeline.
+# ----------------------------------------------------------------------------------------------------------------
+PRECISION_BITS = 32 - 8 - 2
+
+
+def _pil_coeffs(in_size: int, out_size: int):
+    scale = float(in_size) / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds, coefs = [], np.zeros((out_size, ksize), dtype=np.int64)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = np.array([max(0.0, 1.0 - abs((x + xmin - center + 0.5) * ss)) for x in range(xmax)], dtype=np.float64)
+        ww = 0.0
+        for v in w:
+            ww += v
+        if ww != 0.0:
+            w = w / ww
+        coefs[xx, :xmax] = [int(-0.5 + v * (1 << PRECISION_BITS)) if v < 0 else int(0.5 + v * (1 << PRECISION_BITS)) for v in w]
+        bounds.append((xmin, xmax))
+    return bounds, coefs
+
+
+def _clip8(v):
+    return np.clip(v >> PRECISION_BITS, 0, 255)
+
+
+def pil_resize_ref(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """img [H, W, 3] uint8 -> [out_h, out_w, 3] uint8, Pillow's bilinear 8-bit resampler (horizontal pass first,
+    rounded to uint8, then vertical)."""
+    H, W, _ = img.shape
+    src = img.astype(np.int64)
+    bh, ch = _pil_coeffs(W, out_w)
+    tmp = np.empty((H, out_w, 3), dtype=np.int64)
+    for xx, (xmin, cnt) in enumerate(bh):
+        acc = (src[:, xmin:xmin + cnt, :] * ch[xx, :cnt, None]).sum(axis=1) + (1 << (PRECISION_BITS - 1))
+        tmp[:, xx, :] = _clip8(acc)
+    bv, cv = _pil_coeffs(H, out_h)
+    out = np.empty((out_h, out_w, 3), dtype=np.int64)
+    for yy, (ymin, cnt) in enumerate(bv):
+        acc = (tmp[ymin:ymin + cnt] * cv[yy, :cnt, None, None]).sum(axis=0) + (1 << (PRECISION_BITS - 1))
+        out[yy] = _clip8(acc)
+    return out.astype(np.uint8)
+
+
+def preprocess_ref(img: np.ndarray, out_h: int = 224, out_w: int = 224, mean=(0.485, 0.456, 0.406),
+                   std=(0.229, 0.224, 0.225)) -> torch.Tensor:
+    """[H, W, 3] uint8 -> [3, out_h, out_w] float32 (ToTensor: /255 in float32; Normalize: sub then div, float32)."""
+    u8 = torch.from_numpy(pil_resize_ref(img, out_h, out_w)).permute(2, 0, 1).contiguous()
+    x = u8.to(torch.float32).div(255)
+    m = torch.as_tensor(mean, dtype=torch.float32)[:, None, None]
+    s = torch.as_tensor(std, dtype=torch.float32)[:, None, None]
+    return x.sub_(m).div_(s)

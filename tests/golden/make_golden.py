@@ -203,9 +203,43 @@ def make_seam():
     print("seam_golden.npz:", tuple(o.last_hidden_state.shape), "eps", cfg.layer_norm_eps)
 
 
+PREPROCESS_CASES = [(37, 53, 16, 16), (480, 640, 224, 224), (64, 64, 64, 64), (100, 300, 56, 56), (1000, 750, 64, 48),
+                    (17, 9, 40, 33), (333, 517, 46, 46), (64, 500, 64, 64), (3, 2, 5, 7), (2000, 31, 8, 62)]
+
+
+def preprocess_inputs(i):
+    """Seeded uint8 RGB image [H, W, 3]: noise on top of a smooth ramp (both matter: the ramp exercises rounding,
+    the noise every tap of the antialiasing filter)."""
+    H, W, _, _ = PREPROCESS_CASES[i]
+    rng = np.random.RandomState(100 + i)
+    yy, xx = np.mgrid[0:H, 0:W]
+    ramp = np.stack([(xx * 255.0 / max(W - 1, 1)), (yy * 255.0 / max(H - 1, 1)), ((xx + yy) % 256)], axis=2)
+    noise = rng.randint(-40, 41, (H, W, 3))
+    return np.clip(ramp + noise, 0, 255).astype(np.uint8)
+
+
+def make_preprocess():
+    """The reference's transform, dinov2salad/dinov2salad_finetuning.py:45-50, through torchvision + Pillow."""
+    from PIL import Image
+    from torchvision import transforms
+    out = {}
+    for i, (H, W, oh, ow) in enumerate(PREPROCESS_CASES):
+        pil = Image.fromarray(preprocess_inputs(i), "RGB")
+        tf = transforms.Compose([transforms.Resize((oh, ow)), transforms.ToTensor(),
+                                 transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+        out[f"u8_{i}"] = np.array(transforms.Resize((oh, ow))(pil))
+        if oh * ow <= 64 * 64:
+            out[f"f32_{i}"] = tf(pil).numpy()
+        else:                                   # full-size float outputs are large: keep a strided sample
+            out[f"f32s_{i}"] = tf(pil).numpy()[:, ::7, ::5].copy()
+    np.savez_compressed(os.path.join(HERE, "preprocess_golden.npz"), **out)
+    print("preprocess_golden.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     make_heads()
     make_salad()
     make_metrics()
     make_seam()
+    make_preprocess()

@@ -277,3 +277,38 @@ def test_recall_at_k_on_knn_output(vpr):
     assert got[1] <= got[5] <= got[10] <= got[25] <= 1.0 - 1.0 / 7 + 0.01 and got[1] > 0.5
     with pytest.raises(ValueError):
         vpr.recall_at_k(idx, ql.cuda(), gl.cuda(), ks=())
+
+
+
+# ------------------------------------------------------------------ preprocessing
+def test_preprocess_is_bit_identical_to_torchvision_pillow_golden(vpr):
+    from tests.golden.make_golden import PREPROCESS_CASES, preprocess_inputs
+    z = np.load(os.path.join(GOLD, "preprocess_golden.npz"))
+    for i, (H, W, oh, ow) in enumerate(PREPROCESS_CASES):
+        img = preprocess_inputs(i)
+        pre = vpr.GpuPreprocess((oh, ow))
+        out, u8 = pre([torch.from_numpy(img)], return_uint8=True)
+        assert out.shape == (1, 3, oh, ow) and out.dtype == torch.float32
+        assert np.array_equal(u8[0].cpu().numpy(), z[f"u8_{i}"]), (H, W, oh, ow)        # Pillow's resampler, bit for bit
+        got = out[0].cpu().numpy()
+        if f"f32_{i}" in z.files:
+            assert np.array_equal(got, z[f"f32_{i}"])                                  # ToTensor + Normalize, bit for bit
+        else:
+            assert np.array_equal(got[:, ::7, ::5], z[f"f32s_{i}"])
+        want = X.preprocess_ref(img, oh, ow)
+        assert torch.equal(out[0].cpu(), want)
+
+
+def test_preprocess_batch_of_mixed_sizes_and_bf16(vpr):
+    rng = np.random.RandomState(5)
+    imgs = [torch.from_numpy(rng.randint(0, 256, (h, w, 3)).astype(np.uint8)) for h, w in ((300, 400), (50, 20), (224, 224))]
+    pre = vpr.GpuPreprocess((224, 224), out_dtype=torch.bfloat16)
+    out = pre([imgs[0].cuda(), imgs[1], imgs[2].pin_memory()])
+    assert out.shape == (3, 3, 224, 224) and out.dtype == torch.bfloat16
+    for i, im in enumerate(imgs):
+        want = X.preprocess_ref(im.numpy(), 224, 224)
+        assert torch.equal(out[i].cpu(), want.bfloat16())
+    with pytest.raises(ValueError):
+        pre([torch.zeros(4, 4, 4, dtype=torch.uint8)])
+    with pytest.raises(ValueError):
+        pre([torch.zeros(4, 4, 3)])

@@ -105,6 +105,9 @@ def test_next_rows_have_no_cpu_fallback_either(built):
     model = built.DINOv2RegressionModel(torch.nn.Identity()).eval()
     with pytest.raises(RuntimeError, match="CUDA"):
         model(torch.randn(2, 8448))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        built.GpuPreprocess(device="cpu")([torch.zeros(8, 8, 3, dtype=torch.uint8)])
+    assert built.lib().vpr_preprocess_workspace_bytes(480, 640, 224, 224) >= 480 * 224 * 3
 
 
 def test_scaler_mirrors_sklearn_and_joblib(built, tmp_path):

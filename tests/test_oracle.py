@@ -224,3 +224,20 @@ def test_metric_oracles_match_reference_expressions(golden_dir):
     idx = torch.tensor([[3, 1, 2], [0, 0, 0], [2, 3, 1]])
     got = X.recall_at_k_ref(idx, torch.tensor([7, 9, 5]), torch.tensor([1, 7, 5, 8]), (1, 2, 3))
     assert got == {1: 1 / 3, 2: 2 / 3, 3: 2 / 3}
+
+
+
+def test_preprocess_oracle_matches_torchvision_pillow_golden(golden_dir):
+    from oracle import extras_ref as X
+    from tests.golden.make_golden import PREPROCESS_CASES, preprocess_inputs
+    z = np.load(os.path.join(golden_dir, "preprocess_golden.npz"))
+    for i, (H, W, oh, ow) in enumerate(PREPROCESS_CASES):
+        if H * W > 400 * 400:
+            continue                                  # the big cases run on the GPU side only (seconds matter here)
+        img = preprocess_inputs(i)
+        assert np.array_equal(X.pil_resize_ref(img, oh, ow), z[f"u8_{i}"])
+        got = X.preprocess_ref(img, oh, ow).numpy()
+        if f"f32_{i}" in z.files:
+            assert np.array_equal(got, z[f"f32_{i}"])
+        else:
+            assert np.array_equal(got[:, ::7, ::5], z[f"f32s_{i}"])

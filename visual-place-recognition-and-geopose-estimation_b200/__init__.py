@@ -10,11 +10,12 @@ from .parallel import (DataParallelStep, allreduce_grads, init_distributed, over
 from .metrics import LatLonScaler, latlon_metrics, maae, recall_at_k  # noqa: F401
 from .model import (DINOv2RegressionModel, VPRModel, load_reference_checkpoint, load_upstream_salad_weights,  # noqa: F401
                     save_reference_checkpoint)
+from .preprocess import GpuPreprocess  # noqa: F401
 from .seam import BackboneSeam  # noqa: F401
 from .salad import GraphedSaladStep, SaladHead, dropout_keep_mask, sinkhorn, sinkhorn_backward  # noqa: F401
 
 __all__ = ["SaladHead", "GraphedSaladStep", "GeoposeHeads", "knn_topk", "knn_topk_sharded", "merge_topk", "sinkhorn",
            "sinkhorn_backward", "dropout_keep_mask", "DataParallelStep", "allreduce_grads", "overlap_grad_allreduce", "init_distributed",
-           "shard_range", "sincos_to_degrees", "BackboneSeam", "VPRModel", "DINOv2RegressionModel", "load_reference_checkpoint",
+           "shard_range", "sincos_to_degrees", "BackboneSeam", "GpuPreprocess", "VPRModel", "DINOv2RegressionModel", "load_reference_checkpoint",
            "load_upstream_salad_weights", "save_reference_checkpoint", "LatLonScaler", "latlon_metrics", "maae", "recall_at_k",
            "lib", "LIB_PATH"]
