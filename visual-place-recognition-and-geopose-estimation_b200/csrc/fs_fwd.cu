@@ -36,6 +36,7 @@ struct FsArgs {
     int tiles_m, T, hidden;
     int ctas_f, ctas_s;          // CTAs [0, ctas_f) compute F, the next ctas_s compute S, the last two TF
     int tiles_tok;               // 128-row tiles of the token batch
+    int rev;                     // walk the token tiles last-to-first: the rows the H launch wrote last are still in L2
     const float* bias_f; const float* bias_s; const float* bias_t;
 };
 
@@ -89,6 +90,8 @@ fs_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    const bool rev = args.rev != 0 && kind != 2;
+    auto row_tile = [&](int mt) { return rev ? tiles_m - 1 - mt : mt; };
 
     if (warp == FS_W_PROD) {
         if (lane == 0) {
@@ -101,7 +104,7 @@ fs_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
                 for (int kb = 0; kb < FS_KB; ++kb) {
                     mbar_wait(aempty(stage), phase ^ 1u);
                     mbar_expect_tx(afull(stage), FS_A_STAGE);
-                    tma_load_3d(sA + (uint32_t)stage * FS_A_STAGE, tmA, afull(stage), koff + kb * 64, mt * 128, 0);
+                    tma_load_3d(sA + (uint32_t)stage * FS_A_STAGE, tmA, afull(stage), koff + kb * 64, row_tile(mt) * 128, 0);
                     if (++stage == nstages) { stage = 0; phase ^= 1u; }
                 }
         }
@@ -192,7 +195,7 @@ fs_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_3d(tmO, sbuf, thalf * 128 + bx * box_cols, mt * 128 + q * 32, 0);
+                    tma_store_3d(tmO, sbuf, thalf * 128 + bx * box_cols, row_tile(mt) * 128 + q * 32, 0);
                     bulk_commit();
                 }
             }
@@ -238,6 +241,11 @@ int fs_fwd_run(const FsFwdDesc& d, cudaStream_t st) {
     a.T = (int)d.T;
     a.hidden = h;
     a.bias_f = d.bias_f; a.bias_s = d.bias_s; a.bias_t = d.bias_t;
+    {
+        static int rev = -1;
+        if (rev < 0) { const char* e = getenv("VPR_FS_REVERSE"); rev = (e != nullptr && e[0] == '0') ? 0 : 1; }
+        a.rev = rev;
+    }
     int grid = num_sms();
     if (grid > 2 * a.tiles_m + 2) grid = 2 * a.tiles_m + 2;
     if (grid < 4) grid = 4;
