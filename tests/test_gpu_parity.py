@@ -227,6 +227,15 @@ def test_salad_fp32_training_dropout_with_exported_mask(vpr):
     assert mod.last_seed != s1                                   # a fresh mask every training step
 
 
+@pytest.mark.parametrize("B,hw", [(3, 16), (2, 23)])
+def test_salad_bf16_training_dropout_with_exported_mask(vpr, B, hw):
+    """The benchmarked configuration (bf16, train mode, dropout 0.3): the tensor-core epilogue draws the same
+    counter-based mask that vpr_dropout_mask exports, so the oracle can be run on exactly that mask."""
+    ref, mod = _pair(vpr, dropout=0.3, round_weights=True)
+    errs, _ = _run_pair(vpr, ref, mod, B, hw, 78, torch.bfloat16, train=True)
+    assert max(errs.values()) < 2e-2, errs
+
+
 @pytest.mark.parametrize("B,hw", [(2, 16), (4, 23)])
 def test_salad_bf16_matches_oracle_on_same_rounded_operands(vpr, B, hw):
     ref, mod = _pair(vpr, round_weights=True)
@@ -307,7 +316,7 @@ def test_graphed_step_matches_eager_and_redraws_dropout(vpr):
 
 
 @pytest.mark.parametrize("env", [{"VPR_DH_FUSED": "0", "VPR_FS_FUSED": "0", "VPR_AGG_FUSED": "0"},
-                                 {"VPR_GEMM_2CTA": "0"}])
+                                 {"VPR_GEMM_2CTA": "0"}, {"VPR_GEMM_MCB": "1", "VPR_FS_REVERSE": "0"}])
 def test_generic_paths_still_match_when_the_fused_kernels_are_switched_off(vpr, env):
     """The default head shape runs the column-owner / per-image fused kernels and CTA-pair tiles; other shapes fall
     back to the generic grouped GEMMs.  Switch the fused kernels off (environment knobs read once per process, hence
@@ -317,7 +326,7 @@ def test_generic_paths_still_match_when_the_fused_kernels_are_switched_off(vpr, 
     child_env = dict(os.environ, **env)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
-                        "-k", "bf16_matches_oracle or full_size or graphed or gemm_epilogues"],
+                        "-k", "bf16_matches_oracle or full_size or graphed or gemm_epilogues or dropout"],
                        cwd=root, env=child_env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 

@@ -199,6 +199,16 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap*
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// multicast load: the box lands at the same shared-memory offset in every CTA of `cta_mask`, and each of those
+// CTAs' barriers (same offset) is credited with the bytes
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                               int c0, int c1, int c2, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+        : "memory");
+}
 // ---------------------------------------------------------------------------
 // thread-block clusters
 // ---------------------------------------------------------------------------
@@ -281,6 +291,12 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t ncols) 
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
 }
 // arrives (count 1) on the barrier at this shared-memory offset in every CTA of `cta_mask`
+// single-CTA MMAs, arrival delivered to the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_commit_2sm(uint32_t bar, uint16_t cta_mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(cta_mask)

@@ -70,13 +70,17 @@ static_assert(sizeof(TcArgs) % 8 == 0, "TcArgs is copied to shared memory in 4-b
 static constexpr int ARGS_SMEM_BYTES = ((MAX_GROUP * (int)sizeof(TcArgs) + 127) / 128) * 128;
 static constexpr int MISC_SMEM_BYTES = 256 + ARGS_SMEM_BYTES;        // barriers + tmem slot, arguments
 
-template <int BN, bool MASK, bool CTA2>
+template <int BN, bool MASK, bool CTA2, bool MCB = false>
 struct TcCfg {
     // CTA2: a CTA pair (cta_group::2) owns a 256 x BN tile; each CTA stages its own 128 rows of A and
-    // half of the B tile, so a k-block costs 32 KB per SM instead of 48 KB at BN = 256
-    static constexpr int TILE_M = CTA2 ? 2 * BM : BM;
-    static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;                   // B-tile rows (n) staged by one CTA
-    static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;
+    // half of the B tile, so a k-block costs 32 KB per SM instead of 48 KB at BN = 256.
+    // MCB: a cluster of two CTAs with independent single-CTA MMAs on two 128-row blocks of the same N tile;
+    // each CTA fetches half of the B tile and multicasts it into both, so the B tile crosses the L2->SM fabric once
+    // per cluster (32 KB of fetches per SM and k-block instead of 48 KB) while every CTA keeps its own accumulators
+    // and epilogue pace.
+    static constexpr int TILE_M = (CTA2 || MCB) ? 2 * BM : BM;
+    static constexpr int B_ROWS = (CTA2 || MCB) ? BN / 2 : BN;          // B-tile rows (n) fetched by one CTA
+    static constexpr int B_STAGE_BYTES = (CTA2 ? BN / 2 : BN) * BK * 2; // B-tile bytes resident per CTA
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int MASK_BOXES = BN / 64;                          // bf16 mask tile, 64 columns per box
     static constexpr int MASK_BYTES = MASK ? 2 * MASK_BOXES * BOX_BYTES : 0;
@@ -87,7 +91,8 @@ struct TcCfg {
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                      : (2 * BN <= 256) ? 256 : 512;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + MASK_BYTES + STAGING_BYTES + MISC_SMEM_BYTES;
-    static_assert(!(MASK && CTA2), "the relu-mask epilogue runs single-CTA tiles");
+    static_assert(!(MASK && (CTA2 || MCB)), "the relu-mask epilogue runs single-CTA tiles");
+    static_assert(!(CTA2 && MCB), "pair tiles and multicast clusters are alternatives");
     static_assert(STAGES >= 2, "operand ring too small");
     static_assert(2 * STAGES + 8 <= 31, "barrier area overflow");
     static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget");
@@ -191,9 +196,10 @@ __device__ __forceinline__ uint32_t box_addr(uint32_t box, int row, int c16) {
     return box + (uint32_t)row * 128u + (uint32_t)((c16 ^ (row & 7)) << 4);
 }
 
-template <bool A_MN, bool B_MN, int BN, bool MASK, bool CTA2>
+template <bool A_MN, bool B_MN, int BN, bool MASK, bool CTA2, bool MCB = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcGroup grp) {
-    using Cfg = TcCfg<BN, MASK, CTA2>;
+    using Cfg = TcCfg<BN, MASK, CTA2, MCB>;
+    constexpr bool CL2 = CTA2 || MCB;                       // launched as clusters of two CTAs
     constexpr int STAGES = Cfg::STAGES;
     constexpr int SBUF = Cfg::SBUF;
     extern __shared__ uint8_t smem_raw[];
@@ -215,9 +221,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;     // 0 = leader of the pair (issues the MMAs)
-    const int w_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int w_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const uint32_t cta_rank = CL2 ? cluster_ctarank() : 0u;      // 0 = leader of the pair (issues the MMAs)
+    const int w_first = CL2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int w_step = CL2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == W_PROD && lane == 0) {
         for (int g = 0; g < grp.count; ++g) {
@@ -231,7 +237,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) {
                 mbar_init(full_bar(s), 1);
-                mbar_init(empty_bar(s), 1);
+                mbar_init(empty_bar(s), MCB ? 2 : 1);        // MCB: both CTAs' MMAs have read what the peer multicast here
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(tfull_bar(s), 1);
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         reinterpret_cast<uint32_t*>(sargs + gi)[wi] = reinterpret_cast<const uint32_t*>(&grp.p[gi].args)[wi];
     }
     tc_fence_before();
-    if (CTA2) cluster_sync_all();          // the peer's barriers must exist before anything arrives on them
+    if (CL2) cluster_sync_all();           // the peer's barriers must exist before anything arrives on them
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
@@ -289,7 +295,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 const CUtensorMap* tmB = &grp.p[g].tmB;
                 const int bb = sargs[g].b_batched ? b : 0;
                 const int m0 = mt * Cfg::TILE_M + (int)cta_rank * BM;
-                const int n0 = nt * BN + (int)cta_rank * (CTA2 ? Cfg::B_ROWS : 0);
+                const int n0 = nt * BN + (int)cta_rank * (CL2 ? Cfg::B_ROWS : 0);
                 if (MASK && (sargs[g].flags & F_MASK)) {
                     const int mb = mit & 1;
                     mbar_wait(mempty_bar(mb), ((uint32_t)(mit >> 1) & 1u) ^ 1u);
@@ -311,6 +317,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                         if (CTA2) tma_load_3d_2sm(dst, tm, fb, c0, c1, c2);
                         else tma_load_3d(dst, tm, fb, c0, c1, c2);
                     };
+                    // MCB: this CTA's half of the B tile goes to the same place in both CTAs
+                    const uint32_t sbh = sb + (MCB ? cta_rank * (uint32_t)(Cfg::B_ROWS * BK * 2) : 0u);
+                    auto load_b = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2) {
+                        if (MCB) tma_load_3d_mc(dst, tm, fb, c0, c1, c2, (uint16_t)3);
+                        else load(dst, tm, c0, c1, c2);
+                    };
                     if (A_MN) {
 #pragma unroll
                         for (int i = 0; i < BM / 64; ++i) load(sa + i * 8192, tmA, m0 + i * 64, kb * BK, b);
@@ -319,9 +331,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     }
                     if (B_MN) {
 #pragma unroll
-                        for (int i = 0; i < Cfg::B_ROWS / 64; ++i) load(sb + i * 8192, tmB, n0 + i * 64, kb * BK, bb);
+                        for (int i = 0; i < Cfg::B_ROWS / 64; ++i) load_b(sbh + i * 8192, tmB, n0 + i * 64, kb * BK, bb);
                     } else {
-                        load(sb, tmB, kb * BK, n0, bb);
+                        load_b(sbh, tmB, kb * BK, n0, bb);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -329,8 +341,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
     } else if (warp == W_MMA) {
         // ------------------------------ MMA issuer ------------------------------
-        if (lane == 0 && cta_rank == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(Cfg::TILE_M, BN, A_MN, B_MN);
+        if (lane == 0 && (cta_rank == 0 || MCB)) {
+            constexpr uint32_t idesc = make_idesc_bf16(CTA2 ? 2 * BM : BM, BN, A_MN, B_MN);
             constexpr uint32_t A_LBO = A_MN ? 8192u : 16u;
             constexpr uint32_t B_LBO = B_MN ? 8192u : 16u;
             constexpr uint32_t A_KSTEP = A_MN ? 2048u : 32u;   // bytes per UMMA_K = 16 elements
@@ -359,6 +371,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                         else tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     if (CTA2) tc_commit_2sm(empty_bar(stage), 3);     // frees the stage in both CTAs
+                    else if (MCB) tc_commit_mc(empty_bar(stage), 3);  // one of the two releases each CTA's producer waits for
                     else tc_commit(empty_bar(stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -498,7 +511,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
 
     tc_fence_before();
-    if (CTA2) cluster_sync_all();          // the leader's MMAs read the peer's shared memory and write its TMEM
+    if (CL2) cluster_sync_all();           // the leader's MMAs read the peer's shared memory and write its TMEM
     else __syncthreads();
     if (warp == W_MMA) {
         tc_fence_after();
@@ -671,12 +684,12 @@ int make_map(CUtensorMap* map, const void* ptr, int esize, int64_t inner, int64_
     return 0;
 }
 
-template <bool A_MN, bool B_MN, int BN, bool MASK, bool CTA2>
+template <bool A_MN, bool B_MN, int BN, bool MASK, bool CTA2, bool MCB = false>
 static int launch_tc(const TcGroup& grp, int grid, cudaStream_t st) {
-    using Cfg = TcCfg<BN, MASK, CTA2>;
+    using Cfg = TcCfg<BN, MASK, CTA2, MCB>;
     static bool attr_set = false;
     if (!attr_set) {
-        VPR_SMEM_OK((gemm_tc_kernel<A_MN, B_MN, BN, MASK, CTA2>), Cfg::SMEM_BYTES);
+        VPR_SMEM_OK((gemm_tc_kernel<A_MN, B_MN, BN, MASK, CTA2, MCB>), Cfg::SMEM_BYTES);
         attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -686,17 +699,17 @@ static int launch_tc(const TcGroup& grp, int grid, cudaStream_t st) {
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
+    attr[0].val.clusterDim.x = (CTA2 || MCB) ? 2 : 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VPR_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A_MN, B_MN, BN, MASK, CTA2>, grp));
+    VPR_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A_MN, B_MN, BN, MASK, CTA2, MCB>, grp));
     return launch_ok("gemm_tc_kernel");
 }
 
 template <int BN>
-static int dispatch_major(int a_mn, int b_mn, bool mask, bool cta2, const TcGroup& grp, int grid, cudaStream_t st) {
+static int dispatch_major(int a_mn, int b_mn, bool mask, bool cta2, bool mcb, const TcGroup& grp, int grid, cudaStream_t st) {
     if constexpr (BN <= 128) {
         if (mask) {
             VPR_REQUIRE(!a_mn, "the relu-mask epilogue needs a K-major A operand");
@@ -705,6 +718,7 @@ static int dispatch_major(int a_mn, int b_mn, bool mask, bool cta2, const TcGrou
         }
     }
     if constexpr (BN == 256) {
+        if (mcb) return launch_tc<false, false, BN, false, false, true>(grp, grid, st);      // planned only for K-major operands
         if (cta2) {
             if (!a_mn && !b_mn) return launch_tc<false, false, BN, false, true>(grp, grid, st);
             if (!a_mn && b_mn) return launch_tc<false, true, BN, false, true>(grp, grid, st);
@@ -733,7 +747,15 @@ static int auto_bn(int N) { return (N > 128) ? 256 : (N > 64) ? 128 : 64; }
 
 // Tile shape for a group of bf16 problems: the widest N any problem wants; 256 x 256 CTA-pair tiles
 // when that does not inflate the MMA work (short-M problems would leave the peer CTA's rows empty).
-static int plan_group(const GemmDesc* gs, int count, int& bn, bool& any_mask, bool& cta2) {
+static bool mcb_enabled() {
+    static int v = -1;
+    // measured (B200, H = dropout(relu(X W0cat^T + b)) in the graphed step): 97.6 us with the multicast clusters vs
+    // 96.0 us with independent CTAs -- the L2->SM fabric is not what limits this launch -- so it stays opt-in
+    if (v < 0) { const char* e = getenv("VPR_GEMM_MCB"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+static int plan_group(const GemmDesc* gs, int count, int& bn, bool& any_mask, bool& cta2, bool& mcb) {
     VPR_REQUIRE(count >= 1 && count <= MAX_GROUP, "a GEMM group holds 1..%d problems", MAX_GROUP);
     bn = 0;
     any_mask = false;
@@ -759,25 +781,39 @@ static int plan_group(const GemmDesc* gs, int count, int& bn, bool& any_mask, bo
         }
         cta2 = c2 <= 1.05 * c1;
     }
+    // dropout epilogue (kept off pair tiles, see above): two independent CTAs share each B tile by multicast instead
+    mcb = false;
+    if (bn == 256 && !any_mask && !cta2 && single && mcb_enabled() && !gs[0].a_mn && !gs[0].b_mn) {
+        double c1 = 0, c2 = 0;
+        bool forced_single = false;
+        for (int i = 0; i < count; ++i) {
+            const double w = (double)gs[i].batch * ((gs[i].N + bn - 1) / bn) * gs[i].K;
+            c1 += w * ((gs[i].M + BM - 1) / BM) * BM;
+            c2 += w * ((gs[i].M + 2 * BM - 1) / (2 * BM)) * (2 * BM);
+            forced_single = forced_single || gs[i].cta_pair == 2;
+        }
+        mcb = !forced_single && c2 <= 1.05 * c1;
+    }
     return 0;
 }
 
 GemmTilePlan gemm_tile_plan(const GemmDesc* gs, int count) {
     GemmTilePlan p = {BM, 256, num_sms()};
     if (gs[0].dtype != DT_BF16) return p;
-    int bn; bool any_mask, cta2;
-    if (plan_group(gs, count, bn, any_mask, cta2) != 0) return p;
-    p.tile_m = cta2 ? 2 * BM : BM;
+    int bn; bool any_mask, cta2, mcb;
+    if (plan_group(gs, count, bn, any_mask, cta2, mcb) != 0) return p;
+    p.tile_m = (cta2 || mcb) ? 2 * BM : BM;
     p.tile_n = bn;
-    p.slots = cta2 ? num_sms() / 2 : num_sms();
+    p.slots = (cta2 || mcb) ? num_sms() / 2 : num_sms();
     return p;
 }
 
 static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
     int bn;
-    bool any_mask, cta2;
-    VPR_TRY(plan_group(gs, count, bn, any_mask, cta2));
-    const int tile_m = cta2 ? 2 * BM : BM;
+    bool any_mask, cta2, mcb;
+    VPR_TRY(plan_group(gs, count, bn, any_mask, cta2, mcb));
+    const bool cl2 = cta2 || mcb;
+    const int tile_m = cl2 ? 2 * BM : BM;
     TcGroup grp;
     grp.count = count;
     long long total = 0;
@@ -787,7 +823,7 @@ static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
         if (g.a_mn) VPR_TRY(make_map(&p.tmA, g.A, 2, g.M, g.K, g.batch, g.lda, g.a_bs, 64, 64, "GEMM operand A"));
         else        VPR_TRY(make_map(&p.tmA, g.A, 2, g.K, g.M, g.batch, g.lda, g.a_bs, 64, BM, "GEMM operand A"));
         if (g.b_mn) VPR_TRY(make_map(&p.tmB, g.B, 2, g.N, g.K, g.batch, g.ldb, g.b_bs, 64, 64, "GEMM operand B"));
-        else        VPR_TRY(make_map(&p.tmB, g.B, 2, g.K, g.N, g.batch, g.ldb, g.b_bs, 64, cta2 ? bn / 2 : bn, "GEMM operand B"));
+        else        VPR_TRY(make_map(&p.tmB, g.B, 2, g.K, g.N, g.batch, g.ldb, g.b_bs, 64, cl2 ? bn / 2 : bn, "GEMM operand B"));
         if (g.out_kind == OUT_BF16)
             VPR_TRY(make_map(&p.tmO, g.out, 2, g.N, g.M, g.batch, g.ldo, g.out_bs, 64, 32, "GEMM output"));
         else if (g.out_kind == OUT_F32)
@@ -821,15 +857,15 @@ static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
     for (int i = 0; i < count; ++i) if (gs[i].reserve_sms > reserve) reserve = gs[i].reserve_sms;
     if (reserve > num_sms() / 2) reserve = num_sms() / 2;
     int grid;
-    if (cta2) {
+    if (cl2) {
         const int pairs = (num_sms() - reserve) / 2;
         grid = 2 * (int)(total < pairs ? total : pairs);
     } else {
         grid = (int)(total < num_sms() - reserve ? total : num_sms() - reserve);
     }
-    if (bn == 256) return dispatch_major<256>(gs[0].a_mn, gs[0].b_mn, any_mask, cta2, grp, grid, st);
-    if (bn == 128) return dispatch_major<128>(gs[0].a_mn, gs[0].b_mn, any_mask, cta2, grp, grid, st);
-    return dispatch_major<64>(gs[0].a_mn, gs[0].b_mn, any_mask, cta2, grp, grid, st);
+    if (bn == 256) return dispatch_major<256>(gs[0].a_mn, gs[0].b_mn, any_mask, cta2, mcb, grp, grid, st);
+    if (bn == 128) return dispatch_major<128>(gs[0].a_mn, gs[0].b_mn, any_mask, cta2, mcb, grp, grid, st);
+    return dispatch_major<64>(gs[0].a_mn, gs[0].b_mn, any_mask, cta2, mcb, grp, grid, st);
 }
 
 static int gemm_simt(const GemmDesc& g, cudaStream_t st) {
