@@ -30,7 +30,7 @@ def main():
     import argparse
     ap = argparse.ArgumentParser()
     ap.add_argument("B", nargs="?", type=int, default=256)
-    ap.add_argument("--only", default="")          # comma list of: h,hdrop,dx,dw0,dh,f
+    ap.add_argument("--only", default="")          # comma list of: h,hdrop,dx,dw0,dh,f,cublas
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warm", type=int, default=3)
     a = ap.parse_args()
@@ -80,6 +80,16 @@ def main():
         ms = timeit(lambda: ops.gemm(dF, W1c, T, 512, 128, b_mn=True, out_kind=L.OUT_BF16, out=dH, ldo=1024, out_bs=0, mask=H,
                                      mask_scale=1.0 / 0.7, colsum=cs))
         rec("dH half = (dF W1c)*(H>0)        K.MN N=512 K=128", ms, 2.0 * T * 512 * 128, (T * 128 + 2 * T * 512) * 2)
+    if want("cublas"):        # library reference points for the same shapes (not on the product path)
+        Wt = W0.t().contiguous()
+        ms = timeit(lambda: torch.matmul(X, Wt, out=H))
+        rec("cuBLAS  X @ W0^T (no epilogue)   N=1024 K=768", ms, f_h, (T * 768 + T * 1024) * 2)
+        ms = timeit(lambda: torch.matmul(dH, W0, out=dX))
+        rec("cuBLAS  dH @ W0                  N=768 K=1024", ms, 2.0 * T * 768 * 1024, (T * 1024 + T * 768) * 2)
+        dHt = dH.t()
+        g2 = torch.empty(1024, 768, device=dev, dtype=bf)
+        ms = timeit(lambda: torch.matmul(dHt, X, out=g2))
+        rec("cuBLAS  dH^T @ X (both halves)   M=1024 N=768 K=T", ms, 2.0 * 1024 * 768 * T, (T * 1024 + T * 768) * 2)
     if want("f"):
         F = torch.empty(T, 128, device=dev, dtype=bf)
         ms = timeit(lambda: ops.gemm(H, W1c, T, 128, 512, out_kind=L.OUT_BF16, out=F, ldo=128, out_bs=0))
