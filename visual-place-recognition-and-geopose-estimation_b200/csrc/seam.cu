@@ -70,18 +70,20 @@ struct SeamRow {
     long long tok_row;      // row of x_tok, or -1 for the CLS token
     int b;
 };
+// rows = B * (1 + n) < 2^31 is checked by the host entry points, so the split is one 32-bit division
 __device__ __forceinline__ SeamRow seam_row(long long r, int n, int skip) {
     SeamRow o;
-    o.b = (int)(r / (1 + n));
-    const int j = (int)(r - (long long)o.b * (1 + n));
-    o.in_row = (long long)o.b * (1 + skip + n) + (j == 0 ? 0 : j + skip);
-    o.tok_row = j == 0 ? -1 : (long long)o.b * n + (j - 1);
+    const unsigned ru = (unsigned)r, per = (unsigned)(1 + n);
+    const unsigned b = ru / per, j = ru - b * per;
+    o.b = (int)b;
+    o.in_row = (long long)b * (1 + skip + n) + (j == 0 ? 0 : j + skip);
+    o.tok_row = j == 0 ? -1 : (long long)b * n + (j - 1);
     return o;
 }
 
 // Persistent over rows: each warp walks rows r, r + W, r + 2W ... and issues the loads of its next row before it
 // reduces the current one, so two rows per warp (and ~190 KB per SM) are in flight.
-template <typename TI, typename TO, int NCH>
+template <typename TI, typename TO, int NCH, bool FULL>
 __global__ void __launch_bounds__(SEAM_WARPS * 32, NCH <= 4 ? 3 : 1)
 seam_fwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                 TO* __restrict__ x_tok, TO* __restrict__ t, float* __restrict__ stats, long long rows, int n, int skip, int d) {
@@ -96,21 +98,21 @@ seam_fwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, 
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int e = c * 256 + lane * 8;
-            if (e < d) seam_ldraw(x + e, nx[c]);
+            if (FULL || e < d) seam_ldraw(x + e, nx[c]);
         }
     }
     for (; r < rows; r += stride) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int e = c * 256 + lane * 8;
-            if (e < d) seam_unpack(nx[c], v[c]);
+            if (FULL || e < d) seam_unpack(nx[c], v[c]);
         }
         if (r + stride < rows) {
             const TI* xn = hidden + seam_row(r + stride, n, skip).in_row * d;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 const int e = c * 256 + lane * 8;
-                if (e < d) seam_ldraw(xn + e, nx[c]);
+                if (FULL || e < d) seam_ldraw(xn + e, nx[c]);
             }
         }
         const SeamRow rw = seam_row(r, n, skip);
@@ -118,7 +120,7 @@ seam_fwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, 
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int e = c * 256 + lane * 8;
-            if (e < d) {
+            if (FULL || e < d) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) s += v[c][i];
             }
@@ -128,7 +130,7 @@ seam_fwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, 
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int e = c * 256 + lane * 8;
-            if (e < d) {
+            if (FULL || e < d) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { const float u = v[c][i] - mean; q = fmaf(u, u, q); }
             }
@@ -139,7 +141,7 @@ seam_fwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, 
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int e = c * 256 + lane * 8;
-            if (e < d) {
+            if (FULL || e < d) {
                 float g[8], bt[8], o[8];
                 seam_ldg8(gamma + e, g);
                 seam_ldg8(beta + e, bt);
@@ -155,7 +157,7 @@ seam_fwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, 
 // the rows a warp walks, are combined per CTA in shared memory and leave with one atomic per element per CTA
 // (the caller zeroes them).  A row's x and dy slices stay packed in registers and are unpacked twice (once for the
 // two row sums, once for the output) so the next row's loads can already be in flight.
-template <typename TI, typename TO, int NCH>
+template <typename TI, typename TO, int NCH, bool FULL>
 __global__ void __launch_bounds__(SEAM_WARPS * 32, NCH <= 4 ? 2 : 1)
 seam_bwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, const float* __restrict__ stats,
                 const TO* __restrict__ d_x_tok, const TO* __restrict__ d_t, TI* __restrict__ d_hidden,
@@ -186,7 +188,7 @@ seam_bwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, 
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int e = c * 256 + lane * 8;
-            if (e < d) {
+            if (FULL || e < d) {
                 seam_ldraw(x + e, nxx[c]);
                 if (nx_has_dy) seam_ldraw(dy + e, nxd[c]);
             }
@@ -209,7 +211,7 @@ seam_bwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, 
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int e = c * 256 + lane * 8;
-            if (e < d) {
+            if (FULL || e < d) {
                 float xv[8], dv[8], gm[8];
                 seam_unpack(cx[c], xv);
                 if (has_dy) seam_unpack(cd[c], dv);
@@ -232,7 +234,7 @@ seam_bwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, 
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int e = c * 256 + lane * 8;
-            if (e < d) {
+            if (FULL || e < d) {
                 float xv[8], dv[8], gm[8], o[8];
                 seam_unpack(cx[c], xv);
                 if (has_dy) seam_unpack(cd[c], dv);
@@ -255,7 +257,7 @@ seam_bwd_kernel(const TI* __restrict__ hidden, const float* __restrict__ gamma, 
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const int e = c * 256 + lane * 8;
-        if (e < d) {
+        if (FULL || e < d) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { atomicAdd(&sg[e + i], ag[c][i]); atomicAdd(&sb[e + i], ab[c][i]); }
         }
@@ -272,8 +274,12 @@ static int seam_fwd_launch(const void* hidden, const float* g, const float* b, f
                            long long rows, int n, int skip, int d, cudaStream_t st) {
     const long long want = (rows + SEAM_WARPS - 1) / SEAM_WARPS, cap = (long long)num_sms() * (NCH <= 4 ? 3 : 2);
     const unsigned grid = (unsigned)(want < cap ? want : cap);          // all CTAs resident: rows spread evenly
-    seam_fwd_kernel<TI, TO, NCH><<<grid, SEAM_WARPS * 32, 0, st>>>((const TI*)hidden, g, b, eps, (TO*)x_tok, (TO*)t, stats, rows,
-                                                                   n, skip, d);
+    if (d == NCH * 256)      // every lane owns a full slice of every chunk: no bounds predicates
+        seam_fwd_kernel<TI, TO, NCH, true><<<grid, SEAM_WARPS * 32, 0, st>>>((const TI*)hidden, g, b, eps, (TO*)x_tok, (TO*)t,
+                                                                             stats, rows, n, skip, d);
+    else
+        seam_fwd_kernel<TI, TO, NCH, false><<<grid, SEAM_WARPS * 32, 0, st>>>((const TI*)hidden, g, b, eps, (TO*)x_tok, (TO*)t,
+                                                                              stats, rows, n, skip, d);
     return launch_ok("seam_fwd_kernel");
 }
 template <typename TI, typename TO, int NCH>
@@ -281,8 +287,12 @@ static int seam_bwd_launch(const void* hidden, const float* g, const float* stat
                            void* d_hidden, float* dg, float* db, long long rows, int n, int skip, int d, cudaStream_t st) {
     const long long want = (rows + SEAM_WARPS - 1) / SEAM_WARPS, cap = (long long)num_sms() * (NCH <= 4 ? 2 : 1);
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    seam_bwd_kernel<TI, TO, NCH><<<grid, SEAM_WARPS * 32, 0, st>>>((const TI*)hidden, g, stats, (const TO*)dx_tok, (const TO*)dt,
-                                                                   (TI*)d_hidden, dg, db, rows, n, skip, d);
+    if (d == NCH * 256)
+        seam_bwd_kernel<TI, TO, NCH, true><<<grid, SEAM_WARPS * 32, 0, st>>>((const TI*)hidden, g, stats, (const TO*)dx_tok,
+                                                                             (const TO*)dt, (TI*)d_hidden, dg, db, rows, n, skip, d);
+    else
+        seam_bwd_kernel<TI, TO, NCH, false><<<grid, SEAM_WARPS * 32, 0, st>>>((const TI*)hidden, g, stats, (const TO*)dx_tok,
+                                                                              (const TO*)dt, (TI*)d_hidden, dg, db, rows, n, skip, d);
     return launch_ok("seam_bwd_kernel");
 }
 
@@ -320,7 +330,7 @@ extern "C" {
 int vpr_seam_ln_split_fwd(const void* hidden, const float* ln_weight, const float* ln_bias, float eps, void* x_tok, void* t,
                           float* stats, int B, int n, int skip, int d, int dtype_in, int dtype_out, cudaStream_t stream) {
     VPR_REQUIRE(hidden && ln_weight && ln_bias && x_tok && t, "null argument");
-    VPR_REQUIRE(B > 0 && n > 0 && skip >= 0, "bad seam shape");
+    VPR_REQUIRE(B > 0 && n > 0 && skip >= 0 && (long long)B * (1 + n) < (1ll << 31), "bad seam shape");
     VPR_REQUIRE(d > 0 && d % 8 == 0 && d <= SEAM_MAXCH * 256, "d must be a multiple of 8 and at most 2048");
     VPR_REQUIRE((dtype_in == VPR_F32 || dtype_in == VPR_BF16) && (dtype_out == VPR_F32 || dtype_out == VPR_BF16),
                 "dtype must be VPR_F32 or VPR_BF16");
@@ -332,7 +342,7 @@ int vpr_seam_ln_split_bwd(const void* hidden, const float* ln_weight, const floa
                           void* d_hidden, float* d_ln_weight, float* d_ln_bias, int B, int n, int skip, int d, int dtype_in,
                           int dtype_out, cudaStream_t stream) {
     VPR_REQUIRE(hidden && ln_weight && stats && d_hidden, "null argument");
-    VPR_REQUIRE(B > 0 && n > 0 && skip >= 0, "bad seam shape");
+    VPR_REQUIRE(B > 0 && n > 0 && skip >= 0 && (long long)B * (1 + n) < (1ll << 31), "bad seam shape");
     VPR_REQUIRE(d > 0 && d % 8 == 0 && d <= SEAM_MAXCH * 256, "d must be a multiple of 8 and at most 2048");
     VPR_REQUIRE((dtype_in == VPR_F32 || dtype_in == VPR_BF16) && (dtype_out == VPR_F32 || dtype_out == VPR_BF16),
                 "dtype must be VPR_F32 or VPR_BF16");
