@@ -80,6 +80,12 @@ def main():
         ms = timeit(lambda: ops.gemm(dF, W1c, T, 512, 128, b_mn=True, out_kind=L.OUT_BF16, out=dH, ldo=1024, out_bs=0, mask=H,
                                      mask_scale=1.0 / 0.7, colsum=cs))
         rec("dH half = (dF W1c)*(H>0)        K.MN N=512 K=128", ms, 2.0 * T * 512 * 128, (T * 128 + 2 * T * 512) * 2)
+    if want("epi"):           # K = 64: one k-block per tile, so the launch time is the epilogue (+ output write) alone
+        X64 = X[:, :64].contiguous()
+        W64 = W0[:, :64].contiguous()
+        for nm, kw in (("epilogue only, relu+bias (pairs)", {}), ("epilogue only, relu+bias+dropout (single)", {"dropout_p": 0.3, "dropout_seed": 7})):
+            ms = timeit(lambda: ops.gemm(X64, W64, T, 1024, 64, out_kind=L.OUT_BF16, bias=b0, relu=True, out=H, ldo=1024, out_bs=0, **kw))
+            rec(nm + " K=64", ms, 2.0 * T * 1024 * 64, (T * 64 + T * 1024) * 2)
     if want("cublas"):        # library reference points for the same shapes (not on the product path)
         Wt = W0.t().contiguous()
         ms = timeit(lambda: torch.matmul(X, Wt, out=H))

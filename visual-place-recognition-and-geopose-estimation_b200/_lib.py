@@ -10,7 +10,7 @@ import os
 import torch
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libvpr_b200.so")
+LIB_PATH = os.environ.get("VPR_B200_LIB") or os.path.join(PKG_DIR, "libvpr_b200.so")    # override: an alternate build (A/B runs)
 
 VPR_F32, VPR_BF16 = 0, 1
 BWD_ALL, BWD_PARAMS, BWD_INPUTS = 0, 1, 2

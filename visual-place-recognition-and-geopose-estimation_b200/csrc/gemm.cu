@@ -70,6 +70,10 @@ static_assert(sizeof(TcArgs) % 8 == 0, "TcArgs is copied to shared memory in 4-b
 static constexpr int ARGS_SMEM_BYTES = ((MAX_GROUP * (int)sizeof(TcArgs) + 127) / 128) * 128;
 static constexpr int MISC_SMEM_BYTES = 256 + ARGS_SMEM_BYTES;        // barriers + tmem slot, arguments
 
+#ifndef VPR_SBUF256
+#define VPR_SBUF256 1      // 256-wide tiles: one staging box per epilogue warp (a second one costs an operand stage)
+#endif
+
 template <int BN, bool MASK, bool CTA2, bool MCB = false>
 struct TcCfg {
     // CTA2: a CTA pair (cta_group::2) owns a 256 x BN tile; each CTA stages its own 128 rows of A and
@@ -84,7 +88,7 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int MASK_BOXES = BN / 64;                          // bf16 mask tile, 64 columns per box
     static constexpr int MASK_BYTES = MASK ? 2 * MASK_BOXES * BOX_BYTES : 0;
-    static constexpr int SBUF = (BN >= 256) ? 1 : 2;                    // staging boxes per epilogue warp
+    static constexpr int SBUF = (BN >= 256) ? VPR_SBUF256 : 2;          // staging boxes per epilogue warp
     static constexpr int STAGING_BYTES = EPI_WARPS * SBUF * WBOX_BYTES;
     static constexpr int RING_BUDGET = SMEM_LIMIT - 1024 - MISC_SMEM_BYTES - MASK_BYTES - STAGING_BYTES;
     static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
