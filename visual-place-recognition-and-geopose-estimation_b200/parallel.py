@@ -175,7 +175,10 @@ class DataParallelStep:
         total.backward()                       # heads grads + d(desc): already computed by the fused call
         fin_heads = allreduce_grads(self.heads.parameters(), self.group, async_op=True)
         desc.backward(d.grad)                  # SALAD backward overlaps the heads-gradient allreduce
-        fin_salad = allreduce_grads(self.salad.parameters(), self.group, async_op=True)
+        if getattr(self.salad, "_grad_hook", None) is None:
+            fin_salad = allreduce_grads(self.salad.parameters(), self.group, async_op=True)
+        else:                                  # overlap_grad_allreduce(): already reduced from inside the backward
+            fin_salad = lambda: None           # noqa: E731
         fin_heads()
         fin_salad()
         return total.detach(), losses
