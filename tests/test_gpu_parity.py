@@ -315,6 +315,30 @@ def test_graphed_step_matches_eager_and_redraws_dropout(vpr):
     assert rel(o2, o2e) < 1e-6
 
 
+def test_graphed_step_can_be_captured_while_an_eager_graph_is_still_alive(vpr):
+    """The captured step must not go through the autograd engine: a live eager graph pins the parameters'
+    gradient-accumulation nodes to the default stream, and the engine would then pull that stream into the capture
+    (seen with 2 ranks in tools/multi_gpu_check.py)."""
+    torch.manual_seed(0)
+    mod = vpr.SaladHead(dropout=0.0).cuda().train()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(4, 256, 768, device="cuda", generator=g).bfloat16()
+    t = torch.randn(4, 768, device="cuda", generator=g).bfloat16()
+    w = torch.randn(4, 8448, device="cuda", generator=g).bfloat16()
+    xe, te = x.clone().requires_grad_(True), t.clone().requires_grad_(True)
+    held = mod((xe, te))                       # eager graph kept alive across the capture
+    held.backward(w, retain_graph=True)
+    want = [p.grad.clone() for p in mod.parameters()]
+    step = vpr.GraphedSaladStep(mod, batch=4, n_tokens=256)
+    out, dx, dt = step(x, t, w)
+    torch.cuda.synchronize()
+    assert rel(out, held) < 1e-6 and rel(dx, xe.grad) < 1e-6 and rel(dt, te.grad) < 1e-6
+    for p, wg in zip(mod.parameters(), want):
+        if wg.norm() > 1e-6:
+            assert rel(p.grad, wg) < 1e-5
+    assert held.grad_fn is not None
+
+
 @pytest.mark.parametrize("env", [{"VPR_DH_FUSED": "0", "VPR_FS_FUSED": "0", "VPR_AGG_FUSED": "0"},
                                  {"VPR_GEMM_2CTA": "0"}, {"VPR_GEMM_MCB": "1", "VPR_FS_REVERSE": "0"}])
 def test_generic_paths_still_match_when_the_fused_kernels_are_switched_off(vpr, env):

@@ -88,9 +88,40 @@ def main():
                               "ok": good}), flush=True)
         ok = ok and good
     salad.set_grad_ready_hook(None)
+
+    # ---------------- the benchmarked N>1 step: fwd+bwd + overlapped all-reduce replayed from one CUDA graph ----------------
+    Bl = 64
+    xs = torch.randn(Bl, n, 768, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + rank)).bfloat16()
+    ts = torch.randn(Bl, 768, device=dev, generator=torch.Generator(device=dev).manual_seed(200 + rank)).bfloat16()
+    ds = torch.randn(Bl, 8448, device=dev, generator=torch.Generator(device=dev).manual_seed(300 + rank)).bfloat16()
+    for p in salad.parameters():
+        p.grad = None
+    xe, te = xs.clone().requires_grad_(True), ts.clone().requires_grad_(True)
+    salad((xe, te)).backward(ds)
+    local = torch.cat([p.grad.flatten().float() for p in salad.parameters()])
+    want_g = local.clone()
+    dist.all_reduce(want_g)                                   # sum over ranks of the local gradients
+    want_dx = xe.grad.clone()
+    vpr_b200.overlap_grad_allreduce(salad, reserve_sms=32)
+    gstep = vpr_b200.GraphedSaladStep(salad, batch=Bl, n_tokens=n, capture_error_mode=os.environ.get("CAPTURE_MODE", "thread_local"))
+    for rep in range(2):                                      # the second replay must not accumulate
+        out, dx, dt = gstep(xs, ts, ds)
+    torch.cuda.synchronize()
+    got_g = torch.cat([p.grad.flatten().float() for p in salad.parameters()])
+    e = torch.tensor([rel(got_g, want_g), rel(dx, want_dx)], device=dev)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    good = e[0].item() < 1e-5 and e[1].item() < 1e-5
+    if rank == 0:
+        print(json.dumps({"check": "GraphedSaladStep + in-graph NCCL all-reduce == all-reduce of eager local gradients",
+                          "world": world, "launches_per_replay": gstep.launches_per_replay,
+                          "param_grad_rel_err": e[0].item(), "dx_rel_err": e[1].item(), "ok": good}), flush=True)
+    ok = ok and good
+    salad.set_grad_ready_hook(None)
+    del gstep                                                 # the graph holds captured NCCL work: drop it before teardown
+    torch.cuda.synchronize()
     dist.barrier()
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)                                  # skip communicator teardown (it can wait on graph resources)
 
 
 if __name__ == "__main__":

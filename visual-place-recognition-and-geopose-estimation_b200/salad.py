@@ -35,24 +35,73 @@ def _params_struct(cls, tensors):
     return s
 
 
+def _salad_forward(x_tok, t, shape_tuple, dropout_p, seed, seed_dev, params):
+    """One vpr_salad_fwd call (+ the device step-counter advance).  Returns (out, save)."""
+    lib = L.lib()
+    B, n, d, hidden, m, l, g, iters = shape_tuple
+    dt = L.dtype_code(x_tok.dtype)
+    shape = L.SaladShape(B, n, d, hidden, m, l, g, iters)
+    dev = x_tok.device
+    save = torch.empty(lib.vpr_salad_save_bytes(C.byref(shape), dt), dtype=torch.uint8, device=dev)
+    out = torch.empty(B, g + l * m, dtype=x_tok.dtype, device=dev)
+    ps = _params_struct(L.SaladParams, params)
+    L.check(lib.vpr_salad_fwd(C.byref(ps), L.ptr(x_tok), L.ptr(t), L.ptr(out), L.ptr(save), None, 0,
+                              C.byref(shape), dt, float(dropout_p), int(seed), L.ptr(seed_dev), L.stream_ptr(dev)),
+            "vpr_salad_fwd")
+    if seed_dev is not None and dropout_p > 0:      # next call (or next graph replay) draws a fresh mask
+        L.check(lib.vpr_counter_advance(L.ptr(seed_dev), L.stream_ptr(dev)), "vpr_counter_advance")
+    return out, save
+
+
+def _salad_backward(x_tok, t, save, params, shape_tuple, dropout_p, d_out, want_dx, want_dt, hook):
+    """vpr_salad_bwd, in one call or -- with a gradient-ready hook -- in its two phases around the hook.
+    Returns (dx, dt, flat fp32 gradient buffer, per-parameter views of it)."""
+    lib = L.lib()
+    B, n, d, hidden, m, l, g, iters = shape_tuple
+    dt = L.dtype_code(x_tok.dtype)
+    shape = L.SaladShape(B, n, d, hidden, m, l, g, iters)
+    dev = x_tok.device
+    d_out = d_out.contiguous()
+    if d_out.dtype != x_tok.dtype:
+        d_out = d_out.to(x_tok.dtype)
+    ws_bytes = lib.vpr_salad_workspace_bytes(C.byref(shape), dt)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    sizes = [p.numel() for p in params]
+    flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+    grads = list(torch.split(flat, sizes))
+    gs = _params_struct(L.SaladGrads, grads)
+    ps = _params_struct(L.SaladParams, params)
+    dx = torch.empty_like(x_tok) if want_dx else None
+    dtok = torch.empty_like(t) if want_dt else None
+
+    def bwd(phase, reserve):
+        L.check(lib.vpr_salad_bwd(C.byref(ps), L.ptr(x_tok), L.ptr(t), L.ptr(d_out), L.ptr(save), L.ptr(ws),
+                                  ws_bytes, C.byref(gs), L.ptr(dx), L.ptr(dtok), C.byref(shape), dt,
+                                  float(dropout_p), phase, reserve, L.stream_ptr(dev)),
+                "vpr_salad_bwd")
+
+    if hook is None:
+        bwd(L.BWD_ALL, 0)
+    else:
+        # data parallel: every parameter gradient first, hand the flat buffer to the hook (it starts the
+        # all-reduce on the collective's stream), then the input-gradient GEMM on a few SMs less so that the
+        # collective's kernel finds room and the two overlap; finally order later work after the collective
+        fn, reserve = hook
+        bwd(L.BWD_PARAMS, 0)
+        work = fn(flat)
+        if dx is not None or dtok is not None:
+            bwd(L.BWD_INPUTS, int(reserve))
+        if work is not None:
+            work.wait()
+    return dx, dtok, flat, grads
+
+
 class _SaladFn(torch.autograd.Function):
     """x_tok: [B, n, d] contiguous, t: [B, d]; params in _PARAM_ORDER (fp32, contiguous)."""
 
     @staticmethod
     def forward(ctx, x_tok, t, shape_tuple, dropout_p, seed, seed_dev, grad_hook, *params):
-        lib = L.lib()
-        B, n, d, hidden, m, l, g, iters = shape_tuple
-        dt = L.dtype_code(x_tok.dtype)
-        shape = L.SaladShape(B, n, d, hidden, m, l, g, iters)
-        dev = x_tok.device
-        save = torch.empty(lib.vpr_salad_save_bytes(C.byref(shape), dt), dtype=torch.uint8, device=dev)
-        out = torch.empty(B, g + l * m, dtype=x_tok.dtype, device=dev)
-        ps = _params_struct(L.SaladParams, params)
-        L.check(lib.vpr_salad_fwd(C.byref(ps), L.ptr(x_tok), L.ptr(t), L.ptr(out), L.ptr(save), None, 0,
-                                  C.byref(shape), dt, float(dropout_p), int(seed), L.ptr(seed_dev), L.stream_ptr(dev)),
-                "vpr_salad_fwd")
-        if seed_dev is not None and dropout_p > 0:      # next call (or next graph replay) draws a fresh mask
-            L.check(lib.vpr_counter_advance(L.ptr(seed_dev), L.stream_ptr(dev)), "vpr_counter_advance")
+        out, save = _salad_forward(x_tok, t, shape_tuple, dropout_p, seed, seed_dev, params)
         ctx.shape_tuple = shape_tuple
         ctx.dropout_p = float(dropout_p)
         ctx.grad_hook = grad_hook
@@ -61,44 +110,9 @@ class _SaladFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
-        lib = L.lib()
         x_tok, t, save, *params = ctx.saved_tensors
-        B, n, d, hidden, m, l, g, iters = ctx.shape_tuple
-        dt = L.dtype_code(x_tok.dtype)
-        shape = L.SaladShape(B, n, d, hidden, m, l, g, iters)
-        dev = x_tok.device
-        d_out = d_out.contiguous()
-        if d_out.dtype != x_tok.dtype:
-            d_out = d_out.to(x_tok.dtype)
-        ws_bytes = lib.vpr_salad_workspace_bytes(C.byref(shape), dt)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        sizes = [p.numel() for p in params]
-        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-        grads = list(torch.split(flat, sizes))
-        gs = _params_struct(L.SaladGrads, grads)
-        ps = _params_struct(L.SaladParams, params)
-        dx = torch.empty_like(x_tok) if ctx.needs_input_grad[0] else None
-        dtok = torch.empty_like(t) if ctx.needs_input_grad[1] else None
-        def bwd(phase, reserve):
-            L.check(lib.vpr_salad_bwd(C.byref(ps), L.ptr(x_tok), L.ptr(t), L.ptr(d_out), L.ptr(save), L.ptr(ws),
-                                      ws_bytes, C.byref(gs), L.ptr(dx), L.ptr(dtok), C.byref(shape), dt,
-                                      ctx.dropout_p, phase, reserve, L.stream_ptr(dev)),
-                    "vpr_salad_bwd")
-
-        hook = ctx.grad_hook
-        if hook is None:
-            bwd(L.BWD_ALL, 0)
-        else:
-            # data parallel: every parameter gradient first, hand the flat buffer to the hook (it starts the
-            # all-reduce on the collective's stream), then the input-gradient GEMM on a few SMs less so that the
-            # collective's kernel finds room and the two overlap; finally order later work after the collective
-            fn, reserve = hook
-            bwd(L.BWD_PARAMS, 0)
-            work = fn(flat)
-            if dx is not None or dtok is not None:
-                bwd(L.BWD_INPUTS, int(reserve))
-            if work is not None:
-                work.wait()
+        dx, dtok, _flat, grads = _salad_backward(x_tok, t, save, params, ctx.shape_tuple, ctx.dropout_p, d_out,
+                                                 ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.grad_hook)
         pg = [gr.view_as(p) if ctx.needs_input_grad[7 + i] else None
               for i, (gr, p) in enumerate(zip(grads, params))]
         return (dx, dtok, None, None, None, None, None, *pg)
@@ -175,7 +189,9 @@ class SaladHead(nn.Module):
         B, Cc, h, w = f.shape
         return f.permute(0, 2, 3, 1).reshape(B, h * w, Cc).contiguous()   # no copy for channels-last views
 
-    def forward(self, x: Tuple[torch.Tensor, torch.Tensor]) -> torch.Tensor:
+    def _prepare(self, x: Tuple[torch.Tensor, torch.Tensor]):
+        """Checks and per-call state shared by forward() and GraphedSaladStep: token-major input, shape tuple,
+        dropout probability and seed for this call, contiguous fp32 master parameters."""
         f, t = x
         L.require_cuda(f, "patch tokens")
         L.require_cuda(t, "cls token")
@@ -201,7 +217,11 @@ class SaladHead(nn.Module):
             self._step += 1
         shape = (B, n, d, 512, self.num_clusters, self.cluster_dim, self.token_dim, self.sinkhorn_iters)
         self.last_seed = seed if seed_dev is None else None      # device counter: ask current_seed() before the call
-        return _SaladFn.apply(x_tok, t, shape, p_drop, seed, seed_dev, self._grad_hook, *[p.contiguous() for p in params])
+        return x_tok, t, shape, p_drop, seed, seed_dev, [p.contiguous() for p in params]
+
+    def forward(self, x: Tuple[torch.Tensor, torch.Tensor]) -> torch.Tensor:
+        x_tok, t, shape, p_drop, seed, seed_dev, params = self._prepare(x)
+        return _SaladFn.apply(x_tok, t, shape, p_drop, seed, seed_dev, self._grad_hook, *params)
 
 
 class GraphedSaladStep:
@@ -217,52 +237,62 @@ class GraphedSaladStep:
     Dropout masks still differ from call to call (SaladHead.use_device_step_counter)."""
 
     def __init__(self, head: "SaladHead", batch: int, n_tokens: int, dtype=torch.bfloat16, input_grads: bool = True,
-                 warmup: int = 3):
+                 warmup: int = 3, capture_error_mode: str = "thread_local"):
         dev = head.dust_bin.device
         if dev.type != "cuda":
             raise RuntimeError("GraphedSaladStep needs the head on a CUDA device")
         self.head = head
         head.use_device_step_counter(True)
-        self.params = [p for p in head.parameters() if p.requires_grad]
-        self.x = torch.zeros(batch, n_tokens, head.num_channels, dtype=dtype, device=dev, requires_grad=input_grads)
-        self.t = torch.zeros(batch, head.num_channels, dtype=dtype, device=dev, requires_grad=input_grads)
+        self.input_grads = bool(input_grads)
+        self.x = torch.zeros(batch, n_tokens, head.num_channels, dtype=dtype, device=dev)
+        self.t = torch.zeros(batch, head.num_channels, dtype=dtype, device=dev)
         self.d_out = torch.zeros(batch, head.out_dim, dtype=dtype, device=dev)
         lib = L.lib()
+        # The captured step calls the library directly (no autograd engine inside the capture): the engine keys the
+        # stream of every parameter's gradient-accumulation node to the stream that was current when that node was
+        # first created, so an eager graph the caller still holds would drag the default stream into the capture.
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side), torch.no_grad():
             for _ in range(max(1, warmup)):
-                self._clear()
-                head((self.x, self.t)).backward(self.d_out)
+                self._run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self._clear()
         launches0 = lib.vpr_launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = head((self.x, self.t))
-            self.out.backward(self.d_out)
+        # thread_local: other threads of the process (NCCL's watchdog polling the events of earlier eager collectives,
+        # a data-loader thread copying to the device) may keep making CUDA calls while this thread captures
+        with torch.no_grad(), torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
+            self.out, self.dx, self.dt, self.flat_grad, grads = self._run()
         self.launches_per_replay = int(lib.vpr_launch_count() - launches0)
-        self.param_grads = [p.grad for p in self.params]
+        plist = head._param_list()
+        self.param_grads = []
+        self.params = []
+        for p, g in zip(plist, grads):
+            if p.requires_grad:
+                self.params.append(p)
+                self.param_grads.append(g.view_as(p))
 
-    def _clear(self):
-        for p in self.params:
-            p.grad = None
-        self.x.grad = None
-        self.t.grad = None
+    def _run(self):
+        head = self.head
+        x_tok, t, shape, p_drop, seed, seed_dev, params = head._prepare((self.x, self.t))
+        out, save = _salad_forward(x_tok, t, shape, p_drop, seed, seed_dev, params)
+        dx, dt, flat, grads = _salad_backward(x_tok, t, save, params, shape, p_drop, self.d_out, self.input_grads,
+                                              self.input_grads, head._grad_hook)
+        return out, dx, dt, flat, grads
 
     def __call__(self, x_tok=None, t=None, d_out=None):
         if x_tok is not None:
-            self.x.data.copy_(x_tok.reshape(self.x.shape), non_blocking=True)
+            self.x.copy_(x_tok.reshape(self.x.shape), non_blocking=True)
         if t is not None:
-            self.t.data.copy_(t, non_blocking=True)
+            self.t.copy_(t, non_blocking=True)
         if d_out is not None:
             self.d_out.copy_(d_out, non_blocking=True)
         self.graph.replay()
         for p, g in zip(self.params, self.param_grads):
             if p.grad is not g:
                 p.grad = g
-        return self.out, self.x.grad, self.t.grad
+        return self.out, self.dx, self.dt
 
 
 def dropout_keep_mask(seed: int, p: float, rows: int, cols: int, device="cuda") -> torch.Tensor:
