@@ -101,6 +101,8 @@ agg_bwd_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();                  // everything above overlapped the previous launch's tail
+    pdl_launch_dependents();
 
     if (warp == GB_W_PROD) {
         if (lane == 0) {
@@ -333,7 +335,8 @@ int agg_bwd_run(const AggBwdDesc& d, cudaStream_t st) {
     a.n = d.n; a.g = d.g; a.AGG = d.AGG; a.TF = d.TF; a.d_out = reinterpret_cast<const bf16*>(d.d_out);
     a.dTF = reinterpret_cast<bf16*>(d.dTF); a.g_bias_tok = d.g_bias_tok;
     VPR_SMEM_OK(agg_bwd_kernel, GB_SMEM);
-    agg_bwd_kernel<<<d.B, GB_THREADS, GB_SMEM, st>>>(tmP, tmF, tmDF, tmDP, a);
+    VPR_CUDA_OK(launch_ex(agg_bwd_kernel, dim3((unsigned)d.B), dim3(GB_THREADS), (size_t)GB_SMEM, st, d.pdl != 0, 1, tmP, tmF, tmDF,
+                          tmDP, a));
     return launch_ok("agg_bwd_kernel");
 }
 

@@ -86,6 +86,8 @@ agg_fwd_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();                  // everything above overlapped the previous launch's tail
+    pdl_launch_dependents();
 
     if (warp == AG_W_PROD) {
         if (lane == 0) {
@@ -206,7 +208,7 @@ int agg_fwd_run(const AggFwdDesc& d, cudaStream_t st) {
     AgArgs a;
     a.n = d.n; a.g = d.g; a.AGG = d.AGG; a.TF = d.TF; a.out = reinterpret_cast<bf16*>(d.out);
     VPR_SMEM_OK(agg_fwd_kernel, AG_SMEM);
-    agg_fwd_kernel<<<d.B, AG_THREADS, AG_SMEM, st>>>(tmF, tmP, a);
+    VPR_CUDA_OK(launch_ex(agg_fwd_kernel, dim3((unsigned)d.B), dim3(AG_THREADS), (size_t)AG_SMEM, st, d.pdl != 0, 1, tmF, tmP, a));
     return launch_ok("agg_fwd_kernel");
 }
 

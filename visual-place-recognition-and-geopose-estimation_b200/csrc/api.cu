@@ -1,5 +1,7 @@
 // Library-wide state: the error channel, device properties and the C-ABI test hook for the GEMM.
 #include "common.cuh"
+
+#include <stdlib.h>
 #include "gemm.h"
 #include "../../include/vpr_b200.h"
 
@@ -47,6 +49,12 @@ int ensure_dynamic_smem(const void* kernel, size_t bytes) {
     if (sl == nullptr && used < 128) { sl = &slots[used++]; sl->fn = kernel; sl->bytes = 0; }
     if (sl != nullptr) sl->bytes = bytes;
     return 0;
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VPR_PDL"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    return v == 1;
 }
 
 int side_branch(SideBranch** out) {

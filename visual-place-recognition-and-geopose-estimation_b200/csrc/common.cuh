@@ -46,6 +46,36 @@ int ensure_dynamic_smem(const void* kernel, size_t bytes);
 // A side stream + fork/join events (thread-local, created on first use) for small launches that are off the
 // critical path of a call: fork after the producer on the caller's stream, join before the consumer.  Works
 // under stream capture (the side stream joins the capture and becomes a parallel branch of the graph).
+bool pdl_enabled();          // VPR_PDL=0 switches programmatic dependent launches off
+
+// kernel launch with optional cluster width and programmatic-dependent-launch attribute
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                    int cluster, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cluster > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = (unsigned)cluster;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl && pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = (unsigned)na;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct SideBranch { cudaStream_t stream; cudaEvent_t fork, join; };
 int side_branch(SideBranch** out);
 
@@ -209,6 +239,16 @@ __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* 
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
         : "memory");
 }
+// ---------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may become resident
+// while its predecessor in the stream is still running; everything it does before pdl_wait() (barrier init, TMEM
+// allocation, descriptor prefetch) overlaps the predecessor's tail.  pdl_wait() returns once the predecessor grid has
+// completed and its writes are visible (a no-op for a normally launched kernel).  Every kernel here calls
+// pdl_launch_dependents() only AFTER its own pdl_wait(), so completion is transitive along a chain.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------
 // thread-block clusters
 // ---------------------------------------------------------------------------

@@ -111,6 +111,10 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // Programmatic dependent launch: everything above overlapped the previous launch's tail.  The resident W1 slice
+    // comes from the parameter pack of the forward pass (many launches back), so the producer fetches it before it
+    // waits for the previous launch (the Sinkhorn backward, which produces dS) to complete.
+    if (!(warp == DH_W_PROD && lane == 0)) { pdl_wait(); pdl_launch_dependents(); }
 
     if (warp == DH_W_PROD) {
         // ------------------------------ TMA producer ------------------------------
@@ -122,6 +126,8 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
             for (int kb = 0; kb < kboxes; ++kb)
                 for (int i = 0; i < 2; ++i)
                     tma_load_3d(sB + (uint32_t)kb * DH_BOX + (uint32_t)i * 8192u, tmB, bfull, cn * 128 + i * 64, kb * 64, 0);
+            pdl_wait();
+            pdl_launch_dependents();
             int it = 0;
             for (int mt = j0; mt < args.tiles_m; mt += nj, ++it) {
                 const int s = it & 1;
@@ -335,7 +341,8 @@ int dh_fused_run(const DhFusedDesc& d, cudaStream_t st) {
     int grid = (int)(want < num_sms() ? want : num_sms());
     if (grid < nct) grid = nct;                      // every column slice needs at least one CTA
     VPR_SMEM_OK(dh_fused_kernel, DH_SMEM);
-    dh_fused_kernel<<<grid, DH_THREADS, DH_SMEM, st>>>(tmF, tmS, tmW1c, tmW1s, tmH, tmO, a);
+    VPR_CUDA_OK(launch_ex(dh_fused_kernel, dim3((unsigned)grid), dim3(DH_THREADS), (size_t)DH_SMEM, st, d.pdl != 0, 1, tmF, tmS,
+                          tmW1c, tmW1s, tmH, tmO, a));
     return launch_ok("dh_fused_kernel");
 }
 

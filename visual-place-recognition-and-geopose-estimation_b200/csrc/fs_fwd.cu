@@ -90,6 +90,9 @@ fs_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // Programmatic dependent launch: everything above overlapped the previous launch's tail; the resident weights come
+    // from the parameter pack (two launches back), so the producer fetches them before it waits for H to be complete.
+    if (!(warp == FS_W_PROD && lane == 0)) { pdl_wait(); pdl_launch_dependents(); }
     const bool rev = args.rev != 0 && kind != 2;
     auto row_tile = [&](int mt) { return rev ? tiles_m - 1 - mt : mt; };
 
@@ -99,6 +102,8 @@ fs_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
             mbar_expect_tx(bfull, (uint32_t)(FS_KB * nrows * 128));
             for (int kb = 0; kb < FS_KB; ++kb)
                 tma_load_3d(sB + (uint32_t)(kb * nrows * 128), tmB, bfull, kb * 64, thalf * 128, 0);
+            pdl_wait();
+            pdl_launch_dependents();
             int stage = 0; uint32_t phase = 0;
             for (int mt = j0; mt < tiles_m; mt += nj)
                 for (int kb = 0; kb < FS_KB; ++kb) {
@@ -253,7 +258,8 @@ int fs_fwd_run(const FsFwdDesc& d, cudaStream_t st) {
     a.ctas_f = ((grid - 2) * 3 + 2) / 5;
     a.ctas_s = grid - 2 - a.ctas_f;
     VPR_SMEM_OK(fs_fwd_kernel, FS_SMEM);
-    fs_fwd_kernel<<<grid, FS_THREADS, FS_SMEM, st>>>(tmH, tmW1c, tmW1s, tmF, tmS, tmHT, tmWt1, tmTF, a);
+    VPR_CUDA_OK(launch_ex(fs_fwd_kernel, dim3((unsigned)grid), dim3(FS_THREADS), (size_t)FS_SMEM, st, d.pdl != 0, 1, tmH, tmW1c,
+                          tmW1s, tmF, tmS, tmHT, tmWt1, tmTF, a));
     return launch_ok("fs_fwd_kernel");
 }
 

@@ -65,6 +65,7 @@ struct TcGroup {
     TcProblem p[MAX_GROUP];
     int count;
     int total_work;
+    int pdl;                 // launch with the programmatic-dependent-launch attribute
 };
 static_assert(sizeof(TcArgs) % 8 == 0, "TcArgs is copied to shared memory in 4-byte words");
 static constexpr int ARGS_SMEM_BYTES = ((MAX_GROUP * (int)sizeof(TcArgs) + 127) / 128) * 128;
@@ -265,6 +266,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const int total_work = grp.total_work;
+    pdl_wait();                  // everything above overlapped the previous launch's tail
+    pdl_launch_dependents();
 
     // work item -> (problem, batch, m tile, n tile, k-block range)
     auto decode = [&](int w, int& g, int& b, int& mt, int& nt, int& kb0, int& kb1) {
@@ -696,19 +699,8 @@ static int launch_tc(const TcGroup& grp, int grid, cudaStream_t st) {
         VPR_SMEM_OK((gemm_tc_kernel<A_MN, B_MN, BN, MASK, CTA2, MCB>), Cfg::SMEM_BYTES);
         attr_set = true;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (CTA2 || MCB) ? 2 : 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    VPR_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A_MN, B_MN, BN, MASK, CTA2, MCB>, grp));
+    VPR_CUDA_OK(launch_ex(gemm_tc_kernel<A_MN, B_MN, BN, MASK, CTA2, MCB>, dim3((unsigned)grid), dim3(GEMM_THREADS),
+                          (size_t)Cfg::SMEM_BYTES, st, grp.pdl != 0, (CTA2 || MCB) ? 2 : 1, grp));
     return launch_ok("gemm_tc_kernel");
 }
 
@@ -857,6 +849,8 @@ static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
         VPR_REQUIRE(total < (1ll << 31), "too many tiles");
     }
     grp.total_work = (int)total;
+    grp.pdl = 0;
+    for (int i = 0; i < count; ++i) grp.pdl |= gs[i].pdl ? 1 : 0;
     int reserve = 0;
     for (int i = 0; i < count; ++i) if (gs[i].reserve_sms > reserve) reserve = gs[i].reserve_sms;
     if (reserve > num_sms() / 2) reserve = num_sms() / 2;

@@ -36,6 +36,7 @@ struct GemmDesc {
     int bn = 0;                    // tcgen05 tile N (64/128/256); 0 = auto
     int cta_pair = 0;              // 0 = auto (256 x 256 CTA-pair tiles when N > 128), 2 = single-CTA tiles
     int reserve_sms = 0;           // leave this many SMs without a persistent CTA (room for a concurrent collective)
+    int pdl = 0;                   // the previous launch in the stream is one of ours: programmatic dependent launch
 };
 
 // How a group will be tiled: tile shape and the number of tiles that run concurrently (SMs, or SM
@@ -57,6 +58,7 @@ struct DhFusedDesc {
     float* db0c; float* db0s;                // [hidden] fp32 each, accumulated (caller zeroes)
     float* db1c;                             // [128] fp32 column sums of dF (cluster_features.3.bias), or NULL
     long long T; int hidden; float mask_scale;
+    int pdl = 0;
 };
 // SALAD forward, second layer: F = H[:, :h] W1c^T + b1c (bf16), S = H[:, h:] W1s^T + b1s (fp32), weights resident
 // in shared memory, H streamed once.  dtype bf16, l == 128, m == 64, hidden == 512.
@@ -67,6 +69,7 @@ struct FsFwdDesc {
     long long T; int hidden;
     // token MLP second layer on two extra CTAs: TF[B, g] = HT[B, hidden] Wt1[g, hidden]^T + bias_t (g == 256)
     const void* HT; const void* Wt1; const float* bias_t; float* TF; int B; int g;
+    int pdl = 0;
 };
 bool fs_fwd_supported(int dtype, int l, int m, int hidden);
 int fs_fwd_run(const FsFwdDesc& d, cudaStream_t stream);
@@ -79,6 +82,7 @@ struct AggFwdDesc {
     float* AGG;                              // [B, 128, 64] fp32 (kept for the backward)
     void* out;                               // [B, g + 8192] bf16
     int B, n, g;
+    int pdl = 0;
 };
 bool agg_fwd_supported(int dtype, int l, int m, int g, int n);
 int agg_fwd_run(const AggFwdDesc& d, cudaStream_t stream);
@@ -91,6 +95,7 @@ struct AggBwdDesc {
     void* dF; float* dP;                                     // [B, n, 128] bf16, [B, n, 64] fp32
     void* dTF; float* g_bias_tok;                            // [B, g] bf16; [g] += column sums of dTF (or null)
     int B, n, g;
+    int pdl = 0;
 };
 bool agg_bwd_supported(int dtype, int l, int m, int g);
 int agg_bwd_run(const AggBwdDesc& d, cudaStream_t stream);

@@ -57,6 +57,8 @@ struct PackPlan { PackSeg seg[8]; long long total4; };
 // fp32 master weights -> run dtype, four elements per thread (all tensor sizes are multiples of 8)
 template <typename T>
 __global__ void __launch_bounds__(256) pack_params_kernel(const PackPlan plan) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plan.total4;
          i += (long long)gridDim.x * blockDim.x) {
         long long e = i;
@@ -298,7 +300,7 @@ static size_t sink_bwd_smem(int n, int m, int iters) {
 }
 
 static int sinkhorn_fwd(const float* S, const float* dust_bin, void* P, int p_dtype, float* U, float* V, int B, int n,
-                        int m, int iters, cudaStream_t st) {
+                        int m, int iters, cudaStream_t st, bool pdl = false) {
     VPR_REQUIRE(m == 16 || m == 32 || m == 64 || m == 128, "num_clusters must be 16/32/64/128 (got %d)", m);
     VPR_REQUIRE(n > m, "Sinkhorn needs n > m (n=%d, m=%d)", n, m);
     VPR_REQUIRE(iters >= 1 && iters <= 8, "iters out of range");
@@ -312,10 +314,12 @@ static int sinkhorn_fwd(const float* S, const float* dust_bin, void* P, int p_dt
         if (fs <= 227 * 1024) {          // scaled tile (one exp2 per element), log-domain body as its range guard
             if (p_dtype == VPR_BF16) {
                 VPR_SMEM_OK(sinkhorn_fwd_scaled<bf16>, fs);
-                sinkhorn_fwd_scaled<bf16><<<B, SS_NT, fs, st>>>(S, dust_bin, (bf16*)P, U, V, n, iters, k2);
+                VPR_CUDA_OK(launch_ex(sinkhorn_fwd_scaled<bf16>, dim3((unsigned)B), dim3(SS_NT), fs, st, pdl, 1, S, dust_bin, (bf16*)P, U, V, n,
+                                      iters, k2));
             } else {
                 VPR_SMEM_OK(sinkhorn_fwd_scaled<float>, fs);
-                sinkhorn_fwd_scaled<float><<<B, SS_NT, fs, st>>>(S, dust_bin, (float*)P, U, V, n, iters, k2);
+                VPR_CUDA_OK(launch_ex(sinkhorn_fwd_scaled<float>, dim3((unsigned)B), dim3(SS_NT), fs, st, pdl, 1, S, dust_bin, (float*)P, U, V,
+                                      n, iters, k2));
             }
             return launch_ok("sinkhorn_fwd_scaled");
         }
@@ -343,7 +347,7 @@ static int sinkhorn_fwd(const float* S, const float* dust_bin, void* P, int p_dt
 }
 
 static int sinkhorn_bwd(const float* S, const float* dust_bin, const float* U, const float* V, const float* dP, void* dS,
-                        int ds_dtype, float* d_bias, int B, int n, int m, int iters, cudaStream_t st) {
+                        int ds_dtype, float* d_bias, int B, int n, int m, int iters, cudaStream_t st, bool pdl = false) {
     VPR_REQUIRE(m == 16 || m == 32 || m == 64 || m == 128, "num_clusters must be 16/32/64/128 (got %d)", m);
     VPR_REQUIRE(n > m, "Sinkhorn needs n > m");
     if (m == 64) {
@@ -358,7 +362,8 @@ static int sinkhorn_bwd(const float* S, const float* dust_bin, const float* U, c
     do {                                                                                                               \
         VPR_SMEM_OK((sinkhorn_bwd_scaled<TD, KIT>), \
                                          (int)fs);                                                                    \
-        sinkhorn_bwd_scaled<TD, KIT><<<B, SS_NT, fs, st>>>(S, dust_bin, U, V, dP, (TD*)dS, d_bias, n, iters, k2);      \
+        VPR_CUDA_OK(launch_ex(sinkhorn_bwd_scaled<TD, KIT>, dim3((unsigned)B), dim3(SS_NT), fs, st, pdl, 1, S, dust_bin, U, V, dP, (TD*)dS,  \
+                              d_bias, n, iters, k2));                                                                                    \
     } while (0)
             if (ds_dtype == VPR_BF16) { if (iters == 3) VPR_SS_BWD(bf16, 3); else VPR_SS_BWD(bf16, 0); }
             else                      { if (iters == 3) VPR_SS_BWD(float, 3); else VPR_SS_BWD(float, 0); }
@@ -621,6 +626,8 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
     g[1] = GemmDesc(); g[1].dtype = dtype;
     g[1].A = t; g[1].lda = s.d; g[1].B = wt0; g[1].ldb = s.d; g[1].M = s.B; g[1].N = h; g[1].K = s.d;
     g[1].out = HT; g[1].out_kind = okT; g[1].ldo = h; g[1].bias = p.token_b0; g[1].relu = 1;
+    g[0].pdl = 1;        // a chain of our own launches (pack -> H -> F/S/TF -> Sinkhorn -> aggregation): each prologue
+                         // overlaps the previous launch's tail
     VPR_TRY(gemm_run_group(g, 2, st));
     // launch 2: F = H[:, :h] W1c^T + b1c [T, l]   S = H[:, h:] W1s^T + b1s [T, m] fp32   TF = HT Wt1^T + bt1 [B, g] fp32
     const bool fin_fast = finalize_fast_ok(s.l, s.m, s.g);
@@ -631,6 +638,7 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
             fd.H = H; fd.W1c = w1c; fd.W1s = w1s; fd.bias_f = p.cluster_b1; fd.bias_s = p.score_b1;
             fd.F = F; fd.S = S; fd.T = Tk; fd.hidden = h;
             fd.HT = HT; fd.Wt1 = wt1; fd.bias_t = p.token_b1; fd.TF = TF; fd.B = s.B; fd.g = s.g;
+            fd.pdl = 1;
             VPR_TRY(fs_fwd_run(fd, st));
         }
     } else {
@@ -643,14 +651,16 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
         g[2] = GemmDesc(); g[2].dtype = dtype;
         g[2].A = HT; g[2].lda = h; g[2].B = wt1; g[2].ldb = h; g[2].M = s.B; g[2].N = s.g; g[2].K = h;
         g[2].out = TF; g[2].out_kind = OUT_F32; g[2].ldo = s.g; g[2].bias = p.token_b1; g[2].bn = 128;
+        g[0].pdl = 1;
         VPR_TRY(gemm_run_group(g, 3, st));
     }
     // P = sinkhorn(S)
-    VPR_TRY(sinkhorn_fwd(S, p.dust_bin, P, dtype, U, V, s.B, s.n, s.m, s.iters, st));
+    VPR_TRY(sinkhorn_fwd(S, p.dust_bin, P, dtype, U, V, s.B, s.n, s.m, s.iters, st, true));
     if (agg_fwd_supported(dtype, s.l, s.m, s.g, s.n)) {
         if constexpr (sizeof(T) == 2) {          // aggregation + descriptor assembly in one launch, one CTA per image
             AggFwdDesc ad;
             ad.F = F; ad.P = P; ad.TF = TF; ad.AGG = AGG; ad.out = out; ad.B = s.B; ad.n = s.n; ad.g = s.g;
+            ad.pdl = 1;
             return agg_fwd_run(ad, st);
         }
     }
@@ -783,7 +793,7 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         fin_dht = true;
     }
     // ---- Sinkhorn backward: dP -> dS (+ score bias gradient) ----
-    VPR_TRY(sinkhorn_bwd(S, p.dust_bin, U, V, dP, dS, dtype, gr.score_b1, s.B, s.n, s.m, s.iters, st));
+    VPR_TRY(sinkhorn_bwd(S, p.dust_bin, U, V, dP, dS, dtype, gr.score_b1, s.B, s.n, s.m, s.iters, st, true));
 
     if (fused) {
         // ---- one pass over H: dH, the second-layer weight gradients and the first-layer bias gradients ----
@@ -792,6 +802,7 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         fd.dW1c = gr.cluster_w1; fd.dW1s = gr.score_w1; fd.db0c = gr.cluster_b0; fd.db0s = gr.score_b0;
         fd.db1c = gr.cluster_b1;
         fd.T = Tk; fd.hidden = h; fd.mask_scale = keep_scale;
+        fd.pdl = 1;
         VPR_TRY(dh_fused_run(fd, st));
         if (!fin_dht) VPR_TRY(gemm_run(gtokh, st));       // otherwise finalize_bwd_fast already produced dHT
     } else {
@@ -841,6 +852,7 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         const int tiles = 2 * ((h + tp.tile_m - 1) / tp.tile_m) * ((s.d + tp.tile_n - 1) / tp.tile_n);
         int ks = tp.slots / tiles; if (ks < 1) ks = 1; if (ks > kb_tok) ks = kb_tok;
         g4[0].k_splits = ks; g4[1].k_splits = ks;
+        g4[0].pdl = 1;
         VPR_TRY(gemm_run_group(g4, cnt, st));
     }
     }   // phase != VPR_BWD_INPUTS
@@ -854,6 +866,7 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
             g[cnt].A = dH; g[cnt].lda = 2 * h; g[cnt].B = w0cat; g[cnt].b_mn = 1; g[cnt].ldb = s.d; g[cnt].M = (int)Tk; g[cnt].N = s.d;
             g[cnt].K = 2 * h; g[cnt].out = dx; g[cnt].out_kind = okT; g[cnt].ldo = s.d;
             g[cnt].reserve_sms = reserve_sms;
+            g[cnt].pdl = phase == VPR_BWD_ALL ? 1 : 0;     // follows the dW0 launch directly only in the one-call form
             ++cnt;
         }
         if (dt != nullptr) {

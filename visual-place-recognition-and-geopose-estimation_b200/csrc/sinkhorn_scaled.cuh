@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_fwd_scaled(const float* __r
     float* wred = red + NW * SS_RED;             // [32]
     float* scal = wred + 32;                     // [8]  0: A   7: guard flag
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_wait();
+    pdl_launch_dependents();
     const float z2 = __ldg(dust_bin) * VPR_L2E;
     const float* Sb = S + (size_t)b * n * 64;
     if (tid == 0) scal[7] = 0.f;
@@ -254,6 +256,8 @@ __global__ void __launch_bounds__(SS_NT, 2) sinkhorn_bwd_scaled(const float* __r
                                                                 SinkConst2 k) {
     constexpr int NT = SS_NT, NW = SS_NT / 32;
     const int iters = KIT > 0 ? KIT : iters_rt;
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(16) float sk_smem[];
     float* E = sk_smem;                                  // [n][SS_PITCH]
     float* mxs = E + n * SS_PITCH;               // [n]
