@@ -266,8 +266,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const int total_work = grp.total_work;
-    pdl_wait();                  // everything above overlapped the previous launch's tail
-    pdl_launch_dependents();
+    // programmatic dependent launch: everything above overlapped the previous launch's tail.  pdl == 2: no operand of
+    // this launch comes from the launch right before it (dX after the dW0 group), so the whole kernel may overlap that
+    // launch's tail; the wait moves to the end, where it keeps completion transitive for whatever follows.
+    const bool pdl_late = grp.pdl == 2;
+    if (!pdl_late) { pdl_wait(); pdl_launch_dependents(); }
 
     // work item -> (problem, batch, m tile, n tile, k-block range)
     auto decode = [&](int w, int& g, int& b, int& mt, int& nt, int& kb0, int& kb1) {
@@ -517,6 +520,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (lane == 0) bulk_wait_read<0>();   // staging must outlive the last tile stores
     }
 
+    if (pdl_late) { pdl_wait(); pdl_launch_dependents(); }
     tc_fence_before();
     if (CL2) cluster_sync_all();           // the leader's MMAs read the peer's shared memory and write its TMEM
     else __syncthreads();
@@ -850,7 +854,8 @@ static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
     }
     grp.total_work = (int)total;
     grp.pdl = 0;
-    for (int i = 0; i < count; ++i) grp.pdl |= gs[i].pdl ? 1 : 0;
+    for (int i = 0; i < count; ++i) if (gs[i].pdl > grp.pdl) grp.pdl = gs[i].pdl;
+    for (int i = 0; i < count; ++i) if (gs[i].pdl != 2 && grp.pdl == 2) grp.pdl = 1;      // late wait only if every problem allows it
     int reserve = 0;
     for (int i = 0; i < count; ++i) if (gs[i].reserve_sms > reserve) reserve = gs[i].reserve_sms;
     if (reserve > num_sms() / 2) reserve = num_sms() / 2;

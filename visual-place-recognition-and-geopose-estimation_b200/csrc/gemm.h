@@ -36,7 +36,8 @@ struct GemmDesc {
     int bn = 0;                    // tcgen05 tile N (64/128/256); 0 = auto
     int cta_pair = 0;              // 0 = auto (256 x 256 CTA-pair tiles when N > 128), 2 = single-CTA tiles
     int reserve_sms = 0;           // leave this many SMs without a persistent CTA (room for a concurrent collective)
-    int pdl = 0;                   // the previous launch in the stream is one of ours: programmatic dependent launch
+    int pdl = 0;                   // 1: the previous launch in the stream is one of ours: programmatic dependent launch;
+                                   // 2: additionally none of this problem's operands is written by that launch
 };
 
 // How a group will be tiled: tile shape and the number of tiles that run concurrently (SMs, or SM

@@ -512,7 +512,11 @@ __global__ void __launch_bounds__(256) finalize_bwd_kernel(const float* __restri
     }
 }
 
-__global__ void counter_advance_kernel(unsigned long long* c) { *c += 1ull; }
+__global__ void counter_advance_kernel(unsigned long long* c) {
+    pdl_wait();                     // launched programmatically: resident early, increments only once the previous launch is done
+    pdl_launch_dependents();
+    *c += 1ull;
+}
 
 __global__ void dropout_mask_kernel(unsigned long long seed, uint32_t thr, long long total, uint8_t* out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
@@ -866,13 +870,14 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
             g[cnt].A = dH; g[cnt].lda = 2 * h; g[cnt].B = w0cat; g[cnt].b_mn = 1; g[cnt].ldb = s.d; g[cnt].M = (int)Tk; g[cnt].N = s.d;
             g[cnt].K = 2 * h; g[cnt].out = dx; g[cnt].out_kind = okT; g[cnt].ldo = s.d;
             g[cnt].reserve_sms = reserve_sms;
-            g[cnt].pdl = phase == VPR_BWD_ALL ? 1 : 0;     // follows the dW0 launch directly only in the one-call form
+            g[cnt].pdl = phase == VPR_BWD_ALL ? 2 : 0;     // one-call form: follows the dW0 launch, reads nothing it writes
             ++cnt;
         }
         if (dt != nullptr) {
             g[cnt] = GemmDesc(); g[cnt].dtype = dtype;
             g[cnt].A = dHT; g[cnt].lda = h; g[cnt].B = wt0; g[cnt].b_mn = 1; g[cnt].ldb = s.d; g[cnt].M = s.B; g[cnt].N = s.d; g[cnt].K = h;
             g[cnt].out = dt; g[cnt].out_kind = okT; g[cnt].ldo = s.d;
+            g[cnt].pdl = phase == VPR_BWD_ALL ? 2 : 0;
             ++cnt;
         }
         if (cnt > 0) VPR_TRY(gemm_run_group(g, cnt, st));
@@ -918,7 +923,8 @@ int vpr_salad_bwd(const VprSaladParams* p, const void* x, const void* t, const v
 
 int vpr_counter_advance(uint64_t* counter, cudaStream_t stream) {
     VPR_REQUIRE(counter != nullptr, "null counter");
-    counter_advance_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<unsigned long long*>(counter));
+    VPR_CUDA_OK(launch_ex(counter_advance_kernel, dim3(1), dim3(1), (size_t)0, stream, true, 1,
+                          reinterpret_cast<unsigned long long*>(counter)));
     return launch_ok("counter_advance_kernel");
 }
 
