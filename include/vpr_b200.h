@@ -211,6 +211,11 @@ VPR_API int vpr_recall_at_k(const int64_t* idx, const int64_t* gallery_label, co
  * rgb_hwc: [H, W, 3] uint8 (device); mean3 / std3: HOST pointers to 3 floats; out_chw: [3, out_h, out_w] (`dtype_out`);
  * out_u8_hwc: optional [out_h, out_w, 3] uint8 copy of the resized image (NULL to skip). */
 VPR_API size_t vpr_preprocess_workspace_bytes(int H, int W, int out_h, int out_w);
+/* B images of one size, stacked [B, H, W, 3] -> [B, 3, out_h, out_w] with the same four launches as one image. */
+VPR_API size_t vpr_preprocess_batch_workspace_bytes(int B, int H, int W, int out_h, int out_w);
+VPR_API int vpr_preprocess_batch(const uint8_t* rgb_bhwc, int B, int H, int W, int out_h, int out_w, const float* mean3,
+                         const float* std3, void* out_bchw, int dtype_out, uint8_t* out_u8_bhwc, void* workspace,
+                         size_t workspace_bytes, cudaStream_t stream);
 VPR_API int vpr_preprocess_image(const uint8_t* rgb_hwc, int H, int W, int out_h, int out_w, const float* mean3,
                          const float* std3, void* out_chw, int dtype_out, uint8_t* out_u8_hwc, void* workspace,
                          size_t workspace_bytes, cudaStream_t stream);

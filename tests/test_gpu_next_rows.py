@@ -312,3 +312,17 @@ def test_preprocess_batch_of_mixed_sizes_and_bf16(vpr):
         pre([torch.zeros(4, 4, 4, dtype=torch.uint8)])
     with pytest.raises(ValueError):
         pre([torch.zeros(4, 4, 3)])
+
+
+def test_preprocess_same_size_batch_in_one_call(vpr):
+    rng = np.random.RandomState(6)
+    imgs = [torch.from_numpy(rng.randint(0, 256, (120, 200, 3)).astype(np.uint8)) for _ in range(5)]
+    pre = vpr.GpuPreprocess((56, 56))
+    out, u8 = pre(imgs, return_uint8=True)                      # list of equal sizes -> stacked batch path
+    out4 = pre(torch.stack(imgs).cuda())                        # [B, H, W, 3] tensor
+    assert torch.equal(out, out4)
+    for i, im in enumerate(imgs):
+        assert np.array_equal(u8[i].cpu().numpy(), X.pil_resize_ref(im.numpy(), 56, 56))
+        assert torch.equal(out[i].cpu(), X.preprocess_ref(im.numpy(), 56, 56))
+        one = pre([im])
+        assert torch.equal(one[0], out[i])

@@ -78,6 +78,9 @@ EXPORTS = {
     "vpr_metrics_angle": (C.c_int, [_fp, _fp, C.c_int, C.c_int64, _fp, _fp, _fp]),
     "vpr_recall_at_k": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int, C.c_int64, _fp, C.c_int, _fp, _fp]),
     "vpr_preprocess_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vpr_preprocess_batch_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vpr_preprocess_batch": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                       C.POINTER(C.c_float), _fp, C.c_int, _fp, _fp, C.c_size_t, _fp]),
     "vpr_preprocess_image": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                        _fp, C.c_int, _fp, _fp, C.c_size_t, _fp]),
     "vpr_knn_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int, C.c_int]),

@@ -70,7 +70,7 @@ __device__ __forceinline__ int pp_clip8(int v) {
     return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
-// horizontal pass: in [H, W, 3] uint8 -> tmp [H, out_w, 3] uint8
+// horizontal pass: in [H, W, 3] uint8 -> tmp [H, out_w, 3] uint8   (a batch of equal-sized images is simply B * H rows)
 __global__ void __launch_bounds__(256) pp_horizontal_kernel(const uint8_t* __restrict__ in, int H, int W, int out_w, int ksize,
                                                             const int* __restrict__ bounds, const int* __restrict__ coef,
                                                             uint8_t* __restrict__ tmp) {
@@ -98,11 +98,16 @@ struct PpNorm { float mean[3], stdv[3]; };
 // vertical pass + ToTensor + Normalize: tmp [H, out_w, 3] uint8 -> out [3, out_h, out_w] (and optionally the resized
 // uint8 image [out_h, out_w, 3] for inspection / parity)
 template <typename TO>
-__global__ void __launch_bounds__(256) pp_vertical_kernel(const uint8_t* __restrict__ tmp, int out_h, int out_w, int ksize,
-                                                          const int* __restrict__ bounds, const int* __restrict__ coef,
-                                                          const PpNorm nrm, TO* __restrict__ out, uint8_t* __restrict__ out_u8) {
+__global__ void __launch_bounds__(256) pp_vertical_kernel(const uint8_t* __restrict__ tmp_all, int H, int B, int out_h, int out_w,
+                                                          int ksize, const int* __restrict__ bounds, const int* __restrict__ coef,
+                                                          const PpNorm nrm, TO* __restrict__ out_all, uint8_t* __restrict__ out_u8_all) {
     const long long total = (long long)out_h * out_w;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    for (long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x; gi < total * B; gi += (long long)gridDim.x * blockDim.x) {
+        const int img = (int)(gi / total);
+        const long long i = gi - (long long)img * total;
+        const uint8_t* tmp = tmp_all + (size_t)img * H * out_w * 3;
+        TO* out = out_all + (size_t)img * 3 * total;
+        uint8_t* out_u8 = out_u8_all != nullptr ? out_u8_all + (size_t)img * total * 3 : nullptr;
         const int yy = (int)(i / out_w), xx = (int)(i - (long long)yy * out_w);
         const int ymin = __ldg(bounds + 2 * yy), cnt = __ldg(bounds + 2 * yy + 1);
         const int* k = coef + (size_t)yy * ksize;
@@ -125,13 +130,13 @@ __global__ void __launch_bounds__(256) pp_vertical_kernel(const uint8_t* __restr
 }
 
 struct PpPlan { size_t tmp, bh, ch, bv, cv, total; int kh, kv; };
-static PpPlan pp_plan(int H, int W, int out_h, int out_w) {
+static PpPlan pp_plan(int H, int W, int out_h, int out_w, int B = 1) {
     PpPlan p;
     p.kh = pp_ksize(W, out_w);
     p.kv = pp_ksize(H, out_h);
     size_t off = 0;
     auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    p.tmp = carve((size_t)H * out_w * 3);
+    p.tmp = carve((size_t)B * H * out_w * 3);
     p.bh = carve((size_t)out_w * 2 * sizeof(int));
     p.ch = carve((size_t)out_w * p.kh * sizeof(int));
     p.bv = carve((size_t)out_h * 2 * sizeof(int));
@@ -151,13 +156,18 @@ size_t vpr_preprocess_workspace_bytes(int H, int W, int out_h, int out_w) {
     return pp_plan(H, W, out_h, out_w).total;
 }
 
-int vpr_preprocess_image(const uint8_t* rgb_hwc, int H, int W, int out_h, int out_w, const float* mean3, const float* std3,
-                         void* out_chw, int dtype_out, uint8_t* out_u8_hwc, void* workspace, size_t workspace_bytes,
-                         cudaStream_t stream) {
-    VPR_REQUIRE(rgb_hwc && mean3 && std3 && out_chw && workspace, "null argument");
-    VPR_REQUIRE(H > 0 && W > 0 && out_h > 0 && out_w > 0, "bad image shape");
+size_t vpr_preprocess_batch_workspace_bytes(int B, int H, int W, int out_h, int out_w) {
+    if (B <= 0 || H <= 0 || W <= 0 || out_h <= 0 || out_w <= 0) return 0;
+    return pp_plan(H, W, out_h, out_w, B).total;
+}
+
+int vpr_preprocess_batch(const uint8_t* rgb_bhwc, int B, int H, int W, int out_h, int out_w, const float* mean3,
+                         const float* std3, void* out_bchw, int dtype_out, uint8_t* out_u8_bhwc, void* workspace,
+                         size_t workspace_bytes, cudaStream_t stream) {
+    VPR_REQUIRE(rgb_bhwc && mean3 && std3 && out_bchw && workspace, "null argument");
+    VPR_REQUIRE(B > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0 && (long long)B * H < (1ll << 31), "bad image shape");
     VPR_REQUIRE(dtype_out == VPR_F32 || dtype_out == VPR_BF16, "dtype must be VPR_F32 or VPR_BF16");
-    const PpPlan p = pp_plan(H, W, out_h, out_w);
+    const PpPlan p = pp_plan(H, W, out_h, out_w, B);
     VPR_REQUIRE(workspace_bytes >= p.total, "workspace too small");
     uint8_t* ws = (uint8_t*)workspace;
     int* bh = (int*)(ws + p.bh); int* ch = (int*)(ws + p.ch); int* bv = (int*)(ws + p.bv); int* cv = (int*)(ws + p.cv);
@@ -167,17 +177,26 @@ int vpr_preprocess_image(const uint8_t* rgb_hwc, int H, int W, int out_h, int ou
     pp_coeffs_kernel<<<(out_h + 127) / 128, 128, 0, stream>>>(H, out_h, p.kv, bv, cv);
     VPR_TRY(launch_ok("pp_coeffs_kernel"));
     const long long cap = (long long)num_sms() * 8;
-    long long gh = ((long long)H * out_w + 255) / 256; if (gh > cap) gh = cap;
-    pp_horizontal_kernel<<<(unsigned)gh, 256, 0, stream>>>(rgb_hwc, H, W, out_w, p.kh, bh, ch, tmp);
+    long long gh = ((long long)B * H * out_w + 255) / 256; if (gh > cap) gh = cap;
+    pp_horizontal_kernel<<<(unsigned)gh, 256, 0, stream>>>(rgb_bhwc, B * H, W, out_w, p.kh, bh, ch, tmp);
     VPR_TRY(launch_ok("pp_horizontal_kernel"));
     PpNorm nrm;
     for (int c = 0; c < 3; ++c) { nrm.mean[c] = mean3[c]; nrm.stdv[c] = std3[c]; }
-    long long gv = ((long long)out_h * out_w + 255) / 256; if (gv > cap) gv = cap;
+    long long gv = ((long long)B * out_h * out_w + 255) / 256; if (gv > cap) gv = cap;
     if (dtype_out == VPR_F32)
-        pp_vertical_kernel<float><<<(unsigned)gv, 256, 0, stream>>>(tmp, out_h, out_w, p.kv, bv, cv, nrm, (float*)out_chw, out_u8_hwc);
+        pp_vertical_kernel<float><<<(unsigned)gv, 256, 0, stream>>>(tmp, H, B, out_h, out_w, p.kv, bv, cv, nrm, (float*)out_bchw,
+                                                                    out_u8_bhwc);
     else
-        pp_vertical_kernel<bf16><<<(unsigned)gv, 256, 0, stream>>>(tmp, out_h, out_w, p.kv, bv, cv, nrm, (bf16*)out_chw, out_u8_hwc);
+        pp_vertical_kernel<bf16><<<(unsigned)gv, 256, 0, stream>>>(tmp, H, B, out_h, out_w, p.kv, bv, cv, nrm, (bf16*)out_bchw,
+                                                                   out_u8_bhwc);
     return launch_ok("pp_vertical_kernel");
+}
+
+int vpr_preprocess_image(const uint8_t* rgb_hwc, int H, int W, int out_h, int out_w, const float* mean3, const float* std3,
+                         void* out_chw, int dtype_out, uint8_t* out_u8_hwc, void* workspace, size_t workspace_bytes,
+                         cudaStream_t stream) {
+    return vpr_preprocess_batch(rgb_hwc, 1, H, W, out_h, out_w, mean3, std3, out_chw, dtype_out, out_u8_hwc, workspace,
+                                workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -43,6 +43,23 @@ class GpuPreprocess:
         out = torch.empty(B, 3, self.out_h, self.out_w, dtype=self.out_dtype, device=self.device)
         u8 = torch.empty(B, self.out_h, self.out_w, 3, dtype=torch.uint8, device=self.device) if return_uint8 else None
         st = L.stream_ptr(self.device)
+        stacked = images if isinstance(images, torch.Tensor) and images.dim() == 4 else None
+        if stacked is None and B > 1 and all(isinstance(im, torch.Tensor) and im.shape == images[0].shape for im in images):
+            for im in images:
+                if im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3:
+                    raise ValueError("each image must be a [H, W, 3] uint8 tensor (RGB)")
+            stacked = torch.stack([im.to(self.device, non_blocking=True) for im in images])
+        if stacked is not None:                  # one size: the whole batch in the same four launches
+            if stacked.dtype != torch.uint8 or stacked.shape[3] != 3:
+                raise ValueError("a stacked batch must be [B, H, W, 3] uint8 (RGB)")
+            stacked = stacked.to(self.device, non_blocking=True).contiguous()
+            H, W = int(stacked.shape[1]), int(stacked.shape[2])
+            nbytes = lib.vpr_preprocess_batch_workspace_bytes(B, H, W, self.out_h, self.out_w)
+            ws = self._workspace(nbytes)
+            L.check(lib.vpr_preprocess_batch(L.ptr(stacked), B, H, W, self.out_h, self.out_w, self._mean, self._std, L.ptr(out),
+                                             L.dtype_code(self.out_dtype), L.ptr(u8), L.ptr(ws), ws.numel(), st),
+                    "vpr_preprocess_batch")
+            return (out, u8) if return_uint8 else out
         for i, img in enumerate(images):
             if img.dtype != torch.uint8 or img.dim() != 3 or img.shape[2] != 3:
                 raise ValueError("each image must be a [H, W, 3] uint8 tensor (RGB)")
