@@ -326,3 +326,55 @@ def test_preprocess_same_size_batch_in_one_call(vpr):
         assert torch.equal(out[i].cpu(), X.preprocess_ref(im.numpy(), 56, 56))
         one = pre([im])
         assert torch.equal(one[0], out[i])
+
+
+# ------------------------------------------------------------------ BASELINE configs[0] end to end
+def test_config1_images_to_descriptor_pipeline_against_cpu_oracle(vpr):
+    """BASELINE configs[0]: DINOv2 ViT-B/14 + SALAD forward at 224x224, batch 8, random-init weights.  GPU pipeline:
+    GpuPreprocess -> HuggingFace Dinov2Model blocks (the backbone is outside the path; fp32 here) -> BackboneSeam ->
+    SaladHead -> regressor.  CPU oracle: torchvision-equivalent preprocessing restatement -> the same HF model incl. its
+    final LayerNorm -> SaladRef -> LatLonRegressorRef."""
+    transformers = pytest.importorskip("transformers")
+    torch.manual_seed(0)
+    cfg = transformers.Dinov2Config(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, mlp_ratio=4, patch_size=14,
+                                    image_size=224)
+    backbone = transformers.Dinov2Model(cfg).eval()
+    ref_head = O.SaladRef(dropout=0.3).eval()
+    ref_reg = O.LatLonRegressorRef(8448, 512).eval()
+    rng = np.random.RandomState(12)
+    raw = [rng.randint(0, 256, (300, 400, 3)).astype(np.uint8) for _ in range(8)]
+    # ---- CPU oracle
+    with torch.no_grad():
+        x_cpu = torch.stack([X.preprocess_ref(im, 224, 224) for im in raw])
+        hs = backbone(pixel_values=x_cpu).last_hidden_state                       # final LayerNorm applied by HF
+        f = hs[:, 1:].reshape(8, 16, 16, 768).permute(0, 3, 1, 2)
+        want_desc = ref_head((f, hs[:, 0]))
+        want_pred = ref_reg(want_desc)
+    # ---- GPU pipeline
+    class Blocks(torch.nn.Module):                        # the backbone without its final LayerNorm
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, px):
+            return self.m(pixel_values=px, output_hidden_states=True).hidden_states[-1]
+
+    seam = vpr.BackboneSeam(768, eps=cfg.layer_norm_eps, out_dtype=torch.float32)
+    seam.norm.load_state_dict(backbone.layernorm.state_dict())
+    head = vpr.SaladHead(dropout=0.3)
+    head.load_state_dict(ref_head.state_dict())
+    model = vpr.DINOv2RegressionModel(vpr.VPRModel(Blocks(backbone), head, seam)).cuda().eval()
+    model.regressor.load_state_dict(ref_reg.regressor.state_dict())
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        pre = vpr.GpuPreprocess((224, 224))
+        px = pre([torch.from_numpy(im) for im in raw])
+        assert torch.equal(px.cpu(), x_cpu)                                          # bit-identical inputs
+        desc = model.features(px)
+        pred = model(px)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    assert desc.shape == (8, 8448)
+    assert rel(desc, want_desc) < 1e-3                      # fp32 backbone on two devices: summation-order noise only
+    assert rel(pred, want_pred) < 1e-3
