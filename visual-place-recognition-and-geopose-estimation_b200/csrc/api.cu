@@ -58,11 +58,13 @@ bool pdl_enabled() {
 }
 
 int side_branch(SideBranch** out) {
-    static thread_local SideBranch sb = {nullptr, nullptr, nullptr};
+    static thread_local SideBranch sb = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (sb.stream == nullptr) {
         VPR_CUDA_OK(cudaStreamCreateWithFlags(&sb.stream, cudaStreamNonBlocking));
         VPR_CUDA_OK(cudaEventCreateWithFlags(&sb.fork, cudaEventDisableTiming));
         VPR_CUDA_OK(cudaEventCreateWithFlags(&sb.join, cudaEventDisableTiming));
+        VPR_CUDA_OK(cudaEventCreateWithFlags(&sb.fork2, cudaEventDisableTiming));
+        VPR_CUDA_OK(cudaEventCreateWithFlags(&sb.zeroed, cudaEventDisableTiming));
     }
     *out = &sb;
     return 0;

@@ -76,7 +76,7 @@ static inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 bl
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-struct SideBranch { cudaStream_t stream; cudaEvent_t fork, join; };
+struct SideBranch { cudaStream_t stream; cudaEvent_t fork, join, fork2, zeroed; };
 int side_branch(SideBranch** out);
 
 static inline int launch_ok(const char* what) {

@@ -512,6 +512,17 @@ __global__ void __launch_bounds__(256) finalize_bwd_kernel(const float* __restri
     }
 }
 
+// out[c] += sum over rows of x[r][c]  (token_features.2.bias gradient = column sums of dTF); 32 rows per CTA
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_rows_kernel(const T* __restrict__ x, float* __restrict__ out, int rows, int cols) {
+    const int r0 = blockIdx.x * 32, r1 = min(rows, r0 + 32);
+    for (int c = threadIdx.x; c < cols; c += 256) {
+        float acc = 0.f;
+        for (int r = r0; r < r1; ++r) acc += ldf(x + (size_t)r * cols + c);
+        atomicAdd(out + c, acc);
+    }
+}
+
 __global__ void counter_advance_kernel(unsigned long long* c) {
     pdl_wait();                     // launched programmatically: resident early, increments only once the previous launch is done
     pdl_launch_dependents();
@@ -705,6 +716,20 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
     const int nsm = num_sms();
 
     if (phase != VPR_BWD_INPUTS) {
+    const bool fused = dh_fused_supported(dtype, s.l, s.m, h);
+    const bool per_image = fused && h == 512 && s.g <= 1024 && sizeof(T) == 2 && agg_bwd_supported(dtype, s.l, s.m, s.g);
+    static int use_side = -1;
+    if (use_side < 0) { const char* e = getenv("VPR_TOKEN_SIDE"); use_side = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    SideBranch* side = nullptr;                            // memset + token-MLP gradients running beside the main chain
+    cudaStream_t zst = st;
+    if (per_image && use_side) {
+        // the gradient accumulators are first touched by the Sinkhorn backward: zero them on the side stream while the
+        // per-image aggregation backward (which then accumulates nothing) runs on the main one
+        VPR_TRY(side_branch(&side));
+        VPR_CUDA_OK(cudaEventRecord(side->fork, st));
+        VPR_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        zst = side->stream;
+    }
     // zero every gradient buffer that is accumulated with atomics (adjacent buffers -> one memset)
     {
         struct Rng { float* p; size_t n; };
@@ -719,24 +744,24 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
             size_t cnt = r[i].n;
             int j = i + 1;
             while (j < 13 && r[j].p == p0 + cnt) { cnt += r[j].n; ++j; }
-            VPR_CUDA_OK(cudaMemsetAsync(p0, 0, cnt * sizeof(float), st));
+            VPR_CUDA_OK(cudaMemsetAsync(p0, 0, cnt * sizeof(float), zst));
             i = j;
         }
     }
+    if (side != nullptr) VPR_CUDA_OK(cudaEventRecord(side->zeroed, side->stream));
 
     GemmDesc g[3];
     const int kb_tok = (int)((Tk + 63) / 64);
-    const bool fused = dh_fused_supported(dtype, s.l, s.m, h);
     const bool fin_fast = finalize_fast_ok(s.l, s.m, s.g);
-    bool fin_dht = false;                                  // dHT already produced (finalize_bwd_fast / token_bwd_kernel)
-    SideBranch* side = nullptr;                            // token-MLP hidden gradient running beside the main chain
+    bool fin_dht = false;                                  // dHT already produced (finalize_bwd_fast / side-branch GEMM)
     bool tok_side = false;
-    if (fused && h == 512 && s.g <= 1024 && sizeof(T) == 2 && agg_bwd_supported(dtype, s.l, s.m, s.g)) {
+    if (per_image) {
         // ---- one CTA per image: cluster part of the norm backward + dF + dP (dAGG stays in shared memory) ----
         AggBwdDesc ad;
         ad.AGG = AGG; ad.TF = TF; ad.d_out = d_out; ad.P = P; ad.F = F; ad.dF = dF; ad.dP = dP;
-        ad.dTF = dTF; ad.g_bias_tok = gr.token_b1;
+        ad.dTF = dTF; ad.g_bias_tok = side != nullptr ? nullptr : gr.token_b1;    // side branch: column sums taken there
         ad.B = s.B; ad.n = s.n; ad.g = s.g;
+        ad.pdl = side != nullptr ? 1 : 0;                // no memset node between the previous launch and this one
         VPR_TRY(agg_bwd_run(ad, st));
         tok_side = true;
     } else {
@@ -783,14 +808,14 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
     gtokh.out = dHT; gtokh.out_kind = okT; gtokh.ldo = h; gtokh.mask = HT; gtokh.ld_mask = h; gtokh.colsum = gr.token_b0;
     if (tok_side) {
         // dHT depends only on dTF: a few tiles on a side branch next to the Sinkhorn backward / fused dH launch
-        static int use_side = -1;
-        if (use_side < 0) { const char* e = getenv("VPR_TOKEN_SIDE"); use_side = (e != nullptr && e[0] == '0') ? 0 : 1; }
-        if (use_side) {
-            VPR_TRY(side_branch(&side));
-            VPR_CUDA_OK(cudaEventRecord(side->fork, st));
-            VPR_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        if (side != nullptr) {
+            VPR_CUDA_OK(cudaEventRecord(side->fork2, st));                     // dTF is ready
+            VPR_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork2, 0));
+            colsum_rows_kernel<T><<<(s.B + 31) / 32, 256, 0, side->stream>>>(dTF, gr.token_b1, s.B, s.g);
+            VPR_TRY(launch_ok("colsum_rows_kernel"));
             VPR_TRY(gemm_run(gtokh, side->stream));
             VPR_CUDA_OK(cudaEventRecord(side->join, side->stream));
+            VPR_CUDA_OK(cudaStreamWaitEvent(st, side->zeroed, 0));             // the Sinkhorn backward accumulates a bias gradient
         } else {
             VPR_TRY(gemm_run(gtokh, st));
         }
