@@ -1,5 +1,8 @@
 """Per-kernel device times of one SALAD fwd+bwd step (CUPTI via torch.profiler; warm, pipelined --
-complements the cold, serialised ncu launch list).  python tools/step_profile.py [B] [n]"""
+complements the cold, serialised ncu launch list).  python tools/step_profile.py [B] [n]
+
+Run it with VPR_PDL=0 for per-kernel durations: with programmatic dependent launches (the default) a kernel is
+resident, and its CUPTI duration running, while it still waits for the previous launch to finish."""
 import os
 import sys
 
