@@ -362,6 +362,7 @@ def run_own(args, rank, local, world):
     # ---------------- end to end through the public API, host buffers (e2e) ----------------
     # pinned host inputs -> H2D on a copy stream (double buffered) -> SaladHead fwd+bwd -> D2H of the
     # step result (sum of the descriptor . w, 4 bytes)
+    numa = vpr_b200.bind_to_gpu_numa_node(local)      # staging buffers on the GPU's own NUMA node (restored below)
     xp = [x_h.pin_memory(), x_h.clone().pin_memory()]
     tp = [t_h.pin_memory(), t_h.clone().pin_memory()]
     xb = [torch.empty_like(x_d), torch.empty_like(x_d)]
@@ -406,6 +407,8 @@ def run_own(args, rank, local, world):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / (e2e_ms.item() * 1e-3)
     h2d = x_h.numel() * 2 + t_h.numel() * 2
+    if numa is not None:
+        os.sched_setaffinity(0, numa["previous"])     # the CPU baseline below uses every core again
 
     if rank != 0:
         return
@@ -478,7 +481,8 @@ def run_own(args, rank, local, world):
                    "per_gpu_batch": B, "global_batch": B * world, "n": n,
                    "l2": "working set per step (X 100 MB + H 134 MB + dH 134 MB ...) exceeds the 126 MB L2; "
                          "the isolated-kernel roofline timing flushes L2 with a 256 MB write between launches"},
-        "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "host_numa": None if numa is None else {"node": numa["numa_node"], "cpus": numa["cpus"]}},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     line["hbm_kernels"] = hbm_kernels

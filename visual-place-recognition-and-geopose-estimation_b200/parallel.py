@@ -32,6 +32,41 @@ def init_distributed(backend: str | None = None) -> tuple[int, int, int]:
     return rank, local, world
 
 
+def bind_to_gpu_numa_node(device_index: int = 0):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that pinned staging buffers allocated
+    afterwards are local to the GPU's PCIe root (host->device copies from the far socket run at a fraction of the
+    link rate).  Returns ``{"numa_node", "cpus", "previous"}`` (``previous`` = the affinity to restore with
+    ``os.sched_setaffinity(0, previous)``) or None when the topology cannot be read; never raises."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(int(device_index))    # CUDA index (honours CUDA_VISIBLE_DEVICES)
+        if hasattr(props, "pci_bus_id"):
+            bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        else:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(props.uuid)).encode())
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+            if len(bus.split(":")[0]) == 8:          # nvml pads the PCI domain to 8 hex digits, sysfs uses 4
+                bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        prev = os.sched_getaffinity(0)
+        use = cpus & prev
+        if not use:
+            return None
+        os.sched_setaffinity(0, use)
+        return {"numa_node": node, "cpus": len(use), "previous": prev}
+    except Exception:                                # noqa: BLE001  (best effort: containers often hide sysfs)
+        return None
+
+
 def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous [begin, end) of ``total`` rows owned by ``rank`` (first ``total % world`` ranks
     get one extra row).  Used for batch shards and gallery shards alike."""
