@@ -9,6 +9,8 @@
 // top-k of its 128 queries to the workspace; a small merge kernel combines the chunks (and, in
 // the sharded case, the per-rank results after the allgather).
 #include "common.cuh"
+
+#include <stdlib.h>
 #include "../../include/vpr_b200.h"
 
 #include <math.h>
@@ -282,16 +284,26 @@ static int knn_map(CUtensorMap* map, const void* ptr, int64_t rows, int D, int b
     return 0;
 }
 
-// query tiles per group: their operands must fit in about 80 MB of the 126 MB L2
+// query tiles per group: their operands should stay L2-resident while the group walks the gallery
 static int knn_q_group(int D, int tiles_m) {
     const int pairs = num_sms() / 2;
-    long long qt = (80ll << 20) / ((long long)K_TILE_M * D * 2);
-    if (qt < 1) qt = 1;
-    if (qt > pairs) qt = pairs;
-    const int waves = (pairs + (int)qt - 1) / (int)qt;           // gallery chunks in flight
-    qt = pairs / waves;
-    if (qt > tiles_m) qt = tiles_m;
-    return (int)qt;
+    static long long budget_mb = -1;
+    // measured (B200, Q = 8192, G = 1.25 M, D = 8448): 965 / 976 / 987 / 974 TFLOP/s with 80 / 40 / 20 / 9 MB; a ncu capture
+    // at the old 80 MB setting showed the query tiles being re-read from HBM all the same (159 GB of DRAM reads for a
+    // 5 GB gallery, 50 % L2 hit rate), so the budget stays well below the nominal 126 MB
+    if (budget_mb < 0) { const char* e = getenv("VPR_KNN_L2_MB"); budget_mb = (e != nullptr && atoi(e) > 0) ? atoi(e) : 24; }
+    long long qmax = (budget_mb << 20) / ((long long)K_TILE_M * D * 2);
+    if (qmax < 1) qmax = 1;
+    if (qmax > pairs) qmax = pairs;
+    if (qmax > tiles_m) qmax = tiles_m;
+    // q_group x (gallery chunks in flight = pairs / q_group) work items run at a time: take the largest group within
+    // the budget among those that leave the fewest CTA pairs idle
+    int best = 1, best_fill = 0;
+    for (int qg = 1; qg <= (int)qmax; ++qg) {
+        const int fill = qg * (pairs / qg);
+        if (fill >= best_fill) { best_fill = fill; best = qg; }
+    }
+    return best;
 }
 
 static void knn_plan(int64_t Q, int64_t G, int D, int& tiles_m, int& tiles_n, int& chunks, int& tiles_per_chunk) {
