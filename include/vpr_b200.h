@@ -28,6 +28,15 @@
  *                               swin_angle_finetuning_sin_cos.py:56-69.
  *  - vpr_knn_topk             : no reference call site (SURVEY.md section 0 finding 4);
  *                               replaces torch.topk(Q @ G.T, k).
+ *  Rows next to the path, each documented at its declaration below:
+ *  - vpr_seam_ln_split_fwd/_bwd : the backbone's final LayerNorm + CLS / patch-token split ([UPSTREAM] DINOv2
+ *                               forward_features, reached from dinov2salad_finetuning.py:36).
+ *  - vpr_metrics_latlon / _angle, vpr_recall_at_k : dinov2salad_validation.py:84-101,
+ *                               dinov2salad_finetuning_2.py:202-215, angle_prediction/efficient_net/
+ *                               validation_script.py:180-202, dino_v2_gemini.py:117-141.
+ *  - vpr_preprocess_image / _batch : transforms.Resize + ToTensor + Normalize, dinov2salad_finetuning.py:45-50.
+ *  Environment knobs read once per process (A/B measurements): VPR_PDL, VPR_GEMM_2CTA, VPR_GEMM_MCB, VPR_FS_FUSED,
+ *  VPR_FS_REVERSE, VPR_DH_FUSED, VPR_AGG_FUSED, VPR_AGG_BWD_FUSED, VPR_TOKEN_SIDE, VPR_KNN_L2_MB.
  */
 #ifndef VPR_B200_H
 #define VPR_B200_H
