@@ -204,6 +204,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// Same wait for warps that expect to wait long (epilogue warps waiting ~100 us for a kNN tile): after a few failed
+// polls they sleep between polls instead of competing with the MMA / TMA warps for issue slots and power.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned sleep_ns) {
+    uint32_t done;
+    long long t0 = 0;
+    int spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (++spins > 4) __nanosleep(sleep_ns);
+        if (spins == 64) t0 = clock64();
+        if (spins > 64 && (spins & 255) == 0 && clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
 // ---------------------------------------------------------------------------
 // TMA
 // ---------------------------------------------------------------------------

@@ -36,6 +36,7 @@ struct KnnArgs {
     int Q, G, D, k;
     int tiles_m, chunks, tiles_per_chunk, tiles_n, kb_total;
     int q_group;           // query tiles that walk the same gallery chunk at the same time (L2 reuse)
+    int relaxed;           // epilogue warps sleep between polls while they wait for a tile
     float* ws_score;       // [Q, chunks, k]
     int* ws_idx;           // [Q, chunks, k] local gallery row, -1 = empty
 };
@@ -161,7 +162,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             for (int nt = nt0; nt < nt1; ++nt, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(tfull_bar(as), aphase);
+                if (args.relaxed) mbar_wait_relaxed(tfull_bar(as), aphase, 256);   // a tile takes ~100 us: do not spin against the MMA warp
+                else mbar_wait(tfull_bar(as), aphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * KBN);
 #pragma unroll 1
@@ -354,6 +356,11 @@ int vpr_knn_topk(const void* q, const void* g, int64_t Q, int64_t G, int D, int 
     knn_plan(Q, G, D, a.tiles_m, a.tiles_n, a.chunks, a.tiles_per_chunk);
     a.kb_total = (D + KBK - 1) / KBK;
     a.q_group = knn_q_group(D, a.tiles_m);
+    {
+        static int relaxed = -1;
+        if (relaxed < 0) { const char* e = getenv("VPR_KNN_RELAXED"); relaxed = (e != nullptr && e[0] == '0') ? 0 : 1; }
+        a.relaxed = relaxed;
+    }
     size_t off = 0;
     a.ws_score = (float*)((char*)workspace + carve_size(off, (size_t)Q * a.chunks * k * 4));
     a.ws_idx = (int*)((char*)workspace + carve_size(off, (size_t)Q * a.chunks * k * 4));
