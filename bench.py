@@ -410,6 +410,30 @@ def run_own(args, rank, local, world):
     if numa is not None:
         os.sched_setaffinity(0, numa["previous"])     # the CPU baseline below uses every core again
 
+    # ---------------- BASELINE configs[2]: SALAD + lat/lon + sin/cos heads + losses, one graph per step ----------------
+    heads = vpr_b200.GeoposeHeads(latlon_loss="mse", angle_loss="atan2_maae").to(dev).train()
+    ft = vpr_b200.GraphedFinetuneStep(head, heads, B, n, global_batch=B * world)
+    gt = torch.Generator(device=dev).manual_seed(99 + rank)
+    ft(x_d.view(B, n, D), t_d, torch.randn(B, 2, device=dev, generator=gt), torch.rand(B, device=dev, generator=gt) * 360)
+    for _ in range(3):
+        ft()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        ft()
+    f1.record()
+    barrier()
+    ft_ms = torch.tensor([f0.elapsed_time(f1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ft_ms, op=dist.ReduceOp.MAX)
+    finetune = {"workload": "SALAD head + lat/lon regressor (8448-512-2, MSE) + sin/cos head (atan2 MAAE), fwd+bwd of all "
+                            f"{ft.grad_elements()} parameters, one CUDA graph per step"
+                            + (", gradient all-reduces captured in the graph" if world > 1 else ""),
+                "value": world * B / (ft_ms.item() * 1e-3), "unit": "img/s", "ms_per_step": ft_ms.item(),
+                "per_gpu_batch": B, "global_batch": B * world, "launches_per_step": ft.launches_per_replay}
+    del ft
+
     if rank != 0:
         return
 
@@ -486,6 +510,7 @@ def run_own(args, rank, local, world):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     line["hbm_kernels"] = hbm_kernels
+    line["finetune_step"] = finetune
     if knn is not None:
         line["knn"] = knn
     emit(line)

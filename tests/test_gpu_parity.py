@@ -339,6 +339,35 @@ def test_graphed_step_can_be_captured_while_an_eager_graph_is_still_alive(vpr):
     assert held.grad_fn is not None
 
 
+def test_graphed_finetune_step_matches_eager_data_parallel_step(vpr):
+    """BASELINE configs[2] as one graph replay (SALAD fwd -> fused heads + losses -> SALAD bwd) against the eager
+    DataParallelStep on the same inputs; single process, so no collective is involved."""
+    torch.manual_seed(0)
+    salad = vpr.SaladHead(dropout=0.0).cuda().train()
+    heads = vpr.GeoposeHeads(latlon_loss="huber", angle_loss="atan2_maae").cuda().train()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, n = 8, 256
+    x = torch.randn(B, n, 768, device="cuda", generator=g).bfloat16()
+    t = torch.randn(B, 768, device="cuda", generator=g).bfloat16()
+    ll = torch.randn(B, 2, device="cuda", generator=g)
+    ang = torch.rand(B, device="cuda", generator=g) * 360
+    eager = vpr.DataParallelStep(salad, heads)
+    total_e, losses_e = eager.step(x, t, ll, ang, global_B=32)
+    want = {id(p): p.grad.clone() for p in list(salad.parameters()) + list(heads.parameters())}
+    step = vpr.GraphedFinetuneStep(salad, heads, batch=B, n_tokens=n, global_batch=32)
+    assert step.grad_elements() == 5754821                      # 1 411 009 SALAD + 4 326 914 regressor + 16 898 angle head
+    for _ in range(2):                                           # a second replay must not accumulate
+        total_g, losses_g = step(x, t, ll, ang)
+    torch.cuda.synchronize()
+    assert abs(total_g.item() - total_e.item()) < 1e-5 * abs(total_e.item())
+    assert rel(losses_g, losses_e) < 1e-5
+    for p in list(salad.parameters()) + list(heads.parameters()):
+        w = want[id(p)]
+        if w.norm() > 1e-6:
+            assert rel(p.grad, w) < 1e-5, p.shape
+    assert step.dx is None and step.launches_per_replay >= 12
+
+
 @pytest.mark.parametrize("env", [{"VPR_DH_FUSED": "0", "VPR_FS_FUSED": "0", "VPR_AGG_FUSED": "0"},
                                  {"VPR_GEMM_2CTA": "0"}, {"VPR_GEMM_MCB": "1", "VPR_FS_REVERSE": "0"}])
 def test_generic_paths_still_match_when_the_fused_kernels_are_switched_off(vpr, env):

@@ -5,7 +5,7 @@ the directory name carries the reference's hyphenated name)."""
 from ._lib import LIB_PATH, lib  # noqa: F401
 from .heads import GeoposeHeads, sincos_to_degrees  # noqa: F401
 from .knn import knn_topk, knn_topk_sharded, merge_topk  # noqa: F401
-from .parallel import (DataParallelStep, allreduce_grads, bind_to_gpu_numa_node, init_distributed,  # noqa: F401
+from .parallel import (DataParallelStep, GraphedFinetuneStep, allreduce_grads, bind_to_gpu_numa_node, init_distributed,  # noqa: F401
                        overlap_grad_allreduce, shard_range)
 from .metrics import LatLonScaler, latlon_metrics, maae, recall_at_k  # noqa: F401
 from .model import (DINOv2RegressionModel, VPRModel, load_reference_checkpoint, load_upstream_salad_weights,  # noqa: F401
@@ -15,7 +15,7 @@ from .seam import BackboneSeam  # noqa: F401
 from .salad import GraphedSaladStep, SaladHead, dropout_keep_mask, sinkhorn, sinkhorn_backward  # noqa: F401
 
 __all__ = ["SaladHead", "GraphedSaladStep", "GeoposeHeads", "knn_topk", "knn_topk_sharded", "merge_topk", "sinkhorn",
-           "sinkhorn_backward", "dropout_keep_mask", "DataParallelStep", "allreduce_grads", "overlap_grad_allreduce", "init_distributed", "bind_to_gpu_numa_node",
+           "sinkhorn_backward", "dropout_keep_mask", "DataParallelStep", "GraphedFinetuneStep", "allreduce_grads", "overlap_grad_allreduce", "init_distributed", "bind_to_gpu_numa_node",
            "shard_range", "sincos_to_degrees", "BackboneSeam", "GpuPreprocess", "VPRModel", "DINOv2RegressionModel", "load_reference_checkpoint",
            "load_upstream_salad_weights", "save_reference_checkpoint", "LatLonScaler", "latlon_metrics", "maae", "recall_at_k",
            "lib", "LIB_PATH"]

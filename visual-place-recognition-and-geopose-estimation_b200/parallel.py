@@ -217,3 +217,94 @@ class DataParallelStep:
         fin_heads()
         fin_salad()
         return total.detach(), losses
+
+
+class GraphedFinetuneStep:
+    """BASELINE config 3 as ONE CUDA-graph replay: SALAD forward -> fused geopose heads + losses (forward and backward in
+    one library call) -> SALAD backward, for a fixed per-rank batch shape, with the gradient all-reduces captured in the
+    graph when a process group is up (heads gradients start reducing before the SALAD backward, the SALAD gradients from
+    inside it -- see ``overlap_grad_allreduce``).  The backbone is frozen in the reference, so no input gradients are
+    produced unless ``input_grads=True``.
+
+        step = GraphedFinetuneStep(salad, heads, batch=256, n_tokens=256, global_batch=2048)
+        total, losses = step(x_tok, t, latlon_target, angle_target_deg)     # p.grad of both modules is up to date
+
+    The losses are global-batch means (each rank divides by ``global_batch``), so the reduction across ranks is a sum.
+    The regressor's own dropout draws its mask from a host-side step counter and is therefore not supported here."""
+
+    def __init__(self, salad, heads, batch: int, n_tokens: int, dtype=torch.bfloat16, global_batch: int | None = None,
+                 group=None, input_grads: bool = False, warmup: int = 3):
+        from . import _lib as L
+        from .heads import _run as heads_run
+        from .salad import _salad_backward, _salad_forward
+        dev = salad.dust_bin.device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedFinetuneStep needs the modules on a CUDA device")
+        if heads.reg_dropout_p > 0 and heads.training:
+            raise RuntimeError("GraphedFinetuneStep: the regressor's dropout uses a host-side step counter; use dropout=0")
+        self.salad, self.heads, self.group = salad, heads, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.global_batch = int(global_batch) if global_batch is not None else batch * self.world
+        salad.use_device_step_counter(True)
+        if self.world > 1 and salad._grad_hook is None:
+            overlap_grad_allreduce(salad, group)
+        self.x = torch.zeros(batch, n_tokens, salad.num_channels, dtype=dtype, device=dev)
+        self.t = torch.zeros(batch, salad.num_channels, dtype=dtype, device=dev)
+        self.latlon = torch.zeros(batch, 2, dtype=torch.float32, device=dev)
+        self.angle = torch.zeros(batch, dtype=torch.float32, device=dev)
+        use_angle = heads.angle_loss not in (None, "none")
+
+        def run():
+            x_tok, t, shape, p_drop, seed, seed_dev, sparams = salad._prepare((self.x, self.t))
+            desc, save = _salad_forward(x_tok, t, shape, p_drop, seed, seed_dev, sparams)
+            hparams = [p.contiguous() for p in heads._params()]
+            cfg = heads._cfg(global_B=self.global_batch)
+            latlon_pred, sincos_pred, losses, hgrads, d_desc, hflat = heads_run(
+                desc, hparams, self.latlon, self.angle if use_angle else None, cfg, True)
+            hwork = dist.all_reduce(hflat, group=group, async_op=True) if self.world > 1 else None
+            dx, dt, sflat, sgrads = _salad_backward(x_tok, t, save, sparams, shape, p_drop, d_desc, input_grads, input_grads,
+                                                    salad._grad_hook)
+            if hwork is not None:
+                hwork.wait()
+            return desc, losses, latlon_pred, sincos_pred, hgrads, sgrads, dx, dt
+
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(1, warmup)):
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        lib = L.lib()
+        launches0 = lib.vpr_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            (self.desc, self.losses, self.latlon_pred, self.sincos_pred, hgrads, sgrads, self.dx, self.dt) = run()
+        self.launches_per_replay = int(lib.vpr_launch_count() - launches0)
+        self._grads = []
+        for p, g in zip(heads._params(), hgrads):
+            if p.requires_grad and g is not None:
+                self._grads.append((p, g.view_as(p)))
+        for p, g in zip(salad._param_list(), sgrads):
+            if p.requires_grad:
+                self._grads.append((p, g.view_as(p)))
+        self._use_angle = use_angle
+
+    def grad_elements(self) -> int:
+        return sum(g.numel() for _, g in self._grads)
+
+    def __call__(self, x_tok=None, t=None, latlon_target=None, angle_target_deg=None):
+        if x_tok is not None:
+            self.x.copy_(x_tok.reshape(self.x.shape), non_blocking=True)
+        if t is not None:
+            self.t.copy_(t, non_blocking=True)
+        if latlon_target is not None:
+            self.latlon.copy_(latlon_target, non_blocking=True)
+        if angle_target_deg is not None:
+            self.angle.copy_(angle_target_deg, non_blocking=True)
+        self.graph.replay()
+        for p, g in self._grads:
+            if p.grad is not g:
+                p.grad = g
+        total = self.losses[0] + self.losses[1] if self._use_angle else self.losses[0]
+        return total, self.losses
