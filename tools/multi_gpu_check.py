@@ -117,6 +117,28 @@ def main():
                           "param_grad_rel_err": e[0].item(), "dx_rel_err": e[1].item(), "ok": good}), flush=True)
     ok = ok and good
     salad.set_grad_ready_hook(None)
+
+    # ---------------- configs[2] as one graph: SALAD + heads + losses with both all-reduces captured ----------------
+    step = vpr_b200.DataParallelStep(salad, heads)
+    step.step(x[b0:b1], t[b0:b1], ll[b0:b1], ang[b0:b1], global_B=Bg)          # eager, un-hooked: the reference gradients
+    torch.cuda.synchronize()
+    want_f = grads().clone()
+    fstep = vpr_b200.GraphedFinetuneStep(salad, heads, batch=b1 - b0, n_tokens=n, global_batch=Bg)
+    for rep in range(2):
+        tot, _ = fstep(x[b0:b1], t[b0:b1], ll[b0:b1], ang[b0:b1])
+    torch.cuda.synchronize()
+    e = torch.tensor([rel(grads(), want_f)], device=dev)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    lsum = tot.clone()
+    dist.all_reduce(lsum)
+    good = e.item() < 1e-5 and abs(lsum.item() - want_loss) < 1e-3 * abs(want_loss)
+    if rank == 0:
+        print(json.dumps({"check": "GraphedFinetuneStep (in-graph all-reduces) == eager DataParallelStep", "world": world,
+                          "launches_per_replay": fstep.launches_per_replay, "grad_rel_err": e.item(),
+                          "loss_sum": lsum.item(), "loss_single": want_loss, "ok": good}), flush=True)
+    ok = ok and good
+    salad.set_grad_ready_hook(None)
+    del fstep
     del gstep                                                 # the graph holds captured NCCL work: drop it before teardown
     torch.cuda.synchronize()
     dist.barrier()
