@@ -29,6 +29,8 @@ __device__ __forceinline__ float mod360(float x) {
 template <typename T>
 __global__ void pack_heads_kernel(const float* __restrict__ w0, const float* __restrict__ wa, T* __restrict__ waug,
                                   long long hidD, long long D, long long total) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         float v = 0.f;
@@ -43,6 +45,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) angle_fwd_kernel(const T* __restrict__ desc, const float* __restrict__ wa,
                                                         float* __restrict__ sc_raw, int D) {
     __shared__ float red[2][8];
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.x;
     const T* x = desc + (size_t)b * D;
     float a0 = 0.f, a1 = 0.f;
@@ -78,6 +82,8 @@ template <typename T>
 __global__ void __launch_bounds__(128) heads_tail_kernel(const TailArgs a) {
     __shared__ float red[2][4];
     __shared__ float dpred_s[2];
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.x, tid = threadIdx.x;
     const float* zrow = a.zacc + (size_t)b * a.hid;
     // z = dropout(relu(zacc + b0)); pred = W1 z + b1
@@ -185,6 +191,8 @@ __global__ void __launch_bounds__(128) heads_tail_kernel(const TailArgs a) {
 template <typename T>
 __global__ void __launch_bounds__(256) angle_wgrad_kernel(const T* __restrict__ desc, const T* __restrict__ dzaug,
                                                           float* __restrict__ g_wa, int B, int D, int hid, int hid_pad) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int d = blockIdx.x * 256 + threadIdx.x;
     if (d >= D) return;
     float a0 = 0.f, a1 = 0.f;
@@ -224,16 +232,32 @@ static int heads_t(const VprHeadsParams& p, const T* desc, const float* latlon_t
     const int nsm = num_sms();
 
     const long long hidD = (long long)s.hidden * s.D;
-    pack_heads_kernel<T><<<nsm * 4, 256, 0, st>>>(p.reg_w0, angle ? p.ang_w : nullptr, waug, hidD, s.D,
-                                                  (long long)hp.hid_pad * s.D);
+    // accumulators -> 0 first (adjacent buffers in one memset), so that the kernels below form an uninterrupted chain
+    // of programmatic dependent launches
+    {
+        struct Rng { void* p; size_t n; };
+        Rng r[7];
+        int cnt = 0;
+        r[cnt++] = {zacc, (size_t)s.B * s.hidden * 4};
+        r[cnt++] = {losses, 2 * sizeof(float)};
+        r[cnt++] = {gr.reg_b0, sizeof(float) * s.hidden};
+        r[cnt++] = {gr.reg_w1, sizeof(float) * 2 * s.hidden};
+        r[cnt++] = {gr.reg_b1, sizeof(float) * 2};
+        if (gr.ang_w && !angle) r[cnt++] = {gr.ang_w, sizeof(float) * 2 * s.D};
+        if (gr.ang_b) r[cnt++] = {gr.ang_b, sizeof(float) * 2};
+        int i = 0;
+        while (i < cnt) {
+            char* p0 = (char*)r[i].p;
+            size_t nb = r[i].n;
+            int j = i + 1;
+            while (j < cnt && (char*)r[j].p == p0 + nb) { nb += r[j].n; ++j; }
+            VPR_CUDA_OK(cudaMemsetAsync(p0, 0, nb, st));
+            i = j;
+        }
+    }
+    VPR_CUDA_OK(launch_ex(pack_heads_kernel<T>, dim3((unsigned)(nsm * 4)), dim3(256), (size_t)0, st, false, 1, p.reg_w0,
+                          angle ? p.ang_w : (const float*)nullptr, waug, hidD, (long long)s.D, (long long)hp.hid_pad * s.D));
     VPR_TRY(launch_ok("pack_heads_kernel"));
-    VPR_CUDA_OK(cudaMemsetAsync(zacc, 0, (size_t)s.B * s.hidden * 4, st));
-    VPR_CUDA_OK(cudaMemsetAsync(losses, 0, 2 * sizeof(float), st));
-    VPR_CUDA_OK(cudaMemsetAsync(gr.reg_b0, 0, sizeof(float) * s.hidden, st));
-    VPR_CUDA_OK(cudaMemsetAsync(gr.reg_w1, 0, sizeof(float) * 2 * s.hidden, st));
-    VPR_CUDA_OK(cudaMemsetAsync(gr.reg_b1, 0, sizeof(float) * 2, st));
-    if (gr.ang_b) VPR_CUDA_OK(cudaMemsetAsync(gr.ang_b, 0, sizeof(float) * 2, st));
-    if (gr.ang_w && !angle) VPR_CUDA_OK(cudaMemsetAsync(gr.ang_w, 0, sizeof(float) * 2 * s.D, st));
 
     GemmDesc g;
     // zacc = desc W0^T   (split-K: only ceil(B/128) * hidden/256 output tiles exist)
@@ -244,9 +268,10 @@ static int heads_t(const VprHeadsParams& p, const T* desc, const float* latlon_t
         int tiles = ((s.B + 127) / 128) * ((s.hidden + 255) / 256);
         g.k_splits = nsm / tiles; if (g.k_splits < 1) g.k_splits = 1;
     }
+    g.pdl = 1;
     VPR_TRY(gemm_run(g, st));
     if (angle) {
-        angle_fwd_kernel<T><<<s.B, 256, 0, st>>>(desc, p.ang_w, sc_raw, s.D);
+        VPR_CUDA_OK(launch_ex(angle_fwd_kernel<T>, dim3((unsigned)s.B), dim3(256), (size_t)0, st, true, 1, desc, p.ang_w, sc_raw, s.D));
         VPR_TRY(launch_ok("angle_fwd_kernel"));
     }
     TailArgs a;
@@ -260,21 +285,24 @@ static int heads_t(const VprHeadsParams& p, const T* desc, const float* latlon_t
     a.drop_thr = s.reg_dropout_p > 0.f ? dropout_threshold(s.reg_dropout_p) : 0u;
     a.drop_scale = s.reg_dropout_p > 0.f ? 1.f / (1.f - s.reg_dropout_p) : 1.f;
     a.seed = s.seed;
-    heads_tail_kernel<T><<<s.B, 128, 0, st>>>(a);
+    VPR_CUDA_OK(launch_ex(heads_tail_kernel<T>, dim3((unsigned)s.B), dim3(128), (size_t)0, st, true, 1, a));
     VPR_TRY(launch_ok("heads_tail_kernel"));
     // dW0[hid, D] = dZ^T desc
     g = GemmDesc(); g.dtype = dtype;
     g.A = dzaug; g.a_mn = 1; g.lda = hp.hid_pad; g.B = desc; g.b_mn = 1; g.ldb = s.D; g.M = s.hidden; g.N = s.D; g.K = s.B;
     g.out = gr.reg_w0; g.out_kind = OUT_F32; g.ldo = s.D;
+    g.pdl = 1;
     VPR_TRY(gemm_run(g, st));
     if (angle) {
-        angle_wgrad_kernel<T><<<(s.D + 255) / 256, 256, 0, st>>>(desc, dzaug, gr.ang_w, s.B, s.D, s.hidden, hp.hid_pad);
+        VPR_CUDA_OK(launch_ex(angle_wgrad_kernel<T>, dim3((unsigned)((s.D + 255) / 256)), dim3(256), (size_t)0, st, true, 1, desc,
+                              (const T*)dzaug, gr.ang_w, s.B, s.D, s.hidden, hp.hid_pad));
         VPR_TRY(launch_ok("angle_wgrad_kernel"));
     }
     if (d_desc != nullptr) {   // d_desc = [dZ | dsc] [W0 ; Wa]
         g = GemmDesc(); g.dtype = dtype;
         g.A = dzaug; g.lda = hp.hid_pad; g.B = waug; g.b_mn = 1; g.ldb = s.D; g.M = s.B; g.N = s.D; g.K = hp.hid_pad;
         g.out = d_desc; g.out_kind = okT; g.ldo = s.D;
+        g.pdl = 1;
         VPR_TRY(gemm_run(g, st));
     }
     return 0;
