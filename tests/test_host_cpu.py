@@ -110,6 +110,15 @@ def test_next_rows_have_no_cpu_fallback_either(built):
     assert built.lib().vpr_preprocess_workspace_bytes(480, 640, 224, 224) >= 480 * 224 * 3
 
 
+def test_graphed_steps_and_numa_helper_without_a_gpu(built):
+    head, heads = built.SaladHead(), built.GeoposeHeads()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        built.GraphedSaladStep(head, batch=2, n_tokens=256)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        built.GraphedFinetuneStep(head, heads, batch=2, n_tokens=256)
+    assert built.bind_to_gpu_numa_node(0) is None            # no device, no sysfs topology: a no-op, never an exception
+
+
 def test_scaler_mirrors_sklearn_and_joblib(built, tmp_path):
     import joblib
     from sklearn.preprocessing import StandardScaler
