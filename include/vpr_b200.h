@@ -3,8 +3,16 @@
  * (forward + backward), geopose heads + losses, descriptor kNN.
  *
  * Conventions
- *  - Every pointer is a DEVICE pointer owned by the caller (PyTorch); the library
- *    allocates nothing and keeps no state besides lazily-set kernel attributes.
+ *  - Every pointer is a DEVICE pointer owned by the caller (PyTorch); the library allocates no
+ *    device memory.
+ *  - State the library does keep (none of it changes results): per-process, the largest
+ *    MaxDynamicSharedMemorySize set per kernel and the SM count of the device; per calling
+ *    thread, a cache of 512 encoded TMA tensor maps keyed by (pointer, shape, strides) and one
+ *    non-blocking side stream with five events on which vpr_salad_bwd forks its small
+ *    token-MLP launches (created on first use, joined back into `stream` before the call
+ *    returns; under stream capture they become a parallel branch of the caller's graph).
+ *  - One process drives ONE device: the first call binds the library to the current device and
+ *    every later call fails with a clear message if another device is current.
  *  - Every call is asynchronous on `stream`, re-entrant and does not synchronise.
  *  - Return value 0 = success; otherwise vpr_last_error() (thread-local) explains.
  *  - dtype: VPR_F32 = fp32 storage + fp32 FMA GEMMs (1e-4 parity mode),
@@ -49,7 +57,7 @@
 extern "C" {
 #endif
 
-#define VPR_ABI_VERSION 4
+#define VPR_ABI_VERSION 5
 #if defined(__GNUC__)
 #define VPR_API __attribute__((visibility("default")))
 #else
@@ -142,10 +150,18 @@ VPR_API int vpr_sinkhorn_bwd(const float* S, const float* dust_bin, const float*
 /* ---- geopose heads + losses, forward and backward in one call --------------------------- */
 #define VPR_LATLON_MSE 0
 #define VPR_LATLON_HUBER 1
+#define VPR_LATLON_EXTERNAL 2    /* `latlon_target` holds dL/dpred [B,2] computed by the caller (autograd through
+                                    `preds = model(inputs); loss = loss_fn(preds, targets); loss.backward()`,
+                                    dinov2salad_finetuning.py:120-124); reported lat/lon loss is 0 */
 #define VPR_ANGLE_NONE 0
 #define VPR_ANGLE_ATAN2_MAAE 1   /* dino_v2_gemini.py:117-141 */
 #define VPR_ANGLE_ACOS 2         /* swin_angle_finetuning_sin_cos.py:56-69 */
 #define VPR_ANGLE_MSE 3          /* swin_angle_finetuning_gemini.py:183 on [sin,cos] */
+#define VPR_ANGLE_SCALAR_MAAE 4  /* dino_angle_finetuning.py:37-52: head = Linear(D,1), pred = out % 360,
+                                    loss = mean(min(d, 360-d)), d = |pred - target| % 360.  ang_w is [1, D], ang_b [1];
+                                    sincos_pred[b] = (pred in [0,360), raw head output) */
+#define VPR_HEADS_FORWARD_ONLY 1 /* flags: predictions and losses only; `grads` / `d_desc` may be NULL */
+#define VPR_HEADS_PREPACKED 2    /* flags: vpr_heads_pack already filled this workspace from the current weights */
 
 typedef struct {
     int B;          /* rows in this call */
@@ -158,6 +174,11 @@ typedef struct {
     int global_B;       /* denominator of the batch means (== B on one GPU; sum of B over ranks under DP) */
     float reg_dropout_p;   /* Dropout between ReLU and Linear(hidden,2): dinov2salad_finetuning_2.py:121 */
     uint64_t seed;
+    float head_dropout_p;  /* Dropout on the angle head's input: dino_v2_gemini.py:104,111 (mask = vpr_dropout_mask
+                              with seed + 0x9E3779B97F4A7C15 over [B, D]) */
+    int flags;             /* VPR_HEADS_* */
+    const uint64_t* seed_offset_dev;   /* optional device counter added to `seed` (CUDA-graph replays draw fresh
+                                          masks; advance it with vpr_counter_advance) */
 } VprHeadsShape;
 
 typedef struct {
@@ -171,9 +192,15 @@ typedef struct {
 } VprHeadsGrads;
 
 VPR_API size_t vpr_heads_workspace_bytes(const VprHeadsShape* s, int dtype);
+/* Cast the big weight matrices to the run dtype ([regressor.0.weight ; angle head] -> the head of `workspace`).
+ * vpr_heads_loss_fwd_bwd does this itself unless VPR_HEADS_PREPACKED is set; a caller that knows the weights have
+ * not changed since the last call on the same workspace, or that wants the cast off the critical path (a side
+ * stream next to the SALAD forward), calls it explicitly. */
+VPR_API int vpr_heads_pack(const VprHeadsParams* p, void* workspace, size_t workspace_bytes, const VprHeadsShape* s,
+                   int dtype, cudaStream_t stream);
 /* desc: [B, D] (`dtype`); latlon_target: [B,2] fp32 (z-scored); angle_target_deg: [B] fp32.
  * Outputs: latlon_pred [B,2] fp32, sincos_pred [B,2] fp32, losses [2] fp32 (lat/lon, angle),
- * grads (overwritten), d_desc [B, D] (`dtype`) or NULL. */
+ * grads (overwritten; NULL with VPR_HEADS_FORWARD_ONLY), d_desc [B, D] (`dtype`) or NULL. */
 VPR_API int vpr_heads_loss_fwd_bwd(const VprHeadsParams* p, const void* desc, const float* latlon_target,
                            const float* angle_target_deg, float* latlon_pred, float* sincos_pred,
                            float* losses, VprHeadsGrads* grads, void* d_desc, void* workspace,

@@ -193,6 +193,19 @@ class SinCosHeadRef(nn.Module):
         return out
 
 
+class ScalarAngleHeadRef(nn.Module):
+    """``Linear(D,1)`` -> ``squeeze(-1) % 360``: the scalar-angle head of
+    reference angle_prediction/dinov2salad/dino_angle_finetuning.py:37-47."""
+
+    def __init__(self, in_dim=8448):
+        super().__init__()
+        self.head = nn.Linear(in_dim, 1)
+
+    def forward(self, d):
+        angle = self.head(d).squeeze(-1)
+        return angle % 360
+
+
 def mse_loss(pred, target):
     """reference dinov2salad/dinov2salad_finetuning.py:96 (nn.MSELoss, mean over B*2)."""
     return F.mse_loss(pred, target)
@@ -265,25 +278,41 @@ def latlon_validation_score(pred, target):
 
 
 LATLON_LOSSES = ("mse", "huber")
-ANGLE_LOSSES = ("atan2_maae", "acos", "mse")
+ANGLE_LOSSES = ("atan2_maae", "acos", "mse", "scalar_maae")
 
 
-def geopose_loss(desc, latlon_head: LatLonRegressorRef, angle_head: SinCosHeadRef,
-                 latlon_target, angle_target_deg, latlon_loss="mse", angle_loss="atan2_maae"):
-    """One fine-tuning objective over a descriptor batch: lat/lon + sin/cos angle.
+def geopose_loss(desc, latlon_head: LatLonRegressorRef, angle_head,
+                 latlon_target, angle_target_deg, latlon_loss="mse", angle_loss="atan2_maae",
+                 head_keep_mask=None, head_dropout_p=0.0, reg_keep_mask=None, reg_dropout_p=0.0):
+    """One fine-tuning objective over a descriptor batch: lat/lon + angle head.
 
     Returns (total, latlon_loss, angle_loss, latlon_pred, sincos_pred).  The total
     is the plain sum; the reference trains the two tasks in separate scripts, so
     summing is this repo's (documented) choice for BASELINE.json config 3.
+
+    ``head_keep_mask`` [B, D] in {0,1} with ``head_dropout_p``: the ``nn.Dropout`` in front of
+    the angle head (dino_v2_gemini.py:104,111) evaluated with an injected mask (inverted
+    dropout: kept elements are scaled by 1/(1-p)); ``reg_keep_mask`` [B, hidden] likewise for
+    the regressor's Dropout (dinov2salad_finetuning_2.py:121).
     """
-    ll = latlon_head(desc)
+    if reg_keep_mask is None:
+        ll = latlon_head(desc)
+    else:
+        reg = latlon_head.regressor
+        z = torch.relu(reg[0](desc)) * reg_keep_mask / (1.0 - reg_dropout_p)
+        ll = reg[-1](z)
     if latlon_loss == "mse":
         l1 = mse_loss(ll, latlon_target)
     elif latlon_loss == "huber":
         l1 = huber_loss(ll, latlon_target, 1.0)
     else:
         raise ValueError(latlon_loss)
-    sc = angle_head.head(desc)
+    hd = desc if head_keep_mask is None else desc * head_keep_mask / (1.0 - head_dropout_p)
+    sc = angle_head.head(hd)
+    if angle_loss == "scalar_maae":
+        pred = sc.squeeze(-1) % 360                      # dino_angle_finetuning.py:46-47
+        l2 = maae_loss_scalar(pred, angle_target_deg)
+        return l1 + l2, l1, l2, ll, pred
     if angle_loss == "atan2_maae":
         l2 = sincos_atan2_maae(sc, angle_target_deg)
     elif angle_loss == "acos":

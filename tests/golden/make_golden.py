@@ -95,6 +95,11 @@ def make_heads():
         s = sc.clone().requires_grad_(True)
         fn(s).backward()
         out["grad_" + name] = s.grad.numpy()
+    # scalar-angle head (dino_angle_finetuning.py:46-52): gradient w.r.t. the raw head output through `% 360`
+    raw = pred_deg.clone().requires_grad_(True)
+    maae_scalar(raw % 360, tgt_deg % 360).backward()
+    out["maae_scalar_wrapped_targets"] = maae_scalar(pred_deg % 360, tgt_deg % 360).numpy()
+    out["grad_maae_scalar"] = raw.grad.numpy()
     for name, fn in (("mse", torch.nn.MSELoss()), ("huber", torch.nn.HuberLoss(delta=1.0))):
         p = ll_pred.clone().requires_grad_(True)
         fn(p, ll_tgt).backward()
@@ -238,8 +243,8 @@ def make_preprocess():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    make_heads()
-    make_salad()
-    make_metrics()
-    make_seam()
-    make_preprocess()
+    only = sys.argv[1:]
+    for name, fn in (("heads", make_heads), ("salad", make_salad), ("metrics", make_metrics), ("seam", make_seam),
+                     ("preprocess", make_preprocess)):
+        if not only or name in only:
+            fn()

@@ -151,11 +151,25 @@ def test_regression_model_matches_reference_training_lines(vpr, loss, dropout):
     preds = model(x.cuda())
     want = ll(feats)
     assert rel(preds, want) < 1e-4
+    # the reference's training lines, unchanged (dinov2salad_finetuning.py:115-124): model.train();
+    # preds = model(inputs); loss = loss_fn(preds, targets); optimizer.zero_grad(); loss.backward()
     model.train()
-    with pytest.raises(RuntimeError):
-        model(x.cuda())
     if dropout > 0:
-        model.eval()                                   # parity of the loss itself without the random mask
+        model.eval()                                   # parity without the random mask (the masked path is checked below)
+    loss_fn = torch.nn.MSELoss() if loss == "mse" else torch.nn.HuberLoss(delta=1.0)
+    preds_t = model(x.cuda())
+    assert preds_t.requires_grad
+    l3 = loss_fn(preds_t, tg.cuda())
+    l3.backward()
+    ll3 = O.LatLonRegressorRef(8448, 512)
+    ll3.load_state_dict(ll.state_dict())
+    r3 = (O.mse_loss if loss == "mse" else O.huber_loss)(ll3(feats), tg)
+    r3.backward()
+    assert abs(l3.item() - r3.item()) < 1e-4 * abs(r3.item())
+    for pm, pr in ((model.regressor[0].weight, ll3.regressor[0].weight), (model.regressor[0].bias, ll3.regressor[0].bias),
+                   (model.regressor[last].weight, ll3.regressor[2].weight), (model.regressor[last].bias, ll3.regressor[2].bias)):
+        assert rel(pm.grad, pr.grad) < 1e-4
+        pm.grad = None
     out = model.loss(x.cuda(), tg.cuda())
     out.backward()
     ref_loss = (O.mse_loss if loss == "mse" else O.huber_loss)(want, tg)
@@ -168,6 +182,22 @@ def test_regression_model_matches_reference_training_lines(vpr, loss, dropout):
         a = model.loss(x.cuda(), tg.cuda()).item()
         b = model.loss(x.cuda(), tg.cuda()).item()
         assert a != b                                   # a fresh mask every step
+        # train-mode forward(): the backward must replay the mask the forward drew -- check against the oracle with
+        # that exported mask
+        for pm in model.regressor.parameters():
+            pm.grad = None
+        seed = (model.seed * 1000003 + model._step) & 0xFFFFFFFFFFFFFFFF
+        pt = model(x.cuda())
+        loss_fn(pt, tg.cuda()).backward()
+        keep = vpr.dropout_keep_mask(seed, dropout, 24, 512).cpu().float()
+        ll4 = O.LatLonRegressorRef(8448, 512)
+        ll4.load_state_dict(ll.state_dict())
+        z = torch.relu(ll4.regressor[0](feats)) * keep / (1 - dropout)
+        p4 = ll4.regressor[2](z)
+        assert rel(pt, p4) < 1e-4
+        O.huber_loss(p4, tg).backward()
+        assert rel(model.regressor[0].weight.grad, ll4.regressor[0].weight.grad) < 1e-4
+        assert rel(model.regressor[last].weight.grad, ll4.regressor[2].weight.grad) < 1e-4
 
 
 def test_reference_checkpoint_round_trip(vpr, tmp_path):
@@ -277,6 +307,22 @@ def test_recall_at_k_on_knn_output(vpr):
     assert got[1] <= got[5] <= got[10] <= got[25] <= 1.0 - 1.0 / 7 + 0.01 and got[1] > 0.5
     with pytest.raises(ValueError):
         vpr.recall_at_k(idx, ql.cuda(), gl.cuda(), ks=())
+    # cut-offs beyond the list length are refused by the host API ...
+    with pytest.raises(ValueError):
+        vpr.recall_at_k(idx[:, :10].contiguous(), ql.cuda(), gl.cuda(), ks=(1, 5, 10, 25))
+    # ... and at the C boundary a query without any matching neighbour is a miss at every cut-off, including cut-offs
+    # larger than the list (the first-hit rank sentinel is "never", not k)
+    from vpr_b200 import _lib as L
+    lib = vpr.lib()
+    idx10 = idx[:, :10].contiguous()
+    ks = torch.tensor([1, 10, 25], dtype=torch.int32, device="cuda")
+    hits = torch.zeros(3, dtype=torch.int64, device="cuda")
+    glc, qlc = gl.cuda(), ql.cuda()
+    L.check(lib.vpr_recall_at_k(L.ptr(idx10), L.ptr(glc), L.ptr(qlc), Q, 10, G, L.ptr(ks), 3, L.ptr(hits),
+                                L.stream_ptr(idx.device)), "vpr_recall_at_k")
+    want10 = X.recall_at_k_ref(idx10.cpu(), ql, gl, (1, 10))
+    h = hits.tolist()
+    assert h[0] == round(want10[1] * Q) and h[1] == round(want10[10] * Q) and h[2] == h[1] < Q
 
 
 

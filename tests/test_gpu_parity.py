@@ -516,6 +516,143 @@ def test_heads_predict_and_golden_loss_values(vpr, golden_dir):
         np.testing.assert_allclose(dg.grad[:, :2].cpu().numpy(), hg[gkey], rtol=1e-4, atol=1e-7)
 
 
+def test_scalar_angle_head_matches_oracle_and_reference_golden(vpr, golden_dir):
+    """a9 scalar variant: Linear(D,1) -> % 360 -> MAAE (reference angle_prediction/dinov2salad/dino_angle_finetuning.py:37-52)."""
+    torch.manual_seed(4)
+    B, D = 40, 8448
+    ll, ah = O.LatLonRegressorRef(D, 512), O.ScalarAngleHeadRef(D)
+    with torch.no_grad():
+        ah.head.bias.fill_(150.0)                      # predictions spread around the circle, both wrap directions
+        ah.head.weight.mul_(3000.0)
+    heads = vpr.GeoposeHeads(D, 512, latlon_loss="mse", angle_loss="scalar_maae").cuda()
+    assert tuple(heads.head.weight.shape) == (1, D)
+    heads.regressor.load_state_dict(ll.regressor.state_dict())
+    heads.head.load_state_dict(ah.head.state_dict())
+    g = torch.Generator().manual_seed(6)
+    desc = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=1)
+    lt = torch.randn(B, 2, generator=g)
+    at = torch.rand(B, generator=g) * 360.0            # the dataset wraps targets into [0, 360) (:31-32)
+    dg = desc.cuda().requires_grad_(True)
+    total, losses, llp, scp = heads(dg, lt.cuda(), at.cuda())
+    total.backward()
+    dr = desc.clone().requires_grad_(True)
+    tot_r, l1, l2, llr, pred_r = O.geopose_loss(dr, ll, ah, lt, at, "mse", "scalar_maae")
+    tot_r.backward()
+    assert rel(scp[:, 0], pred_r) < 1e-4 and pred_r.min() >= 0 and pred_r.max() < 360
+    assert abs(losses[1].item() - l2.item()) < 1e-4 * abs(l2.item())
+    assert rel(dg.grad, dr.grad) < 1e-4
+    assert rel(heads.head.weight.grad, ah.head.weight.grad) < 1e-4
+    assert rel(heads.head.bias.grad, ah.head.bias.grad) < 1e-4
+    assert rel(heads.regressor[0].weight.grad, ll.regressor[0].weight.grad) < 1e-4
+    lp, sp = heads.predict(dg.detach())
+    assert rel(sp[:, 0], pred_r) < 1e-4 and rel(lp, llr) < 1e-4
+    # golden: the reference's own angular_regression_loss (and autograd through `% 360`) on seeded inputs
+    from tests.golden.make_golden import heads_inputs
+    hg = np.load(os.path.join(golden_dir, "heads_golden.npz"))
+    _, tgt_deg, pred_deg, _, _ = heads_inputs()
+    Bg, Dg = pred_deg.shape[0], 64
+    h2 = vpr.GeoposeHeads(Dg, 8, latlon_loss="mse", angle_loss="scalar_maae").cuda()
+    with torch.no_grad():
+        for p in h2.parameters():
+            p.zero_()
+        h2.head.weight[0, 0] = 1.0
+    d2 = torch.zeros(Bg, Dg)
+    d2[:, 0] = pred_deg
+    d2g = d2.cuda().requires_grad_(True)
+    tot2, losses2, _, sc2 = h2(d2g, torch.zeros(Bg, 2).cuda(), (tgt_deg % 360).cuda())
+    tot2.backward()
+    np.testing.assert_allclose(losses2[1].item(), float(hg["maae_scalar_wrapped_targets"]), rtol=2e-5)
+    np.testing.assert_allclose(d2g.grad[:, 0].cpu().numpy(), hg["grad_maae_scalar"], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(sc2[:, 0].cpu().numpy(), (pred_deg % 360).numpy(), rtol=1e-6, atol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("angle", ["atan2_maae", "acos"])
+def test_heads_dropout_variants_with_exported_masks(vpr, dtype, angle):
+    """Dropout(0.1) in front of the sin/cos head (dino_v2_gemini.py:104,111) and the regressor's Dropout(0.3)
+    (dinov2salad_finetuning_2.py:121): the oracle replays the masks the kernels drew."""
+    from vpr_b200 import _lib as L
+    torch.manual_seed(8)
+    B, D, hid = 37, 8448, 512
+    ll, ah = O.LatLonRegressorRef(D, hid, dropout=0.3), O.SinCosHeadRef(D)
+    if dtype == torch.bfloat16:
+        with torch.no_grad():
+            ll.regressor[0].weight.copy_(ll.regressor[0].weight.bfloat16().float())
+            ah.head.weight.copy_(ah.head.weight.bfloat16().float())
+    heads = vpr.GeoposeHeads(D, hid, dropout=0.3, latlon_loss="huber", angle_loss=angle, head_dropout=0.1).cuda().train()
+    heads.regressor.load_state_dict(ll.regressor.state_dict())
+    heads.head.load_state_dict(ah.head.state_dict())
+    g = torch.Generator().manual_seed(5)
+    desc = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=1) * 8.0
+    if dtype == torch.bfloat16:
+        desc = desc.bfloat16().float()
+    lt = torch.randn(B, 2, generator=g) * 2
+    at = torch.rand(B, generator=g) * 720.0
+    seed = heads.current_seed()
+    dg = desc.cuda().to(dtype).requires_grad_(True)
+    total, losses, llp, scp = heads(dg, lt.cuda(), at.cuda())
+    total.backward()
+    reg_keep = vpr.dropout_keep_mask(seed, 0.3, B, hid).cpu().float()
+    head_keep = vpr.dropout_keep_mask((seed + L.HEAD_DROP_SEED_OFFSET) & 0xFFFFFFFFFFFFFFFF, 0.1, B, D).cpu().float()
+    assert 0.6 < reg_keep.mean() < 0.8 and 0.88 < head_keep.mean() < 0.92
+    dr = desc.clone().requires_grad_(True)
+    tot_r, l1, l2, llr, scr = O.geopose_loss(dr, ll, ah, lt, at, "huber", angle, head_keep_mask=head_keep,
+                                             head_dropout_p=0.1, reg_keep_mask=reg_keep, reg_dropout_p=0.3)
+    tot_r.backward()
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    assert abs(total.item() - tot_r.item()) <= tol * abs(tot_r.item())
+    assert rel(llp, llr) < tol and rel(scp, scr) < tol
+    assert rel(dg.grad, dr.grad) < tol
+    for p, pr in [(heads.regressor[0].weight, ll.regressor[0].weight), (heads.regressor[0].bias, ll.regressor[0].bias),
+                  (heads.regressor[3].weight, ll.regressor[3].weight), (heads.regressor[3].bias, ll.regressor[3].bias),
+                  (heads.head.weight, ah.head.weight), (heads.head.bias, ah.head.bias)]:
+        assert rel(p.grad, pr.grad) < tol
+    # a fresh mask on the next step, none in eval mode
+    t2, *_ = heads(dg.detach(), lt.cuda(), at.cuda())
+    assert t2.item() != total.item()
+    heads.eval()
+    e1, *_ = heads(dg.detach(), lt.cuda(), at.cuda())
+    e2, *_ = heads(dg.detach(), lt.cuda(), at.cuda())
+    assert e1.item() == e2.item()
+
+
+def test_heads_weight_cast_is_redone_when_the_weights_change(vpr):
+    """The bf16 copy of [regressor.0.weight ; head.weight] is cached per shape and keyed on the tensors' version
+    counters: an optimizer step (in-place update) must invalidate it."""
+    torch.manual_seed(9)
+    B, D = 16, 8448
+    heads = vpr.GeoposeHeads(D, 512).cuda()
+    g = torch.Generator().manual_seed(5)
+    desc = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=1).cuda().bfloat16()
+    lt, at = torch.randn(B, 2, generator=g).cuda(), (torch.rand(B, generator=g) * 360).cuda()
+    a1 = heads(desc, lt, at)[2].clone()
+    a2 = heads(desc, lt, at)[2].clone()                     # second call: cached cast
+    assert torch.equal(a1, a2)
+    with torch.no_grad():
+        heads.regressor[0].weight.mul_(2.0)                 # what an optimizer step does (in place)
+        heads.regressor[0].bias.mul_(2.0)
+    a3 = heads(desc, lt, at)[2]
+    fresh = vpr.GeoposeHeads(D, 512).cuda()
+    fresh.load_state_dict(heads.state_dict())
+    a4 = fresh(desc, lt, at)[2]
+    assert torch.equal(a3, a4) and not torch.equal(a3, a1)
+    p1, _ = heads.predict(desc)
+    assert torch.equal(p1, a3)
+
+
+def test_library_refuses_a_second_device_and_follows_the_tensor_device(vpr):
+    """One process per GPU: calls are issued on the tensors' device even when another device is current; a tensor on
+    a second device is refused with a clear message instead of an invalid-handle launch failure."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    S = torch.randn(2, 100, 64, device="cuda:0")
+    with torch.cuda.device(1):
+        P, _, _ = vpr.sinkhorn(S, torch.ones((), device="cuda:0"))
+    assert torch.isfinite(P).all()
+    with pytest.raises(RuntimeError, match="one process per GPU"):
+        vpr.sinkhorn(S.to("cuda:1"), torch.ones((), device="cuda:1"))
+
+
 # ------------------------------------------------------------------ kNN
 def _near_tie_free(scores, k, tol=1e-6):
     """rows whose k-th and (k+1)-th oracle scores are separated by more than tol"""

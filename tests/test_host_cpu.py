@@ -268,3 +268,70 @@ def test_gloo_world2_allreduce_and_sharded_merge(built):
     for p in procs:
         p.join(60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_prediction_csv_writers_reproduce_the_reference_files(built, tmp_path, golden_dir):
+    """f3: the per-image CSV files of swin_transformer/validation_swin_2.py:205-218 and
+    angle_prediction/efficient_net/validation_script.py:211-220.  Golden = the first rows of two files the reference
+    repository itself checked in (swin_transformer/training_gemini_2_20250505_004059/validation_predictions.csv,
+    angle_prediction/efficientnet/sincos/training_20250505_191535/validation_predictions.csv): re-writing their
+    values must give the same bytes; pandas (what the reference calls) must agree on fresh values too."""
+    import csv
+    import pandas as pd
+    want = open(os.path.join(golden_dir, "latlon_predictions_head.csv")).read()
+    rows = list(csv.reader(want.splitlines()))[1:]
+    names = [r[0] for r in rows]
+    true = np.array([[float(r[1]), float(r[2])] for r in rows])
+    pred = torch.tensor([[float(r[3]), float(r[4])] for r in rows], dtype=torch.float64)
+    out = tmp_path / "val.csv"
+    assert built.write_latlon_predictions_csv(out, names, true, pred) == len(rows)
+    assert out.read_text() == want
+    want_a = open(os.path.join(golden_dir, "angle_predictions_head.csv")).read()
+    rows = list(csv.reader(want_a.splitlines()))[1:]
+    out_a = tmp_path / "ang.csv"
+    built.write_angle_predictions_csv(out_a, [r[0] for r in rows], [int(r[1]) for r in rows],
+                                      torch.tensor([float(r[2]) for r in rows], dtype=torch.float32))
+    assert out_a.read_text() == want_a
+    # fresh values against pandas itself, including a name that needs quoting
+    rng = np.random.default_rng(3)
+    t2, p2 = rng.normal(2e5, 1e3, (9, 2)), rng.normal(2e5, 1e3, (9, 2)).astype(np.float32)
+    nm = [f"img_{i:04d}.jpg" for i in range(8)] + ['we,ird "name".jpg']
+    built.write_latlon_predictions_csv(out, nm, t2, p2)
+    df = pd.DataFrame({"filename": nm, "true_latitude": t2[:, 0], "true_longitude": t2[:, 1],
+                       "predicted_latitude": p2[:, 0].astype(np.float64), "predicted_longitude": p2[:, 1].astype(np.float64)})
+    df["error_latitude"] = np.abs(df["true_latitude"] - df["predicted_latitude"])
+    df["error_longitude"] = np.abs(df["true_longitude"] - df["predicted_longitude"])
+    ref = tmp_path / "ref.csv"
+    df.to_csv(ref, index=False, float_format="%.6f")
+    assert out.read_text() == ref.read_text()
+    ta, pa = rng.integers(0, 360, 9).tolist(), (rng.random(9) * 360).astype(np.float32)
+    built.write_angle_predictions_csv(out_a, nm, ta, torch.from_numpy(pa))
+    df = pd.DataFrame({"filename": nm, "true_angle": ta, "predicted_angle": [float(v) for v in pa]})
+    df["angular_error"] = df.apply(lambda row: min(abs(row["predicted_angle"] - row["true_angle"]),
+                                                   360 - abs(row["predicted_angle"] - row["true_angle"])), axis=1)
+    df.to_csv(ref, index=False)
+    assert out_a.read_text() == ref.read_text()
+    with pytest.raises(ValueError):
+        built.write_latlon_predictions_csv(out, nm[:3], t2, p2)
+
+
+def test_heads_variants_mirror_the_reference_modules(built):
+    """a9: the scalar-angle head is Linear(D,1) (dino_angle_finetuning.py:41), the sin/cos head Linear(D,2) behind a
+    Dropout (dino_v2_gemini.py:104-106); state_dict keys as in the reference (`head.weight`, `head.bias`)."""
+    h1 = built.GeoposeHeads(768, 64, angle_loss="scalar_maae")
+    assert tuple(h1.head.weight.shape) == (1, 768)
+    h2 = built.GeoposeHeads(768, 64, angle_loss="atan2_maae", head_dropout=0.1)
+    assert tuple(h2.head.weight.shape) == (2, 768) and isinstance(h2.dropout, torch.nn.Dropout) and h2.dropout.p == 0.1
+    assert {"head.weight", "head.bias"} <= set(h2.state_dict()) and not any(k.startswith("dropout") for k in h2.state_dict())
+    with pytest.raises(ValueError):
+        built.GeoposeHeads(768, 64, angle_loss="nope")
+
+
+def test_decorrelate_dropout_gives_every_rank_its_own_stream(built):
+    seeds = set()
+    for r in range(8):
+        m = built.SaladHead()
+        built.decorrelate_dropout(m, r)
+        built.decorrelate_dropout(m, r)            # idempotent
+        seeds.add(m.seed)
+    assert len(seeds) == 8

@@ -66,6 +66,25 @@ def test_heads_loss_gradients_match_reference_functions(hg):
         close(p.grad, hg["grad_" + name], rtol=1e-6, atol=1e-8)
 
 
+def test_scalar_angle_head_oracle_matches_reference_functions(hg):
+    """dino_angle_finetuning.py:37-52: Linear(D,1) -> % 360 -> |p - t| % 360 -> min(d, 360 - d)."""
+    _, tgt_deg, pred_deg, _, _ = heads_inputs()
+    head = O.ScalarAngleHeadRef(4)
+    with torch.no_grad():
+        head.head.weight.zero_()
+        head.head.weight[0, 0] = 1.0
+        head.head.bias.zero_()
+    d = torch.zeros(pred_deg.shape[0], 4)
+    d[:, 0] = pred_deg
+    d.requires_grad_(True)
+    out = head(d)
+    assert out.shape == pred_deg.shape and out.min() >= 0 and out.max() < 360
+    loss = O.maae_loss_scalar(out, tgt_deg % 360)
+    close(loss, hg["maae_scalar_wrapped_targets"])
+    loss.backward()
+    close(d.grad[:, 0], hg["grad_maae_scalar"], rtol=1e-6, atol=1e-9)
+
+
 def _salad_case(B, hw, seed, aggregate="repeat"):
     torch.manual_seed(0)
     mod = O.SaladRef(dropout=0.0, aggregate=aggregate)

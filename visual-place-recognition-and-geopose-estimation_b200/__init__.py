@@ -5,9 +5,10 @@ the directory name carries the reference's hyphenated name)."""
 from ._lib import LIB_PATH, lib  # noqa: F401
 from .heads import GeoposeHeads, sincos_to_degrees  # noqa: F401
 from .knn import knn_topk, knn_topk_sharded, merge_topk  # noqa: F401
-from .parallel import (DataParallelStep, GraphedFinetuneStep, allreduce_grads, bind_to_gpu_numa_node, init_distributed,  # noqa: F401
-                       overlap_grad_allreduce, shard_range)
-from .metrics import LatLonScaler, latlon_metrics, maae, recall_at_k  # noqa: F401
+from .parallel import (DataParallelStep, GraphedFinetuneStep, allreduce_grads, bind_to_gpu_numa_node, decorrelate_dropout,  # noqa: F401
+                       init_distributed, overlap_grad_allreduce, shard_range)
+from .metrics import (LatLonScaler, latlon_metrics, maae, recall_at_k, write_angle_predictions_csv,  # noqa: F401
+                      write_latlon_predictions_csv)
 from .model import (DINOv2RegressionModel, VPRModel, load_reference_checkpoint, load_upstream_salad_weights,  # noqa: F401
                     save_reference_checkpoint)
 from .preprocess import GpuPreprocess  # noqa: F401
@@ -18,4 +19,4 @@ __all__ = ["SaladHead", "GraphedSaladStep", "GeoposeHeads", "knn_topk", "knn_top
            "sinkhorn_backward", "dropout_keep_mask", "DataParallelStep", "GraphedFinetuneStep", "allreduce_grads", "overlap_grad_allreduce", "init_distributed", "bind_to_gpu_numa_node",
            "shard_range", "sincos_to_degrees", "BackboneSeam", "GpuPreprocess", "VPRModel", "DINOv2RegressionModel", "load_reference_checkpoint",
            "load_upstream_salad_weights", "save_reference_checkpoint", "LatLonScaler", "latlon_metrics", "maae", "recall_at_k",
-           "lib", "LIB_PATH"]
+           "write_latlon_predictions_csv", "write_angle_predictions_csv", "decorrelate_dropout", "lib", "LIB_PATH"]

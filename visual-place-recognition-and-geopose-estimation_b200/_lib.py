@@ -15,9 +15,11 @@ LIB_PATH = os.environ.get("VPR_B200_LIB") or os.path.join(PKG_DIR, "libvpr_b200.
 VPR_F32, VPR_BF16 = 0, 1
 BWD_ALL, BWD_PARAMS, BWD_INPUTS = 0, 1, 2
 OUT_F32, OUT_BF16, OUT_ATOMIC_F32 = 0, 1, 2
-LATLON_MSE, LATLON_HUBER = 0, 1
-ANGLE_NONE, ANGLE_ATAN2_MAAE, ANGLE_ACOS, ANGLE_MSE = 0, 1, 2, 3
-ABI_VERSION = 4
+LATLON_MSE, LATLON_HUBER, LATLON_EXTERNAL = 0, 1, 2
+ANGLE_NONE, ANGLE_ATAN2_MAAE, ANGLE_ACOS, ANGLE_MSE, ANGLE_SCALAR_MAAE = 0, 1, 2, 3, 4
+HEADS_FORWARD_ONLY, HEADS_PREPACKED = 1, 2
+HEAD_DROP_SEED_OFFSET = 0x9E3779B97F4A7C15      # the angle head's input dropout draws from seed + this
+ABI_VERSION = 5
 
 _fp = C.c_void_p
 
@@ -39,7 +41,8 @@ class SaladGrads(C.Structure):
 class HeadsShape(C.Structure):
     _fields_ = [("B", C.c_int), ("D", C.c_int), ("hidden", C.c_int), ("latlon_loss", C.c_int),
                 ("angle_loss", C.c_int), ("huber_delta", C.c_float), ("loss_scale", C.c_float),
-                ("global_B", C.c_int), ("reg_dropout_p", C.c_float), ("seed", C.c_uint64)]
+                ("global_B", C.c_int), ("reg_dropout_p", C.c_float), ("seed", C.c_uint64),
+                ("head_dropout_p", C.c_float), ("flags", C.c_int), ("seed_offset_dev", C.c_void_p)]
 
 
 class HeadsParams(C.Structure):
@@ -67,6 +70,7 @@ EXPORTS = {
     "vpr_sinkhorn_bwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, _fp, C.c_int, C.c_int, C.c_int,
                                    C.c_int, _fp]),
     "vpr_heads_workspace_bytes": (C.c_size_t, [C.POINTER(HeadsShape), C.c_int]),
+    "vpr_heads_pack": (C.c_int, [C.POINTER(HeadsParams), _fp, C.c_size_t, C.POINTER(HeadsShape), C.c_int, _fp]),
     "vpr_heads_loss_fwd_bwd": (C.c_int, [C.POINTER(HeadsParams), _fp, _fp, _fp, _fp, _fp, _fp,
                                          C.POINTER(HeadsGrads), _fp, _fp, C.c_size_t, C.POINTER(HeadsShape),
                                          C.c_int, _fp]),
@@ -129,6 +133,12 @@ def ptr(t):
 
 def stream_ptr(device=None):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def on_device(t: torch.Tensor):
+    """Context manager that makes ``t``'s device current for the duration of a library call: the kernels launch on
+    the current device, and the library refuses to run on a device other than the one it first ran on."""
+    return torch.cuda.device(t.device)
 
 
 def require_cuda(t: torch.Tensor, name: str) -> None:

@@ -25,11 +25,29 @@ int fail(int code, const char* fmt, ...) {
 static std::atomic<unsigned long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static std::atomic<int> g_bound_device{-1};
+
+int check_device() {
+    int dev = 0;
+    VPR_CUDA_OK(cudaGetDevice(&dev));
+    int bound = g_bound_device.load(std::memory_order_relaxed);
+    if (bound < 0) {
+        int expected = -1;
+        g_bound_device.compare_exchange_strong(expected, dev);
+        bound = g_bound_device.load();
+    }
+    VPR_REQUIRE(bound == dev,
+                "libvpr_b200 is bound to CUDA device %d (one process per GPU) but device %d is current: make the tensors' "
+                "device current (torch.cuda.set_device / with torch.cuda.device(...)) or use one process per GPU",
+                bound, dev);
+    return 0;
+}
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
+        int dev = g_bound_device.load();
+        if (dev < 0) cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     }
     return n;
@@ -85,6 +103,7 @@ int vpr_gemm(int dtype, const void* A, int a_mn, int64_t lda, int64_t a_bs, cons
              const float* bias, int relu, const void* mask, int64_t ld_mask, int64_t mask_bs, float mask_scale,
              float alpha, int k_splits, int bn, float* colsum, float dropout_p, uint64_t dropout_seed,
              cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     vpr::GemmDesc g;
     g.dtype = dtype;
     g.A = A; g.a_mn = a_mn; g.lda = lda; g.a_bs = a_bs;

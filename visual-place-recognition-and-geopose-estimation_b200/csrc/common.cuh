@@ -17,6 +17,9 @@ typedef __nv_bfloat16 bf16;
 // ---------------------------------------------------------------------------
 int fail(int code, const char* fmt, ...);
 int num_sms();
+// One process drives one device: the first compute entry binds the library (cached SM count, kernel attributes,
+// side stream) to the current device; later calls fail if another device is current.
+int check_device();
 void note_launch();   // counts kernel launches (vpr_launch_count)
 
 #define VPR_CUDA_OK(expr)                                                          \

@@ -1,7 +1,16 @@
 // Geopose heads + losses, forward and backward in one call (SURVEY.md section 8 rows a8, a9,
-// Appendix B).  The 8448 -> 512 regressor layer and its two backward GEMMs run on the shared
-// tcgen05 GEMM; everything after it (ReLU, dropout, the 512 -> 2 layer, the sin/cos head, all
-// loss variants and their gradients) is one fused per-row kernel.
+// Appendix B).
+//
+//   W_aug [hid_pad, D] = [ regressor.0.weight ; angle head rows ; 0 ]   (run dtype, packed once per weight update)
+//   zacc  [B, hid_pad] = desc W_aug^T            one split-K tcgen05 GEMM: regressor pre-activation AND the angle
+//                                                head's raw outputs (columns hid, hid+1)
+//   tail                                         ReLU, Dropout, Linear(hid,2), every loss variant and its gradient,
+//                                                8 rows per CTA; writes dZ_aug [B, hid_pad] = [dZ | d sin,cos | 0]
+//   d_desc = dZ_aug W_aug                        one GEMM (K = hid_pad): regressor and angle head together
+//   dW0    = dZ^T desc                           one GEMM
+//   dWa    = d(sin,cos)^T desc                   small kernel (2 x B x D)
+// With Dropout in front of the angle head (dino_v2_gemini.py:104,111) the head's mask differs from the regressor's
+// input, so its three products leave the shared GEMMs and run in two small masked kernels instead.
 #include "common.cuh"
 #include "gemm.h"
 #include "../../include/vpr_b200.h"
@@ -15,8 +24,51 @@ __device__ __forceinline__ float hldf(const bf16* p) { return __bfloat162float(*
 __device__ __forceinline__ void hstf(float* p, float v) { *p = v; }
 __device__ __forceinline__ void hstf(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
 
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+    uint4 u;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+// keep flags of 8 consecutive elements starting at idx0 (idx0 % 8 == 0: all in one 32-element run)
+__device__ __forceinline__ void keep8(unsigned long long seed, unsigned long long idx0, uint32_t thr, float scale,
+                                      float (&k)[8]) {
+    uint32_t w = dropout_mix(seed, idx0 >> 5);
+    const int s = (int)(idx0 & 31);
+    for (int q = 0; q < s; ++q) w = w * DROP_LCG_A + DROP_LCG_C;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        k[q] = w >= thr ? scale : 0.f;
+        w = w * DROP_LCG_A + DROP_LCG_C;
+    }
+}
+
 #define RAD2DEG 57.29577951308232f
 #define DEG2RAD 0.017453292519943295f
+// the angle head's input dropout draws from its own stream of the counter-based generator
+#define HEAD_DROP_SEED_OFFSET 0x9E3779B97F4A7C15ull
 
 // python-style remainder, result in [0, 360)
 __device__ __forceinline__ float mod360(float x) {
@@ -25,35 +77,50 @@ __device__ __forceinline__ float mod360(float x) {
     return r;
 }
 
-// W_aug [hid_pad, D]: rows [0,hid) = regressor.0.weight, rows hid, hid+1 = angle head, rest 0
+// W_aug [hid_pad, D]: rows [0,hid) = regressor.0.weight, then the angle head's rows, rest 0; four elements per thread
+struct HeadsPackArgs { const float* w0; const float* wa; void* waug; long long n0_4, na_4, total_4; };
+
 template <typename T>
-__global__ void pack_heads_kernel(const float* __restrict__ w0, const float* __restrict__ wa, T* __restrict__ waug,
-                                  long long hidD, long long D, long long total) {
-    pdl_wait();
-    pdl_launch_dependents();
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+__global__ void __launch_bounds__(256) pack_heads_kernel(const HeadsPackArgs a) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.total_4;
          i += (long long)gridDim.x * blockDim.x) {
-        float v = 0.f;
-        if (i < hidD) v = w0[i];
-        else if (i < hidD + 2 * D && wa != nullptr) v = wa[i - hidD];
-        hstf(waug + i, v);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < a.n0_4) v = __ldg(reinterpret_cast<const float4*>(a.w0) + i);
+        else if (i < a.n0_4 + a.na_4) v = __ldg(reinterpret_cast<const float4*>(a.wa) + (i - a.n0_4));
+        if (sizeof(T) == 2) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(a.waug)[i] = pk;
+        } else {
+            reinterpret_cast<float4*>(a.waug)[i] = v;
+        }
     }
 }
 
-// sc_raw[b][k] = desc[b] . Wa[k]   (fp32 accumulate against the fp32 master head weights)
+// Dropout in front of the angle head: sc_raw[b][k] = sum_d keep[b,d] * desc[b,d] * W_aug[hid+k][d]
 template <typename T>
-__global__ void __launch_bounds__(256) angle_fwd_kernel(const T* __restrict__ desc, const float* __restrict__ wa,
-                                                        float* __restrict__ sc_raw, int D) {
+__global__ void __launch_bounds__(256) angle_fwd_masked_kernel(const T* __restrict__ desc, const T* __restrict__ wa,
+                                                               float* __restrict__ sc_raw, int D, uint32_t thr,
+                                                               float scale, unsigned long long seed,
+                                                               const unsigned long long* __restrict__ seed_dev) {
     __shared__ float red[2][8];
     pdl_wait();
     pdl_launch_dependents();
+    if (seed_dev != nullptr) seed += *seed_dev;
+    seed += HEAD_DROP_SEED_OFFSET;
     const int b = blockIdx.x;
     const T* x = desc + (size_t)b * D;
     float a0 = 0.f, a1 = 0.f;
-    for (int i = threadIdx.x; i < D; i += 256) {
-        const float v = hldf(x + i);
-        a0 += v * __ldg(wa + i);
-        a1 += v * __ldg(wa + D + i);
+    for (int d0 = threadIdx.x * 8; d0 < D; d0 += 256 * 8) {
+        float v[8], w0[8], w1[8], k[8];
+        load8(x + d0, v);
+        load8(wa + d0, w0);
+        load8(wa + D + d0, w1);
+        keep8(seed, (unsigned long long)b * D + d0, thr, scale, k);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { a0 += v[q] * k[q] * w0[q]; a1 += v[q] * k[q] * w1[q]; }
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1);
     if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a0; red[1][threadIdx.x >> 5] = a1; }
@@ -66,143 +133,253 @@ __global__ void __launch_bounds__(256) angle_fwd_kernel(const T* __restrict__ de
 }
 
 struct TailArgs {
-    const float* zacc;      // [B, hid] pre-activation (no bias)
-    const float* sc_raw;    // [B, 2] or null
+    const float* zacc;      // [B, hid_pad] pre-activation (no bias); columns hid, hid+1 = raw angle-head outputs
+    const float* sc_raw;    // [B, 2] raw angle-head outputs when the head has its own dropout, else null
     const float* b0; const float* w1; const float* b1; const float* ba;
     const float* latlon_target; const float* angle_target_deg;
     float* latlon_pred; float* sincos_pred; float* losses;
     float* g_b0; float* g_w1; float* g_b1; float* g_ba;
     void* dzaug;            // [B, hid_pad] run dtype
-    int B, hid, hid_pad, latlon_loss, angle_loss, global_B;
+    int B, hid, hid_pad, latlon_loss, angle_loss, global_B, forward_only;
     float huber_delta, loss_scale;
-    uint32_t drop_thr; float drop_scale; unsigned long long seed;
+    uint32_t drop_thr; float drop_scale; unsigned long long seed; const unsigned long long* seed_dev;
 };
 
+static constexpr int TAIL_ROWS = 8;
+
+// 8 descriptor rows per CTA: the per-column gradient sums (regressor.2.weight, regressor.0.bias) are accumulated over
+// the CTA's rows in registers, so each column costs three atomics per CTA instead of three per row
 template <typename T>
 __global__ void __launch_bounds__(128) heads_tail_kernel(const TailArgs a) {
-    __shared__ float red[2][4];
-    __shared__ float dpred_s[2];
+    __shared__ float part[4][2 * TAIL_ROWS];
+    __shared__ float dpred_s[TAIL_ROWS][2];
+    __shared__ float dsc_s[TAIL_ROWS][2];
     pdl_wait();
     pdl_launch_dependents();
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const float* zrow = a.zacc + (size_t)b * a.hid;
-    // z = dropout(relu(zacc + b0)); pred = W1 z + b1
-    float p0 = 0.f, p1 = 0.f;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = blockIdx.x * TAIL_ROWS;
+    const int rows = min(TAIL_ROWS, a.B - row0);
+    const unsigned long long seed = a.seed + (a.seed_dev != nullptr ? *a.seed_dev : 0ull);
+    // ---- z = dropout(relu(zacc + b0)); pred = W1 z + b1 ----
+    float p[2 * TAIL_ROWS];
+#pragma unroll
+    for (int r = 0; r < 2 * TAIL_ROWS; ++r) p[r] = 0.f;
     for (int i = tid; i < a.hid; i += 128) {
-        float z = fmaxf(zrow[i] + a.b0[i], 0.f);
-        if (a.drop_thr != 0u)
-            z = dropout_keep(a.seed, (unsigned long long)b * a.hid + i, a.drop_thr) ? z * a.drop_scale : 0.f;
-        p0 += z * a.w1[i];
-        p1 += z * a.w1[a.hid + i];
-    }
-    p0 = warp_sum(p0); p1 = warp_sum(p1);
-    if ((tid & 31) == 0) { red[0][tid >> 5] = p0; red[1][tid >> 5] = p1; }
-    __syncthreads();
-    if (tid == 0) {
-        float pred[2];
-        pred[0] = red[0][0] + red[0][1] + red[0][2] + red[0][3] + a.b1[0];
-        pred[1] = red[1][0] + red[1][1] + red[1][2] + red[1][3] + a.b1[1];
-        a.latlon_pred[b * 2 + 0] = pred[0];
-        a.latlon_pred[b * 2 + 1] = pred[1];
-        const float inv2B = 1.f / (2.f * (float)a.global_B);
-        float loss = 0.f;
-        for (int k = 0; k < 2; ++k) {
-            const float e = pred[k] - a.latlon_target[b * 2 + k];
-            float g;
-            if (a.latlon_loss == VPR_LATLON_MSE) { loss += e * e; g = 2.f * e; }
-            else if (fabsf(e) <= a.huber_delta) { loss += 0.5f * e * e; g = e; }
-            else { loss += a.huber_delta * (fabsf(e) - 0.5f * a.huber_delta); g = a.huber_delta * (e > 0.f ? 1.f : -1.f); }
-            g *= inv2B * a.loss_scale;
-            dpred_s[k] = g;
-            atomicAdd(a.g_b1 + k, g);
-        }
-        atomicAdd(a.losses + 0, loss * inv2B);
-        // ---- sin/cos angle head ----
-        float ds = 0.f, dc = 0.f;
-        if (a.angle_loss != VPR_ANGLE_NONE) {
-            const float s = a.sc_raw[b * 2 + 0] + a.ba[0], c = a.sc_raw[b * 2 + 1] + a.ba[1];
-            a.sincos_pred[b * 2 + 0] = s;
-            a.sincos_pred[b * 2 + 1] = c;
-            const float invB = 1.f / (float)a.global_B;
-            const float tdeg = mod360(a.angle_target_deg[b]);
-            float aloss = 0.f;
-            if (a.angle_loss == VPR_ANGLE_ATAN2_MAAE) {
-                const float deg = mod360(atan2f(s, c) * RAD2DEG);
-                const float diff = deg - tdeg;
-                const float d = fabsf(diff);
-                float gd = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-                if (d <= 360.f - d) aloss = d; else { aloss = 360.f - d; gd = -gd; }
-                const float r2 = s * s + c * c;
-                ds = gd * RAD2DEG * c / r2;
-                dc = -gd * RAD2DEG * s / r2;
-            } else if (a.angle_loss == VPR_ANGLE_ACOS) {
-                const float ts = sinf(tdeg * DEG2RAD), tc = cosf(tdeg * DEG2RAD);
-                const float nrm = sqrtf(s * s + c * c);
-                const float den = fmaxf(nrm, 1e-6f);
-                const float ps = s / den, pc = c / den;
-                const float dot = ps * ts + pc * tc;
-                const float cl = fminf(fmaxf(dot, -0.999999f), 0.999999f);
-                aloss = acosf(cl) * RAD2DEG;
-                float gdot = 0.f;
-                if (dot >= -0.999999f && dot <= 0.999999f) gdot = -RAD2DEG / sqrtf(1.f - cl * cl);
-                const float gps = gdot * ts, gpc = gdot * tc;
-                if (nrm > 1e-6f) {
-                    const float pg = ps * gps + pc * gpc;
-                    ds = (gps - ps * pg) / den;
-                    dc = (gpc - pc * pg) / den;
-                } else { ds = gps / den; dc = gpc / den; }
-            } else {   // MSE on [sin, cos], mean over B*2
-                const float ts = sinf(tdeg * DEG2RAD), tc = cosf(tdeg * DEG2RAD);
-                aloss = 0.5f * ((s - ts) * (s - ts) + (c - tc) * (c - tc));
-                ds = (s - ts);
-                dc = (c - tc);
+        const float bi = a.b0[i], w0 = a.w1[i], w1 = a.w1[a.hid + i];
+#pragma unroll
+        for (int r = 0; r < TAIL_ROWS; ++r) {
+            if (r < rows) {
+                float z = fmaxf(a.zacc[(size_t)(row0 + r) * a.hid_pad + i] + bi, 0.f);
+                if (a.drop_thr != 0u)
+                    z = dropout_keep(seed, (unsigned long long)(row0 + r) * a.hid + i, a.drop_thr) ? z * a.drop_scale : 0.f;
+                p[2 * r] += z * w0;
+                p[2 * r + 1] += z * w1;
             }
-            atomicAdd(a.losses + 1, aloss * invB);
-            ds *= invB * a.loss_scale;
-            dc *= invB * a.loss_scale;
-            atomicAdd(a.g_ba + 0, ds);
-            atomicAdd(a.g_ba + 1, dc);
         }
-        hstf(reinterpret_cast<T*>(a.dzaug) + (size_t)b * a.hid_pad + a.hid + 0, ds);
-        hstf(reinterpret_cast<T*>(a.dzaug) + (size_t)b * a.hid_pad + a.hid + 1, dc);
+    }
+#pragma unroll
+    for (int r = 0; r < 2 * TAIL_ROWS; ++r) {
+        const float s = warp_sum(p[r]);
+        if (lane == 0) part[warp][r] = s;
     }
     __syncthreads();
-    const float g0 = dpred_s[0], g1 = dpred_s[1];
-    T* dz = reinterpret_cast<T*>(a.dzaug) + (size_t)b * a.hid_pad;
+    if (warp == 0) {
+        // lane r < rows owns row row0 + r
+        const int r = lane, b = row0 + lane;
+        float loss = 0.f, aloss = 0.f, gb1_0 = 0.f, gb1_1 = 0.f, gba_0 = 0.f, gba_1 = 0.f;
+        if (r < rows) {
+            float pred[2];
+            pred[0] = part[0][2 * r] + part[1][2 * r] + part[2][2 * r] + part[3][2 * r] + a.b1[0];
+            pred[1] = part[0][2 * r + 1] + part[1][2 * r + 1] + part[2][2 * r + 1] + part[3][2 * r + 1] + a.b1[1];
+            a.latlon_pred[b * 2 + 0] = pred[0];
+            a.latlon_pred[b * 2 + 1] = pred[1];
+            const float inv2B = 1.f / (2.f * (float)a.global_B);
+            float gk[2];
+            for (int k = 0; k < 2; ++k) {
+                const float tv = a.latlon_target[b * 2 + k];
+                float g;
+                if (a.latlon_loss == VPR_LATLON_EXTERNAL) {          // tv = dL/dpred handed in by the caller
+                    g = tv * a.loss_scale;
+                } else {
+                    const float e = pred[k] - tv;
+                    if (a.latlon_loss == VPR_LATLON_MSE) { loss += e * e; g = 2.f * e; }
+                    else if (fabsf(e) <= a.huber_delta) { loss += 0.5f * e * e; g = e; }
+                    else { loss += a.huber_delta * (fabsf(e) - 0.5f * a.huber_delta); g = a.huber_delta * (e > 0.f ? 1.f : -1.f); }
+                    g *= inv2B * a.loss_scale;
+                }
+                gk[k] = g;
+                dpred_s[r][k] = g;
+            }
+            loss *= inv2B;
+            gb1_0 = gk[0]; gb1_1 = gk[1];
+            // ---- angle head ----
+            float ds = 0.f, dc = 0.f;
+            if (a.angle_loss != VPR_ANGLE_NONE) {
+                const float raw0 = a.sc_raw != nullptr ? a.sc_raw[b * 2 + 0] : a.zacc[(size_t)b * a.hid_pad + a.hid];
+                const float raw1 = a.sc_raw != nullptr ? a.sc_raw[b * 2 + 1] : a.zacc[(size_t)b * a.hid_pad + a.hid + 1];
+                const float invB = 1.f / (float)a.global_B;
+                if (a.angle_loss == VPR_ANGLE_SCALAR_MAAE) {
+                    // dino_angle_finetuning.py:41-52: pred = head(x) % 360; d = |pred - target| % 360; min(d, 360 - d)
+                    const float rawp = raw0 + a.ba[0];
+                    const float pdeg = mod360(rawp);
+                    a.sincos_pred[b * 2 + 0] = pdeg;
+                    a.sincos_pred[b * 2 + 1] = rawp;
+                    const float diff = pdeg - a.angle_target_deg[b];
+                    const float d = fmodf(fabsf(diff), 360.f);
+                    float gd = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+                    if (d <= 360.f - d) aloss = d; else { aloss = 360.f - d; gd = -gd; }
+                    ds = gd;
+                } else {
+                    const float s = raw0 + a.ba[0], c = raw1 + a.ba[1];
+                    a.sincos_pred[b * 2 + 0] = s;
+                    a.sincos_pred[b * 2 + 1] = c;
+                    const float tdeg = mod360(a.angle_target_deg[b]);
+                    if (a.angle_loss == VPR_ANGLE_ATAN2_MAAE) {
+                        const float deg = mod360(atan2f(s, c) * RAD2DEG);
+                        const float diff = deg - tdeg;
+                        const float d = fabsf(diff);
+                        float gd = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+                        if (d <= 360.f - d) aloss = d; else { aloss = 360.f - d; gd = -gd; }
+                        const float r2 = s * s + c * c;
+                        ds = gd * RAD2DEG * c / r2;
+                        dc = -gd * RAD2DEG * s / r2;
+                    } else if (a.angle_loss == VPR_ANGLE_ACOS) {
+                        const float ts = sinf(tdeg * DEG2RAD), tc = cosf(tdeg * DEG2RAD);
+                        const float nrm = sqrtf(s * s + c * c);
+                        const float den = fmaxf(nrm, 1e-6f);
+                        const float ps = s / den, pc = c / den;
+                        const float dot = ps * ts + pc * tc;
+                        const float cl = fminf(fmaxf(dot, -0.999999f), 0.999999f);
+                        aloss = acosf(cl) * RAD2DEG;
+                        float gdot = 0.f;
+                        if (dot >= -0.999999f && dot <= 0.999999f) gdot = -RAD2DEG / sqrtf(1.f - cl * cl);
+                        const float gps = gdot * ts, gpc = gdot * tc;
+                        if (nrm > 1e-6f) {
+                            const float pg = ps * gps + pc * gpc;
+                            ds = (gps - ps * pg) / den;
+                            dc = (gpc - pc * pg) / den;
+                        } else { ds = gps / den; dc = gpc / den; }
+                    } else {   // MSE on [sin, cos], mean over B*2
+                        const float ts = sinf(tdeg * DEG2RAD), tc = cosf(tdeg * DEG2RAD);
+                        aloss = 0.5f * ((s - ts) * (s - ts) + (c - tc) * (c - tc));
+                        ds = (s - ts);
+                        dc = (c - tc);
+                    }
+                }
+                aloss *= invB;
+                ds *= invB * a.loss_scale;
+                dc *= invB * a.loss_scale;
+                gba_0 = ds; gba_1 = dc;
+            }
+            dsc_s[r][0] = ds;
+            dsc_s[r][1] = dc;
+        }
+        loss = warp_sum(loss); aloss = warp_sum(aloss);
+        gb1_0 = warp_sum(gb1_0); gb1_1 = warp_sum(gb1_1); gba_0 = warp_sum(gba_0); gba_1 = warp_sum(gba_1);
+        if (lane == 0) {
+            atomicAdd(a.losses + 0, loss);
+            if (a.angle_loss != VPR_ANGLE_NONE) atomicAdd(a.losses + 1, aloss);
+            if (!a.forward_only) {
+                atomicAdd(a.g_b1 + 0, gb1_0);
+                atomicAdd(a.g_b1 + 1, gb1_1);
+                if (a.angle_loss != VPR_ANGLE_NONE) {
+                    atomicAdd(a.g_ba + 0, gba_0);
+                    if (a.angle_loss != VPR_ANGLE_SCALAR_MAAE) atomicAdd(a.g_ba + 1, gba_1);
+                }
+            }
+        }
+    }
+    if (a.forward_only) return;
+    __syncthreads();
+    // ---- dZ_aug rows, regressor.2.weight / regressor.0.bias gradients ----
+    T* dz = reinterpret_cast<T*>(a.dzaug);
     for (int i = tid; i < a.hid_pad; i += 128) {
         if (i < a.hid) {
-            float z = fmaxf(zrow[i] + a.b0[i], 0.f);
-            float keep = 1.f;
-            if (a.drop_thr != 0u)
-                keep = dropout_keep(a.seed, (unsigned long long)b * a.hid + i, a.drop_thr) ? a.drop_scale : 0.f;
-            const float zd = z * keep;
-            atomicAdd(a.g_w1 + i, g0 * zd);
-            atomicAdd(a.g_w1 + a.hid + i, g1 * zd);
-            const float d = z > 0.f ? (g0 * a.w1[i] + g1 * a.w1[a.hid + i]) * keep : 0.f;
-            hstf(dz + i, d);
-            if (d != 0.f) atomicAdd(a.g_b0 + i, d);
-        } else if (i >= a.hid + 2) {
-            hstf(dz + i, 0.f);
+            const float bi = a.b0[i], w0 = a.w1[i], w1 = a.w1[a.hid + i];
+            float gw0 = 0.f, gw1 = 0.f, gb = 0.f;
+#pragma unroll
+            for (int r = 0; r < TAIL_ROWS; ++r) {
+                if (r < rows) {
+                    const float z = fmaxf(a.zacc[(size_t)(row0 + r) * a.hid_pad + i] + bi, 0.f);
+                    float keep = 1.f;
+                    if (a.drop_thr != 0u)
+                        keep = dropout_keep(seed, (unsigned long long)(row0 + r) * a.hid + i, a.drop_thr) ? a.drop_scale : 0.f;
+                    const float zd = z * keep;
+                    const float g0 = dpred_s[r][0], g1 = dpred_s[r][1];
+                    gw0 += g0 * zd;
+                    gw1 += g1 * zd;
+                    const float d = z > 0.f ? (g0 * w0 + g1 * w1) * keep : 0.f;
+                    hstf(dz + (size_t)(row0 + r) * a.hid_pad + i, d);
+                    gb += d;
+                }
+            }
+            atomicAdd(a.g_w1 + i, gw0);
+            atomicAdd(a.g_w1 + a.hid + i, gw1);
+            atomicAdd(a.g_b0 + i, gb);
+        } else {
+            for (int r = 0; r < rows; ++r)
+                hstf(dz + (size_t)(row0 + r) * a.hid_pad + i, i - a.hid < 2 ? dsc_s[r][i - a.hid] : 0.f);
         }
     }
 }
 
-// dWa[k][d] = sum_b dzaug[b][hid+k] * desc[b][d]
+// Angle-head weight gradient  dWa[k][d] += sum_b dsc[b][k] * keep[b,d] * desc[b][d]  and -- only when the head has its
+// own input dropout, i.e. its rows were left out of the d_desc GEMM -- d_desc[b][d] += keep[b,d] * sum_k dsc[b][k] Wa[k][d].
+// block (32, 8): x = group of 8 columns, y = row phase; grid (ceil(D / 256), row splits).
 template <typename T>
-__global__ void __launch_bounds__(256) angle_wgrad_kernel(const T* __restrict__ desc, const T* __restrict__ dzaug,
-                                                          float* __restrict__ g_wa, int B, int D, int hid, int hid_pad) {
+__global__ void __launch_bounds__(256) angle_bwd_kernel(const T* __restrict__ desc, const T* __restrict__ dzaug,
+                                                        const T* __restrict__ wa, float* __restrict__ g_wa,
+                                                        T* __restrict__ d_desc, int B, int D, int hid, int hid_pad,
+                                                        int n_ang, int rows_per_block, uint32_t thr, float scale,
+                                                        unsigned long long seed,
+                                                        const unsigned long long* __restrict__ seed_dev) {
+    __shared__ float red[8][32][17];
     pdl_wait();
     pdl_launch_dependents();
-    const int d = blockIdx.x * 256 + threadIdx.x;
-    if (d >= D) return;
-    float a0 = 0.f, a1 = 0.f;
-    for (int b = 0; b < B; ++b) {
-        const float v = hldf(desc + (size_t)b * D + d);
-        a0 += hldf(dzaug + (size_t)b * hid_pad + hid) * v;
-        a1 += hldf(dzaug + (size_t)b * hid_pad + hid + 1) * v;
+    if (seed_dev != nullptr) seed += *seed_dev;
+    seed += HEAD_DROP_SEED_OFFSET;
+    const int d0 = (blockIdx.x * 32 + threadIdx.x) * 8;
+    const bool active = d0 < D;
+    const int b_begin = blockIdx.y * rows_per_block, b_end = min(B, b_begin + rows_per_block);
+    float acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+    if (active) {
+        float w0[8], w1[8];
+        const bool fix = thr != 0u && d_desc != nullptr;
+        if (fix) { load8(wa + d0, w0); load8(wa + D + d0, w1); }
+        for (int b = b_begin + threadIdx.y; b < b_end; b += 8) {
+            const float ds = hldf(dzaug + (size_t)b * hid_pad + hid), dc = hldf(dzaug + (size_t)b * hid_pad + hid + 1);
+            float v[8], k[8];
+            load8(desc + (size_t)b * D + d0, v);
+            if (thr != 0u) keep8(seed, (unsigned long long)b * D + d0, thr, scale, k);
+            else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) k[q] = 1.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { acc[q] += ds * k[q] * v[q]; acc[8 + q] += dc * k[q] * v[q]; }
+            if (fix) {
+                float dd[8];
+                load8(d_desc + (size_t)b * D + d0, dd);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) dd[q] += k[q] * (ds * w0[q] + dc * w1[q]);
+                store8(d_desc + (size_t)b * D + d0, dd);
+            }
+        }
     }
-    g_wa[d] = a0;
-    g_wa[D + d] = a1;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) red[threadIdx.y][threadIdx.x][q] = acc[q];
+    __syncthreads();
+    // 256 threads = 32 column groups x 8 columns: thread (x, y) finishes column d0 + y for both head rows
+    if (active) {
+        for (int k = 0; k < n_ang; ++k) {
+            float t = 0.f;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][8 * k + threadIdx.y];
+            atomicAdd(g_wa + (size_t)k * D + d0 + threadIdx.y, t);
+        }
+    }
 }
 
 struct HeadsPlan { size_t waug, zacc, sc_raw, dzaug, total; int hid_pad; };
@@ -212,39 +389,70 @@ static HeadsPlan heads_plan(const VprHeadsShape& s, int dtype) {
     HeadsPlan p;
     p.hid_pad = (s.hidden + 2 + 7) & ~7;
     size_t off = 0;
-    p.waug = carve_size(off, (size_t)p.hid_pad * s.D * e);
-    p.zacc = carve_size(off, (size_t)s.B * s.hidden * 4);
+    p.waug = carve_size(off, (size_t)p.hid_pad * s.D * e);       // first: vpr_heads_pack fills it ahead of the call
+    p.zacc = carve_size(off, (size_t)s.B * p.hid_pad * 4);
     p.sc_raw = carve_size(off, (size_t)s.B * 2 * 4);
     p.dzaug = carve_size(off, (size_t)s.B * p.hid_pad * e);
     p.total = (off + 255) & ~size_t(255);
     return p;
 }
 
+static int angle_rows(int angle_loss) { return angle_loss == VPR_ANGLE_NONE ? 0 : angle_loss == VPR_ANGLE_SCALAR_MAAE ? 1 : 2; }
+
+template <typename T>
+static int heads_pack_t(const VprHeadsParams& p, char* ws, const VprHeadsShape& s, int dtype, cudaStream_t st) {
+    const HeadsPlan hp = heads_plan(s, dtype);
+    HeadsPackArgs a;
+    a.w0 = p.reg_w0;
+    a.wa = angle_rows(s.angle_loss) > 0 ? p.ang_w : nullptr;
+    a.waug = ws + hp.waug;
+    a.n0_4 = (long long)s.hidden * s.D / 4;
+    a.na_4 = a.wa != nullptr ? (long long)angle_rows(s.angle_loss) * s.D / 4 : 0;
+    a.total_4 = (long long)hp.hid_pad * s.D / 4;
+    VPR_REQUIRE((reinterpret_cast<uintptr_t>(a.w0) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.wa) & 15) == 0,
+                "head weights must be 16-byte aligned");
+    long long blocks = (a.total_4 + 255) / 256;
+    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+    pack_heads_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(a);
+    return launch_ok("pack_heads_kernel");
+}
+
 template <typename T>
 static int heads_t(const VprHeadsParams& p, const T* desc, const float* latlon_target, const float* angle_target_deg,
-                   float* latlon_pred, float* sincos_pred, float* losses, VprHeadsGrads& gr, T* d_desc, char* ws,
+                   float* latlon_pred, float* sincos_pred, float* losses, VprHeadsGrads* grp, T* d_desc, char* ws,
                    const VprHeadsShape& s, int dtype, cudaStream_t st) {
     const HeadsPlan hp = heads_plan(s, dtype);
     T* waug = (T*)(ws + hp.waug); float* zacc = (float*)(ws + hp.zacc); float* sc_raw = (float*)(ws + hp.sc_raw);
     T* dzaug = (T*)(ws + hp.dzaug);
     const int okT = dtype == VPR_BF16 ? OUT_BF16 : OUT_F32;
-    const bool angle = s.angle_loss != VPR_ANGLE_NONE;
+    const int n_ang = angle_rows(s.angle_loss);
+    const bool angle = n_ang > 0;
+    const bool fwd_only = (s.flags & VPR_HEADS_FORWARD_ONLY) != 0;
+    const bool head_drop = angle && s.head_dropout_p > 0.f;
+    const bool fold = angle && !head_drop;             // angle rows ride in the regressor's GEMMs
     const int nsm = num_sms();
+    VprHeadsGrads none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    VprHeadsGrads& gr = grp != nullptr ? *grp : none;
+    const unsigned long long* seed_dev = reinterpret_cast<const unsigned long long*>(s.seed_offset_dev);
 
-    const long long hidD = (long long)s.hidden * s.D;
     // accumulators -> 0 first (adjacent buffers in one memset), so that the kernels below form an uninterrupted chain
     // of programmatic dependent launches
     {
         struct Rng { void* p; size_t n; };
-        Rng r[7];
+        Rng r[8];
         int cnt = 0;
-        r[cnt++] = {zacc, (size_t)s.B * s.hidden * 4};
+        r[cnt++] = {zacc, (size_t)s.B * hp.hid_pad * 4};
         r[cnt++] = {losses, 2 * sizeof(float)};
-        r[cnt++] = {gr.reg_b0, sizeof(float) * s.hidden};
-        r[cnt++] = {gr.reg_w1, sizeof(float) * 2 * s.hidden};
-        r[cnt++] = {gr.reg_b1, sizeof(float) * 2};
-        if (gr.ang_w && !angle) r[cnt++] = {gr.ang_w, sizeof(float) * 2 * s.D};
-        if (gr.ang_b) r[cnt++] = {gr.ang_b, sizeof(float) * 2};
+        if (!fwd_only) {
+            r[cnt++] = {gr.reg_b0, sizeof(float) * s.hidden};
+            r[cnt++] = {gr.reg_w1, sizeof(float) * 2 * s.hidden};
+            r[cnt++] = {gr.reg_b1, sizeof(float) * 2};
+            if (gr.ang_w) r[cnt++] = {gr.ang_w, sizeof(float) * (angle ? n_ang : 2) * s.D};
+            if (gr.ang_b) r[cnt++] = {gr.ang_b, sizeof(float) * (angle ? n_ang : 2)};
+        }
+        // merge ranges that touch (in any order of appearance): sort by address first
+        for (int i = 1; i < cnt; ++i)
+            for (int j = i; j > 0 && (char*)r[j].p < (char*)r[j - 1].p; --j) { Rng t = r[j]; r[j] = r[j - 1]; r[j - 1] = t; }
         int i = 0;
         while (i < cnt) {
             char* p0 = (char*)r[i].p;
@@ -255,38 +463,51 @@ static int heads_t(const VprHeadsParams& p, const T* desc, const float* latlon_t
             i = j;
         }
     }
-    VPR_CUDA_OK(launch_ex(pack_heads_kernel<T>, dim3((unsigned)(nsm * 4)), dim3(256), (size_t)0, st, false, 1, p.reg_w0,
-                          angle ? p.ang_w : (const float*)nullptr, waug, hidD, (long long)s.D, (long long)hp.hid_pad * s.D));
-    VPR_TRY(launch_ok("pack_heads_kernel"));
+    if (!(s.flags & VPR_HEADS_PREPACKED)) VPR_TRY(heads_pack_t<T>(p, ws, s, dtype, st));
 
     GemmDesc g;
-    // zacc = desc W0^T   (split-K: only ceil(B/128) * hidden/256 output tiles exist)
+    // zacc = desc W_aug^T   (split-K: only ceil(B/128) * ceil(N/256) output tiles exist)
     g = GemmDesc(); g.dtype = dtype;
-    g.A = desc; g.lda = s.D; g.B = waug; g.ldb = s.D; g.M = s.B; g.N = s.hidden; g.K = s.D;
-    g.out = zacc; g.out_kind = OUT_ATOMIC_F32; g.ldo = s.hidden;
+    g.A = desc; g.lda = s.D; g.B = waug; g.ldb = s.D; g.M = s.B; g.N = fold ? hp.hid_pad : s.hidden; g.K = s.D;
+    g.out = zacc; g.out_kind = OUT_ATOMIC_F32; g.ldo = hp.hid_pad;
     {
-        int tiles = ((s.B + 127) / 128) * ((s.hidden + 255) / 256);
+        int tiles = ((s.B + 127) / 128) * ((g.N + 255) / 256);
         g.k_splits = nsm / tiles; if (g.k_splits < 1) g.k_splits = 1;
     }
     g.pdl = 1;
     VPR_TRY(gemm_run(g, st));
-    if (angle) {
-        VPR_CUDA_OK(launch_ex(angle_fwd_kernel<T>, dim3((unsigned)s.B), dim3(256), (size_t)0, st, true, 1, desc, p.ang_w, sc_raw, s.D));
-        VPR_TRY(launch_ok("angle_fwd_kernel"));
+    const uint32_t head_thr = head_drop ? dropout_threshold(s.head_dropout_p) : 0u;
+    const float head_scale = head_drop ? 1.f / (1.f - s.head_dropout_p) : 1.f;
+    if (head_drop) {
+        VPR_CUDA_OK(launch_ex(angle_fwd_masked_kernel<T>, dim3((unsigned)s.B), dim3(256), (size_t)0, st, true, 1, desc,
+                              (const T*)(waug + (size_t)s.hidden * s.D), sc_raw, s.D, head_thr, head_scale,
+                              (unsigned long long)s.seed, seed_dev));
+        VPR_TRY(launch_ok("angle_fwd_masked_kernel"));
     }
     TailArgs a;
-    a.zacc = zacc; a.sc_raw = sc_raw; a.b0 = p.reg_b0; a.w1 = p.reg_w1; a.b1 = p.reg_b1; a.ba = p.ang_b;
+    a.zacc = zacc; a.sc_raw = head_drop ? sc_raw : nullptr; a.b0 = p.reg_b0; a.w1 = p.reg_w1; a.b1 = p.reg_b1; a.ba = p.ang_b;
     a.latlon_target = latlon_target; a.angle_target_deg = angle_target_deg;
     a.latlon_pred = latlon_pred; a.sincos_pred = sincos_pred; a.losses = losses;
     a.g_b0 = gr.reg_b0; a.g_w1 = gr.reg_w1; a.g_b1 = gr.reg_b1; a.g_ba = gr.ang_b;
     a.dzaug = dzaug; a.B = s.B; a.hid = s.hidden; a.hid_pad = hp.hid_pad;
     a.latlon_loss = s.latlon_loss; a.angle_loss = s.angle_loss; a.global_B = s.global_B > 0 ? s.global_B : s.B;
+    a.forward_only = fwd_only ? 1 : 0;
     a.huber_delta = s.huber_delta; a.loss_scale = s.loss_scale;
     a.drop_thr = s.reg_dropout_p > 0.f ? dropout_threshold(s.reg_dropout_p) : 0u;
     a.drop_scale = s.reg_dropout_p > 0.f ? 1.f / (1.f - s.reg_dropout_p) : 1.f;
-    a.seed = s.seed;
-    VPR_CUDA_OK(launch_ex(heads_tail_kernel<T>, dim3((unsigned)s.B), dim3(128), (size_t)0, st, true, 1, a));
+    a.seed = s.seed; a.seed_dev = seed_dev;
+    VPR_CUDA_OK(launch_ex(heads_tail_kernel<T>, dim3((unsigned)((s.B + TAIL_ROWS - 1) / TAIL_ROWS)), dim3(128), (size_t)0, st,
+                          true, 1, a));
     VPR_TRY(launch_ok("heads_tail_kernel"));
+    if (fwd_only) return 0;
+    if (d_desc != nullptr) {   // d_desc = [dZ | dsc] [W0 ; Wa]   -- first: the SALAD backward waits for it
+        g = GemmDesc(); g.dtype = dtype;
+        g.A = dzaug; g.lda = hp.hid_pad; g.B = waug; g.b_mn = 1; g.ldb = s.D; g.M = s.B; g.N = s.D;
+        g.K = fold ? hp.hid_pad : s.hidden;
+        g.out = d_desc; g.out_kind = okT; g.ldo = s.D;
+        g.pdl = 1;
+        VPR_TRY(gemm_run(g, st));
+    }
     // dW0[hid, D] = dZ^T desc
     g = GemmDesc(); g.dtype = dtype;
     g.A = dzaug; g.a_mn = 1; g.lda = hp.hid_pad; g.B = desc; g.b_mn = 1; g.ldb = s.D; g.M = s.hidden; g.N = s.D; g.K = s.B;
@@ -294,17 +515,25 @@ static int heads_t(const VprHeadsParams& p, const T* desc, const float* latlon_t
     g.pdl = 1;
     VPR_TRY(gemm_run(g, st));
     if (angle) {
-        VPR_CUDA_OK(launch_ex(angle_wgrad_kernel<T>, dim3((unsigned)((s.D + 255) / 256)), dim3(256), (size_t)0, st, true, 1, desc,
-                              (const T*)dzaug, gr.ang_w, s.B, s.D, s.hidden, hp.hid_pad));
-        VPR_TRY(launch_ok("angle_wgrad_kernel"));
+        const int col_blocks = (s.D + 255) / 256;
+        int splits = (2 * nsm) / col_blocks; if (splits < 1) splits = 1;
+        int rows_per = (s.B + splits - 1) / splits; rows_per = (rows_per + 7) & ~7;
+        splits = (s.B + rows_per - 1) / rows_per;
+        VPR_CUDA_OK(launch_ex(angle_bwd_kernel<T>, dim3((unsigned)col_blocks, (unsigned)splits), dim3(32, 8), (size_t)0, st, true, 1,
+                              desc, (const T*)dzaug, (const T*)(waug + (size_t)s.hidden * s.D), gr.ang_w, d_desc, s.B, s.D,
+                              s.hidden, hp.hid_pad, n_ang, rows_per, head_thr, head_scale, (unsigned long long)s.seed, seed_dev));
+        VPR_TRY(launch_ok("angle_bwd_kernel"));
     }
-    if (d_desc != nullptr) {   // d_desc = [dZ | dsc] [W0 ; Wa]
-        g = GemmDesc(); g.dtype = dtype;
-        g.A = dzaug; g.lda = hp.hid_pad; g.B = waug; g.b_mn = 1; g.ldb = s.D; g.M = s.B; g.N = s.D; g.K = hp.hid_pad;
-        g.out = d_desc; g.out_kind = okT; g.ldo = s.D;
-        g.pdl = 1;
-        VPR_TRY(gemm_run(g, st));
-    }
+    return 0;
+}
+
+static int check_heads_shape(const VprHeadsShape* s, int dtype) {
+    VPR_REQUIRE(dtype == VPR_F32 || dtype == VPR_BF16, "dtype must be VPR_F32 or VPR_BF16");
+    VPR_REQUIRE(s->B > 0 && s->D > 0 && s->D % 8 == 0 && s->hidden % 8 == 0, "bad heads shape");
+    VPR_REQUIRE(s->latlon_loss >= VPR_LATLON_MSE && s->latlon_loss <= VPR_LATLON_EXTERNAL, "bad latlon_loss");
+    VPR_REQUIRE(s->angle_loss >= VPR_ANGLE_NONE && s->angle_loss <= VPR_ANGLE_SCALAR_MAAE, "bad angle_loss");
+    VPR_REQUIRE(s->reg_dropout_p >= 0.f && s->reg_dropout_p < 1.f && s->head_dropout_p >= 0.f && s->head_dropout_p < 1.f,
+                "dropout probability out of range");
     return 0;
 }
 
@@ -316,24 +545,36 @@ extern "C" {
 
 size_t vpr_heads_workspace_bytes(const VprHeadsShape* s, int dtype) { return heads_plan(*s, dtype).total; }
 
+int vpr_heads_pack(const VprHeadsParams* p, void* workspace, size_t workspace_bytes, const VprHeadsShape* s, int dtype,
+                   cudaStream_t stream) {
+    VPR_REQUIRE(p && workspace && s && p->reg_w0, "null argument");
+    VPR_TRY(check_device());
+    VPR_TRY(check_heads_shape(s, dtype));
+    VPR_REQUIRE(angle_rows(s->angle_loss) == 0 || p->ang_w, "angle head requested but its weight is null");
+    VPR_REQUIRE(workspace_bytes >= heads_plan(*s, dtype).total, "workspace too small");
+    if (dtype == VPR_BF16) return heads_pack_t<bf16>(*p, (char*)workspace, *s, dtype, stream);
+    return heads_pack_t<float>(*p, (char*)workspace, *s, dtype, stream);
+}
+
 int vpr_heads_loss_fwd_bwd(const VprHeadsParams* p, const void* desc, const float* latlon_target,
                            const float* angle_target_deg, float* latlon_pred, float* sincos_pred, float* losses,
                            VprHeadsGrads* grads, void* d_desc, void* workspace, size_t workspace_bytes,
                            const VprHeadsShape* s, int dtype, cudaStream_t stream) {
-    VPR_REQUIRE(p && desc && latlon_target && latlon_pred && losses && grads && workspace && s, "null argument");
-    VPR_REQUIRE(dtype == VPR_F32 || dtype == VPR_BF16, "dtype must be VPR_F32 or VPR_BF16");
-    VPR_REQUIRE(s->B > 0 && s->D > 0 && s->D % 8 == 0 && s->hidden % 8 == 0, "bad heads shape");
-    VPR_REQUIRE(s->latlon_loss == VPR_LATLON_MSE || s->latlon_loss == VPR_LATLON_HUBER, "bad latlon_loss");
-    VPR_REQUIRE(s->angle_loss >= VPR_ANGLE_NONE && s->angle_loss <= VPR_ANGLE_MSE, "bad angle_loss");
+    VPR_REQUIRE(p && desc && latlon_target && latlon_pred && losses && workspace && s, "null argument");
+    VPR_TRY(check_device());
+    VPR_TRY(check_heads_shape(s, dtype));
+    const bool fwd_only = (s->flags & VPR_HEADS_FORWARD_ONLY) != 0;
+    VPR_REQUIRE(fwd_only || (grads && grads->reg_w0 && grads->reg_b0 && grads->reg_w1 && grads->reg_b1),
+                "gradient buffers are null (set VPR_HEADS_FORWARD_ONLY for inference)");
     if (s->angle_loss != VPR_ANGLE_NONE)
-        VPR_REQUIRE(angle_target_deg && sincos_pred && p->ang_w && p->ang_b && grads->ang_w && grads->ang_b,
+        VPR_REQUIRE(angle_target_deg && sincos_pred && p->ang_w && p->ang_b && (fwd_only || (grads->ang_w && grads->ang_b)),
                     "angle head requested but its buffers are null");
     VPR_REQUIRE(workspace_bytes >= heads_plan(*s, dtype).total, "workspace too small");
     if (dtype == VPR_BF16)
         return heads_t<bf16>(*p, (const bf16*)desc, latlon_target, angle_target_deg, latlon_pred, sincos_pred, losses,
-                             *grads, (bf16*)d_desc, (char*)workspace, *s, dtype, stream);
+                             grads, (bf16*)d_desc, (char*)workspace, *s, dtype, stream);
     return heads_t<float>(*p, (const float*)desc, latlon_target, angle_target_deg, latlon_pred, sincos_pred, losses,
-                          *grads, (float*)d_desc, (char*)workspace, *s, dtype, stream);
+                          grads, (float*)d_desc, (char*)workspace, *s, dtype, stream);
 }
 
 }  // extern "C"

@@ -345,6 +345,7 @@ size_t vpr_knn_workspace_bytes(int64_t Q, int64_t G, int D, int k) {
 
 int vpr_knn_topk(const void* q, const void* g, int64_t Q, int64_t G, int D, int k, int64_t g_offset, float* out_score,
                  int64_t* out_idx, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     VPR_REQUIRE(q && g && out_score && out_idx && workspace, "null argument");
     VPR_REQUIRE(Q > 0 && G > 0, "empty kNN problem (Q=%lld, G=%lld)", (long long)Q, (long long)G);
     VPR_REQUIRE(k >= 1 && k <= KMAX, "k must be in [1, %d]", KMAX);
@@ -394,6 +395,7 @@ int vpr_knn_topk(const void* q, const void* g, int64_t Q, int64_t G, int D, int 
 
 int vpr_knn_merge(const float* scores, const int64_t* idx, int R, int64_t Q, int k, float* out_score, int64_t* out_idx,
                   cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     VPR_REQUIRE(scores && idx && out_score && out_idx && R > 0 && Q > 0 && k > 0, "bad argument");
     // input layout [R, Q, k]
     knn_merge_kernel<long long><<<(unsigned)((Q * 32 + 255) / 256), 256, 0, stream>>>(

@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(256) recall_kernel(const long long* __restrict
     __syncthreads();
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < Q; q += (long long)gridDim.x * blockDim.x) {
         const long long want = query_label[q];
-        int first = k;                                          // rank of the first correct neighbour
+        int first = 0x7fffffff;                                 // rank of the first correct neighbour (none: never a hit,
+                                                                // whatever cut-offs the caller asks for)
         for (int j = 0; j < k; ++j) {
             const long long g = idx[q * k + j];
             if (g >= 0 && g < G && gallery_label[g] == want) { first = j; break; }
@@ -121,6 +122,7 @@ extern "C" {
 
 int vpr_metrics_latlon(const float* pred, const float* target, const double* scaler_mean, const double* scaler_scale,
                        int targets_scaled, int64_t N, double* out_sums, cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     VPR_REQUIRE(pred && target && out_sums, "null argument");
     VPR_REQUIRE(N >= 0, "bad row count");
     VPR_CUDA_OK(cudaMemsetAsync(out_sums, 0, 4 * sizeof(double), stream));
@@ -131,6 +133,7 @@ int vpr_metrics_latlon(const float* pred, const float* target, const double* sca
 
 int vpr_metrics_angle(const float* sincos_pred, const float* true_deg, int cos_first, int64_t N, float* pred_deg,
                       double* out_sum, cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     VPR_REQUIRE(sincos_pred && true_deg && out_sum, "null argument");
     VPR_REQUIRE(N >= 0, "bad row count");
     VPR_CUDA_OK(cudaMemsetAsync(out_sum, 0, sizeof(double), stream));
@@ -141,6 +144,7 @@ int vpr_metrics_angle(const float* sincos_pred, const float* true_deg, int cos_f
 
 int vpr_recall_at_k(const int64_t* idx, const int64_t* gallery_label, const int64_t* query_label, int64_t Q, int k, int64_t G,
                     const int* ks, int nk, unsigned long long* hits, cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     VPR_REQUIRE(idx && gallery_label && query_label && ks && hits, "null argument");
     VPR_REQUIRE(Q >= 0 && k > 0 && G > 0 && nk > 0 && nk <= 16, "bad recall shape (1 <= nk <= 16)");
     VPR_CUDA_OK(cudaMemsetAsync(hits, 0, nk * sizeof(unsigned long long), stream));

@@ -164,6 +164,7 @@ size_t vpr_preprocess_batch_workspace_bytes(int B, int H, int W, int out_h, int 
 int vpr_preprocess_batch(const uint8_t* rgb_bhwc, int B, int H, int W, int out_h, int out_w, const float* mean3,
                          const float* std3, void* out_bchw, int dtype_out, uint8_t* out_u8_bhwc, void* workspace,
                          size_t workspace_bytes, cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     VPR_REQUIRE(rgb_bhwc && mean3 && std3 && out_bchw && workspace, "null argument");
     VPR_REQUIRE(B > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0 && (long long)B * H < (1ll << 31), "bad image shape");
     VPR_REQUIRE(dtype_out == VPR_F32 || dtype_out == VPR_BF16, "dtype must be VPR_F32 or VPR_BF16");
@@ -195,6 +196,7 @@ int vpr_preprocess_batch(const uint8_t* rgb_bhwc, int B, int H, int W, int out_h
 int vpr_preprocess_image(const uint8_t* rgb_hwc, int H, int W, int out_h, int out_w, const float* mean3, const float* std3,
                          void* out_chw, int dtype_out, uint8_t* out_u8_hwc, void* workspace, size_t workspace_bytes,
                          cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     return vpr_preprocess_batch(rgb_hwc, 1, H, W, out_h, out_w, mean3, std3, out_chw, dtype_out, out_u8_hwc, workspace,
                                 workspace_bytes, stream);
 }

@@ -922,6 +922,7 @@ size_t vpr_salad_workspace_bytes(const VprSaladShape* s, int dtype) { return wor
 int vpr_salad_fwd(const VprSaladParams* p, const void* x, const void* t, void* out, void* save, void* workspace,
                   size_t workspace_bytes, const VprSaladShape* s, int dtype, float dropout_p, uint64_t seed,
                   const uint64_t* seed_offset_dev, cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     (void)workspace; (void)workspace_bytes;
     VPR_REQUIRE(p && x && t && out && save && s, "null argument");
     VPR_TRY(check_shape(*s, dtype));
@@ -934,6 +935,7 @@ int vpr_salad_fwd(const VprSaladParams* p, const void* x, const void* t, void* o
 int vpr_salad_bwd(const VprSaladParams* p, const void* x, const void* t, const void* d_out, const void* save,
                   void* workspace, size_t workspace_bytes, VprSaladGrads* grads, void* dx, void* dt,
                   const VprSaladShape* s, int dtype, float dropout_p, int phase, int reserve_sms, cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     VPR_REQUIRE(p && x && t && d_out && save && workspace && grads && s, "null argument");
     VPR_REQUIRE(phase >= VPR_BWD_ALL && phase <= VPR_BWD_INPUTS && reserve_sms >= 0, "bad phase / reserve_sms");
     VPR_TRY(check_shape(*s, dtype));
@@ -947,6 +949,7 @@ int vpr_salad_bwd(const VprSaladParams* p, const void* x, const void* t, const v
 }
 
 int vpr_counter_advance(uint64_t* counter, cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     VPR_REQUIRE(counter != nullptr, "null counter");
     VPR_CUDA_OK(launch_ex(counter_advance_kernel, dim3(1), dim3(1), (size_t)0, stream, true, 1,
                           reinterpret_cast<unsigned long long*>(counter)));
@@ -954,6 +957,7 @@ int vpr_counter_advance(uint64_t* counter, cudaStream_t stream) {
 }
 
 int vpr_dropout_mask(uint64_t seed, float p, int64_t rows, int64_t cols, uint8_t* out, cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     VPR_REQUIRE(out && rows > 0 && cols > 0, "bad argument");
     dropout_mask_kernel<<<num_sms() * 4, 256, 0, stream>>>(seed, p > 0.f ? dropout_threshold(p) : 0u, rows * cols, out);
     return launch_ok("dropout_mask_kernel");
@@ -961,12 +965,14 @@ int vpr_dropout_mask(uint64_t seed, float p, int64_t rows, int64_t cols, uint8_t
 
 int vpr_sinkhorn_fwd(const float* S, const float* dust_bin, void* P, int p_dtype, float* U, float* V, int B, int n,
                      int m, int iters, cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     VPR_REQUIRE(S && dust_bin && P && U && V && B > 0, "bad argument");
     return sinkhorn_fwd(S, dust_bin, P, p_dtype, U, V, B, n, m, iters, stream);
 }
 
 int vpr_sinkhorn_bwd(const float* S, const float* dust_bin, const float* U, const float* V, const float* dP, void* dS,
                      int ds_dtype, float* d_bias, int B, int n, int m, int iters, cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     VPR_REQUIRE(S && dust_bin && U && V && dP && dS && B > 0, "bad argument");
     return sinkhorn_bwd(S, dust_bin, U, V, dP, dS, ds_dtype, d_bias, B, n, m, iters, stream);
 }

@@ -329,6 +329,7 @@ extern "C" {
 
 int vpr_seam_ln_split_fwd(const void* hidden, const float* ln_weight, const float* ln_bias, float eps, void* x_tok, void* t,
                           float* stats, int B, int n, int skip, int d, int dtype_in, int dtype_out, cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     VPR_REQUIRE(hidden && ln_weight && ln_bias && x_tok && t, "null argument");
     VPR_REQUIRE(B > 0 && n > 0 && skip >= 0 && (long long)B * (1 + n) < (1ll << 31), "bad seam shape");
     VPR_REQUIRE(d > 0 && d % 8 == 0 && d <= SEAM_MAXCH * 256, "d must be a multiple of 8 and at most 2048");
@@ -341,6 +342,7 @@ int vpr_seam_ln_split_fwd(const void* hidden, const float* ln_weight, const floa
 int vpr_seam_ln_split_bwd(const void* hidden, const float* ln_weight, const float* stats, const void* d_x_tok, const void* d_t,
                           void* d_hidden, float* d_ln_weight, float* d_ln_bias, int B, int n, int skip, int d, int dtype_in,
                           int dtype_out, cudaStream_t stream) {
+    VPR_TRY(::vpr::check_device());
     VPR_REQUIRE(hidden && ln_weight && stats && d_hidden, "null argument");
     VPR_REQUIRE(B > 0 && n > 0 && skip >= 0 && (long long)B * (1 + n) < (1ll << 31), "bad seam shape");
     VPR_REQUIRE(d > 0 && d % 8 == 0 && d <= SEAM_MAXCH * 256, "d must be a multiple of 8 and at most 2048");

@@ -5,10 +5,12 @@ Mirrors the reference modules:
   * ``regressor = Sequential(Linear(8448,512), ReLU(), [Dropout(p)], Linear(512,2))`` with MSE or
     Huber(delta) on z-scored lat/lon targets -- dinov2salad/dinov2salad_finetuning.py:28-32,96 and
     dinov2salad/dinov2salad_finetuning_2.py:118-123,154;
-  * ``head = Linear(D, 2)`` = [sin, cos] with the atan2 -> degrees -> MAAE loss of
-    angle_prediction/dinov2salad/dino_v2_gemini.py:106-141, the unit-normalised acos loss of
+  * ``dropout = Dropout(p); head = Linear(D, 2)`` = [sin, cos] with the atan2 -> degrees -> MAAE loss of
+    angle_prediction/dinov2salad/dino_v2_gemini.py:99-141, the unit-normalised acos loss of
     angle_prediction/swin/swin_angle_finetuning_sin_cos.py:56-69, or MSE on [sin, cos]
-    (angle_prediction/swin/swin_angle_finetuning_gemini.py:183).
+    (angle_prediction/swin/swin_angle_finetuning_gemini.py:183);
+  * ``head = Linear(D, 1)``, ``pred = head(x).squeeze(-1) % 360`` with the MAAE loss of
+    angle_prediction/dinov2salad/dino_angle_finetuning.py:37-52 (``angle_loss="scalar_maae"``).
 """
 from __future__ import annotations
 
@@ -19,42 +21,84 @@ import torch.nn as nn
 
 from . import _lib as L
 
-_LATLON = {"mse": L.LATLON_MSE, "huber": L.LATLON_HUBER}
+_LATLON = {"mse": L.LATLON_MSE, "huber": L.LATLON_HUBER, "external": L.LATLON_EXTERNAL}
 _ANGLE = {None: L.ANGLE_NONE, "none": L.ANGLE_NONE, "atan2_maae": L.ANGLE_ATAN2_MAAE, "acos": L.ANGLE_ACOS,
-          "mse": L.ANGLE_MSE}
+          "mse": L.ANGLE_MSE, "scalar_maae": L.ANGLE_SCALAR_MAAE}
+_U64 = 0xFFFFFFFFFFFFFFFF
 
 
-def _run(desc, params, latlon_target, angle_target, cfg, want_d_desc):
+def make_cfg(hidden, latlon, angle=L.ANGLE_NONE, delta=1.0, loss_scale=1.0, global_B=0, reg_dropout_p=0.0, seed=0,
+             head_dropout_p=0.0, seed_dev=None):
+    return {"hidden": int(hidden), "latlon": int(latlon), "angle": int(angle), "delta": float(delta),
+            "loss_scale": float(loss_scale), "global_B": int(global_B), "reg_dropout_p": float(reg_dropout_p),
+            "seed": int(seed) & _U64, "head_dropout_p": float(head_dropout_p), "seed_dev": seed_dev}
+
+
+def _shape(B, D, cfg, flags):
+    return L.HeadsShape(B, D, cfg["hidden"], cfg["latlon"], cfg["angle"], cfg["delta"], cfg["loss_scale"],
+                        cfg["global_B"] or B, cfg["reg_dropout_p"], cfg["seed"], cfg["head_dropout_p"], flags,
+                        cfg["seed_dev"].data_ptr() if cfg.get("seed_dev") is not None else None)
+
+
+def workspace_bytes(B, D, cfg, dtype) -> int:
+    shape = _shape(B, D, cfg, 0)
+    return int(L.lib().vpr_heads_workspace_bytes(C.byref(shape), L.dtype_code(dtype)))
+
+
+def pack_weights(params, ws, B, D, cfg, dtype) -> None:
+    """vpr_heads_pack: cast [regressor.0.weight ; angle head] to the run dtype into the head of ``ws``."""
+    shape = _shape(B, D, cfg, 0)
+    ps = L.HeadsParams(*[p.data_ptr() if p is not None else None for p in params])
+    with L.on_device(ws):
+        L.check(L.lib().vpr_heads_pack(C.byref(ps), L.ptr(ws), ws.numel(), C.byref(shape), L.dtype_code(dtype),
+                                       L.stream_ptr(ws.device)), "vpr_heads_pack")
+
+
+def _run(desc, params, latlon_target, angle_target, cfg, want_d_desc, ws=None, forward_only=False, prepacked=False):
+    """One vpr_heads_loss_fwd_bwd call.  Returns (latlon_pred, sincos_pred, losses, grads, d_desc, flat): ``flat`` is
+    ONE fp32 buffer holding every parameter gradient back to back followed by the two losses, so that a
+    data-parallel caller sums gradients and losses across ranks with a single collective."""
     lib = L.lib()
     B, D = desc.shape
     dt = L.dtype_code(desc.dtype)
     dev = desc.device
-    shape = L.HeadsShape(B, D, cfg["hidden"], cfg["latlon"], cfg["angle"], cfg["delta"], cfg["loss_scale"],
-                         cfg["global_B"] or B, cfg["reg_dropout_p"], cfg["seed"])
+    flags = (L.HEADS_FORWARD_ONLY if forward_only else 0) | (L.HEADS_PREPACKED if prepacked else 0)
+    shape = _shape(B, D, cfg, flags)
     ws_bytes = lib.vpr_heads_workspace_bytes(C.byref(shape), dt)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    sizes = [p.numel() if p is not None else 0 for p in params]      # the angle head may be absent (None, None)
-    flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-    grads = list(torch.split(flat, sizes))
+    if ws is None:
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    elif ws.numel() < ws_bytes or ws.device != dev:
+        raise RuntimeError("heads workspace too small or on another device")
     ps = L.HeadsParams(*[p.data_ptr() if p is not None else None for p in params])
-    gs = L.HeadsGrads(*[g.data_ptr() if p is not None else None for g, p in zip(grads, params)])
     latlon_pred = torch.empty(B, 2, dtype=torch.float32, device=dev)
     sincos_pred = torch.zeros(B, 2, dtype=torch.float32, device=dev)
-    losses = torch.empty(2, dtype=torch.float32, device=dev)
-    d_desc = torch.empty_like(desc) if want_d_desc else None
-    L.check(lib.vpr_heads_loss_fwd_bwd(C.byref(ps), L.ptr(desc), L.ptr(latlon_target), L.ptr(angle_target),
-                                       L.ptr(latlon_pred), L.ptr(sincos_pred), L.ptr(losses), C.byref(gs),
-                                       L.ptr(d_desc), L.ptr(ws), ws_bytes, C.byref(shape), dt, L.stream_ptr(dev)),
-            "vpr_heads_loss_fwd_bwd")
-    return (latlon_pred, sincos_pred, losses, [g.view_as(p) if p is not None else None for g, p in zip(grads, params)],
-            d_desc, flat)
+    if forward_only:
+        flat = torch.empty(2, dtype=torch.float32, device=dev)
+        losses, grads, gs_ref, d_desc = flat, [None] * len(params), None, None
+    else:
+        sizes = [p.numel() if p is not None else 0 for p in params]      # the angle head may be absent (None, None)
+        flat = torch.empty(sum(sizes) + 2, dtype=torch.float32, device=dev)
+        *grads, losses = torch.split(flat, sizes + [2])
+        gs = L.HeadsGrads(*[g.data_ptr() if p is not None else None for g, p in zip(grads, params)])
+        gs_ref = C.byref(gs)
+        grads = [g.view_as(p) if p is not None else None for g, p in zip(grads, params)]
+        d_desc = torch.empty_like(desc) if want_d_desc else None
+    with L.on_device(desc):
+        L.check(lib.vpr_heads_loss_fwd_bwd(C.byref(ps), L.ptr(desc), L.ptr(latlon_target), L.ptr(angle_target),
+                                           L.ptr(latlon_pred), L.ptr(sincos_pred), L.ptr(losses), gs_ref,
+                                           L.ptr(d_desc), L.ptr(ws), ws.numel(), C.byref(shape), dt, L.stream_ptr(dev)),
+                "vpr_heads_loss_fwd_bwd")
+        seed_dev = cfg.get("seed_dev")
+        if seed_dev is not None and not forward_only and (cfg["reg_dropout_p"] > 0 or cfg["head_dropout_p"] > 0):
+            L.check(lib.vpr_counter_advance(L.ptr(seed_dev), L.stream_ptr(dev)), "vpr_counter_advance")
+    return latlon_pred, sincos_pred, losses, grads, d_desc, flat
 
 
 class _HeadsLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, desc, latlon_target, angle_target, cfg, *params):
+    def forward(ctx, desc, latlon_target, angle_target, cfg, ws, prepacked, *params):
         latlon_pred, sincos_pred, losses, grads, d_desc, _ = _run(
-            desc, params, latlon_target, angle_target, cfg, ctx.needs_input_grad[0])
+            desc, params, latlon_target, angle_target, cfg, ctx.needs_input_grad[0], ws=ws, prepacked=prepacked)
         ctx.present = [g is not None for g in grads]
         ctx.save_for_backward(*( [d_desc] if d_desc is not None else [] ), *[g for g in grads if g is not None])
         ctx.has_d_desc = d_desc is not None
@@ -70,28 +114,68 @@ class _HeadsLossFn(torch.autograd.Function):
         out_d = (d_desc * scale.to(d_desc.dtype)) if d_desc is not None else None
         it = iter(saved)
         pg = [next(it) * scale if present else None for present in ctx.present]
-        return (out_d, None, None, None, *pg)
+        return (out_d, None, None, None, None, None, *pg)
+
+
+class _RegressorFn(torch.autograd.Function):
+    """``preds = regressor(features)`` with a real autograd edge, for the reference's training idiom
+    ``preds = model(inputs); loss = loss_fn(preds, targets); loss.backward()`` (dinov2salad_finetuning.py:120-124).
+    forward = the fused call in forward-only mode; backward = the same call again with the caller's dL/dpreds
+    (VPR_LATLON_EXTERNAL) -- same seed, so the regressor's dropout mask is the one the forward drew."""
+
+    @staticmethod
+    def forward(ctx, desc, cfg, *params):
+        B = desc.shape[0]
+        zeros = torch.zeros(B, 2, dtype=torch.float32, device=desc.device)
+        cfg_f = dict(cfg, seed_dev=None)
+        preds, *_ = _run(desc, params, zeros, None, cfg_f, False, forward_only=True)
+        ctx.cfg = cfg_f
+        ctx.save_for_backward(desc, *[p for p in params if p is not None])
+        ctx.present = [p is not None for p in params]
+        return preds
+
+    @staticmethod
+    def backward(ctx, d_preds):
+        desc, *ps = ctx.saved_tensors
+        it = iter(ps)
+        params = [next(it) if present else None for present in ctx.present]
+        cfg = dict(ctx.cfg, latlon=L.LATLON_EXTERNAL, angle=L.ANGLE_NONE)
+        _, _, _, grads, d_desc, _ = _run(desc, params, d_preds.float().contiguous(), None, cfg,
+                                         ctx.needs_input_grad[0])
+        return (d_desc, None, *grads)
 
 
 class GeoposeHeads(nn.Module):
-    """lat/lon regressor + sin/cos angle head on a descriptor batch, with fused losses."""
+    """lat/lon regressor + angle head on a descriptor batch, with fused losses.
+
+    ``dropout``: the regressor's Dropout between ReLU and the last Linear (dinov2salad_finetuning_2.py:121);
+    ``head_dropout``: Dropout on the angle head's input (dino_v2_gemini.py:104,111, rate 0.1 there)."""
 
     def __init__(self, in_dim: int = 8448, hidden: int = 512, dropout: float = 0.0, latlon_loss: str = "mse",
-                 angle_loss: str | None = "atan2_maae", huber_delta: float = 1.0):
+                 angle_loss: str | None = "atan2_maae", huber_delta: float = 1.0, head_dropout: float = 0.0):
         super().__init__()
+        if latlon_loss not in ("mse", "huber") or angle_loss not in _ANGLE:
+            raise ValueError("unknown loss variant")
         layers = [nn.Linear(in_dim, hidden), nn.ReLU()]
         if dropout > 0:
             layers.append(nn.Dropout(dropout))
         layers.append(nn.Linear(hidden, 2))
         self.regressor = nn.Sequential(*layers)       # keys regressor.0.*, regressor.2|3.* as in the reference
-        self.head = nn.Linear(in_dim, 2)              # [sin, cos]
+        self.dropout = nn.Dropout(head_dropout)       # dino_v2_gemini.py:104 (no parameters; the kernel applies it)
+        self.head = nn.Linear(in_dim, 1 if angle_loss == "scalar_maae" else 2)    # [sin, cos] | angle in degrees
         self.in_dim, self.hidden = in_dim, hidden
         self.reg_dropout_p = float(dropout)
-        if latlon_loss not in _LATLON or angle_loss not in _ANGLE:
-            raise ValueError("unknown loss variant")
+        self.head_dropout_p = float(head_dropout)
         self.latlon_loss, self.angle_loss, self.huber_delta = latlon_loss, angle_loss, float(huber_delta)
         self._step = 0
         self.seed = 0xA17
+        self._seed_dev = None
+        self._ws = {}          # (B, dtype, device) -> [workspace, pack key]
+
+    def use_device_step_counter(self, enabled: bool = True) -> None:
+        """Keep the dropout step counter on the device (needed under CUDA-graph capture: a host counter would be
+        frozen into the graph and every replay would draw the same masks)."""
+        self._seed_dev = torch.zeros(1, dtype=torch.int64, device=self.head.weight.device) if enabled else None
 
     def _params(self):
         last = self.regressor[-1]
@@ -99,20 +183,43 @@ class GeoposeHeads(nn.Module):
                 self.head.bias]
 
     def _cfg(self, loss_scale=1.0, global_B=0):
-        seed = (self.seed * 1000003 + self._step) & 0xFFFFFFFFFFFFFFFF
-        if self.training:
+        seed = (self.seed * 1000003 + self._step) & _U64
+        drop = self.training and (self.reg_dropout_p > 0 or self.head_dropout_p > 0)
+        seed_dev = self._seed_dev if drop else None
+        if drop and seed_dev is None:
             self._step += 1
-        return {"hidden": self.hidden, "latlon": _LATLON[self.latlon_loss], "angle": _ANGLE[self.angle_loss],
-                "delta": self.huber_delta, "loss_scale": float(loss_scale), "global_B": int(global_B),
-                "reg_dropout_p": self.reg_dropout_p if self.training else 0.0, "seed": seed}
+        return make_cfg(self.hidden, _LATLON[self.latlon_loss], _ANGLE[self.angle_loss], self.huber_delta, loss_scale,
+                        global_B, self.reg_dropout_p if self.training else 0.0, seed,
+                        self.head_dropout_p if self.training else 0.0, seed_dev)
+
+    def current_seed(self) -> int:
+        """Seed the NEXT training call will use (synchronises when the counter lives on the device)."""
+        base = (self.seed * 1000003 + self._step) & _U64
+        if self._seed_dev is not None:
+            base = (base + int(self._seed_dev.item())) & _U64
+        return base
+
+    def _workspace(self, desc, cfg, params):
+        """Per-shape persistent workspace whose head holds the run-dtype copy of the big weight matrices; the copy is
+        redone only when regressor.0.weight / head.weight changed (tensor version counters) since the last call."""
+        B, D = desc.shape
+        key = (B, desc.dtype, desc.device)
+        ent = self._ws.get(key)
+        if ent is None:
+            ent = [torch.empty(workspace_bytes(B, D, cfg, desc.dtype), dtype=torch.uint8, device=desc.device), None]
+            self._ws[key] = ent
+        pk = tuple((p.data_ptr(), p._version) for p in (params[0], params[4])) + (cfg["angle"],)
+        prepacked = ent[1] == pk
+        ent[1] = pk
+        return ent[0], prepacked
 
     def forward(self, desc: torch.Tensor, latlon_target: torch.Tensor, angle_target_deg: torch.Tensor | None = None,
                 global_B: int = 0):
         """Returns (total_loss, losses[2] = (lat/lon, angle), latlon_pred [B,2], sincos_pred [B,2]).
-        ``total_loss.backward()`` delivers the gradients that the same kernel call already computed."""
+        ``total_loss.backward()`` delivers the gradients that the same kernel call already computed.
+        With ``angle_loss="scalar_maae"`` ``sincos_pred[:, 0]`` is the predicted angle in [0, 360)."""
         L.require_cuda(desc, "descriptor")
         desc = desc.contiguous()
-        B = desc.shape[0]
         lt = latlon_target.to(device=desc.device, dtype=torch.float32).contiguous()
         if self.angle_loss in (None, "none"):
             at = None
@@ -121,19 +228,24 @@ class GeoposeHeads(nn.Module):
                 raise ValueError("angle_target_deg is required for the angle head")
             at = angle_target_deg.to(device=desc.device, dtype=torch.float32).contiguous()
         params = [p.contiguous() for p in self._params()]
-        return _HeadsLossFn.apply(desc, lt, at, self._cfg(global_B=global_B), *params)
+        cfg = self._cfg(global_B=global_B)
+        ws, prepacked = self._workspace(desc, cfg, params)
+        return _HeadsLossFn.apply(desc, lt, at, cfg, ws, prepacked, *params)
 
     @torch.no_grad()
     def predict(self, desc: torch.Tensor):
         """(latlon_pred [B,2], sincos_pred [B,2]) without targets (eval loops of the reference,
-        dinov2salad_finetuning.py:147, dinov2salad_validation.py:81)."""
+        dinov2salad_finetuning.py:147, dinov2salad_validation.py:81): forward-only call, no gradient work."""
+        L.require_cuda(desc, "descriptor")
+        desc = desc.contiguous()
         B = desc.shape[0]
         z = torch.zeros(B, 2, dtype=torch.float32, device=desc.device)
         a = torch.zeros(B, dtype=torch.float32, device=desc.device)
-        cfg = self._cfg()
-        cfg["reg_dropout_p"] = 0.0
-        latlon_pred, sincos_pred, *_ = _run(desc.contiguous(), [p.contiguous() for p in self._params()], z,
-                                            a if cfg["angle"] != L.ANGLE_NONE else None, cfg, False)
+        cfg = make_cfg(self.hidden, _LATLON[self.latlon_loss], _ANGLE[self.angle_loss], self.huber_delta)
+        params = [p.contiguous() for p in self._params()]
+        ws, prepacked = self._workspace(desc, cfg, params)
+        latlon_pred, sincos_pred, *_ = _run(desc, params, z, a if cfg["angle"] != L.ANGLE_NONE else None, cfg, False,
+                                            ws=ws, forward_only=True, prepacked=prepacked)
         return latlon_pred, sincos_pred
 
 

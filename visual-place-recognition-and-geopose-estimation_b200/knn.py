@@ -27,8 +27,9 @@ def knn_topk(q: torch.Tensor, g: torch.Tensor, k: int = 25, g_offset: int = 0):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
     score = torch.empty(Q, k, dtype=torch.float32, device=q.device)
     idx = torch.empty(Q, k, dtype=torch.int64, device=q.device)
-    L.check(lib.vpr_knn_topk(L.ptr(q), L.ptr(g), Q, G, D, k, int(g_offset), L.ptr(score), L.ptr(idx), L.ptr(ws),
-                             ws_bytes, L.stream_ptr(q.device)), "vpr_knn_topk")
+    with L.on_device(q):
+        L.check(lib.vpr_knn_topk(L.ptr(q), L.ptr(g), Q, G, D, k, int(g_offset), L.ptr(score), L.ptr(idx), L.ptr(ws),
+                                 ws_bytes, L.stream_ptr(q.device)), "vpr_knn_topk")
     return score, idx
 
 
@@ -41,8 +42,9 @@ def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k: int):
         raise ValueError("per-rank lists must hold k entries")
     out_s = torch.empty(Q, k, dtype=torch.float32, device=scores.device)
     out_i = torch.empty(Q, k, dtype=torch.int64, device=scores.device)
-    L.check(L.lib().vpr_knn_merge(L.ptr(scores), L.ptr(idx), R, Q, k, L.ptr(out_s), L.ptr(out_i),
-                                  L.stream_ptr(scores.device)), "vpr_knn_merge")
+    with L.on_device(scores):
+        L.check(L.lib().vpr_knn_merge(L.ptr(scores), L.ptr(idx), R, Q, k, L.ptr(out_s), L.ptr(out_i),
+                                      L.stream_ptr(scores.device)), "vpr_knn_merge")
     return out_s, out_i
 
 

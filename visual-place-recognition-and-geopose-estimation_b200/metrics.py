@@ -82,8 +82,9 @@ def latlon_metrics(pred: torch.Tensor, target: torch.Tensor, scaler: LatLonScale
         return {"n": 0}
     m, s = scaler.device_tensors(pred.device) if scaler is not None else (None, None)
     out = torch.empty(4, dtype=torch.float64, device=pred.device)
-    L.check(lib.vpr_metrics_latlon(L.ptr(pred), L.ptr(target), L.ptr(m), L.ptr(s), int(targets_scaled), N, L.ptr(out),
-                                   L.stream_ptr(pred.device)), "vpr_metrics_latlon")
+    with L.on_device(pred):
+        L.check(lib.vpr_metrics_latlon(L.ptr(pred), L.ptr(target), L.ptr(m), L.ptr(s), int(targets_scaled), N, L.ptr(out),
+                                       L.stream_ptr(pred.device)), "vpr_metrics_latlon")
     s0, s1, a0, a1 = out.tolist()
     mse = (s0 + s1) / (2 * N)
     return {"n": N, "final_loss": 0.5 * (s0 + s1) / N, "mse": mse, "rmse": math.sqrt(mse), "mae": (a0 + a1) / (2 * N),
@@ -106,8 +107,9 @@ def maae(sincos_pred: torch.Tensor, true_deg: torch.Tensor, order: str = "sin_co
         return float("nan"), torch.empty(0, dtype=torch.float32, device=p.device)
     pred_deg = torch.empty(N, dtype=torch.float32, device=p.device)
     out = torch.empty(1, dtype=torch.float64, device=p.device)
-    L.check(lib.vpr_metrics_angle(L.ptr(p), L.ptr(t), int(order == "cos_sin"), N, L.ptr(pred_deg), L.ptr(out),
-                                  L.stream_ptr(p.device)), "vpr_metrics_angle")
+    with L.on_device(p):
+        L.check(lib.vpr_metrics_angle(L.ptr(p), L.ptr(t), int(order == "cos_sin"), N, L.ptr(pred_deg), L.ptr(out),
+                                      L.stream_ptr(p.device)), "vpr_metrics_angle")
     return out.item() / N, pred_deg
 
 
@@ -121,6 +123,8 @@ def recall_at_k(idx: torch.Tensor, query_labels: torch.Tensor, gallery_labels: t
     ks = [int(v) for v in ks]
     if not ks or len(ks) > 16 or min(ks) < 1:
         raise ValueError("ks must hold 1..16 positive cut-offs")
+    if max(ks) > k:
+        raise ValueError(f"recall@{max(ks)} needs at least {max(ks)} neighbours per query, idx has {k}")
     ql = query_labels.to(device=idx.device, dtype=torch.int64).contiguous()
     gl = gallery_labels.to(device=idx.device, dtype=torch.int64).contiguous()
     if ql.shape != (Q,):
@@ -129,7 +133,65 @@ def recall_at_k(idx: torch.Tensor, query_labels: torch.Tensor, gallery_labels: t
         return {kk: float("nan") for kk in ks}
     ks_dev = torch.tensor(ks, dtype=torch.int32, device=idx.device)
     hits = torch.empty(len(ks), dtype=torch.int64, device=idx.device)      # uint64 counts < 2^63
-    L.check(lib.vpr_recall_at_k(L.ptr(idx), L.ptr(gl), L.ptr(ql), Q, k, gl.numel(), L.ptr(ks_dev), len(ks), L.ptr(hits),
-                                L.stream_ptr(idx.device)), "vpr_recall_at_k")
+    with L.on_device(idx):
+        L.check(lib.vpr_recall_at_k(L.ptr(idx), L.ptr(gl), L.ptr(ql), Q, k, gl.numel(), L.ptr(ks_dev), len(ks), L.ptr(hits),
+                                    L.stream_ptr(idx.device)), "vpr_recall_at_k")
     h = hits.tolist()
     return {kk: hh / Q for kk, hh in zip(ks, h)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# prediction CSV files (host side; the last step of the reference's validation scripts)
+# ---------------------------------------------------------------------------------------------------------------
+def _host_rows(a, cols):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().double().numpy()
+    a = np.asarray(a, dtype=np.float64)
+    return a.reshape(-1, cols) if cols > 1 else a.reshape(-1)
+
+
+def write_latlon_predictions_csv(path, filenames, true_latlon, pred_latlon) -> int:
+    """The per-image prediction file of swin_transformer/validation_swin_2.py:205-218 (same writer in
+    val_and_test_swin_2.py:280-290): columns ``filename,true_latitude,true_longitude,predicted_latitude,
+    predicted_longitude,error_latitude,error_longitude``, the errors being ``np.abs(true - predicted)``, written
+    like ``DataFrame.to_csv(index=False, float_format='%.6f')``.  Values are in original units (run predictions
+    through ``LatLonScaler.inverse_transform`` first, as the reference does at :176).  Returns the row count."""
+    import csv
+    t, p = _host_rows(true_latlon, 2), _host_rows(pred_latlon, 2)
+    names = list(filenames)
+    if not (len(names) == len(t) == len(p)):
+        raise ValueError("filenames, true_latlon and pred_latlon must have one row per image")
+    err = np.abs(t - p)
+    with open(path, "w", newline="") as f:
+        w = csv.writer(f, lineterminator="\n")
+        w.writerow(["filename", "true_latitude", "true_longitude", "predicted_latitude", "predicted_longitude",
+                    "error_latitude", "error_longitude"])
+        for i, name in enumerate(names):
+            w.writerow([name] + ["%.6f" % v for v in (t[i, 0], t[i, 1], p[i, 0], p[i, 1], err[i, 0], err[i, 1])])
+    return len(names)
+
+
+def write_angle_predictions_csv(path, filenames, true_angle, pred_angle) -> int:
+    """The per-image file of angle_prediction/efficient_net/validation_script.py:211-220: columns
+    ``filename,true_angle,predicted_angle,angular_error`` with ``angular_error = min(|p - t|, 360 - |p - t|)``,
+    written like ``DataFrame.to_csv(index=False)`` (shortest round-trip float text; integer-valued targets that arrive
+    as integers stay integers)."""
+    import csv
+    names = list(filenames)
+    tl = true_angle.detach().cpu().tolist() if isinstance(true_angle, torch.Tensor) else list(true_angle)
+    pl = pred_angle.detach().cpu().tolist() if isinstance(pred_angle, torch.Tensor) else list(pred_angle)
+    if not (len(names) == len(tl) == len(pl)):
+        raise ValueError("filenames, true_angle and pred_angle must have one entry per image")
+
+    def txt(v):
+        if isinstance(v, (int, np.integer)):
+            return str(int(v))
+        return repr(float(v))
+
+    with open(path, "w", newline="") as f:
+        w = csv.writer(f, lineterminator="\n")
+        w.writerow(["filename", "true_angle", "predicted_angle", "angular_error"])
+        for name, t, p in zip(names, tl, pl):
+            d = abs(p - t)
+            w.writerow([name, txt(t), txt(p), txt(min(d, 360 - d))])
+    return len(names)

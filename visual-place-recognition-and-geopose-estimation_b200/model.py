@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .heads import _HeadsLossFn, _run
+from .heads import _HeadsLossFn, _RegressorFn, _run, make_cfg
 from .salad import SaladHead
 
 _LATLON = {"mse": L.LATLON_MSE, "huber": L.LATLON_HUBER}
@@ -44,10 +44,12 @@ class VPRModel(nn.Module):
 class DINOv2RegressionModel(nn.Module):
     """Frozen descriptor extractor + lat/lon regressor.
 
-    ``forward(x)`` is the reference's inference call (``preds = model(inputs)``, dinov2salad_finetuning.py:147,
-    dinov2salad_validation.py:81).  For training, the three reference lines ``preds = model(inputs)``,
-    ``loss = loss_fn(preds, targets)``, ``loss.backward()`` (:120-124) map to ``loss = model.loss(inputs, targets)``,
-    ``loss.backward()``: regressor forward, loss and every regressor gradient come out of one library call."""
+    ``forward(x)`` is the reference's call ``preds = model(inputs)`` in both of its uses: inference
+    (dinov2salad_finetuning.py:147, dinov2salad_validation.py:81: forward-only kernels) and the training loop
+    ``preds = model(inputs); loss = loss_fn(preds, targets); loss.backward()`` (:120-124), where ``preds`` carries an
+    autograd edge whose backward hands ``dL/dpreds`` to the fused kernels.  ``model.loss(inputs, targets)`` is the
+    faster spelling of those three lines for the two losses the reference uses (MSE / Huber): regressor forward,
+    loss and every regressor gradient come out of ONE library call."""
 
     def __init__(self, base_model: nn.Module, in_dim: int = 8448, hidden: int = 512, dropout_prob: float = 0.0,
                  loss: str = "mse", huber_delta: float = 1.0):
@@ -72,26 +74,24 @@ class DINOv2RegressionModel(nn.Module):
 
     def _cfg(self, train: bool):
         seed = (self.seed * 1000003 + self._step) & 0xFFFFFFFFFFFFFFFF
-        if train:
+        if train and self.dropout_prob > 0:
             self._step += 1
-        return {"hidden": self.hidden, "latlon": _LATLON[self.loss_kind], "angle": L.ANGLE_NONE, "delta": self.huber_delta,
-                "loss_scale": 1.0, "global_B": 0, "reg_dropout_p": self.dropout_prob if train else 0.0, "seed": seed}
+        return make_cfg(self.hidden, _LATLON[self.loss_kind], L.ANGLE_NONE, self.huber_delta,
+                        reg_dropout_p=self.dropout_prob if train else 0.0, seed=seed)
 
     def features(self, x) -> torch.Tensor:
         with torch.no_grad():
             return self.feature_extractor(x)              # shape: (B, 8448)
 
     def forward(self, x) -> torch.Tensor:
-        if self.training and torch.is_grad_enabled():
-            raise RuntimeError("training goes through DINOv2RegressionModel.loss(inputs, targets): the regressor, its loss "
-                               "and its gradients are one fused library call; forward() is the inference path "
-                               "(model.eval() / torch.no_grad())")
         feats = self.features(x).contiguous()
         L.require_cuda(feats, "descriptor")
+        params = [p.contiguous() if p is not None else None for p in self._params()]
+        if torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in params):
+            return _RegressorFn.apply(feats, self._cfg(self.training), *params)      # differentiable w.r.t. the regressor
         z = torch.zeros(feats.shape[0], 2, dtype=torch.float32, device=feats.device)
         with torch.no_grad():
-            params = [p.contiguous() if p is not None else None for p in self._params()]
-            preds, *_ = _run(feats, params, z, None, self._cfg(False), False)
+            preds, *_ = _run(feats, params, z, None, self._cfg(self.training), False, forward_only=True)
         return preds
 
     def loss(self, x, targets: torch.Tensor, global_B: int = 0) -> torch.Tensor:
@@ -103,7 +103,7 @@ class DINOv2RegressionModel(nn.Module):
         cfg = self._cfg(self.training)
         cfg["global_B"] = int(global_B)
         params = [p.contiguous() if p is not None else None for p in self._params()]
-        total, _losses, _preds, _sc = _HeadsLossFn.apply(feats, tg, None, cfg, *params)
+        total, _losses, _preds, _sc = _HeadsLossFn.apply(feats, tg, None, cfg, None, False, *params)
         return total
 
 

@@ -24,9 +24,10 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, batch=1, a_bs=0, b_bs=0, out_
     out_bs = out_bs if out_bs is not None else (out.stride(0) if out.dim() == 3 else 0)
     ld_mask = mask.stride(-2) if mask is not None else 0
     mask_bs = (mask.stride(0) if (mask is not None and mask.dim() == 3) else 0)
-    L.check(L.lib().vpr_gemm(dt, L.ptr(A), int(a_mn), lda, a_bs, L.ptr(B), int(b_mn), ldb, b_bs, M, N, K, batch,
-                             L.ptr(out), out_kind, ldo, out_bs, L.ptr(bias), int(relu), L.ptr(mask), ld_mask,
-                             mask_bs, float(mask_scale), float(alpha), k_splits, bn, L.ptr(colsum), float(dropout_p),
-                             int(dropout_seed), L.stream_ptr(dev)),
-            "vpr_gemm")
+    with L.on_device(A):
+        L.check(L.lib().vpr_gemm(dt, L.ptr(A), int(a_mn), lda, a_bs, L.ptr(B), int(b_mn), ldb, b_bs, M, N, K, batch,
+                                 L.ptr(out), out_kind, ldo, out_bs, L.ptr(bias), int(relu), L.ptr(mask), ld_mask,
+                                 mask_bs, float(mask_scale), float(alpha), k_splits, bn, L.ptr(colsum), float(dropout_p),
+                                 int(dropout_seed), L.stream_ptr(dev)),
+                "vpr_gemm")
     return out

@@ -158,6 +158,21 @@ def allreduce_grads(params: Iterable[torch.nn.Parameter], group=None, bucket_byt
     return lambda: None
 
 
+def decorrelate_dropout(module, rank: int | None = None) -> None:
+    """Give this rank's ``module`` (SaladHead / GeoposeHeads) its own dropout stream.  The counter-based masks are
+    keyed on (seed, local element index): with the same seed on every rank, sample i of every shard would draw the same
+    mask, whereas the reference draws independent masks over the global batch.  Idempotent."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if getattr(module, "_seed_rank", None) == rank:
+        return
+    base = getattr(module, "_seed_base", None)
+    if base is None:
+        base = module._seed_base = int(module.seed)
+    module.seed = (base ^ ((rank * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)) & 0x7FFFFFFFFFFF
+    module._seed_rank = rank
+
+
 def overlap_grad_allreduce(head, group=None, reserve_sms: int = 32, average: bool = False) -> None:
     """Make ``head`` (a SaladHead) all-reduce its parameter gradients from inside its own backward: the flat
     gradient buffer is summed across ranks by ONE in-place collective that starts as soon as the last weight
@@ -170,6 +185,7 @@ def overlap_grad_allreduce(head, group=None, reserve_sms: int = 32, average: boo
         head.set_grad_ready_hook(None)
         return
     world = dist.get_world_size(group)
+    decorrelate_dropout(head, dist.get_rank(group))
 
     def start(flat: torch.Tensor):
         work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
@@ -187,14 +203,18 @@ def overlap_grad_allreduce(head, group=None, reserve_sms: int = 32, average: boo
 class DataParallelStep:
     """One fine-tuning step of SALAD head + geopose heads over a batch shard (BASELINE config 3).
 
-    The loss is the global-batch mean (each rank divides by the global batch), so the reduction
-    across ranks is a plain sum.  The geopose-head gradients come out of the fused heads kernel
+    The loss is the global-batch mean (each rank divides its shard's sum by the global batch), so the reduction
+    across ranks is a plain sum -- of the gradients and of the returned losses alike (both are all-reduced: every
+    rank returns the global-batch losses).  The geopose-head gradients come out of the fused heads kernel
     before the SALAD backward starts; their allreduce is launched first and overlaps it.
     """
 
     def __init__(self, salad, heads, group=None):
         self.salad, self.heads, self.group = salad, heads, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if self.world > 1:
+            decorrelate_dropout(salad, dist.get_rank(group))
+            decorrelate_dropout(heads, dist.get_rank(group))
 
     def grad_elements(self) -> int:
         return sum(p.numel() for p in list(self.salad.parameters()) + list(self.heads.parameters()))
@@ -216,6 +236,10 @@ class DataParallelStep:
             fin_salad = lambda: None           # noqa: E731
         fin_heads()
         fin_salad()
+        if self.world > 1:
+            losses = losses.clone()
+            dist.all_reduce(losses, op=dist.ReduceOp.SUM, group=self.group)
+            total = losses.sum() if self.heads.angle_loss not in (None, "none") else losses[0]
         return total.detach(), losses
 
 
@@ -229,23 +253,28 @@ class GraphedFinetuneStep:
         step = GraphedFinetuneStep(salad, heads, batch=256, n_tokens=256, global_batch=2048)
         total, losses = step(x_tok, t, latlon_target, angle_target_deg)     # p.grad of both modules is up to date
 
-    The losses are global-batch means (each rank divides by ``global_batch``), so the reduction across ranks is a sum.
-    The regressor's own dropout draws its mask from a host-side step counter and is therefore not supported here."""
+    The losses are global-batch means (each rank divides its shard's sum by ``global_batch``); they sit at the end of
+    the heads' flat gradient buffer, so the same sum-all-reduce leaves every rank with the global losses.  Dropout
+    (SALAD's 0.3, the regressor's, the angle head's) draws from device-side step counters: every replay gets fresh
+    masks, and every rank its own stream (``decorrelate_dropout``).  The run-dtype cast of the big head weight matrices
+    runs on a forked branch next to the SALAD forward (it only depends on the weights)."""
 
     def __init__(self, salad, heads, batch: int, n_tokens: int, dtype=torch.bfloat16, global_batch: int | None = None,
                  group=None, input_grads: bool = False, warmup: int = 3):
         from . import _lib as L
-        from .heads import _run as heads_run
+        from .heads import _run as heads_run, pack_weights, workspace_bytes
         from .salad import _salad_backward, _salad_forward
         dev = salad.dust_bin.device
         if dev.type != "cuda":
             raise RuntimeError("GraphedFinetuneStep needs the modules on a CUDA device")
-        if heads.reg_dropout_p > 0 and heads.training:
-            raise RuntimeError("GraphedFinetuneStep: the regressor's dropout uses a host-side step counter; use dropout=0")
         self.salad, self.heads, self.group = salad, heads, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.global_batch = int(global_batch) if global_batch is not None else batch * self.world
         salad.use_device_step_counter(True)
+        heads.use_device_step_counter(True)
+        if self.world > 1:
+            decorrelate_dropout(salad, dist.get_rank(group))
+            decorrelate_dropout(heads, dist.get_rank(group))
         if self.world > 1 and salad._grad_hook is None:
             overlap_grad_allreduce(salad, group)
         self.x = torch.zeros(batch, n_tokens, salad.num_channels, dtype=dtype, device=dev)
@@ -254,13 +283,22 @@ class GraphedFinetuneStep:
         self.angle = torch.zeros(batch, dtype=torch.float32, device=dev)
         use_angle = heads.angle_loss not in (None, "none")
 
+        cfg0 = heads._cfg(global_B=self.global_batch)
+        hws = torch.empty(workspace_bytes(batch, salad.out_dim, cfg0, dtype), dtype=torch.uint8, device=dev)
+        pack_stream = torch.cuda.Stream(dev)
+
         def run():
-            x_tok, t, shape, p_drop, seed, seed_dev, sparams = salad._prepare((self.x, self.t))
-            desc, save = _salad_forward(x_tok, t, shape, p_drop, seed, seed_dev, sparams)
             hparams = [p.contiguous() for p in heads._params()]
             cfg = heads._cfg(global_B=self.global_batch)
+            main = torch.cuda.current_stream(dev)
+            pack_stream.wait_stream(main)                       # fork: weight cast beside the SALAD forward
+            with torch.cuda.stream(pack_stream):
+                pack_weights(hparams, hws, batch, salad.out_dim, cfg, dtype)
+            x_tok, t, shape, p_drop, seed, seed_dev, sparams = salad._prepare((self.x, self.t))
+            desc, save = _salad_forward(x_tok, t, shape, p_drop, seed, seed_dev, sparams)
+            main.wait_stream(pack_stream)                       # join
             latlon_pred, sincos_pred, losses, hgrads, d_desc, hflat = heads_run(
-                desc, hparams, self.latlon, self.angle if use_angle else None, cfg, True)
+                desc, hparams, self.latlon, self.angle if use_angle else None, cfg, True, ws=hws, prepacked=True)
             hwork = dist.all_reduce(hflat, group=group, async_op=True) if self.world > 1 else None
             dx, dt, sflat, sgrads = _salad_backward(x_tok, t, save, sparams, shape, p_drop, d_desc, input_grads, input_grads,
                                                     salad._grad_hook)

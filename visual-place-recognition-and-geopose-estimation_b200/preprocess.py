@@ -56,9 +56,10 @@ class GpuPreprocess:
             H, W = int(stacked.shape[1]), int(stacked.shape[2])
             nbytes = lib.vpr_preprocess_batch_workspace_bytes(B, H, W, self.out_h, self.out_w)
             ws = self._workspace(nbytes)
-            L.check(lib.vpr_preprocess_batch(L.ptr(stacked), B, H, W, self.out_h, self.out_w, self._mean, self._std, L.ptr(out),
-                                             L.dtype_code(self.out_dtype), L.ptr(u8), L.ptr(ws), ws.numel(), st),
-                    "vpr_preprocess_batch")
+            with L.on_device(stacked):
+                L.check(lib.vpr_preprocess_batch(L.ptr(stacked), B, H, W, self.out_h, self.out_w, self._mean, self._std, L.ptr(out),
+                                                 L.dtype_code(self.out_dtype), L.ptr(u8), L.ptr(ws), ws.numel(), st),
+                        "vpr_preprocess_batch")
             return (out, u8) if return_uint8 else out
         for i, img in enumerate(images):
             if img.dtype != torch.uint8 or img.dim() != 3 or img.shape[2] != 3:
@@ -67,7 +68,8 @@ class GpuPreprocess:
             H, W = int(img.shape[0]), int(img.shape[1])
             nbytes = lib.vpr_preprocess_workspace_bytes(H, W, self.out_h, self.out_w)
             ws = self._workspace(nbytes)
-            L.check(lib.vpr_preprocess_image(L.ptr(img), H, W, self.out_h, self.out_w, self._mean, self._std, L.ptr(out[i]),
-                                             L.dtype_code(self.out_dtype), L.ptr(u8[i]) if u8 is not None else None,
-                                             L.ptr(ws), ws.numel(), st), "vpr_preprocess_image")
+            with L.on_device(img):
+                L.check(lib.vpr_preprocess_image(L.ptr(img), H, W, self.out_h, self.out_w, self._mean, self._std, L.ptr(out[i]),
+                                                 L.dtype_code(self.out_dtype), L.ptr(u8[i]) if u8 is not None else None,
+                                                 L.ptr(ws), ws.numel(), st), "vpr_preprocess_image")
         return (out, u8) if return_uint8 else out

@@ -45,11 +45,13 @@ def _salad_forward(x_tok, t, shape_tuple, dropout_p, seed, seed_dev, params):
     save = torch.empty(lib.vpr_salad_save_bytes(C.byref(shape), dt), dtype=torch.uint8, device=dev)
     out = torch.empty(B, g + l * m, dtype=x_tok.dtype, device=dev)
     ps = _params_struct(L.SaladParams, params)
-    L.check(lib.vpr_salad_fwd(C.byref(ps), L.ptr(x_tok), L.ptr(t), L.ptr(out), L.ptr(save), None, 0,
-                              C.byref(shape), dt, float(dropout_p), int(seed), L.ptr(seed_dev), L.stream_ptr(dev)),
-            "vpr_salad_fwd")
+    with L.on_device(x_tok):
+        L.check(lib.vpr_salad_fwd(C.byref(ps), L.ptr(x_tok), L.ptr(t), L.ptr(out), L.ptr(save), None, 0,
+                                  C.byref(shape), dt, float(dropout_p), int(seed), L.ptr(seed_dev), L.stream_ptr(dev)),
+                "vpr_salad_fwd")
     if seed_dev is not None and dropout_p > 0:      # next call (or next graph replay) draws a fresh mask
-        L.check(lib.vpr_counter_advance(L.ptr(seed_dev), L.stream_ptr(dev)), "vpr_counter_advance")
+        with L.on_device(x_tok):
+            L.check(lib.vpr_counter_advance(L.ptr(seed_dev), L.stream_ptr(dev)), "vpr_counter_advance")
     return out, save
 
 
@@ -75,10 +77,11 @@ def _salad_backward(x_tok, t, save, params, shape_tuple, dropout_p, d_out, want_
     dtok = torch.empty_like(t) if want_dt else None
 
     def bwd(phase, reserve):
-        L.check(lib.vpr_salad_bwd(C.byref(ps), L.ptr(x_tok), L.ptr(t), L.ptr(d_out), L.ptr(save), L.ptr(ws),
-                                  ws_bytes, C.byref(gs), L.ptr(dx), L.ptr(dtok), C.byref(shape), dt,
-                                  float(dropout_p), phase, reserve, L.stream_ptr(dev)),
-                "vpr_salad_bwd")
+        with L.on_device(x_tok):
+            L.check(lib.vpr_salad_bwd(C.byref(ps), L.ptr(x_tok), L.ptr(t), L.ptr(d_out), L.ptr(save), L.ptr(ws),
+                                      ws_bytes, C.byref(gs), L.ptr(dx), L.ptr(dtok), C.byref(shape), dt,
+                                      float(dropout_p), phase, reserve, L.stream_ptr(dev)),
+                    "vpr_salad_bwd")
 
     if hook is None:
         bwd(L.BWD_ALL, 0)
@@ -299,8 +302,9 @@ def dropout_keep_mask(seed: int, p: float, rows: int, cols: int, device="cuda") 
     """The {0,1} keep mask the fused dropout epilogue used for ``seed`` over the [rows, cols] hidden
     activation (cols = 1024: cluster half then score half).  Test support."""
     out = torch.empty(rows, cols, dtype=torch.uint8, device=device)
-    L.check(L.lib().vpr_dropout_mask(int(seed), float(p), rows, cols, L.ptr(out), L.stream_ptr(out.device)),
-            "vpr_dropout_mask")
+    with L.on_device(out):
+        L.check(L.lib().vpr_dropout_mask(int(seed), float(p), rows, cols, L.ptr(out), L.stream_ptr(out.device)),
+                "vpr_dropout_mask")
     return out
 
 
@@ -314,8 +318,9 @@ def sinkhorn(S: torch.Tensor, dust_bin: torch.Tensor, iters: int = 3, out_dtype=
     U = torch.empty(B, iters, m + 1, dtype=torch.float32, device=S.device)
     V = torch.empty(B, iters, n, dtype=torch.float32, device=S.device)
     db = dust_bin.detach().float().reshape(1).to(S.device)
-    L.check(L.lib().vpr_sinkhorn_fwd(L.ptr(S), L.ptr(db), L.ptr(P), L.dtype_code(out_dtype), L.ptr(U), L.ptr(V),
-                                     B, n, m, iters, L.stream_ptr(S.device)), "vpr_sinkhorn_fwd")
+    with L.on_device(S):
+        L.check(L.lib().vpr_sinkhorn_fwd(L.ptr(S), L.ptr(db), L.ptr(P), L.dtype_code(out_dtype), L.ptr(U), L.ptr(V),
+                                         B, n, m, iters, L.stream_ptr(S.device)), "vpr_sinkhorn_fwd")
     return P, U, V
 
 
@@ -326,7 +331,8 @@ def sinkhorn_backward(S, dust_bin, U, V, dP, iters: int = 3, out_dtype=torch.flo
     dS = torch.empty(B, n, m, dtype=out_dtype, device=S.device)
     dbias = torch.zeros(m, dtype=torch.float32, device=S.device)
     db = dust_bin.detach().float().reshape(1).to(S.device)
-    L.check(L.lib().vpr_sinkhorn_bwd(L.ptr(S), L.ptr(db), L.ptr(U), L.ptr(V), L.ptr(dP), L.ptr(dS),
-                                     L.dtype_code(out_dtype), L.ptr(dbias), B, n, m, iters,
-                                     L.stream_ptr(S.device)), "vpr_sinkhorn_bwd")
+    with L.on_device(S):
+        L.check(L.lib().vpr_sinkhorn_bwd(L.ptr(S), L.ptr(db), L.ptr(U), L.ptr(V), L.ptr(dP), L.ptr(dS),
+                                         L.dtype_code(out_dtype), L.ptr(dbias), B, n, m, iters,
+                                         L.stream_ptr(S.device)), "vpr_sinkhorn_bwd")
     return dS, dbias

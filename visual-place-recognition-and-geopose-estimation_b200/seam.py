@@ -25,9 +25,10 @@ class _SeamFn(torch.autograd.Function):
         t = torch.empty(B, d, dtype=out_dtype, device=dev)
         need_bwd = any(ctx.needs_input_grad[:3])
         stats = torch.empty(B * (1 + n), 2, dtype=torch.float32, device=dev) if need_bwd else None
-        L.check(lib.vpr_seam_ln_split_fwd(L.ptr(hidden), L.ptr(weight), L.ptr(bias), float(eps), L.ptr(x_tok), L.ptr(t),
-                                          L.ptr(stats), B, n, skip, d, L.dtype_code(hidden.dtype),
-                                          L.dtype_code(out_dtype), L.stream_ptr(dev)), "vpr_seam_ln_split_fwd")
+        with L.on_device(hidden):
+            L.check(lib.vpr_seam_ln_split_fwd(L.ptr(hidden), L.ptr(weight), L.ptr(bias), float(eps), L.ptr(x_tok), L.ptr(t),
+                                              L.ptr(stats), B, n, skip, d, L.dtype_code(hidden.dtype),
+                                              L.dtype_code(out_dtype), L.stream_ptr(dev)), "vpr_seam_ln_split_fwd")
         if need_bwd:
             ctx.save_for_backward(hidden, weight, stats)
             ctx.skip, ctx.out_dtype = skip, out_dtype
@@ -46,9 +47,10 @@ class _SeamFn(torch.autograd.Function):
         d_b = torch.empty(d, dtype=torch.float32, device=dev)
         dx = d_x_tok.to(ctx.out_dtype).contiguous() if d_x_tok is not None else None
         dt = d_t.to(ctx.out_dtype).contiguous() if d_t is not None else None
-        L.check(lib.vpr_seam_ln_split_bwd(L.ptr(hidden), L.ptr(weight), L.ptr(stats), L.ptr(dx), L.ptr(dt), L.ptr(d_hidden),
-                                          L.ptr(d_w), L.ptr(d_b), B, n, ctx.skip, d, L.dtype_code(hidden.dtype),
-                                          L.dtype_code(ctx.out_dtype), L.stream_ptr(dev)), "vpr_seam_ln_split_bwd")
+        with L.on_device(hidden):
+            L.check(lib.vpr_seam_ln_split_bwd(L.ptr(hidden), L.ptr(weight), L.ptr(stats), L.ptr(dx), L.ptr(dt), L.ptr(d_hidden),
+                                              L.ptr(d_w), L.ptr(d_b), B, n, ctx.skip, d, L.dtype_code(hidden.dtype),
+                                              L.dtype_code(ctx.out_dtype), L.stream_ptr(dev)), "vpr_seam_ln_split_bwd")
         return d_hidden, d_w, d_b, None, None, None
 
 
