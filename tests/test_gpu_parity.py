@@ -542,7 +542,7 @@ def test_scalar_angle_head_matches_oracle_and_reference_golden(vpr, golden_dir):
     assert abs(losses[1].item() - l2.item()) < 1e-4 * abs(l2.item())
     assert rel(dg.grad, dr.grad) < 1e-4
     assert rel(heads.head.weight.grad, ah.head.weight.grad) < 1e-4
-    assert rel(heads.head.bias.grad, ah.head.bias.grad) < 1e-4
+    assert abs(heads.head.bias.grad.item() - ah.head.bias.grad.item()) < 1e-6       # a sum of +-1/B: cancels to ~0
     assert rel(heads.regressor[0].weight.grad, ll.regressor[0].weight.grad) < 1e-4
     lp, sp = heads.predict(dg.detach())
     assert rel(sp[:, 0], pred_r) < 1e-4 and rel(lp, llr) < 1e-4
@@ -613,7 +613,7 @@ def test_heads_dropout_variants_with_exported_masks(vpr, dtype, angle):
     heads.eval()
     e1, *_ = heads(dg.detach(), lt.cuda(), at.cuda())
     e2, *_ = heads(dg.detach(), lt.cuda(), at.cuda())
-    assert e1.item() == e2.item()
+    assert abs(e1.item() - e2.item()) <= 1e-5 * abs(e1.item())        # split-K atomics: summation order varies
 
 
 def test_heads_weight_cast_is_redone_when_the_weights_change(vpr):
@@ -627,7 +627,7 @@ def test_heads_weight_cast_is_redone_when_the_weights_change(vpr):
     lt, at = torch.randn(B, 2, generator=g).cuda(), (torch.rand(B, generator=g) * 360).cuda()
     a1 = heads(desc, lt, at)[2].clone()
     a2 = heads(desc, lt, at)[2].clone()                     # second call: cached cast
-    assert torch.equal(a1, a2)
+    assert rel(a1, a2.cpu()) < 1e-5
     with torch.no_grad():
         heads.regressor[0].weight.mul_(2.0)                 # what an optimizer step does (in place)
         heads.regressor[0].bias.mul_(2.0)
@@ -635,9 +635,9 @@ def test_heads_weight_cast_is_redone_when_the_weights_change(vpr):
     fresh = vpr.GeoposeHeads(D, 512).cuda()
     fresh.load_state_dict(heads.state_dict())
     a4 = fresh(desc, lt, at)[2]
-    assert torch.equal(a3, a4) and not torch.equal(a3, a1)
+    assert rel(a3, a4.cpu()) < 1e-5 and rel(a3, a1.cpu()) > 0.1
     p1, _ = heads.predict(desc)
-    assert torch.equal(p1, a3)
+    assert rel(p1, a3.cpu()) < 1e-5
 
 
 def test_library_refuses_a_second_device_and_follows_the_tensor_device(vpr):

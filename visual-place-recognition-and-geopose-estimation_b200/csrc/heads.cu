@@ -16,6 +16,7 @@
 #include "../../include/vpr_b200.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace vpr {
 
@@ -145,13 +146,14 @@ struct TailArgs {
     uint32_t drop_thr; float drop_scale; unsigned long long seed; const unsigned long long* seed_dev;
 };
 
-static constexpr int TAIL_ROWS = 8;
+static constexpr int TAIL_ROWS = 8, TAIL_THREADS = 256, TAIL_WARPS = TAIL_THREADS / 32;
 
 // 8 descriptor rows per CTA: the per-column gradient sums (regressor.2.weight, regressor.0.bias) are accumulated over
-// the CTA's rows in registers, so each column costs three atomics per CTA instead of three per row
+// the CTA's rows in registers, so each column costs three atomics per CTA instead of three per row.  Every pass first
+// issues all of its loads (8 rows per column) and only then computes / stores, so the rows' latencies overlap.
 template <typename T>
-__global__ void __launch_bounds__(128) heads_tail_kernel(const TailArgs a) {
-    __shared__ float part[4][2 * TAIL_ROWS];
+__global__ void __launch_bounds__(TAIL_THREADS) heads_tail_kernel(const TailArgs a) {
+    __shared__ float part[TAIL_WARPS][2 * TAIL_ROWS];
     __shared__ float dpred_s[TAIL_ROWS][2];
     __shared__ float dsc_s[TAIL_ROWS][2];
     pdl_wait();
@@ -160,21 +162,26 @@ __global__ void __launch_bounds__(128) heads_tail_kernel(const TailArgs a) {
     const int row0 = blockIdx.x * TAIL_ROWS;
     const int rows = min(TAIL_ROWS, a.B - row0);
     const unsigned long long seed = a.seed + (a.seed_dev != nullptr ? *a.seed_dev : 0ull);
+    const float* __restrict__ zacc = a.zacc;
+    const float* __restrict__ b0 = a.b0;
+    const float* __restrict__ w1p = a.w1;
     // ---- z = dropout(relu(zacc + b0)); pred = W1 z + b1 ----
     float p[2 * TAIL_ROWS];
 #pragma unroll
     for (int r = 0; r < 2 * TAIL_ROWS; ++r) p[r] = 0.f;
-    for (int i = tid; i < a.hid; i += 128) {
-        const float bi = a.b0[i], w0 = a.w1[i], w1 = a.w1[a.hid + i];
+    for (int i = tid; i < a.hid; i += TAIL_THREADS) {
+        const float bi = __ldg(b0 + i), w0 = __ldg(w1p + i), w1 = __ldg(w1p + a.hid + i);
+        float zr[TAIL_ROWS];
+#pragma unroll
+        for (int r = 0; r < TAIL_ROWS; ++r) zr[r] = r < rows ? __ldcg(zacc + (size_t)(row0 + r) * a.hid_pad + i) : 0.f;
 #pragma unroll
         for (int r = 0; r < TAIL_ROWS; ++r) {
-            if (r < rows) {
-                float z = fmaxf(a.zacc[(size_t)(row0 + r) * a.hid_pad + i] + bi, 0.f);
-                if (a.drop_thr != 0u)
-                    z = dropout_keep(seed, (unsigned long long)(row0 + r) * a.hid + i, a.drop_thr) ? z * a.drop_scale : 0.f;
-                p[2 * r] += z * w0;
-                p[2 * r + 1] += z * w1;
-            }
+            float z = fmaxf(zr[r] + bi, 0.f);
+            if (a.drop_thr != 0u && r < rows)
+                z = dropout_keep(seed, (unsigned long long)(row0 + r) * a.hid + i, a.drop_thr) ? z * a.drop_scale : 0.f;
+            if (r >= rows) z = 0.f;
+            p[2 * r] += z * w0;
+            p[2 * r + 1] += z * w1;
         }
     }
 #pragma unroll
@@ -188,9 +195,9 @@ __global__ void __launch_bounds__(128) heads_tail_kernel(const TailArgs a) {
         const int r = lane, b = row0 + lane;
         float loss = 0.f, aloss = 0.f, gb1_0 = 0.f, gb1_1 = 0.f, gba_0 = 0.f, gba_1 = 0.f;
         if (r < rows) {
-            float pred[2];
-            pred[0] = part[0][2 * r] + part[1][2 * r] + part[2][2 * r] + part[3][2 * r] + a.b1[0];
-            pred[1] = part[0][2 * r + 1] + part[1][2 * r + 1] + part[2][2 * r + 1] + part[3][2 * r + 1] + a.b1[1];
+            float pred[2] = {a.b1[0], a.b1[1]};
+#pragma unroll
+            for (int w = 0; w < TAIL_WARPS; ++w) { pred[0] += part[w][2 * r]; pred[1] += part[w][2 * r + 1]; }
             a.latlon_pred[b * 2 + 0] = pred[0];
             a.latlon_pred[b * 2 + 1] = pred[1];
             const float inv2B = 1.f / (2.f * (float)a.global_B);
@@ -215,8 +222,8 @@ __global__ void __launch_bounds__(128) heads_tail_kernel(const TailArgs a) {
             // ---- angle head ----
             float ds = 0.f, dc = 0.f;
             if (a.angle_loss != VPR_ANGLE_NONE) {
-                const float raw0 = a.sc_raw != nullptr ? a.sc_raw[b * 2 + 0] : a.zacc[(size_t)b * a.hid_pad + a.hid];
-                const float raw1 = a.sc_raw != nullptr ? a.sc_raw[b * 2 + 1] : a.zacc[(size_t)b * a.hid_pad + a.hid + 1];
+                const float raw0 = a.sc_raw != nullptr ? a.sc_raw[b * 2 + 0] : __ldcg(zacc + (size_t)b * a.hid_pad + a.hid);
+                const float raw1 = a.sc_raw != nullptr ? a.sc_raw[b * 2 + 1] : __ldcg(zacc + (size_t)b * a.hid_pad + a.hid + 1);
                 const float invB = 1.f / (float)a.global_B;
                 if (a.angle_loss == VPR_ANGLE_SCALAR_MAAE) {
                     // dino_angle_finetuning.py:41-52: pred = head(x) % 360; d = |pred - target| % 360; min(d, 360 - d)
@@ -279,6 +286,7 @@ __global__ void __launch_bounds__(128) heads_tail_kernel(const TailArgs a) {
         if (lane == 0) {
             atomicAdd(a.losses + 0, loss);
             if (a.angle_loss != VPR_ANGLE_NONE) atomicAdd(a.losses + 1, aloss);
+            atomicAdd(a.losses + 2, loss + aloss);
             if (!a.forward_only) {
                 atomicAdd(a.g_b1 + 0, gb1_0);
                 atomicAdd(a.g_b1 + 1, gb1_1);
@@ -292,23 +300,28 @@ __global__ void __launch_bounds__(128) heads_tail_kernel(const TailArgs a) {
     if (a.forward_only) return;
     __syncthreads();
     // ---- dZ_aug rows, regressor.2.weight / regressor.0.bias gradients ----
-    T* dz = reinterpret_cast<T*>(a.dzaug);
-    for (int i = tid; i < a.hid_pad; i += 128) {
+    T* __restrict__ dz = reinterpret_cast<T*>(a.dzaug);
+    float g0s[TAIL_ROWS], g1s[TAIL_ROWS];
+#pragma unroll
+    for (int r = 0; r < TAIL_ROWS; ++r) { g0s[r] = r < rows ? dpred_s[r][0] : 0.f; g1s[r] = r < rows ? dpred_s[r][1] : 0.f; }
+    for (int i = tid; i < a.hid_pad; i += TAIL_THREADS) {
         if (i < a.hid) {
-            const float bi = a.b0[i], w0 = a.w1[i], w1 = a.w1[a.hid + i];
+            const float bi = __ldg(b0 + i), w0 = __ldg(w1p + i), w1 = __ldg(w1p + a.hid + i);
+            float zr[TAIL_ROWS];
+#pragma unroll
+            for (int r = 0; r < TAIL_ROWS; ++r) zr[r] = r < rows ? __ldcg(zacc + (size_t)(row0 + r) * a.hid_pad + i) : 0.f;
             float gw0 = 0.f, gw1 = 0.f, gb = 0.f;
 #pragma unroll
             for (int r = 0; r < TAIL_ROWS; ++r) {
                 if (r < rows) {
-                    const float z = fmaxf(a.zacc[(size_t)(row0 + r) * a.hid_pad + i] + bi, 0.f);
+                    const float z = fmaxf(zr[r] + bi, 0.f);
                     float keep = 1.f;
                     if (a.drop_thr != 0u)
                         keep = dropout_keep(seed, (unsigned long long)(row0 + r) * a.hid + i, a.drop_thr) ? a.drop_scale : 0.f;
                     const float zd = z * keep;
-                    const float g0 = dpred_s[r][0], g1 = dpred_s[r][1];
-                    gw0 += g0 * zd;
-                    gw1 += g1 * zd;
-                    const float d = z > 0.f ? (g0 * w0 + g1 * w1) * keep : 0.f;
+                    gw0 += g0s[r] * zd;
+                    gw1 += g1s[r] * zd;
+                    const float d = z > 0.f ? (g0s[r] * w0 + g1s[r] * w1) * keep : 0.f;
                     hstf(dz + (size_t)(row0 + r) * a.hid_pad + i, d);
                     gb += d;
                 }
@@ -434,6 +447,32 @@ static int heads_t(const VprHeadsParams& p, const T* desc, const float* latlon_t
     VprHeadsGrads none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     VprHeadsGrads& gr = grp != nullptr ? *grp : none;
     const unsigned long long* seed_dev = reinterpret_cast<const unsigned long long*>(s.seed_offset_dev);
+    const bool skip_wgrad = (s.flags & VPR_HEADS_SKIP_WGRAD) != 0, wgrad_only = (s.flags & VPR_HEADS_WGRAD_ONLY) != 0;
+    const uint32_t head_thr = head_drop ? dropout_threshold(s.head_dropout_p) : 0u;
+    const float head_scale = head_drop ? 1.f / (1.f - s.head_dropout_p) : 1.f;
+    GemmDesc g;
+    auto angle_bwd = [&](bool pdl) -> int {
+        const int col_blocks = (s.D + 255) / 256;
+        int splits = (2 * nsm) / col_blocks; if (splits < 1) splits = 1;
+        int rows_per = (s.B + splits - 1) / splits; rows_per = (rows_per + 7) & ~7;
+        splits = (s.B + rows_per - 1) / rows_per;
+        VPR_CUDA_OK(launch_ex(angle_bwd_kernel<T>, dim3((unsigned)col_blocks, (unsigned)splits), dim3(32, 8), (size_t)0, st, pdl, 1,
+                              desc, (const T*)dzaug, (const T*)(waug + (size_t)s.hidden * s.D), gr.ang_w, d_desc, s.B, s.D,
+                              s.hidden, hp.hid_pad, n_ang, rows_per, head_thr, head_scale, (unsigned long long)s.seed, seed_dev));
+        return launch_ok("angle_bwd_kernel");
+    };
+    // the two launches nothing downstream of d_desc waits for: dW0[hid, D] = dZ^T desc and (unless it also patches
+    // d_desc) the angle head's weight gradient
+    auto wgrad = [&](bool first_pdl) -> int {
+        g = GemmDesc(); g.dtype = dtype;
+        g.A = dzaug; g.a_mn = 1; g.lda = hp.hid_pad; g.B = desc; g.b_mn = 1; g.ldb = s.D; g.M = s.hidden; g.N = s.D; g.K = s.B;
+        g.out = gr.reg_w0; g.out_kind = OUT_F32; g.ldo = s.D;
+        g.pdl = first_pdl ? 1 : 0;
+        VPR_TRY(gemm_run(g, st));
+        if (angle && !head_drop) VPR_TRY(angle_bwd(true));
+        return 0;
+    };
+    if (wgrad_only) return wgrad(false);
 
     // accumulators -> 0 first (adjacent buffers in one memset), so that the kernels below form an uninterrupted chain
     // of programmatic dependent launches
@@ -442,7 +481,7 @@ static int heads_t(const VprHeadsParams& p, const T* desc, const float* latlon_t
         Rng r[8];
         int cnt = 0;
         r[cnt++] = {zacc, (size_t)s.B * hp.hid_pad * 4};
-        r[cnt++] = {losses, 2 * sizeof(float)};
+        r[cnt++] = {losses, 3 * sizeof(float)};
         if (!fwd_only) {
             r[cnt++] = {gr.reg_b0, sizeof(float) * s.hidden};
             r[cnt++] = {gr.reg_w1, sizeof(float) * 2 * s.hidden};
@@ -465,19 +504,22 @@ static int heads_t(const VprHeadsParams& p, const T* desc, const float* latlon_t
     }
     if (!(s.flags & VPR_HEADS_PREPACKED)) VPR_TRY(heads_pack_t<T>(p, ws, s, dtype, st));
 
-    GemmDesc g;
     // zacc = desc W_aug^T   (split-K: only ceil(B/128) * ceil(N/256) output tiles exist)
     g = GemmDesc(); g.dtype = dtype;
     g.A = desc; g.lda = s.D; g.B = waug; g.ldb = s.D; g.M = s.B; g.N = fold ? hp.hid_pad : s.hidden; g.K = s.D;
     g.out = zacc; g.out_kind = OUT_ATOMIC_F32; g.ldo = hp.hid_pad;
     {
-        int tiles = ((s.B + 127) / 128) * ((g.N + 255) / 256);
-        g.k_splits = nsm / tiles; if (g.k_splits < 1) g.k_splits = 1;
+        static int bn_env = -2, ks_env = -2;              // A/B knobs: VPR_HEADS_FWD_BN, VPR_HEADS_FWD_KS
+        if (bn_env == -2) { const char* e = getenv("VPR_HEADS_FWD_BN"); bn_env = e ? atoi(e) : 0; }
+        if (ks_env == -2) { const char* e = getenv("VPR_HEADS_FWD_KS"); ks_env = e ? atoi(e) : 0; }
+        g.bn = bn_env;
+        const GemmTilePlan tp = gemm_tile_plan(&g, 1);
+        const int tiles = ((s.B + tp.tile_m - 1) / tp.tile_m) * ((g.N + tp.tile_n - 1) / tp.tile_n);
+        g.k_splits = ks_env > 0 ? ks_env : tp.slots / tiles;
+        if (g.k_splits < 1) g.k_splits = 1;
     }
     g.pdl = 1;
     VPR_TRY(gemm_run(g, st));
-    const uint32_t head_thr = head_drop ? dropout_threshold(s.head_dropout_p) : 0u;
-    const float head_scale = head_drop ? 1.f / (1.f - s.head_dropout_p) : 1.f;
     if (head_drop) {
         VPR_CUDA_OK(launch_ex(angle_fwd_masked_kernel<T>, dim3((unsigned)s.B), dim3(256), (size_t)0, st, true, 1, desc,
                               (const T*)(waug + (size_t)s.hidden * s.D), sc_raw, s.D, head_thr, head_scale,
@@ -496,7 +538,7 @@ static int heads_t(const VprHeadsParams& p, const T* desc, const float* latlon_t
     a.drop_thr = s.reg_dropout_p > 0.f ? dropout_threshold(s.reg_dropout_p) : 0u;
     a.drop_scale = s.reg_dropout_p > 0.f ? 1.f / (1.f - s.reg_dropout_p) : 1.f;
     a.seed = s.seed; a.seed_dev = seed_dev;
-    VPR_CUDA_OK(launch_ex(heads_tail_kernel<T>, dim3((unsigned)((s.B + TAIL_ROWS - 1) / TAIL_ROWS)), dim3(128), (size_t)0, st,
+    VPR_CUDA_OK(launch_ex(heads_tail_kernel<T>, dim3((unsigned)((s.B + TAIL_ROWS - 1) / TAIL_ROWS)), dim3(TAIL_THREADS), (size_t)0, st,
                           true, 1, a));
     VPR_TRY(launch_ok("heads_tail_kernel"));
     if (fwd_only) return 0;
@@ -505,26 +547,16 @@ static int heads_t(const VprHeadsParams& p, const T* desc, const float* latlon_t
         g.A = dzaug; g.lda = hp.hid_pad; g.B = waug; g.b_mn = 1; g.ldb = s.D; g.M = s.B; g.N = s.D;
         g.K = fold ? hp.hid_pad : s.hidden;
         g.out = d_desc; g.out_kind = okT; g.ldo = s.D;
+        // few rows: 128-wide single-CTA tiles fill the machine (2 x 66 tiles at B = 256), 256-wide pair tiles do not
+        static int bn_env = -2;                           // A/B knob: VPR_HEADS_DDESC_BN
+        if (bn_env == -2) { const char* e = getenv("VPR_HEADS_DDESC_BN"); bn_env = e ? atoi(e) : 0; }
+        g.bn = bn_env > 0 ? bn_env : (((s.B + 255) / 256) * ((s.D + 255) / 256) * 2 <= nsm ? 128 : 0);
         g.pdl = 1;
         VPR_TRY(gemm_run(g, st));
     }
-    // dW0[hid, D] = dZ^T desc
-    g = GemmDesc(); g.dtype = dtype;
-    g.A = dzaug; g.a_mn = 1; g.lda = hp.hid_pad; g.B = desc; g.b_mn = 1; g.ldb = s.D; g.M = s.hidden; g.N = s.D; g.K = s.B;
-    g.out = gr.reg_w0; g.out_kind = OUT_F32; g.ldo = s.D;
-    g.pdl = 1;
-    VPR_TRY(gemm_run(g, st));
-    if (angle) {
-        const int col_blocks = (s.D + 255) / 256;
-        int splits = (2 * nsm) / col_blocks; if (splits < 1) splits = 1;
-        int rows_per = (s.B + splits - 1) / splits; rows_per = (rows_per + 7) & ~7;
-        splits = (s.B + rows_per - 1) / rows_per;
-        VPR_CUDA_OK(launch_ex(angle_bwd_kernel<T>, dim3((unsigned)col_blocks, (unsigned)splits), dim3(32, 8), (size_t)0, st, true, 1,
-                              desc, (const T*)dzaug, (const T*)(waug + (size_t)s.hidden * s.D), gr.ang_w, d_desc, s.B, s.D,
-                              s.hidden, hp.hid_pad, n_ang, rows_per, head_thr, head_scale, (unsigned long long)s.seed, seed_dev));
-        VPR_TRY(launch_ok("angle_bwd_kernel"));
-    }
-    return 0;
+    if (angle && head_drop) VPR_TRY(angle_bwd(true));     // patches d_desc: stays on the main chain
+    if (skip_wgrad) return 0;
+    return wgrad(true);
 }
 
 static int check_heads_shape(const VprHeadsShape* s, int dtype) {
@@ -532,6 +564,9 @@ static int check_heads_shape(const VprHeadsShape* s, int dtype) {
     VPR_REQUIRE(s->B > 0 && s->D > 0 && s->D % 8 == 0 && s->hidden % 8 == 0, "bad heads shape");
     VPR_REQUIRE(s->latlon_loss >= VPR_LATLON_MSE && s->latlon_loss <= VPR_LATLON_EXTERNAL, "bad latlon_loss");
     VPR_REQUIRE(s->angle_loss >= VPR_ANGLE_NONE && s->angle_loss <= VPR_ANGLE_SCALAR_MAAE, "bad angle_loss");
+    VPR_REQUIRE(!((s->flags & VPR_HEADS_SKIP_WGRAD) && (s->flags & VPR_HEADS_WGRAD_ONLY)) &&
+                !((s->flags & VPR_HEADS_FORWARD_ONLY) && (s->flags & (VPR_HEADS_SKIP_WGRAD | VPR_HEADS_WGRAD_ONLY))),
+                "contradictory VPR_HEADS_* flags");
     VPR_REQUIRE(s->reg_dropout_p >= 0.f && s->reg_dropout_p < 1.f && s->head_dropout_p >= 0.f && s->head_dropout_p < 1.f,
                 "dropout probability out of range");
     return 0;

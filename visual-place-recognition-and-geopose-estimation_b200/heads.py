@@ -54,16 +54,20 @@ def pack_weights(params, ws, B, D, cfg, dtype) -> None:
                                        L.stream_ptr(ws.device)), "vpr_heads_pack")
 
 
-def _run(desc, params, latlon_target, angle_target, cfg, want_d_desc, ws=None, forward_only=False, prepacked=False):
-    """One vpr_heads_loss_fwd_bwd call.  Returns (latlon_pred, sincos_pred, losses, grads, d_desc, flat): ``flat`` is
-    ONE fp32 buffer holding every parameter gradient back to back followed by the two losses, so that a
-    data-parallel caller sums gradients and losses across ranks with a single collective."""
+def _run(desc, params, latlon_target, angle_target, cfg, want_d_desc, ws=None, forward_only=False, prepacked=False,
+         defer_wgrad=False):
+    """One vpr_heads_loss_fwd_bwd call.  Returns (latlon_pred, sincos_pred, losses, grads, d_desc, flat): ``losses`` =
+    (lat/lon, angle, their sum); ``flat`` is ONE fp32 buffer holding every parameter gradient back to back followed by
+    the three losses, so that a data-parallel caller sums gradients and losses across ranks with a single collective.
+    ``defer_wgrad``: leave out the two weight-gradient launches nothing downstream of ``d_desc`` waits for and return a
+    seventh value, a callable that issues them on whatever stream is current when it is called (the caller orders
+    that stream after this call and joins it before reading ``regressor.0.weight.grad`` / ``head.weight.grad``)."""
     lib = L.lib()
     B, D = desc.shape
     dt = L.dtype_code(desc.dtype)
     dev = desc.device
     flags = (L.HEADS_FORWARD_ONLY if forward_only else 0) | (L.HEADS_PREPACKED if prepacked else 0)
-    shape = _shape(B, D, cfg, flags)
+    shape = _shape(B, D, cfg, flags | (L.HEADS_SKIP_WGRAD if defer_wgrad else 0))
     ws_bytes = lib.vpr_heads_workspace_bytes(C.byref(shape), dt)
     if ws is None:
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -71,27 +75,35 @@ def _run(desc, params, latlon_target, angle_target, cfg, want_d_desc, ws=None, f
         raise RuntimeError("heads workspace too small or on another device")
     ps = L.HeadsParams(*[p.data_ptr() if p is not None else None for p in params])
     latlon_pred = torch.empty(B, 2, dtype=torch.float32, device=dev)
-    sincos_pred = torch.zeros(B, 2, dtype=torch.float32, device=dev)
+    sincos_pred = (torch.empty if cfg["angle"] != L.ANGLE_NONE else torch.zeros)(B, 2, dtype=torch.float32, device=dev)
     if forward_only:
-        flat = torch.empty(2, dtype=torch.float32, device=dev)
+        flat = torch.empty(3, dtype=torch.float32, device=dev)
         losses, grads, gs_ref, d_desc = flat, [None] * len(params), None, None
     else:
         sizes = [p.numel() if p is not None else 0 for p in params]      # the angle head may be absent (None, None)
-        flat = torch.empty(sum(sizes) + 2, dtype=torch.float32, device=dev)
-        *grads, losses = torch.split(flat, sizes + [2])
+        flat = torch.empty(sum(sizes) + 3, dtype=torch.float32, device=dev)
+        *grads, losses = torch.split(flat, sizes + [3])
         gs = L.HeadsGrads(*[g.data_ptr() if p is not None else None for g, p in zip(grads, params)])
         gs_ref = C.byref(gs)
         grads = [g.view_as(p) if p is not None else None for g, p in zip(grads, params)]
         d_desc = torch.empty_like(desc) if want_d_desc else None
-    with L.on_device(desc):
-        L.check(lib.vpr_heads_loss_fwd_bwd(C.byref(ps), L.ptr(desc), L.ptr(latlon_target), L.ptr(angle_target),
-                                           L.ptr(latlon_pred), L.ptr(sincos_pred), L.ptr(losses), gs_ref,
-                                           L.ptr(d_desc), L.ptr(ws), ws.numel(), C.byref(shape), dt, L.stream_ptr(dev)),
-                "vpr_heads_loss_fwd_bwd")
-        seed_dev = cfg.get("seed_dev")
-        if seed_dev is not None and not forward_only and (cfg["reg_dropout_p"] > 0 or cfg["head_dropout_p"] > 0):
+
+    def call(shape_):
+        with L.on_device(desc):
+            L.check(lib.vpr_heads_loss_fwd_bwd(C.byref(ps), L.ptr(desc), L.ptr(latlon_target), L.ptr(angle_target),
+                                               L.ptr(latlon_pred), L.ptr(sincos_pred), L.ptr(losses), gs_ref,
+                                               L.ptr(d_desc), L.ptr(ws), ws.numel(), C.byref(shape_), dt,
+                                               L.stream_ptr(dev)), "vpr_heads_loss_fwd_bwd")
+
+    call(shape)
+    seed_dev = cfg.get("seed_dev")
+    if seed_dev is not None and not forward_only and (cfg["reg_dropout_p"] > 0 or cfg["head_dropout_p"] > 0):
+        with L.on_device(desc):
             L.check(lib.vpr_counter_advance(L.ptr(seed_dev), L.stream_ptr(dev)), "vpr_counter_advance")
-    return latlon_pred, sincos_pred, losses, grads, d_desc, flat
+    out = (latlon_pred, sincos_pred, losses, grads, d_desc, flat)
+    if defer_wgrad:
+        return out + ((lambda: call(_shape(B, D, cfg, L.HEADS_WGRAD_ONLY))),)
+    return out
 
 
 class _HeadsLossFn(torch.autograd.Function):
@@ -103,8 +115,7 @@ class _HeadsLossFn(torch.autograd.Function):
         ctx.save_for_backward(*( [d_desc] if d_desc is not None else [] ), *[g for g in grads if g is not None])
         ctx.has_d_desc = d_desc is not None
         ctx.mark_non_differentiable(latlon_pred, sincos_pred, losses)
-        total = losses[0] + losses[1] if cfg["angle"] != L.ANGLE_NONE else losses[0].clone()
-        return total, losses, latlon_pred, sincos_pred
+        return losses[2].clone(), losses, latlon_pred, sincos_pred
 
     @staticmethod
     def backward(ctx, g_total, g_losses, _g1, _g2):
@@ -215,7 +226,7 @@ class GeoposeHeads(nn.Module):
 
     def forward(self, desc: torch.Tensor, latlon_target: torch.Tensor, angle_target_deg: torch.Tensor | None = None,
                 global_B: int = 0):
-        """Returns (total_loss, losses[2] = (lat/lon, angle), latlon_pred [B,2], sincos_pred [B,2]).
+        """Returns (total_loss, losses[3] = (lat/lon, angle, sum), latlon_pred [B,2], sincos_pred [B,2]).
         ``total_loss.backward()`` delivers the gradients that the same kernel call already computed.
         With ``angle_loss="scalar_maae"`` ``sincos_pred[:, 0]`` is the predicted angle in [0, 360)."""
         L.require_cuda(desc, "descriptor")

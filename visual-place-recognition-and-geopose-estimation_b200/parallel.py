@@ -239,7 +239,7 @@ class DataParallelStep:
         if self.world > 1:
             losses = losses.clone()
             dist.all_reduce(losses, op=dist.ReduceOp.SUM, group=self.group)
-            total = losses.sum() if self.heads.angle_loss not in (None, "none") else losses[0]
+            total = losses[2]
         return total.detach(), losses
 
 
@@ -297,15 +297,24 @@ class GraphedFinetuneStep:
             x_tok, t, shape, p_drop, seed, seed_dev, sparams = salad._prepare((self.x, self.t))
             desc, save = _salad_forward(x_tok, t, shape, p_drop, seed, seed_dev, sparams)
             main.wait_stream(pack_stream)                       # join
-            latlon_pred, sincos_pred, losses, hgrads, d_desc, hflat = heads_run(
-                desc, hparams, self.latlon, self.angle if use_angle else None, cfg, True, ws=hws, prepacked=True)
-            hwork = dist.all_reduce(hflat, group=group, async_op=True) if self.world > 1 else None
+            latlon_pred, sincos_pred, losses, hgrads, d_desc, hflat, head_wgrad = heads_run(
+                desc, hparams, self.latlon, self.angle if use_angle else None, cfg, True, ws=hws, prepacked=True,
+                defer_wgrad=True)
+            # second fork: the heads' two weight-gradient launches and, across ranks, the all-reduce of the whole heads
+            # buffer (gradients + losses) run beside the SALAD backward, which only needs d_desc
+            wgrad_stream.wait_stream(main)
+            with torch.cuda.stream(wgrad_stream):
+                head_wgrad()
+                hwork = dist.all_reduce(hflat, group=group, async_op=True) if self.world > 1 else None
             dx, dt, sflat, sgrads = _salad_backward(x_tok, t, save, sparams, shape, p_drop, d_desc, input_grads, input_grads,
                                                     salad._grad_hook)
             if hwork is not None:
-                hwork.wait()
+                with torch.cuda.stream(wgrad_stream):
+                    hwork.wait()
+            main.wait_stream(wgrad_stream)                      # join
             return desc, losses, latlon_pred, sincos_pred, hgrads, sgrads, dx, dt
 
+        wgrad_stream = torch.cuda.Stream(dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), torch.no_grad():
@@ -344,5 +353,4 @@ class GraphedFinetuneStep:
         for p, g in self._grads:
             if p.grad is not g:
                 p.grad = g
-        total = self.losses[0] + self.losses[1] if self._use_angle else self.losses[0]
-        return total, self.losses
+        return self.losses[2], self.losses
