@@ -271,6 +271,30 @@ VPR_API int vpr_knn_topk(const void* q, const void* g, int64_t Q, int64_t G, int
 VPR_API int vpr_knn_merge(const float* scores, const int64_t* idx, int R, int64_t Q, int k, float* out_score,
                   int64_t* out_idx, cudaStream_t stream);
 
+/* ---- gradient all-reduce over NVLink peer memory (fine-tuning) ---------------------
+ * No reference code (the reference is single-GPU); replaces ncclAllReduce(sum, fp32) for the two
+ * gradient messages of one fine-tuning step.  Every rank holds one symmetric allocation
+ *   [ data (any size) | staging (vpr_comm_staging_elems floats) | flags (vpr_comm_flag_bytes, zeroed once) ]
+ * and passes every rank's addresses of the three areas (peer mappings: CUDA IPC or torch symmetric memory);
+ * mc_data = multicast (NVLS) address of the data area or NULL.  The call sums, in place and on every rank,
+ * floats [offset, offset + count) of the data area; all ranks must issue the same calls in the same order on
+ * the same communicator (= flags area).  Two communicators may be in flight at once.  Stream-ordered,
+ * capturable in a CUDA graph, `ctas` (<= VPR_COMM_MAX_CTAS) small CTAs that can share SMs with a running GEMM. */
+#define VPR_COMM_MAX_WORLD 8
+#define VPR_COMM_MAX_CTAS 64
+typedef struct {
+    int rank, world;
+    void* data[VPR_COMM_MAX_WORLD];
+    void* staging[VPR_COMM_MAX_WORLD];
+    void* flags[VPR_COMM_MAX_WORLD];
+    void* mc_data;
+    size_t staging_elems;       /* floats available in each staging area */
+} VprCommPeers;
+VPR_API size_t vpr_comm_flag_bytes(void);
+VPR_API size_t vpr_comm_staging_elems(size_t max_count, int world);
+VPR_API int vpr_allreduce_sum_f32(const VprCommPeers* peers, size_t offset_elems, size_t count, int ctas,
+                          cudaStream_t stream);
+
 /* ---- test hook: the GEMM every dense step above is built from --------------------------- */
 VPR_API int vpr_gemm(int dtype, const void* A, int a_mn, int64_t lda, int64_t a_bs, const void* B, int b_mn,
              int64_t ldb, int64_t b_bs, int M, int N, int K, int batch, void* out, int out_kind,

@@ -45,6 +45,15 @@ class HeadsShape(C.Structure):
                 ("head_dropout_p", C.c_float), ("flags", C.c_int), ("seed_offset_dev", C.c_void_p)]
 
 
+COMM_MAX_WORLD, COMM_MAX_CTAS = 8, 64
+
+
+class CommPeers(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("data", C.c_void_p * COMM_MAX_WORLD),
+                ("staging", C.c_void_p * COMM_MAX_WORLD), ("flags", C.c_void_p * COMM_MAX_WORLD),
+                ("mc_data", C.c_void_p), ("staging_elems", C.c_size_t)]
+
+
 class HeadsParams(C.Structure):
     _fields_ = [(k, _fp) for k in ("reg_w0", "reg_b0", "reg_w1", "reg_b1", "ang_w", "ang_b")]
 
@@ -74,6 +83,9 @@ EXPORTS = {
     "vpr_heads_loss_fwd_bwd": (C.c_int, [C.POINTER(HeadsParams), _fp, _fp, _fp, _fp, _fp, _fp,
                                          C.POINTER(HeadsGrads), _fp, _fp, C.c_size_t, C.POINTER(HeadsShape),
                                          C.c_int, _fp]),
+    "vpr_comm_flag_bytes": (C.c_size_t, []),
+    "vpr_comm_staging_elems": (C.c_size_t, [C.c_size_t, C.c_int]),
+    "vpr_allreduce_sum_f32": (C.c_int, [C.POINTER(CommPeers), C.c_size_t, C.c_size_t, C.c_int, _fp]),
     "vpr_seam_ln_split_fwd": (C.c_int, [_fp, _fp, _fp, C.c_float, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, _fp]),
     "vpr_seam_ln_split_bwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -55,7 +55,7 @@ def pack_weights(params, ws, B, D, cfg, dtype) -> None:
 
 
 def _run(desc, params, latlon_target, angle_target, cfg, want_d_desc, ws=None, forward_only=False, prepacked=False,
-         defer_wgrad=False):
+         defer_wgrad=False, flat=None):
     """One vpr_heads_loss_fwd_bwd call.  Returns (latlon_pred, sincos_pred, losses, grads, d_desc, flat): ``losses`` =
     (lat/lon, angle, their sum); ``flat`` is ONE fp32 buffer holding every parameter gradient back to back followed by
     the three losses, so that a data-parallel caller sums gradients and losses across ranks with a single collective.
@@ -81,8 +81,11 @@ def _run(desc, params, latlon_target, angle_target, cfg, want_d_desc, ws=None, f
         losses, grads, gs_ref, d_desc = flat, [None] * len(params), None, None
     else:
         sizes = [p.numel() if p is not None else 0 for p in params]      # the angle head may be absent (None, None)
-        flat = torch.empty(sum(sizes) + 3, dtype=torch.float32, device=dev)
-        *grads, losses = torch.split(flat, sizes + [3])
+        if flat is None:
+            flat = torch.empty(sum(sizes) + 3, dtype=torch.float32, device=dev)
+        elif flat.numel() < sum(sizes) + 3 or flat.dtype != torch.float32 or flat.device != dev:
+            raise RuntimeError("flat gradient buffer must be an fp32 tensor on the descriptor's device")
+        *grads, losses = torch.split(flat[: sum(sizes) + 3], sizes + [3])
         gs = L.HeadsGrads(*[g.data_ptr() if p is not None else None for g, p in zip(grads, params)])
         gs_ref = C.byref(gs)
         grads = [g.view_as(p) if p is not None else None for g, p in zip(grads, params)]

@@ -260,7 +260,11 @@ class GraphedFinetuneStep:
     runs on a forked branch next to the SALAD forward (it only depends on the weights)."""
 
     def __init__(self, salad, heads, batch: int, n_tokens: int, dtype=torch.bfloat16, global_batch: int | None = None,
-                 group=None, input_grads: bool = False, warmup: int = 3):
+                 group=None, input_grads: bool = False, warmup: int = 3, comm: str | None = None,
+                 heads_ctas: int | None = None, salad_ctas: int | None = None):
+        """``comm``: how gradients cross ranks -- "peer" (the library's own all-reduce kernel over NVLink peer memory,
+        ``comm.PeerComm``; gradient buffers live in the symmetric allocation), "nccl" (``torch.distributed``), or None =
+        "peer" when the peer mappings can be set up, else "nccl" (env ``VPR_DP_COMM`` overrides)."""
         from . import _lib as L
         from .heads import _run as heads_run, pack_weights, workspace_bytes
         from .salad import _salad_backward, _salad_forward
@@ -275,7 +279,45 @@ class GraphedFinetuneStep:
         if self.world > 1:
             decorrelate_dropout(salad, dist.get_rank(group))
             decorrelate_dropout(heads, dist.get_rank(group))
-        if self.world > 1 and salad._grad_hook is None:
+        comm = os.environ.get("VPR_DP_COMM") or comm
+        self.comm_kind, self.comm_note = "none", ""
+        comm_h = comm_s = None
+        n_h = sum(p.numel() for p in heads._params()) + 3
+        n_s = sum(p.numel() for p in salad._param_list())
+        if self.world > 1 and comm in (None, "peer"):
+            try:
+                from .comm import PeerComm
+                with torch.cuda.device(dev):
+                    comm_h = PeerComm(n_h, group=group, device=dev)
+                    comm_s = PeerComm(n_s, group=group, device=dev)
+                self.comm_kind = "peer/" + comm_h.backend + ("+multimem" if comm_h.mc_ptr else "")
+                self.comm_note = "; ".join(comm_h.setup_errors)
+            except Exception as e:                              # noqa: BLE001
+                if comm == "peer":
+                    raise
+                comm_h = comm_s = None
+                self.comm_note = f"{type(e).__name__}: {e}"
+        if self.world > 1 and comm_h is None:
+            self.comm_kind = "nccl"
+        self._comms = (comm_h, comm_s)
+        heads_ctas = int(os.environ.get("VPR_COMM_CTAS_HEADS", heads_ctas or 16))
+        salad_ctas = int(os.environ.get("VPR_COMM_CTAS_SALAD", salad_ctas or 64))
+        comm_stream = torch.cuda.Stream(dev) if comm_s is not None else None
+        if comm_s is not None:
+            # the SALAD gradients' exchange: our kernel on a forked stream (beside the input-gradient GEMM when there
+            # is one), joined back by .wait()
+            class _Join:
+                def wait(self_inner):
+                    torch.cuda.current_stream(dev).wait_stream(comm_stream)
+
+            def start_salad(flat):
+                comm_stream.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(comm_stream):
+                    comm_s.allreduce_(0, comm_s.numel, ctas=salad_ctas)
+                return _Join()
+
+            salad.set_grad_ready_hook(start_salad, 0)
+        elif self.world > 1 and salad._grad_hook is None:
             overlap_grad_allreduce(salad, group)
         self.x = torch.zeros(batch, n_tokens, salad.num_channels, dtype=dtype, device=dev)
         self.t = torch.zeros(batch, salad.num_channels, dtype=dtype, device=dev)
@@ -299,15 +341,19 @@ class GraphedFinetuneStep:
             main.wait_stream(pack_stream)                       # join
             latlon_pred, sincos_pred, losses, hgrads, d_desc, hflat, head_wgrad = heads_run(
                 desc, hparams, self.latlon, self.angle if use_angle else None, cfg, True, ws=hws, prepacked=True,
-                defer_wgrad=True)
+                defer_wgrad=True, flat=comm_h.data if comm_h is not None else None)
             # second fork: the heads' two weight-gradient launches and, across ranks, the all-reduce of the whole heads
             # buffer (gradients + losses) run beside the SALAD backward, which only needs d_desc
             wgrad_stream.wait_stream(main)
             with torch.cuda.stream(wgrad_stream):
                 head_wgrad()
-                hwork = dist.all_reduce(hflat, group=group, async_op=True) if self.world > 1 else None
+                hwork = None
+                if comm_h is not None:
+                    comm_h.allreduce_(0, comm_h.numel, ctas=heads_ctas)
+                elif self.world > 1:
+                    hwork = dist.all_reduce(hflat, group=group, async_op=True)
             dx, dt, sflat, sgrads = _salad_backward(x_tok, t, save, sparams, shape, p_drop, d_desc, input_grads, input_grads,
-                                                    salad._grad_hook)
+                                                    salad._grad_hook, flat=comm_s.data if comm_s is not None else None)
             if hwork is not None:
                 with torch.cuda.stream(wgrad_stream):
                     hwork.wait()

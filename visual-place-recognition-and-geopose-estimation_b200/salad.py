@@ -55,7 +55,7 @@ def _salad_forward(x_tok, t, shape_tuple, dropout_p, seed, seed_dev, params):
     return out, save
 
 
-def _salad_backward(x_tok, t, save, params, shape_tuple, dropout_p, d_out, want_dx, want_dt, hook):
+def _salad_backward(x_tok, t, save, params, shape_tuple, dropout_p, d_out, want_dx, want_dt, hook, flat=None):
     """vpr_salad_bwd, in one call or -- with a gradient-ready hook -- in its two phases around the hook.
     Returns (dx, dt, flat fp32 gradient buffer, per-parameter views of it)."""
     lib = L.lib()
@@ -69,8 +69,11 @@ def _salad_backward(x_tok, t, save, params, shape_tuple, dropout_p, d_out, want_
     ws_bytes = lib.vpr_salad_workspace_bytes(C.byref(shape), dt)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     sizes = [p.numel() for p in params]
-    flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-    grads = list(torch.split(flat, sizes))
+    if flat is None:
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+    elif flat.numel() < sum(sizes) or flat.dtype != torch.float32 or flat.device != dev or not flat.is_contiguous():
+        raise RuntimeError("flat gradient buffer must be a contiguous fp32 tensor on the input's device")
+    grads = list(torch.split(flat[: sum(sizes)], sizes))
     gs = _params_struct(L.SaladGrads, grads)
     ps = _params_struct(L.SaladParams, params)
     dx = torch.empty_like(x_tok) if want_dx else None
