@@ -129,7 +129,8 @@ VPR_API int vpr_salad_bwd(const VprSaladParams* p, const void* x, const void* t,
                   int phase, int reserve_sms, cudaStream_t stream);
 /* phase: VPR_BWD_ALL, or the same work in two calls -- VPR_BWD_PARAMS (every parameter gradient) then
  * VPR_BWD_INPUTS (dx, dt) -- so that a data-parallel caller can start the gradient all-reduce between them;
- * reserve_sms > 0 keeps that many SMs free of the input-gradient GEMM's persistent CTAs for the collective. */
+ * reserve_sms > 0 keeps that many SMs free of the persistent kernels of the phase(s) this call runs (fused dH pass,
+ * first-layer weight-gradient GEMM, input-gradient GEMM) for a collective that runs beside them. */
 #define VPR_BWD_ALL 0
 #define VPR_BWD_PARAMS 1
 #define VPR_BWD_INPUTS 2
@@ -281,7 +282,7 @@ VPR_API int vpr_knn_merge(const float* scores, const int64_t* idx, int R, int64_
  * the same communicator (= flags area).  Two communicators may be in flight at once.  Stream-ordered,
  * capturable in a CUDA graph, `ctas` (<= VPR_COMM_MAX_CTAS) small CTAs that can share SMs with a running GEMM. */
 #define VPR_COMM_MAX_WORLD 8
-#define VPR_COMM_MAX_CTAS 64
+#define VPR_COMM_MAX_CTAS 160
 typedef struct {
     int rank, world;
     void* data[VPR_COMM_MAX_WORLD];

@@ -54,8 +54,12 @@ def main():
         for e in evs[-per:]:
             print(f"{e.time_range.start - t0:9.1f} .. {e.time_range.end - t0:9.1f}  (+{e.time_range.end - e.time_range.start:7.1f} us)  {e.name[:100]}")
     if world > 1:
+        if rank == 0:
+            print("comm:", step.comm_kind, step.comm_note)
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)             # skip communicator teardown: it can wait on the captured NCCL work the graph holds
 
 
 if __name__ == "__main__":

@@ -45,7 +45,7 @@ class HeadsShape(C.Structure):
                 ("head_dropout_p", C.c_float), ("flags", C.c_int), ("seed_offset_dev", C.c_void_p)]
 
 
-COMM_MAX_WORLD, COMM_MAX_CTAS = 8, 64
+COMM_MAX_WORLD, COMM_MAX_CTAS = 8, 160
 
 
 class CommPeers(C.Structure):

@@ -9,18 +9,25 @@
 //               sum into region p of EVERY rank's data                                   (NVLink stores only)
 // With a multicast (NVLS) mapping of the allocation the switch does both halves instead: multimem.ld_reduce pulls the
 // summed region p, multimem.st broadcasts it.
-// All cross-GPU traffic is posted writes (or switch-side reductions), so a few small CTAs keep the links busy: the
-// kernel runs 256 threads x <= 32 registers, no shared memory to speak of, which lets its CTAs share SMs with the
-// persistent GEMM CTAs of the backward that it overlaps (168 registers x 320 threads leave 11 K registers free).
+// All cross-GPU traffic is posted writes or switch-side reductions.  The multimem loads are round trips through the
+// switch (~5 us under load), so the kernel lives on memory-level parallelism: 1024 threads per CTA, four independent
+// 16-byte accesses in flight per thread.  It runs on SMs of its own: the persistent kernels of the backward it overlaps
+// are launched `reserve_sms` CTAs short (vpr_salad_bwd), and a dummy shared-memory request keeps this kernel's CTAs
+// off the SMs those kernels occupy.  (Small CTAs that share SMs with the GEMM CTAs were measured first: 40 registers x
+// 256 threads do fit beside 168 x 320, but a persistent GEMM with a static tile schedule then waits for the SMs it
+// shares -- dW0 79 -> 141 us at N=2 -- which costs far more than giving up 8 of 148 SMs.)
 // Synchronisation is per CTA index: CTA c of every rank owns slice c of every region, so a flag from peer q's CTA c
 // covers exactly the data CTA c consumes.  Flags carry a call counter kept in device memory (the launch arguments of a
 // captured graph never change), never need resetting, and every wait is bounded (trap instead of a hung box).
 #include "common.cuh"
 #include "../../include/vpr_b200.h"
 
+#include <stdlib.h>
+
 namespace vpr {
 
-static constexpr int COMM_THREADS = 256;
+static constexpr int COMM_THREADS = 1024;
+static constexpr int COMM_DUMMY_SMEM = 64 * 1024;      // > 227 KB minus the big kernels' footprint: no SM sharing with them
 static constexpr int COMM_MAX_WORLD = VPR_COMM_MAX_WORLD;
 static constexpr int COMM_MAX_CTAS = VPR_COMM_MAX_CTAS;
 // flags area of one rank, in 32-bit words: arrive[2 phases][world][ctas] then epoch[ctas]
@@ -68,7 +75,8 @@ __device__ __forceinline__ void comm_barrier(const CommArgs& a, int phase, int c
     __syncthreads();
     const int t = threadIdx.x;
     if (t < a.world && t != a.rank) {
-        __threadfence_system();
+        // st.release.sys orders this thread's earlier writes AND (cumulativity through the bar.sync above) the rest of the
+        // CTA's before the flag; a separate fence.sc.sys in front of it would only add a second NVLink round trip
         const size_t mine = ((size_t)phase * COMM_MAX_WORLD + a.rank) * COMM_MAX_CTAS + cta;      // written by me, at peer t
         st_release_sys(a.flags[t] + mine, epoch);
         const size_t theirs = ((size_t)phase * COMM_MAX_WORLD + t) * COMM_MAX_CTAS + cta;         // written by t, here
@@ -87,8 +95,9 @@ __device__ __forceinline__ void comm_barrier(const CommArgs& a, int phase, int c
 }
 
 template <bool MULTIMEM>
-__global__ void __launch_bounds__(COMM_THREADS, 6) allreduce_kernel(const CommArgs a) {
+__global__ void __launch_bounds__(COMM_THREADS, 1) allreduce_kernel(const CommArgs a) {
     const int cta = blockIdx.x, nct = gridDim.x, tid = threadIdx.x;
+    const int NT = blockDim.x;                      // <= COMM_THREADS (tuning knob VPR_COMM_THREADS)
     __shared__ uint32_t epoch_s;
     uint32_t* my_flags = a.flags[a.rank];
     uint32_t* epoch_p = my_flags + (size_t)2 * COMM_MAX_WORLD * COMM_MAX_CTAS + cta;
@@ -104,7 +113,16 @@ __global__ void __launch_bounds__(COMM_THREADS, 6) allreduce_kernel(const CommAr
         const long long r0 = a.chunk4 * a.rank;
         const long long e1 = r0 + s1 < a.count4 ? r0 + s1 : a.count4;
         float4* mc = reinterpret_cast<float4*>(a.mc_data) + a.off4;
-        for (long long i = r0 + s0 + tid; i < e1; i += COMM_THREADS) multimem_st_f4(mc + i, multimem_ld_reduce_f4(mc + i));
+        long long i = r0 + s0 + tid;
+        for (; i + 3 * NT < e1; i += 4 * NT) {        // four switch round trips in flight per thread
+            const float4 v0 = multimem_ld_reduce_f4(mc + i), v1 = multimem_ld_reduce_f4(mc + i + NT),
+                         v2 = multimem_ld_reduce_f4(mc + i + 2 * NT), v3 = multimem_ld_reduce_f4(mc + i + 3 * NT);
+            multimem_st_f4(mc + i, v0);
+            multimem_st_f4(mc + i + NT, v1);
+            multimem_st_f4(mc + i + 2 * NT, v2);
+            multimem_st_f4(mc + i + 3 * NT, v3);
+        }
+        for (; i < e1; i += NT) multimem_st_f4(mc + i, multimem_ld_reduce_f4(mc + i));
         comm_barrier(a, 1, cta, epoch);                                   // every region has landed here
     } else {
         // ---- shot 1: my slice of region p -> slot `rank` of p's staging ----
@@ -114,21 +132,21 @@ __global__ void __launch_bounds__(COMM_THREADS, 6) allreduce_kernel(const CommAr
             const long long e1 = r0 + s1 < a.count4 ? r0 + s1 : a.count4;
             float4* dst = reinterpret_cast<float4*>(a.staging[p]) + a.chunk4 * a.rank - r0;      // dst[i] <-> region offset i - r0
             long long i = r0 + s0 + tid;
-            for (; i + 3 * COMM_THREADS < e1; i += 4 * COMM_THREADS) {    // four independent 16-byte copies in flight
-                const float4 v0 = mine[i], v1 = mine[i + COMM_THREADS], v2 = mine[i + 2 * COMM_THREADS], v3 = mine[i + 3 * COMM_THREADS];
+            for (; i + 3 * NT < e1; i += 4 * NT) {    // four independent 16-byte copies in flight
+                const float4 v0 = mine[i], v1 = mine[i + NT], v2 = mine[i + 2 * NT], v3 = mine[i + 3 * NT];
                 st_f4_sys(dst + i, v0);
-                st_f4_sys(dst + i + COMM_THREADS, v1);
-                st_f4_sys(dst + i + 2 * COMM_THREADS, v2);
-                st_f4_sys(dst + i + 3 * COMM_THREADS, v3);
+                st_f4_sys(dst + i + NT, v1);
+                st_f4_sys(dst + i + 2 * NT, v2);
+                st_f4_sys(dst + i + 3 * NT, v3);
             }
-            for (; i < e1; i += COMM_THREADS) st_f4_sys(dst + i, mine[i]);
+            for (; i < e1; i += NT) st_f4_sys(dst + i, mine[i]);
         }
         comm_barrier(a, 0, cta, epoch);                                   // all contributions to my region are here
         // ---- shot 2: sum my region in rank order, store it everywhere ----
         const long long r0 = a.chunk4 * a.rank;
         const long long e1 = r0 + s1 < a.count4 ? r0 + s1 : a.count4;
         const float4* stg = reinterpret_cast<const float4*>(a.staging[a.rank]) - r0;             // + chunk4 * q + i
-        for (long long i = r0 + s0 + tid; i < e1; i += COMM_THREADS) {
+        for (long long i = r0 + s0 + tid; i < e1; i += NT) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int q = 0; q < a.world; ++q) {
                 const float4 v = q == a.rank ? mine[i] : ld_f4_sys(stg + a.chunk4 * q + i);
@@ -186,10 +204,19 @@ int vpr_allreduce_sum_f32(const VprCommPeers* peers, size_t offset_elems, size_t
     VPR_REQUIRE((size_t)a.chunk4 * 4 * a.world <= peers->staging_elems, "staging area too small: %zu < %zu floats",
                 peers->staging_elems, (size_t)a.chunk4 * 4 * a.world);
     if ((long long)ctas > a.chunk4) ctas = (int)a.chunk4;
-    if (a.mc_data != nullptr)
-        allreduce_kernel<true><<<ctas, COMM_THREADS, 0, stream>>>(a);
-    else
-        allreduce_kernel<false><<<ctas, COMM_THREADS, 0, stream>>>(a);
+    static int threads = 0;
+    if (threads == 0) {
+        const char* e = getenv("VPR_COMM_THREADS");
+        threads = e ? atoi(e) : COMM_THREADS;
+        if (threads < 32 || threads > COMM_THREADS || threads % 32) threads = COMM_THREADS;
+    }
+    if (a.mc_data != nullptr) {
+        VPR_SMEM_OK(allreduce_kernel<true>, COMM_DUMMY_SMEM);
+        allreduce_kernel<true><<<ctas, threads, COMM_DUMMY_SMEM, stream>>>(a);
+    } else {
+        VPR_SMEM_OK(allreduce_kernel<false>, COMM_DUMMY_SMEM);
+        allreduce_kernel<false><<<ctas, threads, COMM_DUMMY_SMEM, stream>>>(a);
+    }
     return launch_ok("allreduce_kernel");
 }
 

@@ -338,7 +338,9 @@ int dh_fused_run(const DhFusedDesc& d, cudaStream_t st) {
     a.dW1c = d.dW1c; a.dW1s = d.dW1s; a.db0c = d.db0c; a.db0s = d.db0s; a.db1c = d.db1c;
     const int nct = 2 * a.ct_per_half;
     long long want = (long long)a.tiles_m * nct;
-    int grid = (int)(want < num_sms() ? want : num_sms());
+    int reserve = d.reserve_sms < 0 ? 0 : d.reserve_sms;
+    if (reserve > num_sms() / 2) reserve = num_sms() / 2;
+    int grid = (int)(want < num_sms() - reserve ? want : num_sms() - reserve);
     if (grid < nct) grid = nct;                      // every column slice needs at least one CTA
     VPR_SMEM_OK(dh_fused_kernel, DH_SMEM);
     VPR_CUDA_OK(launch_ex(dh_fused_kernel, dim3((unsigned)grid), dim3(DH_THREADS), (size_t)DH_SMEM, st, d.pdl != 0, 1, tmF, tmS,

@@ -60,6 +60,7 @@ struct DhFusedDesc {
     float* db1c;                             // [128] fp32 column sums of dF (cluster_features.3.bias), or NULL
     long long T; int hidden; float mask_scale;
     int pdl = 0;
+    int reserve_sms = 0;                     // leave this many SMs without a CTA (room for a concurrent collective)
 };
 // SALAD forward, second layer: F = H[:, :h] W1c^T + b1c (bf16), S = H[:, h:] W1s^T + b1s (fp32), weights resident
 // in shared memory, H streamed once.  dtype bf16, l == 128, m == 64, hidden == 512.

@@ -512,7 +512,9 @@ static int heads_t(const VprHeadsParams& p, const T* desc, const float* latlon_t
         static int bn_env = -2, ks_env = -2;              // A/B knobs: VPR_HEADS_FWD_BN, VPR_HEADS_FWD_KS
         if (bn_env == -2) { const char* e = getenv("VPR_HEADS_FWD_BN"); bn_env = e ? atoi(e) : 0; }
         if (ks_env == -2) { const char* e = getenv("VPR_HEADS_FWD_KS"); ks_env = e ? atoi(e) : 0; }
-        g.bn = bn_env;
+        // measured (tools/heads_bench.py, B=256): 128-wide single-CTA tiles x 12-16 K-splits 10.5 us, 256-wide pair tiles
+        // x 24 splits 12.4 us -- the launch is all prologue, split-K atomics and drain
+        g.bn = bn_env > 0 ? bn_env : (s.B <= 512 ? 128 : 0);
         const GemmTilePlan tp = gemm_tile_plan(&g, 1);
         const int tiles = ((s.B + tp.tile_m - 1) / tp.tile_m) * ((g.N + tp.tile_n - 1) / tp.tile_n);
         g.k_splits = ks_env > 0 ? ks_env : tp.slots / tiles;

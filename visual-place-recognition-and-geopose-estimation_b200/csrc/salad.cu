@@ -832,6 +832,7 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         fd.db1c = gr.cluster_b1;
         fd.T = Tk; fd.hidden = h; fd.mask_scale = keep_scale;
         fd.pdl = 1;
+        fd.reserve_sms = reserve_sms;
         VPR_TRY(dh_fused_run(fd, st));
         if (!fin_dht) VPR_TRY(gemm_run(gtokh, st));       // otherwise finalize_bwd_fast already produced dHT
     } else {
@@ -882,6 +883,7 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         int ks = tp.slots / tiles; if (ks < 1) ks = 1; if (ks > kb_tok) ks = kb_tok;
         g4[0].k_splits = ks; g4[1].k_splits = ks;
         g4[0].pdl = 1;
+        g4[0].reserve_sms = reserve_sms;
         VPR_TRY(gemm_run_group(g4, cnt, st));
     }
     }   // phase != VPR_BWD_INPUTS

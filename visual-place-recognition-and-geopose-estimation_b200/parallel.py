@@ -32,12 +32,14 @@ def init_distributed(backend: str | None = None) -> tuple[int, int, int]:
     return rank, local, world
 
 
-def bind_to_gpu_numa_node(device_index: int = 0):
+def bind_to_gpu_numa_node(device_index: int = 0, explain: bool = False):
     """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that pinned staging buffers allocated
     afterwards are local to the GPU's PCIe root (host->device copies from the far socket run at a fraction of the
     link rate).  Returns ``{"numa_node", "cpus", "previous"}`` (``previous`` = the affinity to restore with
-    ``os.sched_setaffinity(0, previous)``) or None when the topology cannot be read; never raises."""
+    ``os.sched_setaffinity(0, previous)``) or None when the topology cannot be read -- with ``explain=True``,
+    ``{"error": why}`` instead of None; never raises."""
     import os
+    why = "unknown"
     try:
         props = torch.cuda.get_device_properties(int(device_index))    # CUDA index (honours CUDA_VISIBLE_DEVICES)
         if hasattr(props, "pci_bus_id"):
@@ -52,7 +54,7 @@ def bind_to_gpu_numa_node(device_index: int = 0):
                 bus = bus[4:]
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
         if node < 0:
-            return None
+            return {"error": f"/sys/bus/pci/devices/{bus}/numa_node reports {node} (single-node host or virtualised PCI)"} if explain else None
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
@@ -60,11 +62,12 @@ def bind_to_gpu_numa_node(device_index: int = 0):
         prev = os.sched_getaffinity(0)
         use = cpus & prev
         if not use:
-            return None
+            return {"error": f"no CPU of NUMA node {node} is in this process's affinity mask"} if explain else None
         os.sched_setaffinity(0, use)
         return {"numa_node": node, "cpus": len(use), "previous": prev}
-    except Exception:                                # noqa: BLE001  (best effort: containers often hide sysfs)
-        return None
+    except Exception as e:                           # noqa: BLE001  (best effort: containers often hide sysfs)
+        why = f"{type(e).__name__}: {e}"
+        return {"error": why} if explain else None
 
 
 def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
@@ -281,42 +284,52 @@ class GraphedFinetuneStep:
             decorrelate_dropout(heads, dist.get_rank(group))
         comm = os.environ.get("VPR_DP_COMM") or comm
         self.comm_kind, self.comm_note = "none", ""
-        comm_h = comm_s = None
+        pc = None
         n_h = sum(p.numel() for p in heads._params()) + 3
         n_s = sum(p.numel() for p in salad._param_list())
+        n_h4 = (n_h + 3) // 4 * 4
         if self.world > 1 and comm in (None, "peer"):
             try:
                 from .comm import PeerComm
                 with torch.cuda.device(dev):
-                    comm_h = PeerComm(n_h, group=group, device=dev)
-                    comm_s = PeerComm(n_s, group=group, device=dev)
-                self.comm_kind = "peer/" + comm_h.backend + ("+multimem" if comm_h.mc_ptr else "")
-                self.comm_note = "; ".join(comm_h.setup_errors)
+                    pc = PeerComm(n_h4 + n_s, group=group, device=dev)      # [ heads grads + losses | SALAD grads ]
+                self.comm_kind = "peer/" + pc.backend + ("+multimem" if pc.mc_ptr else "")
+                self.comm_note = "; ".join(pc.setup_errors)
             except Exception as e:                              # noqa: BLE001
                 if comm == "peer":
                     raise
-                comm_h = comm_s = None
+                pc = None
                 self.comm_note = f"{type(e).__name__}: {e}"
-        if self.world > 1 and comm_h is None:
+        if self.world > 1 and pc is None:
             self.comm_kind = "nccl"
-        self._comms = (comm_h, comm_s)
-        heads_ctas = int(os.environ.get("VPR_COMM_CTAS_HEADS", heads_ctas or 16))
-        salad_ctas = int(os.environ.get("VPR_COMM_CTAS_SALAD", salad_ctas or 64))
-        comm_stream = torch.cuda.Stream(dev) if comm_s is not None else None
-        if comm_s is not None:
-            # the SALAD gradients' exchange: our kernel on a forked stream (beside the input-gradient GEMM when there
-            # is one), joined back by .wait()
+        self._comm = pc
+        comm_ctas = int(os.environ.get("VPR_COMM_CTAS", heads_ctas or salad_ctas or 0)) or None
+        if pc is not None:
+            # ONE exchange of all 5.75 M gradients + the losses at the end of the backward, with the whole machine:
+            # at these sizes (23 MB) the transfer is a few tens of microseconds when every SM posts NVLink traffic,
+            # whereas an exchange squeezed beside the backward's persistent single-wave GEMMs takes their SMs away and
+            # costs them a second wave (measured at N=2: dW0 79 -> 132 us with 8 SMs reserved; NCCL's kernel does the
+            # same to it).  With input gradients requested the exchange runs beside the dX GEMM instead (768 tiles: it
+            # tolerates losing a few SMs).
+            comm_stream = torch.cuda.Stream(dev)
+            overlap_ctas = 16
+
             class _Join:
                 def wait(self_inner):
                     torch.cuda.current_stream(dev).wait_stream(comm_stream)
 
-            def start_salad(flat):
-                comm_stream.wait_stream(torch.cuda.current_stream(dev))
+            def start_all(flat):
+                main_ = torch.cuda.current_stream(dev)
+                main_.wait_stream(wgrad_stream)                 # the heads' deferred weight gradients are in
+                if not input_grads:
+                    pc.allreduce_(0, pc.numel, ctas=comm_ctas or L.COMM_MAX_CTAS)
+                    return None
+                comm_stream.wait_stream(main_)
                 with torch.cuda.stream(comm_stream):
-                    comm_s.allreduce_(0, comm_s.numel, ctas=salad_ctas)
+                    pc.allreduce_(0, pc.numel, ctas=comm_ctas or overlap_ctas)
                 return _Join()
 
-            salad.set_grad_ready_hook(start_salad, 0)
+            salad.set_grad_ready_hook(start_all, (comm_ctas or overlap_ctas) if input_grads else 0, 0)
         elif self.world > 1 and salad._grad_hook is None:
             overlap_grad_allreduce(salad, group)
         self.x = torch.zeros(batch, n_tokens, salad.num_channels, dtype=dtype, device=dev)
@@ -341,19 +354,17 @@ class GraphedFinetuneStep:
             main.wait_stream(pack_stream)                       # join
             latlon_pred, sincos_pred, losses, hgrads, d_desc, hflat, head_wgrad = heads_run(
                 desc, hparams, self.latlon, self.angle if use_angle else None, cfg, True, ws=hws, prepacked=True,
-                defer_wgrad=True, flat=comm_h.data if comm_h is not None else None)
+                defer_wgrad=True, flat=pc.data[:n_h4] if pc is not None else None)
             # second fork: the heads' two weight-gradient launches and, across ranks, the all-reduce of the whole heads
             # buffer (gradients + losses) run beside the SALAD backward, which only needs d_desc
             wgrad_stream.wait_stream(main)
             with torch.cuda.stream(wgrad_stream):
                 head_wgrad()
                 hwork = None
-                if comm_h is not None:
-                    comm_h.allreduce_(0, comm_h.numel, ctas=heads_ctas)
-                elif self.world > 1:
+                if pc is None and self.world > 1:
                     hwork = dist.all_reduce(hflat, group=group, async_op=True)
             dx, dt, sflat, sgrads = _salad_backward(x_tok, t, save, sparams, shape, p_drop, d_desc, input_grads, input_grads,
-                                                    salad._grad_hook, flat=comm_s.data if comm_s is not None else None)
+                                                    salad._grad_hook, flat=pc.data[n_h4:] if pc is not None else None)
             if hwork is not None:
                 with torch.cuda.stream(wgrad_stream):
                     hwork.wait()

@@ -92,8 +92,8 @@ def _salad_backward(x_tok, t, save, params, shape_tuple, dropout_p, d_out, want_
         # data parallel: every parameter gradient first, hand the flat buffer to the hook (it starts the
         # all-reduce on the collective's stream), then the input-gradient GEMM on a few SMs less so that the
         # collective's kernel finds room and the two overlap; finally order later work after the collective
-        fn, reserve = hook
-        bwd(L.BWD_PARAMS, 0)
+        fn, reserve = hook[0], hook[1]
+        bwd(L.BWD_PARAMS, int(hook[2]) if len(hook) > 2 else 0)
         work = fn(flat)
         if dx is not None or dtok is not None:
             bwd(L.BWD_INPUTS, int(reserve))
@@ -161,13 +161,15 @@ class SaladHead(nn.Module):
         counter would be frozen into the graph and every replay would draw the same mask)."""
         self._seed_dev = torch.zeros(1, dtype=torch.int64, device=self.dust_bin.device) if enabled else None
 
-    def set_grad_ready_hook(self, fn, reserve_sms: int = 32) -> None:
+    def set_grad_ready_hook(self, fn, reserve_sms: int = 32, reserve_sms_params: int = 0) -> None:
         """``fn(flat)`` is called inside backward as soon as ALL parameter gradients (one flat fp32 buffer, the
         ``p.grad`` views point into it) have been enqueued and before the input-gradient GEMM is launched; it may
         start an asynchronous collective on ``flat`` and return its work handle (``.wait()`` is called after the
         remaining launches).  ``reserve_sms`` SMs are kept free of the input-gradient GEMM for the collective's
-        kernel.  ``fn=None`` removes the hook.  See ``parallel.overlap_grad_allreduce``."""
-        self._grad_hook = None if fn is None else (fn, int(reserve_sms))
+        kernel; ``reserve_sms_params`` SMs are kept free of the persistent kernels that run BEFORE the hook (fused dH
+        pass, first-layer weight-gradient GEMM) for a collective the caller started earlier (the geopose-head
+        gradients').  ``fn=None`` removes the hook.  See ``parallel.overlap_grad_allreduce``."""
+        self._grad_hook = None if fn is None else (fn, int(reserve_sms), int(reserve_sms_params))
 
     def current_seed(self) -> int:
         """Seed the NEXT training forward will use (synchronises when the counter lives on the device)."""
