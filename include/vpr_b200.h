@@ -129,8 +129,9 @@ VPR_API int vpr_salad_bwd(const VprSaladParams* p, const void* x, const void* t,
                   int phase, int reserve_sms, cudaStream_t stream);
 /* phase: VPR_BWD_ALL, or the same work in two calls -- VPR_BWD_PARAMS (every parameter gradient) then
  * VPR_BWD_INPUTS (dx, dt) -- so that a data-parallel caller can start the gradient all-reduce between them;
- * reserve_sms > 0 keeps that many SMs free of the persistent kernels of the phase(s) this call runs (fused dH pass,
- * first-layer weight-gradient GEMM, input-gradient GEMM) for a collective that runs beside them. */
+ * reserve_sms > 0 keeps that many SMs free of the two many-tile persistent kernels of the phase(s) this call runs
+ * (fused dH pass in VPR_BWD_PARAMS, input-gradient GEMM in VPR_BWD_INPUTS) for a collective that runs beside them;
+ * the first-layer weight-gradient GEMM is a single wave sized to the whole machine and never gives SMs up. */
 #define VPR_BWD_ALL 0
 #define VPR_BWD_PARAMS 1
 #define VPR_BWD_INPUTS 2

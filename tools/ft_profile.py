@@ -55,7 +55,7 @@ def main():
             print(f"{e.time_range.start - t0:9.1f} .. {e.time_range.end - t0:9.1f}  (+{e.time_range.end - e.time_range.start:7.1f} us)  {e.name[:100]}")
     if world > 1:
         if rank == 0:
-            print("comm:", step.comm_kind, step.comm_note)
+            print("comm:", step.comm_kind, step.comm_placement, step.comm_note)
         torch.cuda.synchronize()
         dist.barrier()
         sys.stdout.flush()

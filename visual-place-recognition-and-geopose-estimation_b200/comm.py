@@ -132,6 +132,11 @@ class PeerComm:
             ptrs.append(view.data_ptr() + off)
         self._peer_ptrs = ptrs
 
+    def use_multimem(self, enabled: bool) -> None:
+        """Switch between the switch-side reduction (multimem, needs the multicast mapping) and the peer-store path.
+        Collective in effect: every rank must choose the same."""
+        self._peers.mc_data = (self.mc_ptr or None) if enabled else None
+
     # ---- the collective -----------------------------------------------------------------------------------------
     def allreduce_(self, offset: int = 0, count: int | None = None, ctas: int = 16) -> None:
         """In-place sum over ranks of ``data[offset : offset + count]`` on the current stream (no host sync; safe to

@@ -883,7 +883,10 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
         int ks = tp.slots / tiles; if (ks < 1) ks = 1; if (ks > kb_tok) ks = kb_tok;
         g4[0].k_splits = ks; g4[1].k_splits = ks;
         g4[0].pdl = 1;
-        g4[0].reserve_sms = reserve_sms;
+        // no reserve_sms here: this launch is ONE wave of split-K work items sized to the machine (12 pair tiles x 6
+        // K-splits on 74 CTA pairs); with fewer CTAs the leftover items form a second wave and the launch takes twice
+        // as long (measured: 79 -> 132 us with 8 SMs held back).  A collective that runs beside the backward has to be
+        // done by the time this launch starts.
         VPR_TRY(gemm_run_group(g4, cnt, st));
     }
     }   // phase != VPR_BWD_INPUTS

@@ -303,14 +303,24 @@ class GraphedFinetuneStep:
         if self.world > 1 and pc is None:
             self.comm_kind = "nccl"
         self._comm = pc
-        comm_ctas = int(os.environ.get("VPR_COMM_CTAS", heads_ctas or salad_ctas or 0)) or None
+        # Two ways to place the exchange, chosen by what was measured on B200 / NVLink 5 (tools/comm_bench.py,
+        # tools/ft_profile.py; numbers in DESIGN.md section 5):
+        #  "overlap"  the 17 MB of geopose-head gradients (final right after the heads call) are reduced on a forked
+        #             stream beside the Sinkhorn backward and the fused dH pass, which is launched `heads_ctas` CTAs
+        #             short; only the 5.6 MB of SALAD gradients are exchanged after the backward.  Pays when the heads
+        #             message fits into that ~90 us window on a handful of SMs: with the switch reducing (multimem) at
+        #             4+ ranks it does (56 us on 8 CTAs at 8 ranks).
+        #  "end"      ONE exchange of all 23 MB after the backward, on 64 CTAs.  At 2 ranks every byte crosses the SMs
+        #             (no switch-side reduction to speak of): 8 CTAs would need 113 us and run into the single-wave dW0
+        #             GEMM, 64 CTAs do the whole buffer in 48 us.
+        mode = os.environ.get("VPR_DP_PLACEMENT") or ("overlap" if (pc is not None and pc.mc_ptr and self.world >= 4) else "end")
+        self.comm_placement = mode if pc is not None else ("nccl-overlap" if self.world > 1 else "none")
+        heads_ctas = int(os.environ.get("VPR_COMM_CTAS_HEADS", heads_ctas or 8))
+        salad_ctas = int(os.environ.get("VPR_COMM_CTAS_SALAD", salad_ctas or 64))
+        if pc is not None and mode == "end" and self.world == 2 and os.environ.get("VPR_COMM_MULTIMEM") is None:
+            pc.use_multimem(False)
+            self.comm_kind = "peer/" + pc.backend
         if pc is not None:
-            # ONE exchange of all 5.75 M gradients + the losses at the end of the backward, with the whole machine:
-            # at these sizes (23 MB) the transfer is a few tens of microseconds when every SM posts NVLink traffic,
-            # whereas an exchange squeezed beside the backward's persistent single-wave GEMMs takes their SMs away and
-            # costs them a second wave (measured at N=2: dW0 79 -> 132 us with 8 SMs reserved; NCCL's kernel does the
-            # same to it).  With input gradients requested the exchange runs beside the dX GEMM instead (768 tiles: it
-            # tolerates losing a few SMs).
             comm_stream = torch.cuda.Stream(dev)
             overlap_ctas = 16
 
@@ -320,16 +330,17 @@ class GraphedFinetuneStep:
 
             def start_all(flat):
                 main_ = torch.cuda.current_stream(dev)
-                main_.wait_stream(wgrad_stream)                 # the heads' deferred weight gradients are in
+                main_.wait_stream(wgrad_stream)                 # the heads' deferred weight gradients (and, in "overlap"
+                off, cnt = (n_h4, pc.numel - n_h4) if mode == "overlap" else (0, pc.numel)     # mode, their exchange) are in
                 if not input_grads:
-                    pc.allreduce_(0, pc.numel, ctas=comm_ctas or L.COMM_MAX_CTAS)
+                    pc.allreduce_(off, cnt, ctas=salad_ctas)
                     return None
-                comm_stream.wait_stream(main_)
+                comm_stream.wait_stream(main_)                  # beside the dX GEMM (768 tiles: it tolerates losing SMs)
                 with torch.cuda.stream(comm_stream):
-                    pc.allreduce_(0, pc.numel, ctas=comm_ctas or overlap_ctas)
+                    pc.allreduce_(off, cnt, ctas=overlap_ctas)
                 return _Join()
 
-            salad.set_grad_ready_hook(start_all, (comm_ctas or overlap_ctas) if input_grads else 0, 0)
+            salad.set_grad_ready_hook(start_all, overlap_ctas if input_grads else 0, heads_ctas if mode == "overlap" else 0)
         elif self.world > 1 and salad._grad_hook is None:
             overlap_grad_allreduce(salad, group)
         self.x = torch.zeros(batch, n_tokens, salad.num_channels, dtype=dtype, device=dev)
@@ -361,7 +372,9 @@ class GraphedFinetuneStep:
             with torch.cuda.stream(wgrad_stream):
                 head_wgrad()
                 hwork = None
-                if pc is None and self.world > 1:
+                if pc is not None and mode == "overlap":
+                    pc.allreduce_(0, n_h4, ctas=heads_ctas)
+                elif pc is None and self.world > 1:
                     hwork = dist.all_reduce(hflat, group=group, async_op=True)
             dx, dt, sflat, sgrads = _salad_backward(x_tok, t, save, sparams, shape, p_drop, d_desc, input_grads, input_grads,
                                                     salad._grad_hook, flat=pc.data[n_h4:] if pc is not None else None)
