@@ -429,6 +429,59 @@ def test_salad_full_size_properties_bf16(vpr):
     assert mod.dust_bin.grad.abs().item() == 0.0
 
 
+@pytest.mark.parametrize("B,hw", [(256, 16), (1024, 23)])
+def test_salad_full_size_matches_the_oracle_run_on_the_device(vpr, B, hw):
+    """BASELINE configs[1] (B=256, n=256) and configs[3] (B=1024, n=529) at FULL size against the oracle itself: the
+    restated upstream module (oracle.SaladRef, fp32, autograd) evaluated on the GPU as the checker, on the same
+    bf16-rounded inputs and weights the tensor cores consume.  Every descriptor and every gradient within the
+    north-star's bf16 tolerance (2e-2 relative)."""
+    torch.backends.cudnn.allow_tf32 = False              # the checker computes in true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    ref = O.SaladRef(dropout=0.0, aggregate="einsum")
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.copy_(p.bfloat16().float())
+    mod = vpr.SaladHead(dropout=0.0).cuda()
+    mod.load_state_dict(ref.state_dict())
+    ref = ref.cuda()
+    n = hw * hw
+    g = torch.Generator(device="cuda").manual_seed(B + n)
+    x = torch.randn(B, n, 768, device="cuda", generator=g).bfloat16()
+    t = torch.randn(B, 768, device="cuda", generator=g).bfloat16()
+    w = torch.randn(B, 8448, device="cuda", generator=g).bfloat16()
+    xg, tg = x.clone().requires_grad_(True), t.clone().requires_grad_(True)
+    out = mod((O.tokens_to_salad_input(xg, hw, hw), tg))
+    out.backward(w)
+    got = {"desc": out.detach().float(), "dx": xg.grad.float(), "dt": tg.grad.float()}
+    got.update({k: p.grad.clone() for k, p in mod.named_parameters()})
+    del out, xg, tg
+    want = {}
+    parts = 4 if B >= 1024 else 1                         # the fp32 oracle keeps ~12 GB of activations per 256 images at n=529
+    pgrads = None
+    descs, dxs, dts = [], [], []
+    for c in range(parts):
+        sl = slice(c * B // parts, (c + 1) * B // parts)
+        xr, tr = x[sl].float().requires_grad_(True), t[sl].float().requires_grad_(True)
+        for p in ref.parameters():
+            p.grad = None
+        o = ref((O.tokens_to_salad_input(xr, hw, hw), tr))
+        (o * w[sl].float()).sum().backward()
+        descs.append(o.detach()); dxs.append(xr.grad); dts.append(tr.grad)
+        cur = {k: p.grad.clone() for k, p in ref.named_parameters()}
+        pgrads = cur if pgrads is None else {k: pgrads[k] + cur[k] for k in cur}
+        del o, xr, tr
+    want = {"desc": torch.cat(descs), "dx": torch.cat(dxs), "dt": torch.cat(dts), **pgrads}
+    worst = {}
+    for k, wv in want.items():
+        if wv.norm() > 1e-6:
+            worst[k] = rel(got[k], wv)
+        else:
+            assert got[k].abs().max() < 1e-4, k               # dust_bin: identically zero
+    assert max(worst.values()) < 2e-2, worst
+    np.testing.assert_allclose(got["desc"].norm(dim=1).cpu().numpy(), 1.0, atol=4e-3)
+
+
 # ------------------------------------------------------------------ geopose heads
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("latlon,angle", [("mse", "atan2_maae"), ("huber", "acos"), ("mse", "mse"), ("mse", None)])
@@ -698,3 +751,41 @@ def test_knn_sharded_merge_equals_unsharded(vpr):
         parts = [vpr.knn_topk(q, ga[b:e], 25, g_offset=b) for b, e in (vpr.shard_range(9000, r, R) for r in range(R))]
         ms, mi = vpr.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), 25)
         assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
+
+
+def test_knn_at_a_million_gallery_rows_against_a_chunked_device_oracle(vpr):
+    """configs[4] width (D=8448) and a gallery shard of 10^6 + 3 rows (a ragged last tile): index sets equal outside
+    1e-6 ties and scores within 2e-6 of topk(Q @ G^T) computed by the oracle's formula in fp32 on the device, 32 768 rows
+    at a time, merged with the oracle's own merge_topk (score descending, ties to the lower index)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    Q, G, D, k = 192, 1_000_003, 8448, 25
+    g = torch.Generator(device="cuda").manual_seed(21)
+    gal = torch.empty(G, D, dtype=torch.bfloat16, device="cuda")
+    for r0 in range(0, G, 65536):
+        r1 = min(G, r0 + 65536)
+        gal[r0:r1] = torch.nn.functional.normalize(torch.randn(r1 - r0, D, device="cuda", generator=g), dim=1).bfloat16()
+    q = torch.nn.functional.normalize(torch.randn(Q, D, device="cuda", generator=g), dim=1).bfloat16()
+    # plant exact duplicates far apart: ties must resolve to the lower index
+    gal[900_000] = gal[17]
+    gal[G - 1] = gal[17]
+    q[0] = gal[17]
+    s, i = vpr.knn_topk(q, gal, k, g_offset=5_000_000)
+    qf = q.float()
+    best_s = torch.empty(Q, 0, device="cuda")
+    best_i = torch.empty(Q, 0, dtype=torch.int64, device="cuda")
+    for r0 in range(0, G, 32768):
+        sc = qf @ gal[r0:r0 + 32768].float().T
+        idx = torch.arange(r0, r0 + sc.shape[1], device="cuda").expand_as(sc) + 5_000_000
+        best_s, best_i = O.merge_topk(torch.cat([best_s, sc], 1), torch.cat([best_i, idx], 1), k)
+    assert (s - best_s).abs().max().item() < 2e-6
+    assert i[0, :3].tolist() == [5_000_017, 5_900_000, 5_000_000 + G - 1]
+    bad = 0
+    for r in range(Q):
+        a, b = set(i[r].tolist()), set(best_i[r].tolist())
+        if a != b:
+            kth = best_s[r, -1].item()
+            extra = [s[r, (i[r] == v).nonzero()[0, 0]].item() for v in a - b] + \
+                    [best_s[r, (best_i[r] == v).nonzero()[0, 0]].item() for v in b - a]
+            bad += int(any(abs(v - kth) > 1e-6 for v in extra))
+    assert bad == 0
+    assert (s[:, :-1] >= s[:, 1:]).all()

@@ -95,7 +95,7 @@ __device__ __forceinline__ void comm_barrier(const CommArgs& a, int phase, int c
 }
 
 template <bool MULTIMEM>
-__global__ void __launch_bounds__(COMM_THREADS, 1) allreduce_kernel(const CommArgs a) {
+__global__ void __launch_bounds__(COMM_THREADS, 2) allreduce_kernel(const CommArgs a) {
     const int cta = blockIdx.x, nct = gridDim.x, tid = threadIdx.x;
     const int NT = blockDim.x;                      // <= COMM_THREADS (tuning knob VPR_COMM_THREADS)
     __shared__ uint32_t epoch_s;
@@ -104,17 +104,25 @@ __global__ void __launch_bounds__(COMM_THREADS, 1) allreduce_kernel(const CommAr
     if (tid == 0) epoch_s = *epoch_p + 1u;
     __syncthreads();
     const uint32_t epoch = epoch_s;
-    // slice of a region this CTA owns: float4 [s0, s1) relative to the region start (the same on every rank)
-    const long long per = (a.chunk4 + nct - 1) / nct;
-    const long long s0 = per * cta, s1 = s0 + per < a.chunk4 ? s0 + per : a.chunk4;
+    // slice of a region this CTA owns: float4 [s0, s1) relative to the region start (the same on every rank); all
+    // loop indices are 32-bit offsets from per-region base pointers (the kernel is capped at 32 registers so that its
+    // CTAs fit beside a half-occupied SM of the kernels it overlaps)
+    const int chunk = (int)a.chunk4;
+    const int per = (chunk + nct - 1) / nct;
+    const int s0 = per * cta;
+    auto slice_end = [&](int region) {              // exclusive end of this CTA's slice inside `region`, clipped to the message
+        long long lim = a.count4 - (long long)chunk * region;
+        int e = s0 + per < chunk ? s0 + per : chunk;
+        if (lim < e) e = lim < 0 ? 0 : (int)lim;
+        return e;
+    };
     float4* mine = reinterpret_cast<float4*>(a.data[a.rank]) + a.off4;
     if (MULTIMEM) {
         comm_barrier(a, 0, cta, epoch);                                   // every rank's data is final
-        const long long r0 = a.chunk4 * a.rank;
-        const long long e1 = r0 + s1 < a.count4 ? r0 + s1 : a.count4;
-        float4* mc = reinterpret_cast<float4*>(a.mc_data) + a.off4;
-        long long i = r0 + s0 + tid;
-        for (; i + 3 * NT < e1; i += 4 * NT) {        // four switch round trips in flight per thread
+        float4* mc = reinterpret_cast<float4*>(a.mc_data) + a.off4 + (long long)chunk * a.rank;
+        const int e1 = slice_end(a.rank);
+        int i = s0 + tid;
+        for (; i + 3 * NT < e1; i += 4 * NT) {                            // four switch round trips in flight per thread
             const float4 v0 = multimem_ld_reduce_f4(mc + i), v1 = multimem_ld_reduce_f4(mc + i + NT),
                          v2 = multimem_ld_reduce_f4(mc + i + 2 * NT), v3 = multimem_ld_reduce_f4(mc + i + 3 * NT);
             multimem_st_f4(mc + i, v0);
@@ -128,33 +136,34 @@ __global__ void __launch_bounds__(COMM_THREADS, 1) allreduce_kernel(const CommAr
         // ---- shot 1: my slice of region p -> slot `rank` of p's staging ----
         for (int k = 1; k < a.world; ++k) {
             const int p = (a.rank + k) % a.world;                         // staggered: no two ranks start on the same peer
-            const long long r0 = a.chunk4 * p;
-            const long long e1 = r0 + s1 < a.count4 ? r0 + s1 : a.count4;
-            float4* dst = reinterpret_cast<float4*>(a.staging[p]) + a.chunk4 * a.rank - r0;      // dst[i] <-> region offset i - r0
-            long long i = r0 + s0 + tid;
-            for (; i + 3 * NT < e1; i += 4 * NT) {    // four independent 16-byte copies in flight
-                const float4 v0 = mine[i], v1 = mine[i + NT], v2 = mine[i + 2 * NT], v3 = mine[i + 3 * NT];
+            const float4* src = mine + (long long)chunk * p;
+            float4* dst = reinterpret_cast<float4*>(a.staging[p]) + (long long)chunk * a.rank;
+            const int e1 = slice_end(p);
+            int i = s0 + tid;
+            for (; i + 3 * NT < e1; i += 4 * NT) {                        // four independent 16-byte copies in flight
+                const float4 v0 = src[i], v1 = src[i + NT], v2 = src[i + 2 * NT], v3 = src[i + 3 * NT];
                 st_f4_sys(dst + i, v0);
                 st_f4_sys(dst + i + NT, v1);
                 st_f4_sys(dst + i + 2 * NT, v2);
                 st_f4_sys(dst + i + 3 * NT, v3);
             }
-            for (; i < e1; i += NT) st_f4_sys(dst + i, mine[i]);
+            for (; i < e1; i += NT) st_f4_sys(dst + i, src[i]);
         }
         comm_barrier(a, 0, cta, epoch);                                   // all contributions to my region are here
         // ---- shot 2: sum my region in rank order, store it everywhere ----
-        const long long r0 = a.chunk4 * a.rank;
-        const long long e1 = r0 + s1 < a.count4 ? r0 + s1 : a.count4;
-        const float4* stg = reinterpret_cast<const float4*>(a.staging[a.rank]) - r0;             // + chunk4 * q + i
-        for (long long i = r0 + s0 + tid; i < e1; i += NT) {
+        const float4* own = mine + (long long)chunk * a.rank;
+        const float4* stg = reinterpret_cast<const float4*>(a.staging[a.rank]);
+        const long long out_off = a.off4 + (long long)chunk * a.rank;
+        const int e1 = slice_end(a.rank);
+        for (int i = s0 + tid; i < e1; i += NT) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int q = 0; q < a.world; ++q) {
-                const float4 v = q == a.rank ? mine[i] : ld_f4_sys(stg + a.chunk4 * q + i);
+                const float4 v = q == a.rank ? own[i] : ld_f4_sys(stg + (long long)chunk * q + i);
                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             }
             for (int k = 0; k < a.world; ++k) {
                 const int p = (a.rank + k) % a.world;
-                st_f4_sys(reinterpret_cast<float4*>(a.data[p]) + a.off4 + i, acc);
+                st_f4_sys(reinterpret_cast<float4*>(a.data[p]) + out_off + i, acc);
             }
         }
         comm_barrier(a, 1, cta, epoch);                                   // every region has landed here
