@@ -777,8 +777,11 @@ def test_knn_at_a_million_gallery_rows_against_a_chunked_device_oracle(vpr):
         sc = qf @ gal[r0:r0 + 32768].float().T
         idx = torch.arange(r0, r0 + sc.shape[1], device="cuda").expand_as(sc) + 5_000_000
         best_s, best_i = O.merge_topk(torch.cat([best_s, sc], 1), torch.cat([best_i, idx], 1), k)
-    assert (s - best_s).abs().max().item() < 2e-6
-    assert i[0, :3].tolist() == [5_000_017, 5_900_000, 5_000_000 + G - 1]
+    # random unit vectors score ~1e-2 (fp32 summation-order noise ~1e-8); the planted exact duplicates of row 0 score
+    # ~1.0 from 8448 positive products, where the two summation orders differ by a few 1e-5
+    assert (s[1:] - best_s[1:]).abs().max().item() < 2e-6, (s[1:] - best_s[1:]).abs().max().item()
+    assert (s[0] - best_s[0]).abs().max().item() < 1e-4, (s[0] - best_s[0]).abs().max().item()
+    assert i[0, :3].tolist() == [5_000_017, 5_900_000, 5_000_000 + G - 1], (i[0, :4].tolist(), s[0, :4].tolist(), best_i[0, :4].tolist())
     bad = 0
     for r in range(Q):
         a, b = set(i[r].tolist()), set(best_i[r].tolist())
@@ -787,5 +790,5 @@ def test_knn_at_a_million_gallery_rows_against_a_chunked_device_oracle(vpr):
             extra = [s[r, (i[r] == v).nonzero()[0, 0]].item() for v in a - b] + \
                     [best_s[r, (best_i[r] == v).nonzero()[0, 0]].item() for v in b - a]
             bad += int(any(abs(v - kth) > 1e-6 for v in extra))
-    assert bad == 0
+    assert bad == 0, bad
     assert (s[:, :-1] >= s[:, 1:]).all()
