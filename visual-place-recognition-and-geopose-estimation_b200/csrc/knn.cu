@@ -37,9 +37,32 @@ struct KnnArgs {
     int tiles_m, chunks, tiles_per_chunk, tiles_n, kb_total;
     int q_group;           // query tiles that walk the same gallery chunk at the same time (L2 reuse)
     int relaxed;           // epilogue warps sleep between polls while they wait for a tile
+    int throttle;          // > 0: the q_group producers of a chunk keep within `throttle` k-blocks of each other
+    int* sync;             // [query groups][chunks][8] progress words (zeroed by the host), used when throttle > 0
     float* ws_score;       // [Q, chunks, k]
     int* ws_idx;           // [Q, chunks, k] local gallery row, -1 = empty
 };
+
+// L2 eviction policies for the two operand streams: the group's query tiles are re-read for every gallery tile
+// (keep them), a gallery tile is dead once the group's CTA pairs have pulled it through (drop it first)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_3d_2sm_hint(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                                     uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
 
 __global__ void __launch_bounds__(K_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG, const KnnArgs args) {
@@ -80,12 +103,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     // concurrently are (q_group query tiles) x (a few gallery chunks) walking their gallery tiles in
     // lock step: every gallery tile is fetched from HBM once per group and shared through L2, and the
     // group's query tiles (q_group * 128 * D * 2 bytes) stay L2-resident.
+    int grp_idx = 0, grp_members = 1;               // of the last decoded work item (the producer's throttle uses them)
     auto tile_range = [&](int w, int& mt, int& ch, int& nt0, int& nt1) {
         const int per_group = args.q_group * args.chunks;
         const int qg = w / per_group;
         const int r = w - qg * per_group;
         int qt = args.tiles_m - qg * args.q_group;
         if (qt > args.q_group) qt = args.q_group;
+        grp_idx = qg; grp_members = qt;
         ch = r / qt;
         mt = qg * args.q_group + (r - ch * qt);
         nt0 = ch * args.tiles_per_chunk;
@@ -97,17 +122,44 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             const uint32_t full0 = mapa_shared(full_bar(0), 0u);     // both producers credit the leader's barrier
+            const uint64_t pol_q = l2_policy_evict_last(), pol_g = l2_policy_evict_first();
             for (int w = w_first; w < total_work; w += w_step) {
                 int mt, ch, nt0, nt1;
                 tile_range(w, mt, ch, nt0, nt1);
                 const int q0 = mt * K_TILE_M + (int)cta_rank * KBM;
+                // Lock step: the q_group CTA pairs that scan this gallery chunk (one per query tile of the group; the host
+                // plans q_group x chunks == CTA pairs, so they all run now) pull the same gallery k-blocks through L2.
+                // Left alone they drift apart -- top-k insertions are data dependent -- by more than L2 holds, and every
+                // pair ends up streaming the gallery from HBM on its own (measured: 32 x the gallery at Q = 8192).  So the
+                // leader's producer publishes its progress every `throttle` k-blocks and waits until every member of the
+                // group has published the step before; the 6-stage operand ring hides the wait.
+                const bool paced = args.throttle > 0 && cta_rank == 0 && grp_members > 1;
+                volatile int* prog = paced ? args.sync + ((size_t)grp_idx * args.chunks + ch) * 8 : nullptr;
+                const int me = mt - grp_idx * args.q_group;
+                int kbi = 0;
                 for (int nt = nt0; nt < nt1; ++nt)
-                    for (int kb = 0; kb < args.kb_total; ++kb) {
+                    for (int kb = 0; kb < args.kb_total; ++kb, ++kbi) {
+                        if (paced && kbi % args.throttle == 0) {
+                            const int step = kbi / args.throttle;
+                            prog[me] = step + 1;                                     // "I am issuing step `step`"
+                            if (step > 0) {
+                                long long t0 = 0;
+                                int spins = 0;
+                                for (int m = 0; m < grp_members; ++m)                // everyone is at least issuing step - 1
+                                    while (prog[m] < step) {
+                                        if (++spins == 64) t0 = clock64();
+                                        if (spins > 64) {
+                                            __nanosleep(100);
+                                            if ((spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
+                                        }
+                                    }
+                            }
+                        }
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         const uint32_t sa = smem_base + stage * K_STAGE_BYTES, sb = sa + K_A_BYTES;
                         if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * K_STAGE_BYTES);
-                        tma_load_3d_2sm(sa, &tmQ, full0 + 8u * stage, kb * KBK, q0, 0);
-                        tma_load_3d_2sm(sb, &tmG, full0 + 8u * stage, kb * KBK, nt * KBN + (int)cta_rank * (KBN / 2), 0);
+                        tma_load_3d_2sm_hint(sa, &tmQ, full0 + 8u * stage, kb * KBK, q0, 0, pol_q);
+                        tma_load_3d_2sm_hint(sb, &tmG, full0 + 8u * stage, kb * KBK, nt * KBN + (int)cta_rank * (KBN / 2), 0, pol_g);
                         if (++stage == K_STAGES) { stage = 0; phase ^= 1u; }
                     }
             }
@@ -286,24 +338,23 @@ static int knn_map(CUtensorMap* map, const void* ptr, int64_t rows, int D, int b
     return 0;
 }
 
-// query tiles per group: their operands should stay L2-resident while the group walks the gallery
+// Schedule: q_group query tiles x `chunks` gallery chunks = the CTA pairs of one launch wave, i.e. every pair keeps ONE
+// gallery chunk for the whole launch and walks it once per group of query tiles, in lock step with the q_group - 1
+// pairs that scan the same chunk for the other query tiles of the group.  DRAM traffic: (query tiles / q_group) gallery
+// passes; the group's query tiles (q_group x 256 x D x 2 bytes, evict-last) stay in L2.
 static int knn_q_group(int D, int tiles_m) {
-    const int pairs = num_sms() / 2;
     static long long budget_mb = -1;
-    // measured (B200, Q = 8192, G = 1.25 M, D = 8448): 965 / 976 / 987 / 974 TFLOP/s with 80 / 40 / 20 / 9 MB; a ncu capture
-    // at the old 80 MB setting showed the query tiles being re-read from HBM all the same (159 GB of DRAM reads for a
-    // 5 GB gallery, 50 % L2 hit rate), so the budget stays well below the nominal 126 MB
-    if (budget_mb < 0) { const char* e = getenv("VPR_KNN_L2_MB"); budget_mb = (e != nullptr && atoi(e) > 0) ? atoi(e) : 24; }
+    if (budget_mb < 0) { const char* e = getenv("VPR_KNN_L2_MB"); budget_mb = (e != nullptr && atoi(e) > 0) ? atoi(e) : 40; }
     long long qmax = (budget_mb << 20) / ((long long)K_TILE_M * D * 2);
+    if (qmax > 8) qmax = 8;                     // beyond 8 the gallery passes saved no longer pay for the idle pairs
     if (qmax < 1) qmax = 1;
-    if (qmax > pairs) qmax = pairs;
     if (qmax > tiles_m) qmax = tiles_m;
-    // q_group x (gallery chunks in flight = pairs / q_group) work items run at a time: take the largest group within
-    // the budget among those that leave the fewest CTA pairs idle
+    const int pairs = num_sms() / 2;
+    // among the group sizes within budget prefer the one that leaves the fewest pairs idle, then the largest
     int best = 1, best_fill = 0;
     for (int qg = 1; qg <= (int)qmax; ++qg) {
         const int fill = qg * (pairs / qg);
-        if (fill >= best_fill) { best_fill = fill; best = qg; }
+        if (fill > best_fill || (fill >= best_fill - 2 && qg > best)) { best_fill = fill > best_fill ? fill : best_fill; best = qg; }
     }
     return best;
 }
@@ -312,18 +363,10 @@ static void knn_plan(int64_t Q, int64_t G, int D, int& tiles_m, int& tiles_n, in
     tiles_m = (int)((Q + K_TILE_M - 1) / K_TILE_M);
     tiles_n = (int)((G + KBN - 1) / KBN);
     const int pairs = num_sms() / 2;
-    // aim for >= 8 work items per CTA pair so the last wave is short, and for enough chunks that ONE query group
-    // (q_group tiles x chunks work items) fills the machine -- otherwise two groups run side by side and their
-    // query tiles no longer fit in L2; but keep >= 8 gallery tiles per chunk
-    int want = (8 * pairs + tiles_m - 1) / tiles_m;
     const int qg = knn_q_group(D, tiles_m);
-    const int fill = (pairs + qg - 1) / qg;
-    if (want < fill) want = fill;
-    if (want < 1) want = 1;
-    int max_chunks = (tiles_n + 7) / 8;
-    if (max_chunks < 1) max_chunks = 1;
-    chunks = want < max_chunks ? want : max_chunks;
-    if (chunks > 64) chunks = 64;
+    chunks = pairs / qg;                        // q_group x chunks work items = one wave of CTA pairs
+    if (chunks > tiles_n) chunks = tiles_n;
+    if (chunks < 1) chunks = 1;
     tiles_per_chunk = (tiles_n + chunks - 1) / chunks;
     chunks = (tiles_n + tiles_per_chunk - 1) / tiles_per_chunk;
 }
@@ -340,6 +383,7 @@ size_t vpr_knn_workspace_bytes(int64_t Q, int64_t G, int D, int k) {
     size_t off = 0;
     carve_size(off, (size_t)Q * ch * k * 4);
     carve_size(off, (size_t)Q * ch * k * 4);
+    carve_size(off, (size_t)(tm + 1) * ch * 8 * sizeof(int));   // lock-step progress words, 8 per (query group, chunk)
     return (off + 255) & ~size_t(255);
 }
 
@@ -365,6 +409,7 @@ int vpr_knn_topk(const void* q, const void* g, int64_t Q, int64_t G, int D, int 
     size_t off = 0;
     a.ws_score = (float*)((char*)workspace + carve_size(off, (size_t)Q * a.chunks * k * 4));
     a.ws_idx = (int*)((char*)workspace + carve_size(off, (size_t)Q * a.chunks * k * 4));
+    a.sync = (int*)((char*)workspace + carve_size(off, (size_t)(a.tiles_m + 1) * a.chunks * 8 * sizeof(int)));
     CUtensorMap tq, tg;
     VPR_TRY(knn_map(&tq, q, Q, D, KBM));
     VPR_TRY(knn_map(&tg, g, G, D, KBN / 2));
@@ -375,8 +420,23 @@ int vpr_knn_topk(const void* q, const void* g, int64_t Q, int64_t G, int D, int 
     }
     long long total = (long long)a.tiles_m * a.chunks;
     const int pairs = num_sms() / 2;
+    // one wave = q_group x chunks pairs: then the members of a chunk group run at the same time and can be paced
+    long long launch_pairs = (long long)a.q_group * a.chunks;
+    if (launch_pairs > pairs || launch_pairs > total) launch_pairs = total < pairs ? total : pairs;
+    {
+        static int thr_env = -2;                   // VPR_KNN_THROTTLE: k-blocks between lock-step points, 0 = off
+        if (thr_env == -2) { const char* e = getenv("VPR_KNN_THROTTLE"); thr_env = e ? atoi(e) : -1; }
+        // measured (B200, Q = 8192, G = 1.25 M, D = 8448, 132 k-blocks per gallery tile): lock-step points every
+        // 11 / 22 / 44 / 66 / 132 / 264 k-blocks -> 841 / 976 / 1097 / 1135 / 1186 / 1184 TFLOP/s; no pacing 991.
+        // Once per gallery tile is enough to keep the group's pairs within L2 reach and cheap enough not to drain the ring.
+        int per_tile = a.kb_total >= 64 ? a.kb_total : ((64 + a.kb_total - 1) / a.kb_total) * a.kb_total;
+        int thr = thr_env >= 0 ? thr_env : per_tile;
+        a.throttle = (launch_pairs == (long long)a.q_group * a.chunks && a.q_group > 1) ? thr : 0;
+    }
+    if (a.throttle > 0)
+        VPR_CUDA_OK(cudaMemsetAsync(a.sync, 0, (size_t)(a.tiles_m + 1) * a.chunks * 8 * sizeof(int), stream));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(2 * (total < pairs ? total : pairs)));
+    cfg.gridDim = dim3((unsigned)(2 * launch_pairs));
     cfg.blockDim = dim3(K_THREADS);
     cfg.dynamicSmemBytes = K_SMEM_BYTES;
     cfg.stream = stream;
