@@ -315,7 +315,10 @@ class GraphedFinetuneStep:
         #             GEMM, 64 CTAs do the whole buffer in 48 us.
         mode = os.environ.get("VPR_DP_PLACEMENT") or ("overlap" if (pc is not None and pc.mc_ptr and self.world >= 4) else "end")
         self.comm_placement = mode if pc is not None else ("nccl-overlap" if self.world > 1 else "none")
-        heads_ctas = int(os.environ.get("VPR_COMM_CTAS_HEADS", heads_ctas or 8))
+        # CTAs of the overlapped heads exchange: at 8 ranks the switch is the limit and 8 CTAs are as fast as 64; at 4
+        # ranks each rank pulls and broadcasts twice the bytes through its SMs (measured N=4: 474 us/step with 8 CTAs,
+        # 438 with 16)
+        heads_ctas = int(os.environ.get("VPR_COMM_CTAS_HEADS", heads_ctas or (8 if self.world >= 8 else 16)))
         salad_ctas = int(os.environ.get("VPR_COMM_CTAS_SALAD", salad_ctas or 64))
         if pc is not None and mode == "end" and self.world == 2 and os.environ.get("VPR_COMM_MULTIMEM") is None:
             pc.use_multimem(False)
@@ -340,7 +343,11 @@ class GraphedFinetuneStep:
                     pc.allreduce_(off, cnt, ctas=overlap_ctas)
                 return _Join()
 
-            salad.set_grad_ready_hook(start_all, overlap_ctas if input_grads else 0, heads_ctas if mode == "overlap" else 0)
+            # SMs the fused dH pass leaves free in "overlap" mode: the exchange's CTAs plus the 8 CTAs of the token-MLP
+            # gradient GEMM that vpr_salad_bwd forks beside it (measured: that launch otherwise takes exactly the SMs
+            # meant for the exchange, which then starts 25 us late and runs into the dW0 GEMM)
+            salad.set_grad_ready_hook(start_all, overlap_ctas if input_grads else 0,
+                                      heads_ctas + 8 if mode == "overlap" else 0)
         elif self.world > 1 and salad._grad_hook is None:
             overlap_grad_allreduce(salad, group)
         self.x = torch.zeros(batch, n_tokens, salad.num_channels, dtype=dtype, device=dev)
@@ -384,6 +391,8 @@ class GraphedFinetuneStep:
             main.wait_stream(wgrad_stream)                      # join
             return desc, losses, latlon_pred, sincos_pred, hgrads, sgrads, dx, dt
 
+        # (a high-priority stream was tried for this branch: the exchange then lands on its SMs while the Sinkhorn
+        # backward is still placing CTAs and costs that launch a second wave: 25 -> 56 us at N=4)
         wgrad_stream = torch.cuda.Stream(dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
