@@ -376,10 +376,23 @@ def run_own(args, rank, local, world):
     x_d, t_d, w_d = x_h.to(dev), t_h.to(dev), w_h.to(dev)
     params = list(head.parameters())
 
-    if world > 1 and not args.no_overlap:
-        # the head all-reduces its flat gradient buffer from inside backward, overlapped with the dX GEMM
-        vpr_b200.overlap_grad_allreduce(head, reserve_sms=args.reserve_sms)
-    graphed = None if args.eager else vpr_b200.GraphedSaladStep(head, B, n)
+    comm_kind = "none"
+    graphed = None
+    if world > 1 and not args.no_overlap and not args.eager and args.comm == "peer":
+        # the library's own all-reduce over NVLink peer memory, on a forked stream beside the dX GEMM
+        try:
+            graphed = vpr_b200.GraphedSaladStep(head, B, n, comm="peer")
+            comm_kind = graphed.comm_kind
+        except Exception as e:                                  # noqa: BLE001  (no peer mapping: NCCL below)
+            sys.stderr.write(f"peer all-reduce unavailable ({type(e).__name__}: {e}); using NCCL\n")
+            head.set_grad_ready_hook(None)
+            graphed = None
+    if graphed is None:
+        if world > 1 and not args.no_overlap:
+            # the head all-reduces its flat gradient buffer from inside backward, overlapped with the dX GEMM
+            vpr_b200.overlap_grad_allreduce(head, reserve_sms=args.reserve_sms)
+            comm_kind = "nccl"
+        graphed = None if args.eager else vpr_b200.GraphedSaladStep(head, B, n)
 
     def fwd_bwd(x_tok, t, w):
         """One step through the public API.  Default: vpr_b200.GraphedSaladStep (fwd+bwd of SaladHead captured in
@@ -690,7 +703,7 @@ def run_own(args, rank, local, world):
                                f"g=256, 3 Sinkhorn iters, dropout 0.3 (train mode), batch {B} per GPU, "
                                + ("SaladHead + torch autograd (eager)" if graphed is None else
                                   "fwd+bwd replayed from one CUDA graph (vpr_b200.GraphedSaladStep)")
-                               + (", + NCCL allreduce of 1,411,009 head grads" + ("" if args.no_overlap else " overlapped with the dX GEMM")
+                               + (f", + all-reduce of 1,411,009 head grads ({comm_kind})" + ("" if args.no_overlap else " overlapped with the dX GEMM")
                                   if world > 1 else ""),
                    "per_gpu_batch": B, "global_batch": B * world, "n": n,
                    "l2": "working set per step (X 100 MB + H 134 MB + dH 134 MB ...) exceeds the 126 MB L2; "
@@ -738,6 +751,8 @@ def main():
     ap.add_argument("--eager", action="store_true", help="SaladHead + autograd per step instead of the CUDA-graph step")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: all-reduce after backward instead of inside it")
     ap.add_argument("--reserve-sms", type=int, default=32, help="N>1: SMs the dX GEMM leaves to the collective")
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
+                    help="N>1 headline step: own all-reduce kernel over NVLink peer memory, or NCCL")
     ap.add_argument("--no-knn", action="store_true", help="skip the kNN leg")
     ap.add_argument("--knn-queries", type=int, default=65536)
     ap.add_argument("--no-strong", action="store_true", help="skip the fixed-global-batch fine-tuning leg")

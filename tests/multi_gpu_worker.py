@@ -170,6 +170,22 @@ def main():
                           "param_grad_rel_err": e[0].item(), "dx_rel_err": e[1].item(), "ok": good}), flush=True)
     ok = ok and good
     salad.set_grad_ready_hook(None)
+    # the same step with the library's own all-reduce kernel (gradient buffer in the symmetric allocation)
+    pstep = vpr_b200.GraphedSaladStep(salad, batch=Bl, n_tokens=n, comm="peer")
+    for rep in range(3):
+        out, dx, dt = pstep(xs, ts, ds)
+    torch.cuda.synchronize()
+    got_g = torch.cat([p.grad.flatten().float() for p in salad.parameters()])
+    e = torch.tensor([rel(got_g, want_g), rel(dx, want_dx)], device=dev)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    good = e[0].item() < 1e-5 and e[1].item() < 1e-5
+    if rank == 0:
+        print(json.dumps({"check": "GraphedSaladStep + own peer-memory all-reduce == all-reduce of eager local gradients",
+                          "world": world, "comm": pstep.comm_kind, "param_grad_rel_err": e[0].item(),
+                          "dx_rel_err": e[1].item(), "ok": good}), flush=True)
+    ok = ok and good
+    salad.set_grad_ready_hook(None)
+    del pstep
 
     # ---------------- configs[2] as one graph: SALAD + heads + losses with both all-reduces captured ----------------
     step = vpr_b200.DataParallelStep(salad, heads)

@@ -245,7 +245,13 @@ class GraphedSaladStep:
     Dropout masks still differ from call to call (SaladHead.use_device_step_counter)."""
 
     def __init__(self, head: "SaladHead", batch: int, n_tokens: int, dtype=torch.bfloat16, input_grads: bool = True,
-                 warmup: int = 3, capture_error_mode: str = "thread_local"):
+                 warmup: int = 3, capture_error_mode: str = "thread_local", comm: str | None = None, group=None,
+                 comm_ctas: int = 16):
+        """``comm="peer"`` (under torchrun): the parameter gradients are summed over the ranks of ``group`` by the
+        library's own all-reduce kernel over NVLink peer memory (``comm.PeerComm``) from inside the step -- the flat
+        gradient buffer lives in the symmetric allocation and the exchange runs on a forked stream beside the
+        input-gradient GEMM, which is launched ``comm_ctas`` CTAs short.  Default: whatever hook the head carries
+        (``parallel.overlap_grad_allreduce`` installs the NCCL one)."""
         dev = head.dust_bin.device
         if dev.type != "cuda":
             raise RuntimeError("GraphedSaladStep needs the head on a CUDA device")
@@ -256,6 +262,32 @@ class GraphedSaladStep:
         self.t = torch.zeros(batch, head.num_channels, dtype=dtype, device=dev)
         self.d_out = torch.zeros(batch, head.out_dim, dtype=dtype, device=dev)
         lib = L.lib()
+        self._flat = None
+        self.comm_kind = "hook" if head._grad_hook is not None else "none"
+        if comm == "peer":
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size(group) > 1:
+                from .comm import PeerComm
+                pc = PeerComm(sum(p.numel() for p in head._param_list()), group=group, device=dev)
+                comm_stream = torch.cuda.Stream(dev)
+                self._comm, self._flat = pc, pc.data
+                self.comm_kind = "peer/" + pc.backend + ("+multimem" if pc.mc_ptr else "")
+                full = L.COMM_MAX_CTAS if not self.input_grads else int(comm_ctas)
+
+                class _Join:
+                    def wait(self_inner):
+                        torch.cuda.current_stream(dev).wait_stream(comm_stream)
+
+                def start(flat):
+                    if not self.input_grads:                    # nothing left to hide behind: the whole machine
+                        pc.allreduce_(0, pc.numel, ctas=min(full, 64))
+                        return None
+                    comm_stream.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(comm_stream):
+                        pc.allreduce_(0, pc.numel, ctas=full)
+                    return _Join()
+
+                head.set_grad_ready_hook(start, int(comm_ctas) if self.input_grads else 0, 0)
         # The captured step calls the library directly (no autograd engine inside the capture): the engine keys the
         # stream of every parameter's gradient-accumulation node to the stream that was current when that node was
         # first created, so an eager graph the caller still holds would drag the default stream into the capture.
@@ -286,7 +318,7 @@ class GraphedSaladStep:
         x_tok, t, shape, p_drop, seed, seed_dev, params = head._prepare((self.x, self.t))
         out, save = _salad_forward(x_tok, t, shape, p_drop, seed, seed_dev, params)
         dx, dt, flat, grads = _salad_backward(x_tok, t, save, params, shape, p_drop, self.d_out, self.input_grads,
-                                              self.input_grads, head._grad_hook)
+                                              self.input_grads, head._grad_hook, flat=self._flat)
         return out, dx, dt, flat, grads
 
     def __call__(self, x_tok=None, t=None, d_out=None):
