@@ -368,6 +368,39 @@ def test_graphed_finetune_step_matches_eager_data_parallel_step(vpr):
     assert step.dx is None and step.launches_per_replay >= 12
 
 
+def test_graphed_finetune_step_with_huber_and_both_dropouts_redraws_masks(vpr):
+    """dinov2salad_finetuning_2.py's head (Huber + Dropout(0.3) in the regressor) and dino_v2_gemini.py's Dropout(0.1)
+    in front of the angle head inside the one-graph step: the masks come from device-side counters, so every replay
+    draws fresh ones; with the modules in eval mode the replays are deterministic and equal the eager step."""
+    torch.manual_seed(0)
+    salad = vpr.SaladHead(dropout=0.0).cuda().eval()
+    heads = vpr.GeoposeHeads(dropout=0.3, latlon_loss="huber", angle_loss="atan2_maae", head_dropout=0.1).cuda().train()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, n = 8, 256
+    x = torch.randn(B, n, 768, device="cuda", generator=g).bfloat16()
+    t = torch.randn(B, 768, device="cuda", generator=g).bfloat16()
+    ll = torch.randn(B, 2, device="cuda", generator=g)
+    ang = torch.rand(B, device="cuda", generator=g) * 360
+    step = vpr.GraphedFinetuneStep(salad, heads, batch=B, n_tokens=n)
+    vals, g0 = [], []
+    for _ in range(3):
+        total, losses = step(x, t, ll, ang)
+        vals.append(total.item())
+        g0.append(heads.regressor[0].weight.grad.clone())
+        assert abs(losses[0].item() + losses[1].item() - losses[2].item()) < 1e-4 * abs(losses[2].item())
+    assert len(set(vals)) == 3 and rel(g0[0], g0[1]) > 1e-2          # a different mask every replay
+    assert all(torch.isfinite(p.grad).all() for p in heads.parameters())
+    heads.eval()
+    step_e = vpr.GraphedFinetuneStep(salad, heads, batch=B, n_tokens=n)
+    a, _ = step_e(x, t, ll, ang)
+    a = a.item()
+    b, _ = step_e(x, t, ll, ang)
+    assert abs(a - b.item()) <= 1e-5 * abs(a)
+    eager = vpr.DataParallelStep(salad, heads)
+    te, _ = eager.step(x, t, ll, ang)
+    assert abs(te.item() - a) <= 1e-4 * abs(a)
+
+
 @pytest.mark.parametrize("env", [{"VPR_DH_FUSED": "0", "VPR_FS_FUSED": "0", "VPR_AGG_FUSED": "0"},
                                  {"VPR_GEMM_2CTA": "0"}, {"VPR_GEMM_MCB": "1", "VPR_FS_REVERSE": "0"}])
 def test_generic_paths_still_match_when_the_fused_kernels_are_switched_off(vpr, env):
