@@ -18,7 +18,7 @@
 // shares -- dW0 79 -> 141 us at N=2 -- which costs far more than giving up 8 of 148 SMs.)
 // Synchronisation is per CTA index: CTA c of every rank owns slice c of every region, so a flag from peer q's CTA c
 // covers exactly the data CTA c consumes.  Flags carry a call counter kept in device memory (the launch arguments of a
-// captured graph never change), never need resetting, and every wait is bounded (trap instead of a hung box).
+// captured graph never change), never need resetting, and every wait is bounded (trap after ~20 s instead of a hung box).
 #include "common.cuh"
 #include "../../include/vpr_b200.h"
 
@@ -87,7 +87,7 @@ __device__ __forceinline__ void comm_barrier(const CommArgs& a, int phase, int c
             if (++spins == 256) t0 = clock64();
             if (spins > 256) {
                 __nanosleep(64);
-                if ((spins & 1023) == 0 && clock64() - t0 > 6000000000LL) __trap();      // ~3 s: a peer is gone
+                if ((spins & 1023) == 0 && clock64() - t0 > 40000000000LL) __trap();     // ~20 s: a peer is gone
             }
         }
     }
