@@ -166,6 +166,8 @@ VPR_API int vpr_sinkhorn_bwd(const float* S, const float* dust_bin, const float*
 #define VPR_HEADS_PREPACKED 2    /* flags: vpr_heads_pack already filled this workspace from the current weights */
 #define VPR_HEADS_SKIP_WGRAD 4   /* flags: everything except the two launches nothing downstream of d_desc waits for
                                     (the regressor.0.weight gradient GEMM and the angle head's weight gradient) ... */
+#define VPR_HEADS_PREZEROED 16   /* flags: vpr_heads_zero already cleared this call's accumulators (workspace, losses,
+                                    gradient buffers), e.g. on a side stream during the SALAD forward */
 #define VPR_HEADS_WGRAD_ONLY 8   /* ... which a second call with the same arguments and workspace then issues, e.g. on
                                     another stream after an event, so that they run beside the SALAD backward */
 
@@ -204,6 +206,10 @@ VPR_API size_t vpr_heads_workspace_bytes(const VprHeadsShape* s, int dtype);
  * stream next to the SALAD forward), calls it explicitly. */
 VPR_API int vpr_heads_pack(const VprHeadsParams* p, void* workspace, size_t workspace_bytes, const VprHeadsShape* s,
                    int dtype, cudaStream_t stream);
+/* The memsets vpr_heads_loss_fwd_bwd starts with (split-K accumulator in the workspace, the three losses, the gradient
+ * buffers that are reduced into with atomics), for callers that take them off the critical path (VPR_HEADS_PREZEROED). */
+VPR_API int vpr_heads_zero(float* losses, const VprHeadsGrads* grads, void* workspace, size_t workspace_bytes,
+                   const VprHeadsShape* s, int dtype, cudaStream_t stream);
 /* desc: [B, D] (`dtype`); latlon_target: [B,2] fp32 (z-scored); angle_target_deg: [B] fp32.
  * Outputs: latlon_pred [B,2] fp32, sincos_pred [B,2] fp32, losses [3] fp32 (lat/lon, angle, their sum),
  * grads (overwritten; NULL with VPR_HEADS_FORWARD_ONLY), d_desc [B, D] (`dtype`) or NULL. */

@@ -17,7 +17,7 @@ BWD_ALL, BWD_PARAMS, BWD_INPUTS = 0, 1, 2
 OUT_F32, OUT_BF16, OUT_ATOMIC_F32 = 0, 1, 2
 LATLON_MSE, LATLON_HUBER, LATLON_EXTERNAL = 0, 1, 2
 ANGLE_NONE, ANGLE_ATAN2_MAAE, ANGLE_ACOS, ANGLE_MSE, ANGLE_SCALAR_MAAE = 0, 1, 2, 3, 4
-HEADS_FORWARD_ONLY, HEADS_PREPACKED, HEADS_SKIP_WGRAD, HEADS_WGRAD_ONLY = 1, 2, 4, 8
+HEADS_FORWARD_ONLY, HEADS_PREPACKED, HEADS_SKIP_WGRAD, HEADS_WGRAD_ONLY, HEADS_PREZEROED = 1, 2, 4, 8, 16
 HEAD_DROP_SEED_OFFSET = 0x9E3779B97F4A7C15      # the angle head's input dropout draws from seed + this
 ABI_VERSION = 5
 
@@ -80,6 +80,7 @@ EXPORTS = {
                                    C.c_int, _fp]),
     "vpr_heads_workspace_bytes": (C.c_size_t, [C.POINTER(HeadsShape), C.c_int]),
     "vpr_heads_pack": (C.c_int, [C.POINTER(HeadsParams), _fp, C.c_size_t, C.POINTER(HeadsShape), C.c_int, _fp]),
+    "vpr_heads_zero": (C.c_int, [_fp, C.POINTER(HeadsGrads), _fp, C.c_size_t, C.POINTER(HeadsShape), C.c_int, _fp]),
     "vpr_heads_loss_fwd_bwd": (C.c_int, [C.POINTER(HeadsParams), _fp, _fp, _fp, _fp, _fp, _fp,
                                          C.POINTER(HeadsGrads), _fp, _fp, C.c_size_t, C.POINTER(HeadsShape),
                                          C.c_int, _fp]),

@@ -395,6 +395,8 @@ __global__ void __launch_bounds__(256) angle_bwd_kernel(const T* __restrict__ de
     }
 }
 
+static int angle_rows(int angle_loss) { return angle_loss == VPR_ANGLE_NONE ? 0 : angle_loss == VPR_ANGLE_SCALAR_MAAE ? 1 : 2; }
+
 struct HeadsPlan { size_t waug, zacc, sc_raw, dzaug, total; int hid_pad; };
 
 static HeadsPlan heads_plan(const VprHeadsShape& s, int dtype) {
@@ -409,8 +411,6 @@ static HeadsPlan heads_plan(const VprHeadsShape& s, int dtype) {
     p.total = (off + 255) & ~size_t(255);
     return p;
 }
-
-static int angle_rows(int angle_loss) { return angle_loss == VPR_ANGLE_NONE ? 0 : angle_loss == VPR_ANGLE_SCALAR_MAAE ? 1 : 2; }
 
 template <typename T>
 static int heads_pack_t(const VprHeadsParams& p, char* ws, const VprHeadsShape& s, int dtype, cudaStream_t st) {
@@ -428,6 +428,38 @@ static int heads_pack_t(const VprHeadsParams& p, char* ws, const VprHeadsShape& 
     if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
     pack_heads_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(a);
     return launch_ok("pack_heads_kernel");
+}
+
+// zero every accumulator of one call: zacc (workspace), the three losses and the gradient buffers that are reduced
+// into with atomics; ranges that touch are merged into one memset
+static int heads_zero(float* losses, const VprHeadsGrads& gr, float* zacc, const VprHeadsShape& s, const HeadsPlan& hp,
+                      bool fwd_only, cudaStream_t st) {
+    const int n_ang = angle_rows(s.angle_loss);
+    const bool angle = n_ang > 0;
+    struct Rng { void* p; size_t n; };
+    Rng r[8];
+    int cnt = 0;
+    r[cnt++] = {zacc, (size_t)s.B * hp.hid_pad * 4};
+    r[cnt++] = {losses, 3 * sizeof(float)};
+    if (!fwd_only) {
+        r[cnt++] = {gr.reg_b0, sizeof(float) * s.hidden};
+        r[cnt++] = {gr.reg_w1, sizeof(float) * 2 * s.hidden};
+        r[cnt++] = {gr.reg_b1, sizeof(float) * 2};
+        if (gr.ang_w) r[cnt++] = {gr.ang_w, sizeof(float) * (angle ? n_ang : 2) * s.D};
+        if (gr.ang_b) r[cnt++] = {gr.ang_b, sizeof(float) * (angle ? n_ang : 2)};
+    }
+    for (int i = 1; i < cnt; ++i)
+        for (int j = i; j > 0 && (char*)r[j].p < (char*)r[j - 1].p; --j) { Rng t = r[j]; r[j] = r[j - 1]; r[j - 1] = t; }
+    int i = 0;
+    while (i < cnt) {
+        char* p0 = (char*)r[i].p;
+        size_t nb = r[i].n;
+        int j = i + 1;
+        while (j < cnt && (char*)r[j].p == p0 + nb) { nb += r[j].n; ++j; }
+        VPR_CUDA_OK(cudaMemsetAsync(p0, 0, nb, st));
+        i = j;
+    }
+    return 0;
 }
 
 template <typename T>
@@ -474,34 +506,9 @@ static int heads_t(const VprHeadsParams& p, const T* desc, const float* latlon_t
     };
     if (wgrad_only) return wgrad(false);
 
-    // accumulators -> 0 first (adjacent buffers in one memset), so that the kernels below form an uninterrupted chain
-    // of programmatic dependent launches
-    {
-        struct Rng { void* p; size_t n; };
-        Rng r[8];
-        int cnt = 0;
-        r[cnt++] = {zacc, (size_t)s.B * hp.hid_pad * 4};
-        r[cnt++] = {losses, 3 * sizeof(float)};
-        if (!fwd_only) {
-            r[cnt++] = {gr.reg_b0, sizeof(float) * s.hidden};
-            r[cnt++] = {gr.reg_w1, sizeof(float) * 2 * s.hidden};
-            r[cnt++] = {gr.reg_b1, sizeof(float) * 2};
-            if (gr.ang_w) r[cnt++] = {gr.ang_w, sizeof(float) * (angle ? n_ang : 2) * s.D};
-            if (gr.ang_b) r[cnt++] = {gr.ang_b, sizeof(float) * (angle ? n_ang : 2)};
-        }
-        // merge ranges that touch (in any order of appearance): sort by address first
-        for (int i = 1; i < cnt; ++i)
-            for (int j = i; j > 0 && (char*)r[j].p < (char*)r[j - 1].p; --j) { Rng t = r[j]; r[j] = r[j - 1]; r[j - 1] = t; }
-        int i = 0;
-        while (i < cnt) {
-            char* p0 = (char*)r[i].p;
-            size_t nb = r[i].n;
-            int j = i + 1;
-            while (j < cnt && (char*)r[j].p == p0 + nb) { nb += r[j].n; ++j; }
-            VPR_CUDA_OK(cudaMemsetAsync(p0, 0, nb, st));
-            i = j;
-        }
-    }
+    // accumulators -> 0 first, so that the kernels below form an uninterrupted chain of programmatic dependent
+    // launches (or, with VPR_HEADS_PREZEROED, already done by the caller off the critical path: vpr_heads_zero)
+    if (!(s.flags & VPR_HEADS_PREZEROED)) VPR_TRY(heads_zero(losses, gr, zacc, s, hp, fwd_only, st));
     if (!(s.flags & VPR_HEADS_PREPACKED)) VPR_TRY(heads_pack_t<T>(p, ws, s, dtype, st));
 
     // zacc = desc W_aug^T   (split-K: only ceil(B/128) * ceil(N/256) output tiles exist)
@@ -591,6 +598,19 @@ int vpr_heads_pack(const VprHeadsParams* p, void* workspace, size_t workspace_by
     VPR_REQUIRE(workspace_bytes >= heads_plan(*s, dtype).total, "workspace too small");
     if (dtype == VPR_BF16) return heads_pack_t<bf16>(*p, (char*)workspace, *s, dtype, stream);
     return heads_pack_t<float>(*p, (char*)workspace, *s, dtype, stream);
+}
+
+int vpr_heads_zero(float* losses, const VprHeadsGrads* grads, void* workspace, size_t workspace_bytes, const VprHeadsShape* s,
+                   int dtype, cudaStream_t stream) {
+    VPR_REQUIRE(losses && workspace && s, "null argument");
+    VPR_TRY(check_device());
+    VPR_TRY(check_heads_shape(s, dtype));
+    const bool fwd_only = (s->flags & VPR_HEADS_FORWARD_ONLY) != 0;
+    VPR_REQUIRE(fwd_only || (grads && grads->reg_b0 && grads->reg_w1 && grads->reg_b1), "gradient buffers are null");
+    const HeadsPlan hp = heads_plan(*s, dtype);
+    VPR_REQUIRE(workspace_bytes >= hp.total, "workspace too small");
+    VprHeadsGrads none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    return heads_zero(losses, grads ? *grads : none, (float*)((char*)workspace + hp.zacc), *s, hp, fwd_only, stream);
 }
 
 int vpr_heads_loss_fwd_bwd(const VprHeadsParams* p, const void* desc, const float* latlon_target,

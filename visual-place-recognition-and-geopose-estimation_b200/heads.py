@@ -54,6 +54,75 @@ def pack_weights(params, ws, B, D, cfg, dtype) -> None:
                                        L.stream_ptr(ws.device)), "vpr_heads_pack")
 
 
+class _HeadsCall:
+    """Buffers and argument structs of ONE vpr_heads_loss_fwd_bwd call.  Split from the launch so that the part that
+    does not depend on the descriptor -- clearing the call's accumulators -- can be issued ahead of time on another
+    stream (``zero()``, then ``run(..., prezeroed=True)``)."""
+
+    def __init__(self, B, D, dtype, dev, params, cfg, want_d_desc, ws=None, forward_only=False, flat=None):
+        lib = L.lib()
+        self.B, self.D, self.cfg, self.dev, self.forward_only = B, D, cfg, dev, forward_only
+        self.dt = L.dtype_code(dtype)
+        shape = _shape(B, D, cfg, 0)
+        ws_bytes = lib.vpr_heads_workspace_bytes(C.byref(shape), self.dt)
+        if ws is None:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        elif ws.numel() < ws_bytes or ws.device != dev:
+            raise RuntimeError("heads workspace too small or on another device")
+        self.ws = ws
+        self.ps = L.HeadsParams(*[p.data_ptr() if p is not None else None for p in params])
+        self._params = params                       # keep the (possibly .contiguous()) tensors alive
+        self.latlon_pred = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        self.sincos_pred = (torch.empty if cfg["angle"] != L.ANGLE_NONE else torch.zeros)(B, 2, dtype=torch.float32, device=dev)
+        if forward_only:
+            self.flat = torch.empty(3, dtype=torch.float32, device=dev)
+            self.losses, self.grads, self.gs, self.d_desc = self.flat, [None] * len(params), None, None
+        else:
+            sizes = [p.numel() if p is not None else 0 for p in params]      # the angle head may be absent (None, None)
+            if flat is None:
+                flat = torch.empty(sum(sizes) + 3, dtype=torch.float32, device=dev)
+            elif flat.numel() < sum(sizes) + 3 or flat.dtype != torch.float32 or flat.device != dev:
+                raise RuntimeError("flat gradient buffer must be an fp32 tensor on the descriptor's device")
+            self.flat = flat
+            *grads, self.losses = torch.split(flat[: sum(sizes) + 3], sizes + [3])
+            self.gs = L.HeadsGrads(*[g.data_ptr() if p is not None else None for g, p in zip(grads, params)])
+            self.grads = [g.view_as(p) if p is not None else None for g, p in zip(grads, params)]
+            self.d_desc = torch.empty(B, D, dtype=dtype, device=dev) if want_d_desc else None
+
+    def _flags(self, extra=0):
+        return (L.HEADS_FORWARD_ONLY if self.forward_only else 0) | extra
+
+    def zero(self):
+        """vpr_heads_zero on the current stream."""
+        shape = _shape(self.B, self.D, self.cfg, self._flags())
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().vpr_heads_zero(L.ptr(self.losses), C.byref(self.gs) if self.gs is not None else None,
+                                           L.ptr(self.ws), self.ws.numel(), C.byref(shape), self.dt,
+                                           L.stream_ptr(self.dev)), "vpr_heads_zero")
+
+    def _call(self, desc, latlon_target, angle_target, flags):
+        shape = _shape(self.B, self.D, self.cfg, flags)
+        with L.on_device(desc):
+            L.check(L.lib().vpr_heads_loss_fwd_bwd(
+                C.byref(self.ps), L.ptr(desc), L.ptr(latlon_target), L.ptr(angle_target), L.ptr(self.latlon_pred),
+                L.ptr(self.sincos_pred), L.ptr(self.losses), C.byref(self.gs) if self.gs is not None else None,
+                L.ptr(self.d_desc), L.ptr(self.ws), self.ws.numel(), C.byref(shape), self.dt, L.stream_ptr(self.dev)),
+                "vpr_heads_loss_fwd_bwd")
+
+    def run(self, desc, latlon_target, angle_target, prepacked=False, defer_wgrad=False, prezeroed=False):
+        cfg = self.cfg
+        base = self._flags((L.HEADS_PREPACKED if prepacked else 0) | (L.HEADS_PREZEROED if prezeroed else 0))
+        self._call(desc, latlon_target, angle_target, base | (L.HEADS_SKIP_WGRAD if defer_wgrad else 0))
+        seed_dev = cfg.get("seed_dev")
+        if seed_dev is not None and not self.forward_only and (cfg["reg_dropout_p"] > 0 or cfg["head_dropout_p"] > 0):
+            with L.on_device(desc):
+                L.check(L.lib().vpr_counter_advance(L.ptr(seed_dev), L.stream_ptr(self.dev)), "vpr_counter_advance")
+        out = (self.latlon_pred, self.sincos_pred, self.losses, self.grads, self.d_desc, self.flat)
+        if defer_wgrad:
+            return out + ((lambda: self._call(desc, latlon_target, angle_target, self._flags(L.HEADS_WGRAD_ONLY))),)
+        return out
+
+
 def _run(desc, params, latlon_target, angle_target, cfg, want_d_desc, ws=None, forward_only=False, prepacked=False,
          defer_wgrad=False, flat=None):
     """One vpr_heads_loss_fwd_bwd call.  Returns (latlon_pred, sincos_pred, losses, grads, d_desc, flat): ``losses`` =
@@ -62,51 +131,9 @@ def _run(desc, params, latlon_target, angle_target, cfg, want_d_desc, ws=None, f
     ``defer_wgrad``: leave out the two weight-gradient launches nothing downstream of ``d_desc`` waits for and return a
     seventh value, a callable that issues them on whatever stream is current when it is called (the caller orders
     that stream after this call and joins it before reading ``regressor.0.weight.grad`` / ``head.weight.grad``)."""
-    lib = L.lib()
     B, D = desc.shape
-    dt = L.dtype_code(desc.dtype)
-    dev = desc.device
-    flags = (L.HEADS_FORWARD_ONLY if forward_only else 0) | (L.HEADS_PREPACKED if prepacked else 0)
-    shape = _shape(B, D, cfg, flags | (L.HEADS_SKIP_WGRAD if defer_wgrad else 0))
-    ws_bytes = lib.vpr_heads_workspace_bytes(C.byref(shape), dt)
-    if ws is None:
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    elif ws.numel() < ws_bytes or ws.device != dev:
-        raise RuntimeError("heads workspace too small or on another device")
-    ps = L.HeadsParams(*[p.data_ptr() if p is not None else None for p in params])
-    latlon_pred = torch.empty(B, 2, dtype=torch.float32, device=dev)
-    sincos_pred = (torch.empty if cfg["angle"] != L.ANGLE_NONE else torch.zeros)(B, 2, dtype=torch.float32, device=dev)
-    if forward_only:
-        flat = torch.empty(3, dtype=torch.float32, device=dev)
-        losses, grads, gs_ref, d_desc = flat, [None] * len(params), None, None
-    else:
-        sizes = [p.numel() if p is not None else 0 for p in params]      # the angle head may be absent (None, None)
-        if flat is None:
-            flat = torch.empty(sum(sizes) + 3, dtype=torch.float32, device=dev)
-        elif flat.numel() < sum(sizes) + 3 or flat.dtype != torch.float32 or flat.device != dev:
-            raise RuntimeError("flat gradient buffer must be an fp32 tensor on the descriptor's device")
-        *grads, losses = torch.split(flat[: sum(sizes) + 3], sizes + [3])
-        gs = L.HeadsGrads(*[g.data_ptr() if p is not None else None for g, p in zip(grads, params)])
-        gs_ref = C.byref(gs)
-        grads = [g.view_as(p) if p is not None else None for g, p in zip(grads, params)]
-        d_desc = torch.empty_like(desc) if want_d_desc else None
-
-    def call(shape_):
-        with L.on_device(desc):
-            L.check(lib.vpr_heads_loss_fwd_bwd(C.byref(ps), L.ptr(desc), L.ptr(latlon_target), L.ptr(angle_target),
-                                               L.ptr(latlon_pred), L.ptr(sincos_pred), L.ptr(losses), gs_ref,
-                                               L.ptr(d_desc), L.ptr(ws), ws.numel(), C.byref(shape_), dt,
-                                               L.stream_ptr(dev)), "vpr_heads_loss_fwd_bwd")
-
-    call(shape)
-    seed_dev = cfg.get("seed_dev")
-    if seed_dev is not None and not forward_only and (cfg["reg_dropout_p"] > 0 or cfg["head_dropout_p"] > 0):
-        with L.on_device(desc):
-            L.check(lib.vpr_counter_advance(L.ptr(seed_dev), L.stream_ptr(dev)), "vpr_counter_advance")
-    out = (latlon_pred, sincos_pred, losses, grads, d_desc, flat)
-    if defer_wgrad:
-        return out + ((lambda: call(_shape(B, D, cfg, L.HEADS_WGRAD_ONLY))),)
-    return out
+    call = _HeadsCall(B, D, desc.dtype, desc.device, params, cfg, want_d_desc, ws=ws, forward_only=forward_only, flat=flat)
+    return call.run(desc, latlon_target, angle_target, prepacked=prepacked, defer_wgrad=defer_wgrad)
 
 
 class _HeadsLossFn(torch.autograd.Function):

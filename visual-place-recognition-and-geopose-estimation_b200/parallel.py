@@ -269,7 +269,7 @@ class GraphedFinetuneStep:
         ``comm.PeerComm``; gradient buffers live in the symmetric allocation), "nccl" (``torch.distributed``), or None =
         "peer" when the peer mappings can be set up, else "nccl" (env ``VPR_DP_COMM`` overrides)."""
         from . import _lib as L
-        from .heads import _run as heads_run, pack_weights, workspace_bytes
+        from .heads import _HeadsCall, pack_weights, workspace_bytes
         from .salad import _salad_backward, _salad_forward
         dev = salad.dust_bin.device
         if dev.type != "cuda":
@@ -364,15 +364,17 @@ class GraphedFinetuneStep:
             hparams = [p.contiguous() for p in heads._params()]
             cfg = heads._cfg(global_B=self.global_batch)
             main = torch.cuda.current_stream(dev)
-            pack_stream.wait_stream(main)                       # fork: weight cast beside the SALAD forward
-            with torch.cuda.stream(pack_stream):
+            hcall = _HeadsCall(batch, salad.out_dim, dtype, dev, hparams, cfg, True, ws=hws,
+                               flat=pc.data[:n_h4] if pc is not None else None)
+            pack_stream.wait_stream(main)                       # fork: weight cast and accumulator memsets beside the
+            with torch.cuda.stream(pack_stream):                # SALAD forward (neither depends on the descriptor)
                 pack_weights(hparams, hws, batch, salad.out_dim, cfg, dtype)
+                hcall.zero()
             x_tok, t, shape, p_drop, seed, seed_dev, sparams = salad._prepare((self.x, self.t))
             desc, save = _salad_forward(x_tok, t, shape, p_drop, seed, seed_dev, sparams)
             main.wait_stream(pack_stream)                       # join
-            latlon_pred, sincos_pred, losses, hgrads, d_desc, hflat, head_wgrad = heads_run(
-                desc, hparams, self.latlon, self.angle if use_angle else None, cfg, True, ws=hws, prepacked=True,
-                defer_wgrad=True, flat=pc.data[:n_h4] if pc is not None else None)
+            latlon_pred, sincos_pred, losses, hgrads, d_desc, hflat, head_wgrad = hcall.run(
+                desc, self.latlon, self.angle if use_angle else None, prepacked=True, defer_wgrad=True, prezeroed=True)
             # second fork: the heads' two weight-gradient launches and, across ranks, the all-reduce of the whole heads
             # buffer (gradients + losses) run beside the SALAD backward, which only needs d_desc
             wgrad_stream.wait_stream(main)
