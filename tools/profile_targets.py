@@ -28,6 +28,15 @@ def main():
         xt, tt = seam(hidden)
         torch.autograd.backward([xt, tt], [torch.ones_like(xt), torch.ones_like(tt)])
         hidden.grad = None
+    # geopose heads on the descriptor batch (fused forward + backward call), twice
+    heads = vpr_b200.GeoposeHeads(latlon_loss="mse", angle_loss="atan2_maae").cuda().train()
+    desc = out.detach()
+    ll = torch.randn(B, 2, device="cuda")
+    ang = torch.rand(B, device="cuda") * 360
+    for _ in range(2):
+        d = desc.clone().requires_grad_(True)
+        total, *_ = heads(d, ll, ang)
+        total.backward()
     torch.cuda.synchronize()
     print("done")
 
