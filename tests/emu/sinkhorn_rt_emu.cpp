@@ -1,0 +1,41 @@
+// C entry points that run csrc/sinkhorn_rt.cuh on the CPU through tests/emu/simt_emu.h (test infrastructure only).
+#include "simt_emu.h"
+
+#include "../../visual-place-recognition-and-geopose-estimation_b200/csrc/sinkhorn_rt.cuh"
+
+namespace {
+vpr::SinkConst2 consts(int n) {
+    vpr::SinkConst2 k;
+    k.norm2 = (float)(-std::log2((double)(n + 64)));
+    k.log_a_m2 = k.norm2 + (float)std::log2((double)(n - 64));
+    return k;
+}
+}  // namespace
+
+extern "C" {
+// returns the number of images that asked for the log-domain guard path (their outputs are then not written)
+int emu_sinkhorn_fwd_rt(const float* S, const float* dust_bin, void* P, int p_bf16, float* U, float* V, int B, int n, int iters) {
+    simt_emu::guard_count = 0;
+    const vpr::SinkConst2 k = consts(n);
+    const size_t smem = vpr::sinkrt_fwd_floats() * sizeof(float);
+    if (p_bf16)
+        simt_emu::launch(B, vpr::RT_NT, smem, [=]() { vpr::sinkhorn_fwd_rt<__nv_bfloat16>(S, dust_bin, (__nv_bfloat16*)P, U, V, n, iters, k); });
+    else
+        simt_emu::launch(B, vpr::RT_NT, smem, [=]() { vpr::sinkhorn_fwd_rt<float>(S, dust_bin, (float*)P, U, V, n, iters, k); });
+    return simt_emu::guard_count.load();
+}
+int emu_sinkhorn_bwd_rt3(const float* S, const float* dust_bin, const float* U, const float* V, const float* dP, void* dS, int ds_bf16,
+                         float* d_bias, int B, int n) {
+    simt_emu::guard_count = 0;
+    const vpr::SinkConst2 k = consts(n);
+    const size_t smem = vpr::sinkrt_bwd_floats(3) * sizeof(float);
+    if (ds_bf16)
+        simt_emu::launch(B, vpr::RT_NT, smem,
+                         [=]() { vpr::sinkhorn_bwd_rt<__nv_bfloat16, 3>(S, dust_bin, U, V, dP, (__nv_bfloat16*)dS, d_bias, n, k); });
+    else
+        simt_emu::launch(B, vpr::RT_NT, smem, [=]() { vpr::sinkhorn_bwd_rt<float, 3>(S, dust_bin, U, V, dP, (float*)dS, d_bias, n, k); });
+    return simt_emu::guard_count.load();
+}
+size_t emu_sinkrt_fwd_bytes() { return vpr::sinkrt_fwd_floats() * sizeof(float); }
+size_t emu_sinkrt_bwd_bytes(int iters) { return vpr::sinkrt_bwd_floats(iters) * sizeof(float); }
+}

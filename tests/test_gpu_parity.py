@@ -140,6 +140,34 @@ def test_sinkhorn_dustbin_value_is_irrelevant(vpr):
     assert rel(P1, P2) < 1e-5
 
 
+@pytest.mark.parametrize("rt", ["1", "0"])
+@pytest.mark.parametrize("B,n", [(3, 256), (2, 196), (300, 256)])
+def test_sinkhorn_register_tile_and_shared_tile_kernels_agree_with_the_oracle(vpr, monkeypatch, rt, B, n):
+    """n <= 256 runs the register-tile kernels (csrc/sinkhorn_rt.cuh); VPR_SINK_RT=0 keeps the shared-memory-tile
+    kernels (csrc/sinkhorn_scaled.cuh) on those shapes.  Both against the fp64 oracle, fp32 and bf16 outputs, a batch
+    larger than one wave of CTAs, and the bias gradient accumulated across the batch (identically zero in exact
+    arithmetic: a per-cluster score offset is absorbed by u)."""
+    monkeypatch.setenv("VPR_SINK_RT", rt)
+    g = torch.Generator().manual_seed(B * 1000 + n)
+    S = torch.randn(B, 64, n, generator=g) * 2.0
+    db = torch.tensor(0.7)
+    Sd = S.double().requires_grad_(True)
+    Pd = O.get_matching_probs(Sd, db.double(), 3, const_dtype=torch.float64).exp()
+    St = S.transpose(1, 2).contiguous().cuda()
+    P, U, V = vpr.sinkhorn(St, db.cuda(), 3)
+    assert rel(P, Pd[:, :64].transpose(1, 2)) < 1e-5
+    Pb, Ub, Vb = vpr.sinkhorn(St, db.cuda(), 3, out_dtype=torch.bfloat16)
+    assert torch.equal(Pb, P.bfloat16()) and torch.equal(Ub, U) and torch.equal(Vb, V)
+    dP = torch.randn(B, n, 64, generator=g)
+    (Pd[:, :64] * dP.double().transpose(1, 2)).sum().backward()
+    dS, d_bias = vpr.sinkhorn_backward(St, db.cuda(), U, V, dP.cuda(), 3)
+    assert rel(dS, Sd.grad.transpose(1, 2)) < 1e-5
+    if d_bias is not None:
+        assert d_bias.abs().max() < 1e-3
+    dSb, _ = vpr.sinkhorn_backward(St, db.cuda(), U, V, dP.cuda(), 3, out_dtype=torch.bfloat16)
+    assert rel(dSb, dS) < 4e-3
+
+
 # ------------------------------------------------------------------ SALAD head
 def _pair(vpr, dropout=0.0, round_weights=False):
     torch.manual_seed(0)

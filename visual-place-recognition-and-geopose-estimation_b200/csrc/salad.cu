@@ -10,7 +10,7 @@
 //   out [B, g + l*m]  normalize(cat(normalize(TF), normalize(AGG, over l).flatten))
 #include "common.cuh"
 #include "gemm.h"
-#include "sinkhorn_scaled.cuh"
+#include "sinkhorn_rt.cuh"
 #include "finalize_fast.cuh"
 #include "../../include/vpr_b200.h"
 
@@ -299,6 +299,13 @@ static size_t sink_bwd_smem(int n, int m, int iters) {
             (size_t)iters * (m + 1) + 256) * sizeof(float);
 }
 
+// VPR_SINK_RT=0 keeps n <= 256 on the shared-memory-tile kernels of sinkhorn_scaled.cuh (A/B timing, and the parity
+// test that keeps that path covered at n <= 256)
+static bool sink_rt_enabled() {
+    const char* e = getenv("VPR_SINK_RT");
+    return !(e != nullptr && e[0] == '0');
+}
+
 static int sinkhorn_fwd(const float* S, const float* dust_bin, void* P, int p_dtype, float* U, float* V, int B, int n,
                         int m, int iters, cudaStream_t st, bool pdl = false) {
     VPR_REQUIRE(m == 16 || m == 32 || m == 64 || m == 128, "num_clusters must be 16/32/64/128 (got %d)", m);
@@ -309,6 +316,20 @@ static int sinkhorn_fwd(const float* S, const float* dust_bin, void* P, int p_dt
         k2.norm2 = (float)(-log2((double)(n + m)));
         k2.log_a_m2 = k2.norm2 + (float)log2((double)(n - m));
         const size_t guard = sinkfast_fwd_floats<64>(n) * sizeof(float);
+        if (n <= RT_ROWS && sink_rt_enabled()) {   // 224 x 224 images: register-resident tile, two barriers per iteration
+            size_t rs = sinkrt_fwd_floats() * sizeof(float);
+            if (rs < guard) rs = guard;
+            if (p_dtype == VPR_BF16) {
+                VPR_SMEM_OK(sinkhorn_fwd_rt<bf16>, rs);
+                VPR_CUDA_OK(launch_ex(sinkhorn_fwd_rt<bf16>, dim3((unsigned)B), dim3(RT_NT), rs, st, pdl, 1, S, dust_bin, (bf16*)P, U, V, n,
+                                      iters, k2));
+            } else {
+                VPR_SMEM_OK(sinkhorn_fwd_rt<float>, rs);
+                VPR_CUDA_OK(launch_ex(sinkhorn_fwd_rt<float>, dim3((unsigned)B), dim3(RT_NT), rs, st, pdl, 1, S, dust_bin, (float*)P, U, V, n,
+                                      iters, k2));
+            }
+            return launch_ok("sinkhorn_fwd_rt");
+        }
         size_t fs = sinkscaled_fwd_floats(n) * sizeof(float);
         if (fs < guard) fs = guard;
         if (fs <= 227 * 1024) {          // scaled tile (one exp2 per element), log-domain body as its range guard
@@ -355,6 +376,20 @@ static int sinkhorn_bwd(const float* S, const float* dust_bin, const float* U, c
         k2.norm2 = (float)(-log2((double)(n + m)));
         k2.log_a_m2 = k2.norm2 + (float)log2((double)(n - m));
         const size_t guard = sinkfast_bwd_floats<64>(n, iters) * sizeof(float);
+        if (n <= RT_ROWS && iters == 3 && sink_rt_enabled()) {
+            size_t rs = sinkrt_bwd_floats(3) * sizeof(float);
+            if (rs < guard) rs = guard;
+            if (ds_dtype == VPR_BF16) {
+                VPR_SMEM_OK((sinkhorn_bwd_rt<bf16, 3>), rs);
+                VPR_CUDA_OK(launch_ex(sinkhorn_bwd_rt<bf16, 3>, dim3((unsigned)B), dim3(RT_NT), rs, st, pdl, 1, S, dust_bin, U, V, dP, (bf16*)dS,
+                                      d_bias, n, k2));
+            } else {
+                VPR_SMEM_OK((sinkhorn_bwd_rt<float, 3>), rs);
+                VPR_CUDA_OK(launch_ex(sinkhorn_bwd_rt<float, 3>, dim3((unsigned)B), dim3(RT_NT), rs, st, pdl, 1, S, dust_bin, U, V, dP, (float*)dS,
+                                      d_bias, n, k2));
+            }
+            return launch_ok("sinkhorn_bwd_rt");
+        }
         size_t fs = sinkscaled_bwd_floats(n, iters) * sizeof(float);
         if (fs < guard) fs = guard;
         if (fs <= 227 * 1024) {
