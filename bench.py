@@ -169,45 +169,47 @@ def run_reference(args, rank, world):
 # saved potentials) divided by the CUDA-event time of the launch alone, against the measured copy bandwidth.
 # ------------------------------------------------------------------------------------------
 def hbm_kernel_leg(dev, lib, L, B, n, peaks, flush, m=64, iters=3):
-    S = torch.randn(B, n, m, device=dev) * 2
-    dP = torch.randn(B, n, m, device=dev)
+    # 6 rotating working sets (S, dP, P, dS: 50 MB each at B=256, n=256 -> 300 MB, more than twice the 126 MB L2), 24
+    # launches back to back between two events: per-launch time without the host's launch gap, operands never L2-resident
+    nsets = 6
+    sets = [(torch.randn(B, n, m, device=dev) * 2, torch.randn(B, n, m, device=dev),
+             torch.empty(B, n, m, dtype=torch.bfloat16, device=dev), torch.empty(B, n, m, dtype=torch.bfloat16, device=dev),
+             torch.empty(B, iters, m + 1, device=dev), torch.empty(B, iters, n, device=dev)) for _ in range(nsets)]
     db = torch.ones(1, device=dev)
-    P = torch.empty(B, n, m, dtype=torch.bfloat16, device=dev)
-    dS = torch.empty(B, n, m, dtype=torch.bfloat16, device=dev)
-    U = torch.empty(B, iters, m + 1, device=dev)
-    V = torch.empty(B, iters, n, device=dev)
     dbias = torch.zeros(m, device=dev)
     st = L.stream_ptr(dev)
 
-    def fwd():
+    def fwd(i):
+        S, dP, P, dS, U, V = sets[i % nsets]
         L.check(lib.vpr_sinkhorn_fwd(L.ptr(S), L.ptr(db), L.ptr(P), L.VPR_BF16, L.ptr(U), L.ptr(V), B, n, m, iters, st), "sinkhorn_fwd")
 
-    def bwd():
+    def bwd(i):
+        S, dP, P, dS, U, V = sets[i % nsets]
         L.check(lib.vpr_sinkhorn_bwd(L.ptr(S), L.ptr(db), L.ptr(U), L.ptr(V), L.ptr(dP), L.ptr(dS), L.VPR_BF16, L.ptr(dbias),
                                      B, n, m, iters, st), "sinkhorn_bwd")
 
     def timed(fn):
-        ts = []
-        for i in range(3 + 8):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            torch.cuda.synchronize()
-            if i >= 3:
-                ts.append(e0.elapsed_time(e1))
-        return sum(ts) / len(ts)
+        for i in range(nsets):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(24):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 24
 
+    rt = n <= 256 and m == 64 and os.environ.get("VPR_SINK_RT", "1") != "0"
     pot = B * iters * (m + 1 + n) * 4
     out = {}
-    for name, fn, nbytes in (("sinkhorn_fwd_scaled", fwd, B * n * m * (4 + 2) + pot),
-                             ("sinkhorn_bwd_scaled", bwd, B * n * m * (4 + 4 + 2) + pot)):
+    for name, kern, fn, nbytes in (("sinkhorn_fwd", "sinkhorn_fwd_rt" if rt else "sinkhorn_fwd_scaled", fwd, B * n * m * (4 + 2) + pot),
+                                   ("sinkhorn_bwd", "sinkhorn_bwd_rt" if rt else "sinkhorn_bwd_scaled", bwd, B * n * m * (4 + 4 + 2) + pot)):
         ms = timed(fn)
         gbs = nbytes / (ms * 1e-3) / 1e9
-        out[name] = {"bound": "hbm", "ms": ms, "bytes": nbytes, "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": gbs / peaks["hbm_gbs"]}
-    del S, dP, P, dS
+        out[name] = {"kernel": kern, "bound": "hbm", "ms": ms, "bytes": nbytes, "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": gbs / peaks["hbm_gbs"], "how": "24 launches back to back over 6 rotating working sets (300 MB)"}
+    del sets
     # backbone->head seam (final LayerNorm + CLS/patch split + cast): 24 back-to-back launches over 4 rotating
     # working sets (800 MB, so no launch finds its operands in L2), bf16 in / bf16 out
     d, sets = 768, []
@@ -236,6 +238,55 @@ def hbm_kernel_leg(dev, lib, L, B, n, peaks, flush, m=64, iters=3):
     out["seam_fwd_kernel"] = {"bound": "hbm", "ms": ms, "bytes": nbytes, "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                               "frac": gbs / peaks["hbm_gbs"]}
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# Every kernel of the step with its own roofline: CUPTI durations inside the running (eager) step from
+# tools/step_profile.py in a child process with VPR_PDL=0 (with programmatic dependent launches a kernel's CUPTI
+# duration also counts the time it sits resident waiting for its predecessor), algorithmic bytes / FLOPs per launch
+# from DESIGN.md 4.5, fractions against MEASURED_PEAKS.json.  Shares of the step, not a replacement for the event-timed
+# `roofline` block of the dominant launch.
+# ------------------------------------------------------------------------------------------
+def step_kernel_table(B, n, peaks, device_index):
+    T, m, l, hid, d, g = B * n, M_CL, L_CL, HID, D, G_TOK
+    big = 2.0 * T * 2 * hid * d
+    spec = [
+        ("gemm_tc_kernel<false, false, 256", "H = dropout(relu(X W0cat^T + b))", "tensor", big),
+        ("gemm_tc_kernel<true, true, 256", "dW0 = dH^T X (split-K, CTA pairs)", "tensor", big),
+        ("gemm_tc_kernel<false, true, 256", "dX = dH W0cat (CTA pairs)", "tensor", big),
+        ("dh_fused_kernel", "dH, dW1, bias gradients in one pass over H", "hbm", T * (2 * hid * 2 * 2 + l * 2 + m * 2)),
+        ("fs_fwd_kernel", "F, S (second MLP layers), H streamed once", "hbm", T * (2 * hid * 2 + l * 2 + m * 4)),
+        ("sinkhorn_bwd", "Sinkhorn backward", "hbm", T * m * (4 + 4 + 2)),
+        ("sinkhorn_fwd", "Sinkhorn forward", "hbm", T * m * (4 + 2)),
+        ("agg_bwd_kernel", "norms backward + dF + dP per image", "hbm", T * (m * 2 + l * 2 + l * 2 + m * 4) + B * (l * m * 4 + (g + l * m) * 2)),
+        ("agg_fwd_kernel", "AGG = F^T P + norms + concat per image", "hbm", T * (l * 2 + m * 2) + B * (l * m * 4 + (g + l * m) * 2)),
+        ("pack_params_kernel", "fp32 master weights -> bf16 operands", "hbm", 1411009 * 6),
+    ]
+    env = dict(os.environ, VPR_PDL="0", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device_index)))
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "step_profile.py"), str(B), str(n), "--json"], env=env,
+                           capture_output=True, text=True, timeout=240)
+        prof = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    except Exception as e:                                       # noqa: BLE001  (reporting only: never fails the bench)
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    rows = []
+    for k in prof["kernels"]:
+        row = {"kernel": k["name"].replace("void ", "").replace("vpr::", "")[:90], "us": round(k["us"], 2),
+               "share": round(k["us"] / prof["sum_us"], 4)}
+        for key, what, bound, work in spec:
+            if key in k["name"]:
+                row["what"], row["bound"] = what, bound
+                if bound == "tensor":
+                    tf = work / (k["us"] * 1e-6) / 1e12
+                    row.update(achieved=round(tf, 1), unit="TFLOP/s", frac_of_burst=round(tf / peaks["bf16_tflops"], 3),
+                               frac_of_sustained=round(tf / peaks["bf16_tflops_sustained"], 3))
+                else:
+                    gbs = work / (k["us"] * 1e-6) / 1e9
+                    row.update(achieved=round(gbs, 1), unit="GB/s", bytes=int(work), frac=round(gbs / peaks["hbm_gbs"], 3))
+                break
+        rows.append(row)
+    return {"how": "CUPTI (torch.profiler) over 10 eager steps in a child process, VPR_PDL=0; algorithmic bytes/FLOPs per launch",
+            "sum_us": round(prof["sum_us"], 1), "kernels": rows}
 
 
 # ------------------------------------------------------------------------------------------
@@ -500,9 +551,11 @@ def run_own(args, rank, local, world):
         torch.cuda.empty_cache()
         return roofline, hbm_kernels
 
-    roofline = hbm_kernels = None
+    roofline = hbm_kernels = step_kernels = None
     if rank == 0:
         roofline, hbm_kernels = isolated_kernel_leg(ms_step)
+        if world == 1 and not args.no_kernel_table:
+            step_kernels = step_kernel_table(B, n, load_peaks(), local)
 
     # ---------------- end to end through the public API, host buffers (e2e) ----------------
     # pinned host inputs -> H2D on a copy stream (double buffered) -> SaladHead fwd+bwd -> D2H of the
@@ -724,6 +777,8 @@ def run_own(args, rank, local, world):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     line["hbm_kernels"] = hbm_kernels
+    if step_kernels is not None:
+        line["step_kernels"] = step_kernels
     line["finetune_step"] = finetune
     if finetune_strong is not None:
         line["finetune_step_global_batch"] = finetune_strong
@@ -764,6 +819,7 @@ def main():
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="N>1 headline step: own all-reduce kernel over NVLink peer memory, or NCCL")
     ap.add_argument("--no-knn", action="store_true", help="skip the kNN leg")
+    ap.add_argument("--no-kernel-table", action="store_true", help="skip the per-kernel CUPTI table (child process)")
     ap.add_argument("--knn-queries", type=int, default=65536)
     ap.add_argument("--no-strong", action="store_true", help="skip the fixed-global-batch fine-tuning leg")
     ap.add_argument("--global-batch", type=int, default=2048, help="global batch of the strong-scaling fine-tuning leg")

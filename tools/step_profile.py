@@ -15,8 +15,10 @@ import vpr_b200  # noqa: E402
 
 
 def main():
-    B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-    n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+    as_json = "--json" in sys.argv                 # one JSON line {"kernels": [{"name", "us", "launches_per_step"}, ...]} for bench.py
+    argv = [a for a in sys.argv[1:] if a != "--json"]
+    B = int(argv[0]) if len(argv) > 0 else 256
+    n = int(argv[1]) if len(argv) > 1 else 256
     hw = int(round(n ** 0.5))
     torch.manual_seed(0)
     head = vpr_b200.SaladHead(dropout=0.3).cuda().train()
@@ -42,7 +44,8 @@ def main():
     t1 = time.perf_counter()
     torch.cuda.synchronize()
     t2 = time.perf_counter()
-    print(f"host issue time {1e6 * (t1 - t0) / 50:.0f} us/step, wall incl. drain {1e6 * (t2 - t0) / 50:.0f} us/step")
+    if not as_json:
+        print(f"host issue time {1e6 * (t1 - t0) / 50:.0f} us/step, wall incl. drain {1e6 * (t2 - t0) / 50:.0f} us/step")
     steps = 10
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(steps):
@@ -57,6 +60,11 @@ def main():
             rows.append((dt / steps, e.count / steps, e.key))
     rows.sort(reverse=True)
     tot = sum(r[0] for r in rows)
+    if as_json:
+        import json
+        print(json.dumps({"B": B, "n": n, "pdl": os.environ.get("VPR_PDL", "1") != "0", "sum_us": tot,
+                          "kernels": [{"name": key, "us": dt, "launches_per_step": cnt} for dt, cnt, key in rows]}))
+        return
     print(f"B={B} n={n}: sum of kernel time per step {tot:.1f} us")
     for dt, cnt, key in rows:
         print(f"{dt:9.1f} us  x{cnt:4.1f}  {key[:150]}")
