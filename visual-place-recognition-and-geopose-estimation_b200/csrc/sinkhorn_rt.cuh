@@ -33,7 +33,7 @@
 // (sinkhorn_fast.cuh).  Rows >= n are held as zeros.
 //
 // This header also compiles as plain host C++ under tests/emu/simt_emu.h (VPR_SIMT_EMU): the CPU test
-// suite runs these very kernels, one OS thread per CUDA thread, against the fp64 oracle.
+// suite runs these very kernels, one OS thread per CUDA thread, against an fp64 restatement of the algorithm.
 #pragma once
 #ifndef VPR_SIMT_EMU
 #include "sinkhorn_scaled.cuh"
