@@ -14,26 +14,36 @@ vpr::SinkConst2 consts(int n) {
 
 extern "C" {
 // returns the number of images that asked for the log-domain guard path (their outputs are then not written)
-int emu_sinkhorn_fwd_rt(const float* S, const float* dust_bin, void* P, int p_bf16, float* U, float* V, int B, int n, int iters) {
+// nt: threads per block, 512 (two per token row) or 256 (one per row)
+int emu_sinkhorn_fwd_rt(const float* S, const float* dust_bin, void* P, int p_bf16, float* U, float* V, int B, int n, int iters, int nt) {
     simt_emu::guard_count = 0;
     const vpr::SinkConst2 k = consts(n);
     const size_t smem = vpr::sinkrt_fwd_floats() * sizeof(float);
-    if (p_bf16)
-        simt_emu::launch(B, vpr::RT_NT, smem, [=]() { vpr::sinkhorn_fwd_rt<__nv_bfloat16>(S, dust_bin, (__nv_bfloat16*)P, U, V, n, iters, k); });
+    if (nt != 512 && nt != 256) return -1;
+    if (p_bf16 && nt == 512)
+        simt_emu::launch(B, nt, smem, [=]() { vpr::sinkhorn_fwd_rt<__nv_bfloat16, 512>(S, dust_bin, (__nv_bfloat16*)P, U, V, n, iters, k); });
+    else if (p_bf16)
+        simt_emu::launch(B, nt, smem, [=]() { vpr::sinkhorn_fwd_rt<__nv_bfloat16, 256>(S, dust_bin, (__nv_bfloat16*)P, U, V, n, iters, k); });
+    else if (nt == 512)
+        simt_emu::launch(B, nt, smem, [=]() { vpr::sinkhorn_fwd_rt<float, 512>(S, dust_bin, (float*)P, U, V, n, iters, k); });
     else
-        simt_emu::launch(B, vpr::RT_NT, smem, [=]() { vpr::sinkhorn_fwd_rt<float>(S, dust_bin, (float*)P, U, V, n, iters, k); });
+        simt_emu::launch(B, nt, smem, [=]() { vpr::sinkhorn_fwd_rt<float, 256>(S, dust_bin, (float*)P, U, V, n, iters, k); });
     return simt_emu::guard_count.load();
 }
 int emu_sinkhorn_bwd_rt3(const float* S, const float* dust_bin, const float* U, const float* V, const float* dP, void* dS, int ds_bf16,
-                         float* d_bias, int B, int n) {
+                         float* d_bias, int B, int n, int nt) {
     simt_emu::guard_count = 0;
     const vpr::SinkConst2 k = consts(n);
     const size_t smem = vpr::sinkrt_bwd_floats(3) * sizeof(float);
-    if (ds_bf16)
-        simt_emu::launch(B, vpr::RT_NT, smem,
-                         [=]() { vpr::sinkhorn_bwd_rt<__nv_bfloat16, 3>(S, dust_bin, U, V, dP, (__nv_bfloat16*)dS, d_bias, n, k); });
+    if (nt != 512 && nt != 256) return -1;
+    if (ds_bf16 && nt == 512)
+        simt_emu::launch(B, nt, smem, [=]() { vpr::sinkhorn_bwd_rt<__nv_bfloat16, 3, 512>(S, dust_bin, U, V, dP, (__nv_bfloat16*)dS, d_bias, n, k); });
+    else if (ds_bf16)
+        simt_emu::launch(B, nt, smem, [=]() { vpr::sinkhorn_bwd_rt<__nv_bfloat16, 3, 256>(S, dust_bin, U, V, dP, (__nv_bfloat16*)dS, d_bias, n, k); });
+    else if (nt == 512)
+        simt_emu::launch(B, nt, smem, [=]() { vpr::sinkhorn_bwd_rt<float, 3, 512>(S, dust_bin, U, V, dP, (float*)dS, d_bias, n, k); });
     else
-        simt_emu::launch(B, vpr::RT_NT, smem, [=]() { vpr::sinkhorn_bwd_rt<float, 3>(S, dust_bin, U, V, dP, (float*)dS, d_bias, n, k); });
+        simt_emu::launch(B, nt, smem, [=]() { vpr::sinkhorn_bwd_rt<float, 3, 256>(S, dust_bin, U, V, dP, (float*)dS, d_bias, n, k); });
     return simt_emu::guard_count.load();
 }
 size_t emu_sinkrt_fwd_bytes() { return vpr::sinkrt_fwd_floats() * sizeof(float); }

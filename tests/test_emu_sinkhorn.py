@@ -60,25 +60,26 @@ def potentials_fp64(S, dust, iters):
     return torch.stack(us, 1), torch.stack(vs, 1)
 
 
-def run_fwd(emu, St, db, iters, bf16=False):
+def run_fwd(emu, St, db, iters, bf16=False, nt=512):
     B, n, _ = St.shape
     P = torch.full((B, n, 64), float("nan"), dtype=torch.bfloat16 if bf16 else torch.float32)
     U = torch.full((B, iters, 65), float("nan"))
     V = torch.full((B, iters, n), float("nan"))
-    guards = emu.emu_sinkhorn_fwd_rt(ptr(St), ptr(db), ptr(P), int(bf16), ptr(U), ptr(V), B, n, iters)
+    guards = emu.emu_sinkhorn_fwd_rt(ptr(St), ptr(db), ptr(P), int(bf16), ptr(U), ptr(V), B, n, iters, nt)
     return P, U, V, guards
 
 
+@pytest.mark.parametrize("nt", [512, 256])
 @pytest.mark.parametrize("B,n,scale,dust", [(2, 256, 2.0, 1.0), (2, 100, 2.0, 1.0), (1, 65, 2.0, -3.0), (2, 200, 6.0, 0.5),
                                              (1, 255, 1.0, 9.0)])
-def test_register_tile_kernels_match_the_fp64_oracle(emu, B, n, scale, dust):
+def test_register_tile_kernels_match_the_fp64_oracle(emu, B, n, scale, dust, nt):
     g = torch.Generator().manual_seed(n)
     S = torch.randn(B, 64, n, generator=g) * scale
     db = torch.tensor([dust])
     Sd = S.double().requires_grad_(True)
     Pd = O.get_matching_probs(Sd, db.double()[0], 3, const_dtype=torch.float64).exp()
     St = S.transpose(1, 2).contiguous()
-    P, U, V, guards = run_fwd(emu, St, db, 3)
+    P, U, V, guards = run_fwd(emu, St, db, 3, nt=nt)
     assert guards == 0
     assert rel(P, Pd[:, :64].transpose(1, 2)) < 1e-5
     u64, v64 = potentials_fp64(S, dust, 3)
@@ -87,7 +88,7 @@ def test_register_tile_kernels_match_the_fp64_oracle(emu, B, n, scale, dust):
     (Pd[:, :64] * dP.double().transpose(1, 2)).sum().backward()
     dS = torch.full((B, n, 64), float("nan"))
     d_bias = torch.zeros(64)
-    guards = emu.emu_sinkhorn_bwd_rt3(ptr(St), ptr(db), ptr(U), ptr(V), ptr(dP), ptr(dS), 0, ptr(d_bias), B, n)
+    guards = emu.emu_sinkhorn_bwd_rt3(ptr(St), ptr(db), ptr(U), ptr(V), ptr(dP), ptr(dS), 0, ptr(d_bias), B, n, nt)
     assert guards == 0
     assert rel(dS, Sd.grad.transpose(1, 2)) < 1e-5
     # explicit recurrence (SURVEY A-3) agrees too; a per-cluster score offset cannot change the plan
@@ -95,29 +96,31 @@ def test_register_tile_kernels_match_the_fp64_oracle(emu, B, n, scale, dust):
     assert d_bias.abs().max() < 1e-4
 
 
-def test_register_tile_forward_other_iteration_counts_and_bf16_outputs(emu):
+@pytest.mark.parametrize("nt", [512, 256])
+def test_register_tile_forward_other_iteration_counts_and_bf16_outputs(emu, nt):
     g = torch.Generator().manual_seed(11)
     S = torch.randn(2, 64, 256, generator=g) * 2.0
     db = torch.tensor([1.0])
     St = S.transpose(1, 2).contiguous()
     for iters in (1, 5, 8):
         Pd = O.get_matching_probs(S.double(), db.double()[0], iters, const_dtype=torch.float64).exp()
-        P, U, V, guards = run_fwd(emu, St, db, iters)
+        P, U, V, guards = run_fwd(emu, St, db, iters, nt=nt)
         assert guards == 0 and rel(P, Pd[:, :64].transpose(1, 2)) < 1e-5, iters
     Pd = O.get_matching_probs(S.double(), db.double()[0], 3, const_dtype=torch.float64).exp()[:, :64].transpose(1, 2)
-    P32, U, V, _ = run_fwd(emu, St, db, 3)
-    Pb, _, _, _ = run_fwd(emu, St, db, 3, bf16=True)
+    P32, U, V, _ = run_fwd(emu, St, db, 3, nt=nt)
+    Pb, _, _, _ = run_fwd(emu, St, db, 3, bf16=True, nt=nt)
     assert torch.equal(Pb, P32.bfloat16())                       # same values, rounded once (round to nearest even)
     dP = torch.randn(2, 256, 64, generator=g)
     dS32 = torch.full((2, 256, 64), float("nan"))
     dSb = torch.full((2, 256, 64), float("nan"), dtype=torch.bfloat16)
     d_bias = torch.zeros(64)
-    emu.emu_sinkhorn_bwd_rt3(ptr(St), ptr(db), ptr(U), ptr(V), ptr(dP), ptr(dS32), 0, ptr(d_bias), 2, 256)
-    emu.emu_sinkhorn_bwd_rt3(ptr(St), ptr(db), ptr(U), ptr(V), ptr(dP), ptr(dSb), 1, ptr(d_bias), 2, 256)
+    emu.emu_sinkhorn_bwd_rt3(ptr(St), ptr(db), ptr(U), ptr(V), ptr(dP), ptr(dS32), 0, ptr(d_bias), 2, 256, nt)
+    emu.emu_sinkhorn_bwd_rt3(ptr(St), ptr(db), ptr(U), ptr(V), ptr(dP), ptr(dSb), 1, ptr(d_bias), 2, 256, nt)
     assert torch.isfinite(dS32).all() and rel(dSb, dS32) < 4e-3
 
 
-def test_register_tile_range_guard_asks_for_the_log_domain_body(emu):
+@pytest.mark.parametrize("nt", [512, 256])
+def test_register_tile_range_guard_asks_for_the_log_domain_body(emu, nt):
     """Image 1 spans several hundred nats: its factors leave fp32 range, the CTA must hand the image to the
     log-domain body (compiled out under the emulation: the entry point counts the request)."""
     g = torch.Generator().manual_seed(5)
@@ -125,7 +128,7 @@ def test_register_tile_range_guard_asks_for_the_log_domain_body(emu):
     S[1] *= 40.0
     db = torch.tensor([1.0])
     St = S.transpose(1, 2).contiguous()
-    P, U, V, guards = run_fwd(emu, St, db, 3)
+    P, U, V, guards = run_fwd(emu, St, db, 3, nt=nt)
     assert guards == 1
     Pd = O.get_matching_probs(S.double(), db.double()[0], 3, const_dtype=torch.float64).exp()
     assert rel(P[0], Pd[0, :64].transpose(0, 1)) < 1e-5 and torch.isnan(P[1]).all()
@@ -134,7 +137,7 @@ def test_register_tile_range_guard_asks_for_the_log_domain_body(emu):
     dP = torch.randn(2, 256, 64, generator=g)
     dS = torch.full((2, 256, 64), float("nan"))
     U32, V32, d_bias = u64.float().contiguous(), v64.float().contiguous(), torch.zeros(64)
-    guards = emu.emu_sinkhorn_bwd_rt3(ptr(St), ptr(db), ptr(U32), ptr(V32), ptr(dP), ptr(dS), 0, ptr(d_bias), 2, 256)
+    guards = emu.emu_sinkhorn_bwd_rt3(ptr(St), ptr(db), ptr(U32), ptr(V32), ptr(dP), ptr(dS), 0, ptr(d_bias), 2, 256, nt)
     assert guards == 1 and torch.isfinite(dS[0]).all() and torch.isnan(dS[1]).all()
 
 

@@ -109,10 +109,12 @@ def test_sinkhorn_forward_backward(vpr, B, n, m):
     assert rel(dS, dS2.transpose(1, 2)) < 1e-5
 
 
-@pytest.mark.parametrize("n,iters", [(256, 3), (529, 3), (200, 5)])
-def test_sinkhorn_wide_score_range_takes_the_log_domain_guard_path(vpr, n, iters):
+@pytest.mark.parametrize("n,iters,rt", [(256, 3, "1"), (256, 3, "2"), (256, 3, "0"), (529, 3, "1"), (200, 5, "1"), (200, 5, "2")])
+def test_sinkhorn_wide_score_range_takes_the_log_domain_guard_path(vpr, monkeypatch, n, iters, rt):
     """Image 0 has ordinary scores (scaled-tile path), image 1 a spread of several hundred nats, far outside
-    what an exponentiated tile can hold in fp32: its CTA must fall back to the element-wise log-domain body."""
+    what an exponentiated tile can hold in fp32: its CTA must fall back to the element-wise log-domain body
+    (from 512-thread CTAs, and from the 256-thread CTAs of the one-thread-per-row register-tile variant)."""
+    monkeypatch.setenv("VPR_SINK_RT", rt)
     g = torch.Generator().manual_seed(n)
     S = torch.randn(2, 64, n, generator=g) * 2.0
     S[1] *= 40.0
@@ -140,11 +142,11 @@ def test_sinkhorn_dustbin_value_is_irrelevant(vpr):
     assert rel(P1, P2) < 1e-5
 
 
-@pytest.mark.parametrize("rt", ["1", "0"])
+@pytest.mark.parametrize("rt", ["1", "2", "0"])
 @pytest.mark.parametrize("B,n", [(3, 256), (2, 196), (300, 256)])
 def test_sinkhorn_register_tile_and_shared_tile_kernels_agree_with_the_oracle(vpr, monkeypatch, rt, B, n):
-    """n <= 256 runs the register-tile kernels (csrc/sinkhorn_rt.cuh); VPR_SINK_RT=0 keeps the shared-memory-tile
-    kernels (csrc/sinkhorn_scaled.cuh) on those shapes.  Both against the fp64 oracle, fp32 and bf16 outputs, a batch
+    """n <= 256 runs the register-tile kernels (csrc/sinkhorn_rt.cuh; VPR_SINK_RT=2: their one-thread-per-row variant);
+    VPR_SINK_RT=0 keeps the shared-memory-tile kernels (csrc/sinkhorn_scaled.cuh) on those shapes.  Both against the fp64 oracle, fp32 and bf16 outputs, a batch
     larger than one wave of CTAs, and the bias gradient accumulated across the batch (identically zero in exact
     arithmetic: a per-cluster score offset is absorbed by u)."""
     monkeypatch.setenv("VPR_SINK_RT", rt)

@@ -299,11 +299,14 @@ static size_t sink_bwd_smem(int n, int m, int iters) {
             (size_t)iters * (m + 1) + 256) * sizeof(float);
 }
 
-// VPR_SINK_RT=0 keeps n <= 256 on the shared-memory-tile kernels of sinkhorn_scaled.cuh (A/B timing, and the parity
-// test that keeps that path covered at n <= 256)
-static bool sink_rt_enabled() {
+// Threads per image of the register-tile Sinkhorn kernels (n <= 256): 512 = two per token row (default), 256 = one per
+// row (VPR_SINK_RT=2), 0 = stay on the shared-memory-tile kernels of sinkhorn_scaled.cuh (VPR_SINK_RT=0; A/B timing, and
+// the parity test that keeps that path covered at n <= 256).  Read at every call.
+static int sink_rt_threads() {
     const char* e = getenv("VPR_SINK_RT");
-    return !(e != nullptr && e[0] == '0');
+    if (e != nullptr && e[0] == '0') return 0;
+    if (e != nullptr && e[0] == '2') return 256;
+    return 512;
 }
 
 static int sinkhorn_fwd(const float* S, const float* dust_bin, void* P, int p_dtype, float* U, float* V, int B, int n,
@@ -316,18 +319,19 @@ static int sinkhorn_fwd(const float* S, const float* dust_bin, void* P, int p_dt
         k2.norm2 = (float)(-log2((double)(n + m)));
         k2.log_a_m2 = k2.norm2 + (float)log2((double)(n - m));
         const size_t guard = sinkfast_fwd_floats<64>(n) * sizeof(float);
-        if (n <= RT_ROWS && sink_rt_enabled()) {   // 224 x 224 images: register-resident tile, two barriers per iteration
+        if (n <= RT_ROWS && sink_rt_threads() != 0) {   // 224 x 224 images: register-resident tile, two barriers per iteration
             size_t rs = sinkrt_fwd_floats() * sizeof(float);
             if (rs < guard) rs = guard;
-            if (p_dtype == VPR_BF16) {
-                VPR_SMEM_OK(sinkhorn_fwd_rt<bf16>, rs);
-                VPR_CUDA_OK(launch_ex(sinkhorn_fwd_rt<bf16>, dim3((unsigned)B), dim3(RT_NT), rs, st, pdl, 1, S, dust_bin, (bf16*)P, U, V, n,
-                                      iters, k2));
-            } else {
-                VPR_SMEM_OK(sinkhorn_fwd_rt<float>, rs);
-                VPR_CUDA_OK(launch_ex(sinkhorn_fwd_rt<float>, dim3((unsigned)B), dim3(RT_NT), rs, st, pdl, 1, S, dust_bin, (float*)P, U, V, n,
-                                      iters, k2));
-            }
+#define VPR_RT_FWD(TP, NT)                                                                                              \
+    do {                                                                                                                \
+        VPR_SMEM_OK((sinkhorn_fwd_rt<TP, NT>), rs);                                                                     \
+        VPR_CUDA_OK(launch_ex(sinkhorn_fwd_rt<TP, NT>, dim3((unsigned)B), dim3(NT), rs, st, pdl, 1, S, dust_bin, (TP*)P, U, V, n, iters, \
+                              k2));                                                                                     \
+    } while (0)
+            const bool fat = sink_rt_threads() == 256;
+            if (p_dtype == VPR_BF16) { if (fat) VPR_RT_FWD(bf16, 256); else VPR_RT_FWD(bf16, 512); }
+            else                     { if (fat) VPR_RT_FWD(float, 256); else VPR_RT_FWD(float, 512); }
+#undef VPR_RT_FWD
             return launch_ok("sinkhorn_fwd_rt");
         }
         size_t fs = sinkscaled_fwd_floats(n) * sizeof(float);
@@ -376,18 +380,19 @@ static int sinkhorn_bwd(const float* S, const float* dust_bin, const float* U, c
         k2.norm2 = (float)(-log2((double)(n + m)));
         k2.log_a_m2 = k2.norm2 + (float)log2((double)(n - m));
         const size_t guard = sinkfast_bwd_floats<64>(n, iters) * sizeof(float);
-        if (n <= RT_ROWS && iters == 3 && sink_rt_enabled()) {
+        if (n <= RT_ROWS && iters == 3 && sink_rt_threads() != 0) {
             size_t rs = sinkrt_bwd_floats(3) * sizeof(float);
             if (rs < guard) rs = guard;
-            if (ds_dtype == VPR_BF16) {
-                VPR_SMEM_OK((sinkhorn_bwd_rt<bf16, 3>), rs);
-                VPR_CUDA_OK(launch_ex(sinkhorn_bwd_rt<bf16, 3>, dim3((unsigned)B), dim3(RT_NT), rs, st, pdl, 1, S, dust_bin, U, V, dP, (bf16*)dS,
-                                      d_bias, n, k2));
-            } else {
-                VPR_SMEM_OK((sinkhorn_bwd_rt<float, 3>), rs);
-                VPR_CUDA_OK(launch_ex(sinkhorn_bwd_rt<float, 3>, dim3((unsigned)B), dim3(RT_NT), rs, st, pdl, 1, S, dust_bin, U, V, dP, (float*)dS,
-                                      d_bias, n, k2));
-            }
+#define VPR_RT_BWD(TD, NT)                                                                                              \
+    do {                                                                                                                \
+        VPR_SMEM_OK((sinkhorn_bwd_rt<TD, 3, NT>), rs);                                                                  \
+        VPR_CUDA_OK(launch_ex(sinkhorn_bwd_rt<TD, 3, NT>, dim3((unsigned)B), dim3(NT), rs, st, pdl, 1, S, dust_bin, U, V, dP, (TD*)dS,   \
+                              d_bias, n, k2));                                                                          \
+    } while (0)
+            const bool fat = sink_rt_threads() == 256;
+            if (ds_dtype == VPR_BF16) { if (fat) VPR_RT_BWD(bf16, 256); else VPR_RT_BWD(bf16, 512); }
+            else                      { if (fat) VPR_RT_BWD(float, 256); else VPR_RT_BWD(float, 512); }
+#undef VPR_RT_BWD
             return launch_ok("sinkhorn_bwd_rt");
         }
         size_t fs = sinkscaled_bwd_floats(n, iters) * sizeof(float);

@@ -71,13 +71,16 @@ __host__ __device__ constexpr size_t sinkfast_bwd_floats(int n, int iters) {
            (size_t)iters * (M_ + 1) + SK_NT + 32;
 }
 
-template <typename TP, int M_>
+// NT: threads of the calling CTA (512 for the stand-alone kernels below and the shared-tile kernels; the register-tile
+// kernels also call these bodies from 256-thread CTAs)
+template <typename TP, int M_, int NT = 512>
 __device__ __noinline__ void sinkhorn_fwd_logdomain(float* sm, const float* __restrict__ S,
                                                     const float* __restrict__ dust_bin, TP* __restrict__ P,
                                                     float* __restrict__ U, float* __restrict__ V, int n, int iters,
                                                     SinkConst2 k) {
     static_assert(M_ == 64, "column-pass register tiling assumes 64 clusters");
-    constexpr int PITCH = M_ + 1, NT = SK_NT, PARTS = NT / M_;
+    constexpr int PITCH = M_ + 1, PARTS = NT / M_;
+    static_assert(NT % M_ == 0 && NT <= 512, "thread count: a multiple of the cluster count, at most the 512 the scratch is sized for");
     float* Ms = sm;
     float* vs = Ms + (size_t)n * PITCH;
     float* us = vs + n;
@@ -158,14 +161,15 @@ __device__ __noinline__ void sinkhorn_fwd_logdomain(float* sm, const float* __re
     }
 }
 
-template <typename TD, int M_>
+template <typename TD, int M_, int NT = 512>
 __device__ __noinline__ void sinkhorn_bwd_logdomain(float* sm, const float* __restrict__ S,
                                                     const float* __restrict__ dust_bin, const float* __restrict__ U,
                                                     const float* __restrict__ V, const float* __restrict__ dP,
                                                     TD* __restrict__ dS, float* __restrict__ d_bias, int n, int iters,
                                                     SinkConst2 k) {
     static_assert(M_ == 64, "column-pass register tiling assumes 64 clusters");
-    constexpr int PITCH = M_ + 1, NT = SK_NT, PARTS = NT / M_;
+    constexpr int PITCH = M_ + 1, PARTS = NT / M_;
+    static_assert(NT % M_ == 0 && NT <= 512, "thread count: a multiple of the cluster count, at most the 512 the scratch is sized for");
     float* Ms = sm;                                   // [n][PITCH]        scores * log2(e)
     float* vs = Ms + (size_t)n * PITCH;               // [iters+1][n]      v^0..v^K (log2 units)
     float* us = vs + (size_t)(iters + 1) * n;         // [iters][M_+1]     u^1..u^K (log2 units)

@@ -42,8 +42,8 @@
 
 namespace vpr {
 
-static constexpr int RT_NT = 512;          // threads per CTA
-static constexpr int RT_ROWS = 256;        // token rows a CTA can hold (two threads per row)
+static constexpr int RT_NT = 512;          // threads per CTA, two per token row (the default); NT = 256: one per row
+static constexpr int RT_ROWS = 256;        // token rows a CTA can hold
 static constexpr int RT_PITCH = 68;        // floats per row of the shared tile
 static constexpr int RT_VEC = 72;          // floats per per-cluster vector (64 clusters + dustbin entries, padded)
 static constexpr float RT_LO = 1e-20f, RT_HI = 1e20f;
@@ -53,7 +53,7 @@ __host__ __device__ constexpr size_t sinkrt_fwd_floats() {
 }
 __host__ __device__ constexpr size_t sinkrt_bwd_floats(int iters) {
     return (size_t)RT_ROWS * RT_PITCH + (size_t)(2 + 2 * iters) * RT_ROWS + (size_t)2 * iters * RT_VEC + 16 + 32 +
-           (RT_NT / 32) * 64;
+           (RT_NT / 32) * 64;       // sized for the larger thread count
 }
 
 #ifndef VPR_SIMT_EMU
@@ -75,89 +75,112 @@ __device__ __forceinline__ float rt_warp_max(float v) {
     return v;
 }
 
-// Sum a0..a3 over the 32 lanes of the warp.  Every lane returns the total of the value with index
-// ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)  (reduce-scatter: 6 shuffles instead of 20).
-__device__ __forceinline__ float rt_colreduce4(float a0, float a1, float a2, float a3, int lane) {
-    const bool hi = (lane & 16) != 0;
-    float k0 = hi ? a2 : a0, k1 = hi ? a3 : a1;
-    const float s0 = hi ? a0 : a2, s1 = hi ? a1 : a3;
-    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-    const bool b8 = (lane & 8) != 0;
-    float kk = b8 ? k1 : k0;
-    const float ss = b8 ? k0 : k1;
-    kk += __shfl_xor_sync(0xffffffffu, ss, 8);
-    kk += __shfl_xor_sync(0xffffffffu, kk, 4);
-    kk += __shfl_xor_sync(0xffffffffu, kk, 2);
-    kk += __shfl_xor_sync(0xffffffffu, kk, 1);
-    return kk;
+// Sum a[0..CW) over the 32 lanes of the warp (CW = 4 or 8).  Every lane returns the total of ONE of the values: the one
+// with index rt_col_of_lane<CW>(lane)  (reduce-scatter: CW - 1 + log2(32 / CW) shuffles instead of 5 * CW).
+template <int CW>
+__device__ __forceinline__ int rt_col_of_lane(int lane) {
+    return CW == 8 ? ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1) : ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+}
+template <int CW>
+__device__ __forceinline__ float rt_colreduce(float (&a)[CW], int lane) {
+    static_assert(CW == 4 || CW == 8, "a warp owns 4 or 8 clusters");
+#pragma unroll
+    for (int w = CW / 2, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const float keep = up ? a[i + w] : a[i];
+            const float send = up ? a[i] : a[i + w];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    float t = a[0];
+#pragma unroll
+    for (int bit = 16 / CW; bit >= 1; bit >>= 1) t += __shfl_xor_sync(0xffffffffu, t, bit);
+    return t;
 }
 
-// Column sums of the shared tile for the clusters this warp owns (4*warp .. 4*warp+3), over all RT_ROWS rows:
-//   tot  = sum_j tile_jc * x_j   (UNIT: sum_j tile_jc)   for c = 4*warp + ((lane>>4)&1)*2 + ((lane>>3)&1)
+// Column sums of the shared tile for the CW = 2048 / NT clusters this warp owns (CW*warp ..), over all RT_ROWS rows:
+//   tot  = sum_j tile_jc * x_j   (UNIT: sum_j tile_jc)   for c = CW*warp + rt_col_of_lane<CW>(lane)
 //   dtot = sum_j dcol_j * x_j    (warp 0 only: the dustbin column)
-template <bool UNIT>
+template <int NT, bool UNIT>
 __device__ __forceinline__ void rt_col_sums(const float* tile, const float* x, const float* dcol, int warp, int lane,
                                             float& tot, float& dtot) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, ad = 0.f;
-    const float* tp = tile + lane * RT_PITCH + 4 * warp;
+    constexpr int CW = 2048 / NT;
+    float a[CW], ad = 0.f;
+#pragma unroll
+    for (int c = 0; c < CW; ++c) a[c] = 0.f;
+    const float* tp = tile + lane * RT_PITCH + CW * warp;
 #pragma unroll
     for (int i = 0; i < RT_ROWS / 32; ++i) {
         const float xr = x[lane + 32 * i];
-        const float4 t = *reinterpret_cast<const float4*>(tp + i * 32 * RT_PITCH);
-        if (UNIT) {
-            a0 += t.x; a1 += t.y; a2 += t.z; a3 += t.w;
-        } else {
-            a0 = fmaf(t.x, xr, a0); a1 = fmaf(t.y, xr, a1); a2 = fmaf(t.z, xr, a2); a3 = fmaf(t.w, xr, a3);
+#pragma unroll
+        for (int q = 0; q < CW / 4; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(tp + i * 32 * RT_PITCH + 4 * q);
+            if (UNIT) {
+                a[4 * q] += t.x; a[4 * q + 1] += t.y; a[4 * q + 2] += t.z; a[4 * q + 3] += t.w;
+            } else {
+                a[4 * q] = fmaf(t.x, xr, a[4 * q]); a[4 * q + 1] = fmaf(t.y, xr, a[4 * q + 1]);
+                a[4 * q + 2] = fmaf(t.z, xr, a[4 * q + 2]); a[4 * q + 3] = fmaf(t.w, xr, a[4 * q + 3]);
+            }
         }
         if (warp == 0) ad = fmaf(dcol[lane + 32 * i], xr, ad);
     }
-    tot = rt_colreduce4(a0, a1, a2, a3, lane);
+    tot = rt_colreduce<CW>(a, lane);
     dtot = 0.f;
     if (warp == 0) dtot = rt_warp_sum(ad);
 }
 
-// Load this thread's half row of scores and turn it into E (in place).  Returns mx_j (base-2 units) and the
-// dustbin entry of the row; rows >= n give zeros.
-__device__ __forceinline__ void rt_load_row(const float* __restrict__ src, bool valid, float z2, float (&e)[32], float& mx2,
+// Load this thread's EW = 64 / (threads per row) scores of its row and turn them into E (in place).  Returns mx_j (base-2
+// units) and the dustbin entry of the row; rows >= n give zeros.
+template <int EW>
+__device__ __forceinline__ void rt_load_row(const float* __restrict__ src, bool valid, float z2, float (&e)[EW], float& mx2,
                                             float& dj) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < EW / 4; ++i) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
         e[4 * i] = v.x; e[4 * i + 1] = v.y; e[4 * i + 2] = v.z; e[4 * i + 3] = v.w;
     }
     float mx = e[0];
 #pragma unroll
-    for (int i = 1; i < 32; ++i) mx = fmaxf(mx, e[i]);
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    for (int i = 1; i < EW; ++i) mx = fmaxf(mx, e[i]);
+    if (EW == 32) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
     mx2 = fmaxf(mx * VPR_L2E, z2);
     dj = valid ? fex2(z2 - mx2) : 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) e[i] = valid ? fex2(fmaf(e[i], VPR_L2E, -mx2)) : 0.f;
+    for (int i = 0; i < EW; ++i) e[i] = valid ? fex2(fmaf(e[i], VPR_L2E, -mx2)) : 0.f;
 }
 
-__device__ __forceinline__ void rt_store_row(float* trow, const float (&e)[32]) {
+template <int EW>
+__device__ __forceinline__ void rt_store_row(float* trow, const float (&e)[EW]) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < EW / 4; ++i)
         *reinterpret_cast<float4*>(trow + 4 * i) = make_float4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]);
 }
 
-// sum_c e_c * y_c over this thread's 32 clusters (y: the half's 32 entries in shared memory)
-__device__ __forceinline__ float rt_row_dot(const float (&e)[32], const float* yh) {
+// sum_c e_c * y_c over this thread's EW clusters (y: their entries in shared memory), completed over the row
+template <int EW>
+__device__ __forceinline__ float rt_row_dot(const float (&e)[EW], const float* yh) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < EW / 4; ++i) {
         const float4 y = *reinterpret_cast<const float4*>(yh + 4 * i);
         s0 = fmaf(e[4 * i], y.x, s0); s1 = fmaf(e[4 * i + 1], y.y, s1);
         s2 = fmaf(e[4 * i + 2], y.z, s2); s3 = fmaf(e[4 * i + 3], y.w, s3);
     }
-    return (s0 + s1) + (s2 + s3);
+    float s = (s0 + s1) + (s2 + s3);
+    if (EW == 32) s += __shfl_xor_sync(0xffffffffu, s, 16);
+    return s;
 }
 
-template <typename TP>
-__global__ void __launch_bounds__(RT_NT, 2) sinkhorn_fwd_rt(const float* __restrict__ S, const float* __restrict__ dust_bin,
-                                                            TP* __restrict__ P, float* __restrict__ U,
-                                                            float* __restrict__ V, int n, int iters, SinkConst2 k) {
+template <typename TP, int NT>
+__global__ void __launch_bounds__(NT, 2) sinkhorn_fwd_rt(const float* __restrict__ S, const float* __restrict__ dust_bin,
+                                                         TP* __restrict__ P, float* __restrict__ U, float* __restrict__ V,
+                                                         int n, int iters, SinkConst2 k) {
+    static_assert(NT == 512 || NT == 256, "two threads or one thread per token row");
+    constexpr int EW = 64 * RT_ROWS / NT;          // tile entries a thread holds (32 or 64)
+    constexpr int CW = 2048 / NT;                  // clusters a warp owns in the column passes (4 or 8)
+    constexpr int NW = NT / 32;
     VPR_RT_SMEM(sk_smem);
     float* tile = sk_smem;                         // [RT_ROWS][RT_PITCH]  E
     float* beta = tile + RT_ROWS * RT_PITCH;       // [RT_ROWS]  2^(v_j + mx_j - B0)
@@ -165,42 +188,41 @@ __global__ void __launch_bounds__(RT_NT, 2) sinkhorn_fwd_rt(const float* __restr
     float* alpha = dcol + RT_ROWS;                 // [RT_VEC]   2^(u_c - (norm - B0)); [64]: dustbin row
     float* misc = alpha + RT_VEC;                  // [0..15] per-warp max of mx, [16] guard flag
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row = warp * 16 + (lane & 15), half = lane >> 4;
+    const int row = EW == 32 ? warp * 16 + (lane & 15) : tid, half = EW == 32 ? lane >> 4 : 0;
     const bool valid = row < n;
     pdl_wait();
     pdl_launch_dependents();
     const float z2 = __ldg(dust_bin) * VPR_L2E;
-    float e[32], mx2, dj;
-    rt_load_row(S + ((size_t)b * n + (valid ? row : n - 1)) * 64 + half * 32, valid, z2, e, mx2, dj);
-    rt_store_row(tile + row * RT_PITCH + half * 32, e);
+    float e[EW], mx2, dj;
+    rt_load_row<EW>(S + ((size_t)b * n + (valid ? row : n - 1)) * 64 + half * EW, valid, z2, e, mx2, dj);
+    rt_store_row<EW>(tile + row * RT_PITCH + half * EW, e);
     if (half == 0) dcol[row] = dj;
     {
-        float wm = valid ? mx2 : -INFINITY;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+        const float wm = rt_warp_max(valid ? mx2 : -INFINITY);
         if (lane == 0) misc[warp] = wm;
         if (tid == 0) misc[16] = 0.f;
     }
     __syncthreads();
     float B0 = misc[0];
 #pragma unroll
-    for (int w = 1; w < RT_NT / 32; ++w) B0 = fmaxf(B0, misc[w]);
+    for (int w = 1; w < NW; ++w) B0 = fmaxf(B0, misc[w]);
     float bj = valid ? fex2(mx2 - B0) : 0.f;                     // beta_j with v = 0
     if (half == 0) beta[row] = bj;
     const float kappa = fex2(k.log_a_m2 - k.norm2);              // a_dustbin / a_cluster = n - m
-    const int cl = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+    const int cl = rt_col_of_lane<CW>(lane);
+    const bool writer = (lane & (32 / CW - 1)) == 0;
     bool bad = false;
     __syncthreads();
 
     for (int it = 0; it < iters; ++it) {
         // ---- u_c = log_a_c - LSE_j(M_jc + v_j) = log_a_c - (B0 + log2 r_c),  r_c = sum_j E_jc beta_j ----
         float tot, dtot;
-        rt_col_sums<false>(tile, beta, dcol, warp, lane, tot, dtot);
+        rt_col_sums<NT, false>(tile, beta, dcol, warp, lane, tot, dtot);
         bad |= !rt_in_range(tot);
         float* Ub = U + ((size_t)b * iters + it) * 65;
-        if ((lane & 7) == 0) {
-            alpha[4 * warp + cl] = rt_rcp(tot);
-            Ub[4 * warp + cl] = (k.norm2 - B0 - flg2(tot)) * VPR_LN2;
+        if (writer) {
+            alpha[CW * warp + cl] = rt_rcp(tot);
+            Ub[CW * warp + cl] = (k.norm2 - B0 - flg2(tot)) * VPR_LN2;
         }
         if (tid == 0) {
             bad |= !rt_in_range(dtot);
@@ -209,8 +231,7 @@ __global__ void __launch_bounds__(RT_NT, 2) sinkhorn_fwd_rt(const float* __restr
         }
         __syncthreads();
         // ---- v_j = log_b - LSE_c(M_jc + u_c) = B0 - mx_j - log2 s_j,  s_j = sum_c E_jc alpha_c ----
-        float s = rt_row_dot(e, alpha + half * 32);
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        float s = rt_row_dot<EW>(e, alpha + half * EW);
         s = fmaf(dj, alpha[64], s);
         if (!valid) s = 1.f;
         bad |= !rt_in_range(s);
@@ -227,16 +248,16 @@ __global__ void __launch_bounds__(RT_NT, 2) sinkhorn_fwd_rt(const float* __restr
         simt_emu::note_guard();
 #else
         __syncthreads();
-        sinkhorn_fwd_logdomain<TP, 64>(sk_smem, S, dust_bin, P, U, V, n, iters, k);
+        sinkhorn_fwd_logdomain<TP, 64, NT>(sk_smem, S, dust_bin, P, U, V, n, iters, k);
 #endif
         return;
     }
     // ---- P_jc = 2^(M_jc + u_c + v_j - norm) = E_jc * alpha_c * beta_j ----
     if (valid) {
-        TP* Pr = P + ((size_t)b * n + row) * 64 + half * 32;
-        const float* ah = alpha + half * 32;
+        TP* Pr = P + ((size_t)b * n + row) * 64 + half * EW;
+        const float* ah = alpha + half * EW;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < EW / 8; ++i) {
             const float4 x = *reinterpret_cast<const float4*>(ah + 8 * i);
             const float4 y = *reinterpret_cast<const float4*>(ah + 8 * i + 4);
             const float p0 = e[8 * i] * bj * x.x, p1 = e[8 * i + 1] * bj * x.y, p2 = e[8 * i + 2] * bj * x.z,
@@ -258,11 +279,13 @@ __global__ void __launch_bounds__(RT_NT, 2) sinkhorn_fwd_rt(const float* __restr
 }
 
 // K: Sinkhorn iteration count (compile time: the per-iteration row factors live in registers).
-template <typename TD, int K>
-__global__ void __launch_bounds__(RT_NT, 2) sinkhorn_bwd_rt(const float* __restrict__ S, const float* __restrict__ dust_bin,
-                                                            const float* __restrict__ U, const float* __restrict__ V,
-                                                            const float* __restrict__ dP, TD* __restrict__ dS,
-                                                            float* __restrict__ d_bias, int n, SinkConst2 k) {
+template <typename TD, int K, int NT>
+__global__ void __launch_bounds__(NT, 2) sinkhorn_bwd_rt(const float* __restrict__ S, const float* __restrict__ dust_bin,
+                                                         const float* __restrict__ U, const float* __restrict__ V,
+                                                         const float* __restrict__ dP, TD* __restrict__ dS,
+                                                         float* __restrict__ d_bias, int n, SinkConst2 k) {
+    static_assert(NT == 512 || NT == 256, "two threads or one thread per token row");
+    constexpr int EW = 64 * RT_ROWS / NT, CW = 2048 / NT, NW = NT / 32;
     VPR_RT_SMEM(sk_smem);
     float* tile = sk_smem;                         // [RT_ROWS][RT_PITCH]  E*X - Gt first, E afterwards
     float* dcol = tile + RT_ROWS * RT_PITCH;       // [RT_ROWS]  dustbin column of E
@@ -273,21 +296,21 @@ __global__ void __launch_bounds__(RT_NT, 2) sinkhorn_bwd_rt(const float* __restr
     float* Y = aK + K * RT_VEC;                    // [K][RT_VEC]  du^k_c * a^k_c ; [64] dustbin
     float* Ak = Y + K * RT_VEC;                    // [16]  shift of iteration k
     float* misc = Ak + 16;                         // [0] guard flag
-    float* red = misc + 32;                        // [RT_NT/32][64]  score-bias partial sums
+    float* red = misc + 32;                        // [NW][64]  score-bias partial sums
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row = warp * 16 + (lane & 15), half = lane >> 4;
+    const int row = EW == 32 ? warp * 16 + (lane & 15) : tid, half = EW == 32 ? lane >> 4 : 0;
     const bool valid = row < n;
     const int rowc = valid ? row : n - 1;
     pdl_wait();
     pdl_launch_dependents();
     const float z2 = __ldg(dust_bin) * VPR_L2E;
-    float e[32], mx2, dj;
-    rt_load_row(S + ((size_t)b * n + rowc) * 64 + half * 32, valid, z2, e, mx2, dj);
+    float e[EW], mx2, dj;
+    rt_load_row<EW>(S + ((size_t)b * n + rowc) * 64 + half * EW, valid, z2, e, mx2, dj);
     float vk[K];
 #pragma unroll
     for (int kk = 0; kk < K; ++kk) vk[kk] = __ldg(V + ((size_t)b * K + kk) * n + rowc) * VPR_L2E;
     // per-iteration cluster factors: warp kk handles iteration kk
-    for (int kk = warp; kk < K; kk += RT_NT / 32) {
+    for (int kk = warp; kk < K; kk += NW) {
         const float* Ub = U + ((size_t)b * K + kk) * 65;
         const float u0 = __ldg(Ub + lane) * VPR_L2E, u1 = __ldg(Ub + 32 + lane) * VPR_L2E, um = __ldg(Ub + 64) * VPR_L2E;
         const float A = rt_warp_max(fmaxf(fmaxf(u0, u1), um));
@@ -301,8 +324,8 @@ __global__ void __launch_bounds__(RT_NT, 2) sinkhorn_bwd_rt(const float* __restr
     }
     if (tid == 0) misc[0] = 0.f;
     if (half == 0) dcol[row] = dj;
-    // first half of this row's dP is requested before the barrier: its latency hides behind it
-    const float4* dsrc = reinterpret_cast<const float4*>(dP + ((size_t)b * n + rowc) * 64 + half * 32);
+    // the first four 16-byte pieces of this row's dP are requested before the barrier: their latency hides behind it
+    const float4* dsrc = reinterpret_cast<const float4*>(dP + ((size_t)b * n + rowc) * 64 + half * EW);
     float4 d[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) d[u] = __ldg(dsrc + u);
@@ -329,16 +352,16 @@ __global__ void __launch_bounds__(RT_NT, 2) sinkhorn_bwd_rt(const float* __restr
         }
     }
     // ---- G = dP * P (P = Wv^{K-1}):  Gt_jc = dP_jc E_jc bv_j into the tile,  dv_j = bv_j * sum_c dP_jc E_jc a_c ----
-    float* trow = tile + row * RT_PITCH + half * 32;
+    float* trow = tile + row * RT_PITCH + half * EW;
     const float bvL = bv[K - 1];
     {
-        const float* aL = aK + (K - 1) * RT_VEC + half * 32;
+        const float* aL = aK + (K - 1) * RT_VEC + half * EW;
         float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-        for (int h4 = 0; h4 < 2; ++h4) {
-            if (h4 == 1) {
+        for (int h4 = 0; h4 < EW / 16; ++h4) {
+            if (h4 > 0) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) d[u] = __ldg(dsrc + 4 + u);
+                for (int u = 0; u < 4; ++u) d[u] = __ldg(dsrc + 4 * h4 + u);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -351,11 +374,11 @@ __global__ void __launch_bounds__(RT_NT, 2) sinkhorn_bwd_rt(const float* __restr
             }
         }
         float rs = rs0 + rs1;
-        rs += __shfl_xor_sync(0xffffffffu, rs, 16);
+        if (EW == 32) rs += __shfl_xor_sync(0xffffffffu, rs, 16);
         const float Xl = rs * bvL * bvL;                         // dv^{K-1}_j * bv^{K-1}_j
         // the row becomes E*X - Gt: the column sums of the first adjoint step and of G are one pass
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < EW / 4; ++i) {
             float4 t = *reinterpret_cast<const float4*>(trow + 4 * i);
             t.x = fmaf(e[4 * i], Xl, -t.x); t.y = fmaf(e[4 * i + 1], Xl, -t.y);
             t.z = fmaf(e[4 * i + 2], Xl, -t.z); t.w = fmaf(e[4 * i + 3], Xl, -t.w);
@@ -369,29 +392,29 @@ __global__ void __launch_bounds__(RT_NT, 2) sinkhorn_bwd_rt(const float* __restr
         simt_emu::note_guard();
 #else
         __syncthreads();
-        sinkhorn_bwd_logdomain<TD, 64>(sk_smem, S, dust_bin, U, V, dP, dS, d_bias, n, K, k);
+        sinkhorn_bwd_logdomain<TD, 64, NT>(sk_smem, S, dust_bin, U, V, dP, dS, d_bias, n, K, k);
 #endif
         return;
     }
-    const int cl = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+    const int cl = rt_col_of_lane<CW>(lane);
+    const bool writer = (lane & (32 / CW - 1)) == 0;
 #pragma unroll
     for (int kk = K - 1; kk >= 0; --kk) {
         const float* ak = aK + kk * RT_VEC;
         // du^k_c = [k = K-1: sum_j G_jc] - sum_j dv^k_j Wv^k_jc = -a^k_c * sum_j (E_jc X^k_j [- Gt_jc])
         float tot, dtot;
-        if (kk == K - 1) rt_col_sums<true>(tile, xs + kk * RT_ROWS, dcol, warp, lane, tot, dtot);
-        else rt_col_sums<false>(tile, xs + kk * RT_ROWS, dcol, warp, lane, tot, dtot);
-        if ((lane & 7) == 0) {
-            const float ac = ak[4 * warp + cl];
-            Y[kk * RT_VEC + 4 * warp + cl] = -ac * ac * tot;
+        if (kk == K - 1) rt_col_sums<NT, true>(tile, xs + kk * RT_ROWS, dcol, warp, lane, tot, dtot);
+        else rt_col_sums<NT, false>(tile, xs + kk * RT_ROWS, dcol, warp, lane, tot, dtot);
+        if (writer) {
+            const float ac = ak[CW * warp + cl];
+            Y[kk * RT_VEC + CW * warp + cl] = -ac * ac * tot;
         }
         if (tid == 0) Y[kk * RT_VEC + 64] = -ak[64] * dtot * ak[65];
         __syncthreads();                                         // Y^k ready, every read of the tile done
-        if (kk == K - 1) rt_store_row(trow, e);                  // the tile is E from here on
+        if (kk == K - 1) rt_store_row<EW>(trow, e);              // the tile is E from here on
         if (kk > 0) {
             // dv^{k-1}_j = - sum_c du^k_c Wu^k_jc = - bu^k_j * sum_c E_jc y^k_c
-            float s = rt_row_dot(e, Y + kk * RT_VEC + half * 32);
-            s += __shfl_xor_sync(0xffffffffu, s, 16);
+            float s = rt_row_dot<EW>(e, Y + kk * RT_VEC + half * EW);
             s = fmaf(dj, Y[kk * RT_VEC + 64], s);
             const float Xp = -bu[kk] * s * bv[kk - 1];
             if (half == 0) xs[(kk - 1) * RT_ROWS + row] = Xp;
@@ -402,8 +425,10 @@ __global__ void __launch_bounds__(RT_NT, 2) sinkhorn_bwd_rt(const float* __restr
     }
     // ---- dM_jc = G_jc - sum_k (dv^k_j Wv^k_jc + du^k_c Wu^k_jc)
     //            = E_jc * (dP_jc a^{K-1}_c bv^{K-1}_j - sum_k (a^k_c x^k_j + y^k_c bu^k_j)) ----
-    // column-owner mapping: thread = (4 clusters cg, 8 rows), per-cluster coefficients in registers, dP / dS coalesced
+    // column-owner mapping: thread = (4 clusters cg, every (NT/16)-th row), per-cluster coefficients in registers,
+    // dP / dS coalesced
     {
+        constexpr int RSTEP = NT / 16, RPT = RT_ROWS / RSTEP;    // rows per thread: 8 or 16
         const int cg = tid & 15, jr = tid >> 4;
         float4 ar[K], yr[K];
 #pragma unroll
@@ -416,16 +441,16 @@ __global__ void __launch_bounds__(RT_NT, 2) sinkhorn_bwd_rt(const float* __restr
         TD* dSb = dS + (size_t)b * n * 64;
         float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int h4 = 0; h4 < 2; ++h4) {
+        for (int h4 = 0; h4 < RPT / 4; ++h4) {
             float4 g[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int j = (h4 * 4 + u) * 32 + jr;
+                const int j = (h4 * 4 + u) * RSTEP + jr;
                 g[u] = __ldg(reinterpret_cast<const float4*>(dPb + (size_t)(j < n ? j : n - 1) * 64) + cg);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int j = (h4 * 4 + u) * 32 + jr;
+                const int j = (h4 * 4 + u) * RSTEP + jr;
                 if (j < n) {
                     const float4 e4 = *reinterpret_cast<const float4*>(tile + j * RT_PITCH + cg * 4);
                     const float bjl = bvl[j];
@@ -459,7 +484,7 @@ __global__ void __launch_bounds__(RT_NT, 2) sinkhorn_bwd_rt(const float* __restr
             if (tid < 64) {
                 float t = 0.f;
 #pragma unroll
-                for (int w = 0; w < RT_NT / 32; ++w) t += red[w * 64 + tid];
+                for (int w = 0; w < NW; ++w) t += red[w * 64 + tid];
                 atomicAdd(d_bias + tid, t);
             }
         }
