@@ -45,7 +45,8 @@
  *  - vpr_preprocess_image / _batch : transforms.Resize + ToTensor + Normalize, dinov2salad_finetuning.py:45-50.
  *  Environment knobs read once per process (A/B measurements): VPR_PDL, VPR_GEMM_2CTA, VPR_GEMM_MCB, VPR_FS_FUSED,
  *  VPR_FS_REVERSE, VPR_DH_FUSED, VPR_AGG_FUSED, VPR_AGG_BWD_FUSED, VPR_TOKEN_SIDE, VPR_KNN_L2_MB.  Read at every call:
- *  VPR_SINK_RT (0 = n <= 256 stays on the shared-memory-tile Sinkhorn kernels instead of the register-tile ones).
+ *  VPR_SINK_RT (0 = n <= 256 stays on the shared-memory-tile Sinkhorn kernels instead of the register-tile ones, 2 = their
+ *  one-thread-per-row variant), VPR_SINKAGG_FUSED (1 = Sinkhorn + aggregation + descriptor assembly in one launch).
  */
 #ifndef VPR_B200_H
 #define VPR_B200_H

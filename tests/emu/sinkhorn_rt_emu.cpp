@@ -46,6 +46,25 @@ int emu_sinkhorn_bwd_rt3(const float* S, const float* dust_bin, const float* U, 
         simt_emu::launch(B, nt, smem, [=]() { vpr::sinkhorn_bwd_rt<float, 3, 256>(S, dust_bin, U, V, dP, (float*)dS, d_bias, n, k); });
     return simt_emu::guard_count.load();
 }
+// Forward with the plan ALSO written as the aggregation MMA's shared-memory B operand (what the fused Sinkhorn +
+// aggregation kernel does); the operand bytes of every image ([op_rows / 128] chunks of 16 KB) are copied out to `op_out`.
+int emu_sinkhorn_fwd_rt_operand(const float* S, const float* dust_bin, void* P, float* U, float* V, unsigned char* op_out, int B, int n,
+                                int iters) {
+    simt_emu::guard_count = 0;
+    const vpr::SinkConst2 k = consts(n);
+    const size_t smem = vpr::sinkrt_fwd_floats() * sizeof(float);
+    const int op_rows = (n + 127) / 128 * 128;
+    simt_emu::launch(B, 512, smem, [=]() {
+        float* sk = simt_emu::dyn_smem();
+        vpr::RtFwdState<512> st;
+        if (vpr::rt_fwd_iterate<512>(sk, S, dust_bin, U, V, n, iters, k, st)) { simt_emu::note_guard(); return; }
+        uint8_t* op = reinterpret_cast<uint8_t*>(sk);            // over the dead tile, as in the fused kernel
+        vpr::rt_fwd_plan<__nv_bfloat16, 512, true>(sk + vpr::RT_ROWS * vpr::RT_PITCH + 2 * vpr::RT_ROWS, st, (__nv_bfloat16*)P, n, op, op_rows);
+        __syncthreads();
+        for (int i = threadIdx.x; i < op_rows * 128; i += 512) op_out[(size_t)blockIdx.x * op_rows * 128 + i] = op[i];
+    });
+    return simt_emu::guard_count.load();
+}
 size_t emu_sinkrt_fwd_bytes() { return vpr::sinkrt_fwd_floats() * sizeof(float); }
 size_t emu_sinkrt_bwd_bytes(int iters) { return vpr::sinkrt_bwd_floats(iters) * sizeof(float); }
 }

@@ -141,6 +141,33 @@ def test_register_tile_range_guard_asks_for_the_log_domain_body(emu, nt):
     assert guards == 1 and torch.isfinite(dS[0]).all() and torch.isnan(dS[1]).all()
 
 
+@pytest.mark.parametrize("n", [256, 196, 100])
+def test_plan_written_as_the_aggregation_mma_operand(emu, n):
+    """The fused Sinkhorn + aggregation kernel never reads the plan back: the row owners write it, as bf16, straight into
+    the SWIZZLE_128B layout the tcgen05 B operand expects (what a TMA load of the [tokens, 64] plan with a 64 x 128 box
+    would have produced): 128-token chunks of 16 KB, one 128-byte row per token, 16-byte unit q at q ^ (row & 7)."""
+    g = torch.Generator().manual_seed(n + 7)
+    S = (torch.randn(2, 64, n, generator=g) * 2.0).transpose(1, 2).contiguous()
+    db = torch.tensor([1.0])
+    P = torch.full((2, n, 64), float("nan"), dtype=torch.bfloat16)
+    U = torch.empty(2, 3, 65)
+    V = torch.empty(2, 3, n)
+    rows = (n + 127) // 128 * 128
+    op = torch.full((2, rows * 128), 0xAB, dtype=torch.uint8)
+    assert emu.emu_sinkhorn_fwd_rt_operand(ptr(S), ptr(db), ptr(P), ptr(U), ptr(V), ptr(op), 2, n, 3) == 0
+    Pref, _, _, _ = run_fwd(emu, S, db, 3, bf16=True)
+    assert torch.equal(P, Pref)
+    want = torch.zeros(2, rows, 64, dtype=torch.bfloat16)
+    want[:, :n] = Pref
+    units = want.view(torch.uint8).reshape(2, rows // 128, 128, 8, 16)        # [image, chunk, row, unit, 16 bytes]
+    r = torch.arange(128)
+    q = torch.arange(8)
+    phys = (q[None, :] ^ (r[:, None] & 7))                                      # unit q of row r lives at unit q ^ (r & 7)
+    laid = torch.empty_like(units)
+    laid[:, :, r[:, None], phys] = units[:, :, r[:, None], q[None, :]]
+    assert torch.equal(op, laid.reshape(2, rows * 128))
+
+
 def test_register_tile_shared_memory_budget_keeps_two_ctas_per_sm(emu):
     # 227 KB usable per SM, 1 KB reserved per CTA: two CTAs of either kernel must fit side by side
     assert 2 * (emu.emu_sinkrt_fwd_bytes() + 1024) <= 227 * 1024

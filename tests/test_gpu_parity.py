@@ -217,6 +217,37 @@ def _run_pair(vpr, ref, mod, B, hw, seed, dtype, train=False, nchw=False):
     return errs, out
 
 
+@pytest.mark.parametrize("B,hw,scale", [(3, 16, 1.0), (2, 14, 1.0), (5, 10, 1.0), (300, 16, 1.0), (3, 16, 200.0), (2, 12, 200.0)])
+def test_fused_sinkhorn_aggregation_launch_matches_the_two_launch_path(vpr, monkeypatch, B, hw, scale):
+    """VPR_SINKAGG_FUSED=1: n <= 256 in bf16 runs Sinkhorn + aggregation + descriptor assembly as ONE launch
+    (csrc/sink_agg_fwd.cu: the plan goes from the solver's registers into the MMA operand in shared memory); the default
+    keeps the two launches (sinkhorn_fwd_rt, agg_fwd_kernel), which measured faster at the benchmarked batch.  Same plan bits either way, so descriptors and every gradient agree to reduction
+    order.  scale = 200 blows the score range up to thousands of nats: every image takes the fused kernel's range-guard
+    path (log-domain body, plan re-read into the operand layout)."""
+    ref, mod = _pair(vpr, dropout=0.0, round_weights=True)
+    with torch.no_grad():
+        mod.score[3].weight.mul_(scale)
+    g = torch.Generator().manual_seed(B * 100 + hw)
+    n = hw * hw
+    x = torch.randn(B, n, 768, generator=g).bfloat16().cuda()
+    t = torch.randn(B, 768, generator=g).bfloat16().cuda()
+    w = torch.randn(B, 8448, generator=g).cuda()
+    res = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("VPR_SINKAGG_FUSED", fused)
+        for p in mod.parameters():
+            p.grad = None
+        xg, tg = x.clone().requires_grad_(True), t.clone().requires_grad_(True)
+        out = mod((O.tokens_to_salad_input(xg, hw, hw), tg))
+        (out.float() * w).sum().backward()
+        res[fused] = (out.detach().float(), xg.grad.float(), mod.cluster_features[3].weight.grad.clone(),
+                      mod.score[0].weight.grad.clone())
+    assert torch.isfinite(res["1"][0]).all()
+    np.testing.assert_allclose(res["1"][0].norm(dim=1).cpu().numpy(), 1.0, atol=5e-3)
+    for a, b in zip(res["1"], res["0"]):
+        assert rel(a, b) < 5e-3
+
+
 @pytest.mark.parametrize("B,hw", [(2, 16), (2, 23), (1, 9), (5, 10)])
 def test_salad_fp32_matches_oracle(vpr, B, hw):
     ref, mod = _pair(vpr)

@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libvpr_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "dh_fused.cu", "fs_fwd.cu", "agg_fwd.cu", "agg_bwd.cu", "salad.cu", "heads.cu", "knn.cu", "seam.cu",
+SOURCES = ["api.cu", "gemm.cu", "dh_fused.cu", "fs_fwd.cu", "agg_fwd.cu", "sink_agg_fwd.cu", "agg_bwd.cu", "salad.cu", "heads.cu", "knn.cu", "seam.cu",
            "metrics.cu", "preprocess.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -89,6 +89,21 @@ struct AggFwdDesc {
 bool agg_fwd_supported(int dtype, int l, int m, int g, int n);
 int agg_fwd_run(const AggFwdDesc& d, cudaStream_t stream);
 
+// SALAD forward, Sinkhorn + aggregation + descriptor assembly in one launch, one CTA per image (sink_agg_fwd.cu):
+// n <= 256 tokens, l == 128, m == 64, bf16.  The plan goes from the solver's registers into the MMA operand in shared memory.
+struct SinkAggFwdDesc {
+    const float* S; const float* dust_bin;   // [B, n, 64] fp32 scores, device scalar
+    const void* F;                           // [B, n, 128] bf16
+    void* P; float* U; float* V;             // [B, n, 64] bf16 plan and [B, iters, 65] / [B, iters, n] potentials (kept for the backward)
+    const float* TF;                         // [B, g] fp32
+    float* AGG;                              // [B, 128, 64] fp32 (kept for the backward)
+    void* out;                               // [B, g + 8192] bf16
+    int B, n, g, iters;
+    int pdl = 0;
+};
+bool sink_agg_fwd_supported(int dtype, int l, int m, int g, int n, int iters);
+int sink_agg_fwd_run(const SinkAggFwdDesc& d, cudaStream_t stream);
+
 // SALAD backward, first step, one CTA per image: cluster part of the descriptor-assembly backward fused with
 // dF = P dAGG^T and dP = F dAGG (dAGG never leaves shared memory).  dtype bf16, l == 128, m == 64.
 struct AggBwdDesc {

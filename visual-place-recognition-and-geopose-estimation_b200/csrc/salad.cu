@@ -709,6 +709,15 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
         g[0].pdl = 1;
         VPR_TRY(gemm_run_group(g, 3, st));
     }
+    if (sink_agg_fwd_supported(dtype, s.l, s.m, s.g, s.n, s.iters) && agg_fwd_supported(dtype, s.l, s.m, s.g, s.n)) {
+        if constexpr (sizeof(T) == 2) {          // Sinkhorn + aggregation + descriptor assembly in one launch, one CTA per image
+            SinkAggFwdDesc sd;
+            sd.S = S; sd.dust_bin = p.dust_bin; sd.F = F; sd.P = P; sd.U = U; sd.V = V; sd.TF = TF; sd.AGG = AGG; sd.out = out;
+            sd.B = s.B; sd.n = s.n; sd.g = s.g; sd.iters = s.iters;
+            sd.pdl = 1;
+            return sink_agg_fwd_run(sd, st);
+        }
+    }
     // P = sinkhorn(S)
     VPR_TRY(sinkhorn_fwd(S, p.dust_bin, P, dtype, U, V, s.B, s.n, s.m, s.iters, st, true));
     if (agg_fwd_supported(dtype, s.l, s.m, s.g, s.n)) {

@@ -173,15 +173,28 @@ __device__ __forceinline__ float rt_row_dot(const float (&e)[EW], const float* y
     return s;
 }
 
-template <typename TP, int NT>
-__global__ void __launch_bounds__(NT, 2) sinkhorn_fwd_rt(const float* __restrict__ S, const float* __restrict__ dust_bin,
-                                                         TP* __restrict__ P, float* __restrict__ U, float* __restrict__ V,
-                                                         int n, int iters, SinkConst2 k) {
+// Where a thread sits in the forward: its token row, which part of the row it holds, and what it keeps in registers.
+template <int NT>
+struct RtFwdState {
+    static constexpr int EW = 64 * RT_ROWS / NT;   // tile entries a thread holds (32 or 64)
+    float e[EW];        // E_j,c for the thread's clusters
+    float bj;           // beta_j = 2^(v_j + mx_j - B0) after the last iteration (0 for rows >= n)
+    int row, half;
+    bool valid;
+};
+
+// Everything of the forward up to the plan: load, exponentiate, iterate.  `sk_smem` holds sinkrt_fwd_floats() floats;
+// on return alpha (sk_smem + RT_ROWS * RT_PITCH + 2 * RT_ROWS) holds the last iteration's 2^(u_c - (norm - B0)) and the
+// tile region [0, RT_ROWS * RT_PITCH) is dead.  Returns true (block-uniform) if the factors left fp32 range and the
+// image has to go through the log-domain body instead.  Ends with a block barrier.
+template <int NT>
+__device__ __forceinline__ bool rt_fwd_iterate(float* sk_smem, const float* __restrict__ S, const float* __restrict__ dust_bin,
+                                               float* __restrict__ U, float* __restrict__ V, int n, int iters, SinkConst2 k,
+                                               RtFwdState<NT>& st) {
     static_assert(NT == 512 || NT == 256, "two threads or one thread per token row");
-    constexpr int EW = 64 * RT_ROWS / NT;          // tile entries a thread holds (32 or 64)
+    constexpr int EW = RtFwdState<NT>::EW;
     constexpr int CW = 2048 / NT;                  // clusters a warp owns in the column passes (4 or 8)
     constexpr int NW = NT / 32;
-    VPR_RT_SMEM(sk_smem);
     float* tile = sk_smem;                         // [RT_ROWS][RT_PITCH]  E
     float* beta = tile + RT_ROWS * RT_PITCH;       // [RT_ROWS]  2^(v_j + mx_j - B0)
     float* dcol = beta + RT_ROWS;                  // [RT_ROWS]  dustbin column of E
@@ -190,10 +203,10 @@ __global__ void __launch_bounds__(NT, 2) sinkhorn_fwd_rt(const float* __restrict
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row = EW == 32 ? warp * 16 + (lane & 15) : tid, half = EW == 32 ? lane >> 4 : 0;
     const bool valid = row < n;
-    pdl_wait();
-    pdl_launch_dependents();
+    st.row = row; st.half = half; st.valid = valid;
+    float (&e)[EW] = st.e;
     const float z2 = __ldg(dust_bin) * VPR_L2E;
-    float e[EW], mx2, dj;
+    float mx2, dj;
     rt_load_row<EW>(S + ((size_t)b * n + (valid ? row : n - 1)) * 64 + half * EW, valid, z2, e, mx2, dj);
     rt_store_row<EW>(tile + row * RT_PITCH + half * EW, e);
     if (half == 0) dcol[row] = dj;
@@ -243,7 +256,65 @@ __global__ void __launch_bounds__(NT, 2) sinkhorn_fwd_rt(const float* __restrict
         if (bad) misc[16] = 1.f;
         __syncthreads();
     }
-    if (misc[16] != 0.f) {                                       // block-uniform: out of fp32 range -> exact path
+    st.bj = bj;
+    return misc[16] != 0.f;
+}
+
+// Byte offset of the 16-byte unit `q` (clusters 8q .. 8q+7) of token `j` inside the bf16 plan laid out as the
+// aggregation MMA's B operand: 128-token chunks of 16 KB, one 128-byte row per token, SWIZZLE_128B (unit ^= row & 7) --
+// the bytes a TMA load of the [tokens, 64] bf16 plan with a 64 x 128 box would have produced.
+__device__ __forceinline__ uint32_t rt_plan_operand_offset(int j, int q) {
+    const int r = j & 127;
+    return (uint32_t)((j >> 7) * 16384 + r * 128 + ((q ^ (r & 7)) << 4));
+}
+
+// P_jc = 2^(M_jc + u_c + v_j - norm) = E_jc * alpha_c * beta_j: this thread's part of its row to global memory
+// (rows < n) and, OPERAND, also as bf16 into the shared-memory MMA operand `op` (rows >= n as zeros up to `op_rows`).
+template <typename TP, int NT, bool OPERAND>
+__device__ __forceinline__ void rt_fwd_plan(const float* alpha, const RtFwdState<NT>& st, TP* __restrict__ P, int n,
+                                            uint8_t* op, int op_rows) {
+    constexpr int EW = RtFwdState<NT>::EW;
+    static_assert(!OPERAND || sizeof(TP) == 2, "the MMA operand is bf16");
+    const int b = blockIdx.x;
+    const float bj = st.bj;
+    TP* Pr = P + ((size_t)b * n + st.row) * 64 + st.half * EW;
+    const float* ah = alpha + st.half * EW;
+    if (st.valid || (OPERAND && st.row < op_rows)) {
+#pragma unroll
+        for (int i = 0; i < EW / 8; ++i) {
+            const float4 x = *reinterpret_cast<const float4*>(ah + 8 * i);
+            const float4 y = *reinterpret_cast<const float4*>(ah + 8 * i + 4);
+            const float p0 = st.e[8 * i] * bj * x.x, p1 = st.e[8 * i + 1] * bj * x.y, p2 = st.e[8 * i + 2] * bj * x.z,
+                        p3 = st.e[8 * i + 3] * bj * x.w, p4 = st.e[8 * i + 4] * bj * y.x, p5 = st.e[8 * i + 5] * bj * y.y,
+                        p6 = st.e[8 * i + 6] * bj * y.z, p7 = st.e[8 * i + 7] * bj * y.w;
+            if constexpr (sizeof(TP) == 2) {
+                __nv_bfloat162 q0 = __floats2bfloat162_rn(p0, p1), q1 = __floats2bfloat162_rn(p2, p3),
+                               q2 = __floats2bfloat162_rn(p4, p5), q3 = __floats2bfloat162_rn(p6, p7);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&q0); pk.y = *reinterpret_cast<uint32_t*>(&q1);
+                pk.z = *reinterpret_cast<uint32_t*>(&q2); pk.w = *reinterpret_cast<uint32_t*>(&q3);
+                if (st.valid) *reinterpret_cast<uint4*>(Pr + 8 * i) = pk;
+                if constexpr (OPERAND) {
+                    if (!st.valid) pk.x = pk.y = pk.z = pk.w = 0u;     // (e and beta are zeros there anyway)
+                    *reinterpret_cast<uint4*>(op + rt_plan_operand_offset(st.row, st.half * (EW / 8) + i)) = pk;
+                }
+            } else {
+                *reinterpret_cast<float4*>(Pr + 8 * i) = make_float4(p0, p1, p2, p3);
+                *reinterpret_cast<float4*>(Pr + 8 * i + 4) = make_float4(p4, p5, p6, p7);
+            }
+        }
+    }
+}
+
+template <typename TP, int NT>
+__global__ void __launch_bounds__(NT, 2) sinkhorn_fwd_rt(const float* __restrict__ S, const float* __restrict__ dust_bin,
+                                                         TP* __restrict__ P, float* __restrict__ U, float* __restrict__ V,
+                                                         int n, int iters, SinkConst2 k) {
+    VPR_RT_SMEM(sk_smem);
+    pdl_wait();
+    pdl_launch_dependents();
+    RtFwdState<NT> st;
+    if (rt_fwd_iterate<NT>(sk_smem, S, dust_bin, U, V, n, iters, k, st)) {     // block-uniform: out of fp32 range -> exact path
 #ifdef VPR_SIMT_EMU
         simt_emu::note_guard();
 #else
@@ -252,30 +323,7 @@ __global__ void __launch_bounds__(NT, 2) sinkhorn_fwd_rt(const float* __restrict
 #endif
         return;
     }
-    // ---- P_jc = 2^(M_jc + u_c + v_j - norm) = E_jc * alpha_c * beta_j ----
-    if (valid) {
-        TP* Pr = P + ((size_t)b * n + row) * 64 + half * EW;
-        const float* ah = alpha + half * EW;
-#pragma unroll
-        for (int i = 0; i < EW / 8; ++i) {
-            const float4 x = *reinterpret_cast<const float4*>(ah + 8 * i);
-            const float4 y = *reinterpret_cast<const float4*>(ah + 8 * i + 4);
-            const float p0 = e[8 * i] * bj * x.x, p1 = e[8 * i + 1] * bj * x.y, p2 = e[8 * i + 2] * bj * x.z,
-                        p3 = e[8 * i + 3] * bj * x.w, p4 = e[8 * i + 4] * bj * y.x, p5 = e[8 * i + 5] * bj * y.y,
-                        p6 = e[8 * i + 6] * bj * y.z, p7 = e[8 * i + 7] * bj * y.w;
-            if constexpr (sizeof(TP) == 2) {
-                __nv_bfloat162 q0 = __floats2bfloat162_rn(p0, p1), q1 = __floats2bfloat162_rn(p2, p3),
-                               q2 = __floats2bfloat162_rn(p4, p5), q3 = __floats2bfloat162_rn(p6, p7);
-                uint4 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&q0); pk.y = *reinterpret_cast<uint32_t*>(&q1);
-                pk.z = *reinterpret_cast<uint32_t*>(&q2); pk.w = *reinterpret_cast<uint32_t*>(&q3);
-                *reinterpret_cast<uint4*>(Pr + 8 * i) = pk;
-            } else {
-                *reinterpret_cast<float4*>(Pr + 8 * i) = make_float4(p0, p1, p2, p3);
-                *reinterpret_cast<float4*>(Pr + 8 * i + 4) = make_float4(p4, p5, p6, p7);
-            }
-        }
-    }
+    rt_fwd_plan<TP, NT, false>(sk_smem + RT_ROWS * RT_PITCH + 2 * RT_ROWS, st, P, n, nullptr, 0);
 }
 
 // K: Sinkhorn iteration count (compile time: the per-iteration row factors live in registers).
