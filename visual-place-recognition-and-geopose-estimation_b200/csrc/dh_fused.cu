@@ -53,6 +53,7 @@ struct DhArgs {
     int hidden;
     int T;
     float mask_scale;
+    int l2_hints;            // H loads evict-first (its last use in the step), dH stores evict-last (the next two launches read it)
     float* dW1c; float* dW1s; float* db0c; float* db0s; float* db1c;
 };
 
@@ -148,7 +149,11 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
                 mbar_wait(mempty(s), ph ^ 1u);
                 mbar_expect_tx(mfull(s), DH_MASK_BYTES);
                 for (int i = 0; i < 2; ++i)
-                    tma_load_3d(sM + (uint32_t)s * DH_MASK_BYTES + (uint32_t)i * DH_BOX, &tmH, mfull(s), col0 + i * 64, mt * 128, 0);
+                    if (args.l2_hints != 0)
+                        tma_load_3d_hint(sM + (uint32_t)s * DH_MASK_BYTES + (uint32_t)i * DH_BOX, &tmH, mfull(s), col0 + i * 64, mt * 128, 0,
+                                         l2_evict_first_policy());
+                    else
+                        tma_load_3d(sM + (uint32_t)s * DH_MASK_BYTES + (uint32_t)i * DH_BOX, &tmH, mfull(s), col0 + i * 64, mt * 128, 0);
             }
         }
     } else if (warp == DH_W_MMA) {
@@ -271,7 +276,8 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
             }
             named_bar_sync(1 + eg, 128);
             if (issuer) {
-                tma_store_3d(&tmO, sbox, col0 + eg * 64, mt * 128, 0);
+                if (args.l2_hints != 0) tma_store_3d_hint(&tmO, sbox, col0 + eg * 64, mt * 128, 0, l2_evict_last_policy());
+                else tma_store_3d(&tmO, sbox, col0 + eg * 64, mt * 128, 0);
                 bulk_commit();
             }
         }
@@ -345,6 +351,11 @@ int dh_fused_run(const DhFusedDesc& d, cudaStream_t st) {
     a.hidden = h;
     a.T = (int)d.T;
     a.mask_scale = d.mask_scale;
+    {
+        static int hints = -1;
+        if (hints < 0) { const char* e = getenv("VPR_DH_L2HINT"); hints = (e != nullptr && e[0] == '0') ? 0 : 1; }
+        a.l2_hints = hints;
+    }
     a.dW1c = d.dW1c; a.dW1s = d.dW1s; a.db0c = d.db0c; a.db0s = d.db0s; a.db1c = d.db1c;
     const int nct = 2 * a.ct_per_half;
     long long want = (long long)a.tiles_m * nct;

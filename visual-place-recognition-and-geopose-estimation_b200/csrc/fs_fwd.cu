@@ -37,6 +37,7 @@ struct FsArgs {
     int ctas_f, ctas_s;          // CTAs [0, ctas_f) compute F, the next ctas_s compute S, the last two TF
     int tiles_tok;               // 128-row tiles of the token batch
     int rev;                     // walk the token tiles last-to-first: the rows the H launch wrote last are still in L2
+    int l2_hints;                // H loads evict-first, F / S stores evict-last (VPR_FS_L2HINT=0 switches them off)
     const float* bias_f; const float* bias_s; const float* bias_t;
 };
 
@@ -105,11 +106,16 @@ fs_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
             pdl_wait();
             pdl_launch_dependents();
             int stage = 0; uint32_t phase = 0;
+            // H is read exactly once here (the backward's pass over it is a whole forward tail away): evict-first, so
+            // that the 134 MB stream does not push F and S -- which the next two launches read back -- out of L2
+            const uint64_t pol_h = l2_evict_first_policy();
+            const bool hint = args.l2_hints != 0;
             for (int mt = j0; mt < tiles_m; mt += nj)
                 for (int kb = 0; kb < FS_KB; ++kb) {
                     mbar_wait(aempty(stage), phase ^ 1u);
                     mbar_expect_tx(afull(stage), FS_A_STAGE);
-                    tma_load_3d(sA + (uint32_t)stage * FS_A_STAGE, tmA, afull(stage), koff + kb * 64, row_tile(mt) * 128, 0);
+                    if (hint) tma_load_3d_hint(sA + (uint32_t)stage * FS_A_STAGE, tmA, afull(stage), koff + kb * 64, row_tile(mt) * 128, 0, pol_h);
+                    else tma_load_3d(sA + (uint32_t)stage * FS_A_STAGE, tmA, afull(stage), koff + kb * 64, row_tile(mt) * 128, 0);
                     if (++stage == nstages) { stage = 0; phase ^= 1u; }
                 }
         }
@@ -143,6 +149,7 @@ fs_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
         const uint32_t sbuf = sStage + (uint32_t)ew * FS_WBOX;
         const float* bias = kind == 0 ? args.bias_f : kind == 1 ? args.bias_s : args.bias_t + thalf * 128;
         const bool bf = kind == 0;                       // F is stored in bf16, S and TF in fp32
+        const uint64_t pol_out = l2_evict_last_policy();  // the Sinkhorn and aggregation launches read F and S right back
         const int box_cols = bf ? 64 : 32;
         const int nbox = nrows / box_cols;               // F: 2, S: 2, TF half: 4
         int it = 0;
@@ -200,7 +207,8 @@ fs_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_3d(tmO, sbuf, thalf * 128 + bx * box_cols, row_tile(mt) * 128 + q * 32, 0);
+                    if (args.l2_hints != 0) tma_store_3d_hint(tmO, sbuf, thalf * 128 + bx * box_cols, row_tile(mt) * 128 + q * 32, 0, pol_out);
+                    else tma_store_3d(tmO, sbuf, thalf * 128 + bx * box_cols, row_tile(mt) * 128 + q * 32, 0);
                     bulk_commit();
                 }
             }
@@ -250,6 +258,9 @@ int fs_fwd_run(const FsFwdDesc& d, cudaStream_t st) {
         static int rev = -1;
         if (rev < 0) { const char* e = getenv("VPR_FS_REVERSE"); rev = (e != nullptr && e[0] == '0') ? 0 : 1; }
         a.rev = rev;
+        static int hints = -1;
+        if (hints < 0) { const char* e = getenv("VPR_FS_L2HINT"); hints = (e != nullptr && e[0] == '0') ? 0 : 1; }
+        a.l2_hints = hints;
     }
     int grid = num_sms();
     if (grid > 2 * a.tiles_m + 2) grid = 2 * a.tiles_m + 2;
