@@ -304,12 +304,11 @@ static size_t sink_bwd_smem(int n, int m, int iters) {
 // CTAs that hold the other column tiles of the same rows, and marked evict-first it is gone before the last of them has
 // pulled it (dW0 78 -> 100 us, dX 78 -> 94 us, H 92 -> 96 us).  The hints that pay are on the kernels whose streams
 // really have a single reader (fs_fwd, dh_fused).
-static int gemm_l2_hint_mode() {      // 0 none, 1 all three GEMMs' streams, 2 only "H stays in L2 for the next launch"
+static bool gemm_l2_hints() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("VPR_GEMM_L2HINT"); v = (e != nullptr && e[0] == '1') ? 1 : (e != nullptr && e[0] == '2') ? 2 : 0; }
-    return v;
+    if (v < 0) { const char* e = getenv("VPR_GEMM_L2HINT"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }
+    return v == 1;
 }
-static bool gemm_l2_hints() { return gemm_l2_hint_mode() == 1; }
 
 // Threads per image of the register-tile Sinkhorn kernels (n <= 256): 512 = two per token row (default), 256 = one per
 // row (VPR_SINK_RT=2), 0 = stay on the shared-memory-tile kernels of sinkhorn_scaled.cuh (VPR_SINK_RT=0; A/B timing, and
@@ -690,7 +689,6 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
     g[0].A = x; g[0].lda = s.d; g[0].B = w0cat; g[0].ldb = s.d; g[0].M = (int)Tk; g[0].N = 2 * h; g[0].K = s.d;
     g[0].out = H; g[0].out_kind = okT; g[0].ldo = 2 * h; g[0].bias = b0cat; g[0].relu = 1;
     g[0].dropout_p = drop_p; g[0].dropout_seed = seed; g[0].dropout_seed_dev = seed_dev;
-    if (gemm_l2_hint_mode() == 2) g[0].out_l2 = 2;
     if (gemm_l2_hints()) { g[0].a_l2 = 1; g[0].b_l2 = 2; g[0].out_l2 = 2; }   // X streams through, W0cat and H (read back by
                                                                              // the next launch) stay
     g[1] = GemmDesc(); g[1].dtype = dtype;
