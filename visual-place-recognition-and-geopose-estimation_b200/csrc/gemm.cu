@@ -55,7 +55,6 @@ struct TcArgs {
     uint32_t drop_thr; float drop_scale;
     unsigned long long drop_seed;
     const unsigned long long* drop_seed_dev;   // optional device-side offset of the seed
-    int a_l2, b_l2, out_l2, pad_l2;            // L2 eviction hints: 0 none, 1 evict-first, 2 evict-last
 };
 
 struct TcProblem {
@@ -299,14 +298,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             int mit = 0;                                  // masked tiles so far (mask buffer = mit & 1)
             // CTA pair: both producers credit the leader's full barrier, which expects both CTAs' bytes
             const uint32_t full0 = CTA2 ? mapa_shared(full_bar(0), 0u) : full_bar(0);
-            const uint64_t pol_first = l2_evict_first_policy(), pol_last = l2_evict_last_policy();
             for (int w = w_first; w < total_work; w += w_step) {
                 int g, b, mt, nt, kb0, kb1;
                 decode(w, g, b, mt, nt, kb0, kb1);
                 const CUtensorMap* tmA = &grp.p[g].tmA;
                 const CUtensorMap* tmB = &grp.p[g].tmB;
                 const int bb = sargs[g].b_batched ? b : 0;
-                const int a_l2 = sargs[g].a_l2, b_l2 = sargs[g].b_l2;
                 const int m0 = mt * Cfg::TILE_M + (int)cta_rank * BM;
                 const int n0 = nt * BN + (int)cta_rank * (CL2 ? Cfg::B_ROWS : 0);
                 if (MASK && (sargs[g].flags & F_MASK)) {
@@ -326,28 +323,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     const uint32_t sb = sa + A_STAGE_BYTES;
                     const uint32_t fb = full0 + 8u * stage;
                     if (!CTA2 || cta_rank == 0) mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * (CTA2 ? 2 : 1));
-                    auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int l2) {
-                        if (l2 != 0) {
-                            const uint64_t pol = l2 == 1 ? pol_first : pol_last;
-                            if (CTA2) tma_load_3d_2sm_hint(dst, tm, fb, c0, c1, c2, pol);
-                            else tma_load_3d_hint(dst, tm, fb, c0, c1, c2, pol);
-                        } else if (CTA2) {
-                            tma_load_3d_2sm(dst, tm, fb, c0, c1, c2);
-                        } else {
-                            tma_load_3d(dst, tm, fb, c0, c1, c2);
-                        }
+                    auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2) {
+                        if (CTA2) tma_load_3d_2sm(dst, tm, fb, c0, c1, c2);
+                        else tma_load_3d(dst, tm, fb, c0, c1, c2);
                     };
                     // MCB: this CTA's half of the B tile goes to the same place in both CTAs
                     const uint32_t sbh = sb + (MCB ? cta_rank * (uint32_t)(Cfg::B_ROWS * BK * 2) : 0u);
                     auto load_b = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2) {
                         if (MCB) tma_load_3d_mc(dst, tm, fb, c0, c1, c2, (uint16_t)3);
-                        else load(dst, tm, c0, c1, c2, b_l2);
+                        else load(dst, tm, c0, c1, c2);
                     };
                     if (A_MN) {
 #pragma unroll
-                        for (int i = 0; i < BM / 64; ++i) load(sa + i * 8192, tmA, m0 + i * 64, kb * BK, b, a_l2);
+                        for (int i = 0; i < BM / 64; ++i) load(sa + i * 8192, tmA, m0 + i * 64, kb * BK, b);
                     } else {
-                        load(sa, tmA, kb * BK, m0, b, a_l2);
+                        load(sa, tmA, kb * BK, m0, b);
                     }
                     if (B_MN) {
 #pragma unroll
@@ -512,11 +502,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        if (args.out_l2 != 0)
-                            tma_store_3d_hint(&grp.p[g].tmO, sbuf, nt * BN + bx * box_cols, m_base + q * 32, b,
-                                              args.out_l2 == 1 ? l2_evict_first_policy() : l2_evict_last_policy());
-                        else
-                            tma_store_3d(&grp.p[g].tmO, sbuf, nt * BN + bx * box_cols, m_base + q * 32, b);
+                        tma_store_3d(&grp.p[g].tmO, sbuf, nt * BN + bx * box_cols, m_base + q * 32, b);
                         bulk_commit();
                     }
                 }
@@ -858,7 +844,6 @@ static int gemm_tc_group(const GemmDesc* gs, int count, cudaStream_t st) {
         a.drop_thr = g.dropout_p > 0.f ? dropout_threshold(g.dropout_p) : 0u;
         a.drop_scale = g.dropout_p > 0.f ? 1.f / (1.f - g.dropout_p) : 1.f; a.drop_seed = g.dropout_seed;
         a.drop_seed_dev = reinterpret_cast<const unsigned long long*>(g.dropout_seed_dev);
-        a.a_l2 = g.a_l2; a.b_l2 = g.b_l2; a.out_l2 = g.out_l2; a.pad_l2 = 0;
         a.flags = (g.bias ? F_BIAS : 0u) | (g.relu ? F_RELU : 0u) | (a.drop_thr ? F_DROP : 0u) | (g.mask ? F_MASK : 0u) |
                   (g.alpha != 1.f ? F_ALPHA : 0u) | (g.colsum ? F_COLSUM : 0u);
         VPR_REQUIRE(g.colsum == nullptr || g.out_kind == OUT_BF16, "fused column sums need a bf16 output");

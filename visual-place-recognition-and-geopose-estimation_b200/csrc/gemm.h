@@ -34,8 +34,6 @@ struct GemmDesc {
     float* colsum = nullptr;
     int k_splits = 1;              // > 1 requires OUT_ATOMIC_F32 (caller zeroes out)
     int bn = 0;                    // tcgen05 tile N (64/128/256); 0 = auto
-    int a_l2 = 0, b_l2 = 0, out_l2 = 0;   // L2 eviction hint for the A / B operand loads and the output tile stores (bf16 TMA
-                                   // path): 0 = none, 1 = evict-first (streamed once), 2 = evict-last (read back next)
     int cta_pair = 0;              // 0 = auto (256 x 256 CTA-pair tiles when N > 128), 2 = single-CTA tiles
     int reserve_sms = 0;           // leave this many SMs without a persistent CTA (room for a concurrent collective)
     int pdl = 0;                   // 1: the previous launch in the stream is one of ours: programmatic dependent launch;

@@ -55,7 +55,14 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-// (the hinted CTA-pair TMA load itself lives in common.cuh: tma_load_3d_2sm_hint)
+__device__ __forceinline__ void tma_load_3d_2sm_hint(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                                     uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
 
 __global__ void __launch_bounds__(K_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG, const KnnArgs args) {

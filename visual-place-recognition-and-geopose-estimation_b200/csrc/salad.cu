@@ -299,17 +299,6 @@ static size_t sink_bwd_smem(int n, int m, int iters) {
             (size_t)iters * (m + 1) + 256) * sizeof(float);
 }
 
-// L2 eviction hints on the three big GEMMs' operand streams: opt-in (VPR_GEMM_L2HINT=1, read once).  Measured on B200,
-// same box, alternating runs: 0.4445 ms/step with them against 0.4211 without -- an operand tile is shared by the 3-4
-// CTAs that hold the other column tiles of the same rows, and marked evict-first it is gone before the last of them has
-// pulled it (dW0 78 -> 100 us, dX 78 -> 94 us, H 92 -> 96 us).  The hints that pay are on the kernels whose streams
-// really have a single reader (fs_fwd, dh_fused).
-static bool gemm_l2_hints() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("VPR_GEMM_L2HINT"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
-
 // Threads per image of the register-tile Sinkhorn kernels (n <= 256): 512 = two per token row (default), 256 = one per
 // row (VPR_SINK_RT=2), 0 = stay on the shared-memory-tile kernels of sinkhorn_scaled.cuh (VPR_SINK_RT=0; A/B timing, and
 // the parity test that keeps that path covered at n <= 256).  Read at every call.
@@ -689,8 +678,6 @@ static int salad_fwd_t(const VprSaladParams& p, const T* x, const T* t, T* out, 
     g[0].A = x; g[0].lda = s.d; g[0].B = w0cat; g[0].ldb = s.d; g[0].M = (int)Tk; g[0].N = 2 * h; g[0].K = s.d;
     g[0].out = H; g[0].out_kind = okT; g[0].ldo = 2 * h; g[0].bias = b0cat; g[0].relu = 1;
     g[0].dropout_p = drop_p; g[0].dropout_seed = seed; g[0].dropout_seed_dev = seed_dev;
-    if (gemm_l2_hints()) { g[0].a_l2 = 1; g[0].b_l2 = 2; g[0].out_l2 = 2; }   // X streams through, W0cat and H (read back by
-                                                                             // the next launch) stay
     g[1] = GemmDesc(); g[1].dtype = dtype;
     g[1].A = t; g[1].lda = s.d; g[1].B = wt0; g[1].ldb = s.d; g[1].M = s.B; g[1].N = h; g[1].K = s.d;
     g[1].out = HT; g[1].out_kind = okT; g[1].ldo = h; g[1].bias = p.token_b0; g[1].relu = 1;
@@ -934,7 +921,6 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
             g4[half].A = dH + half * h; g4[half].a_mn = 1; g4[half].lda = 2 * h; g4[half].B = x; g4[half].b_mn = 1; g4[half].ldb = s.d;
             g4[half].M = h; g4[half].N = s.d; g4[half].K = (int)Tk;
             g4[half].out = half == 0 ? gr.cluster_w0 : gr.score_w0; g4[half].out_kind = OUT_ATOMIC_F32; g4[half].ldo = s.d;
-            if (gemm_l2_hints()) { g4[half].a_l2 = 2; g4[half].b_l2 = 1; }   // dH is read again by the dX launch, X is not
         }
         g4[2] = GemmDesc(); g4[2].dtype = dtype;
         g4[2].A = dHT; g4[2].a_mn = 1; g4[2].lda = h; g4[2].B = t; g4[2].b_mn = 1; g4[2].ldb = s.d; g4[2].M = h; g4[2].N = s.d; g4[2].K = s.B;
@@ -962,7 +948,6 @@ static int salad_bwd_t(const VprSaladParams& p, const T* x, const T* t, const T*
             g[cnt] = GemmDesc(); g[cnt].dtype = dtype;
             g[cnt].A = dH; g[cnt].lda = 2 * h; g[cnt].B = w0cat; g[cnt].b_mn = 1; g[cnt].ldb = s.d; g[cnt].M = (int)Tk; g[cnt].N = s.d;
             g[cnt].K = 2 * h; g[cnt].out = dx; g[cnt].out_kind = okT; g[cnt].ldo = s.d;
-            if (gemm_l2_hints()) { g[cnt].a_l2 = 1; g[cnt].b_l2 = 2; }       // last use of dH; W0cat is every tile's operand
             g[cnt].reserve_sms = reserve_sms;
             g[cnt].pdl = phase == VPR_BWD_ALL ? 2 : 0;     // one-call form: follows the dW0 launch, reads nothing it writes
             ++cnt;
