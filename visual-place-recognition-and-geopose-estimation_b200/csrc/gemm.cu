@@ -224,7 +224,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     // per-problem arguments in shared memory: dynamically indexed by every role without touching param space
     TcArgs* sargs = reinterpret_cast<TcArgs*>(smem_al + (bar_base + 256 - smem_base));
 
-    const int warp = threadIdx.x >> 5;
+    // warp index through a shuffle: the compiler then knows every branch on it is warp-uniform (uniform datapath, no
+    // per-lane election loops around the single-thread instructions of the producer and MMA warps)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = CL2 ? cluster_ctarank() : 0u;      // 0 = leader of the pair (issues the MMAs)
     const int w_first = CL2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -292,7 +294,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
     if (warp == W_PROD) {
         // ------------------------------ TMA producer ------------------------------
-        if (lane == 0) {
+        // The WHOLE warp walks the loop (convergent control flow: addresses and coordinates live in uniform registers);
+        // one elected lane issues.  With `if (lane == 0)` around the loop every cp.async.bulk.tensor / tcgen05.mma /
+        // tcgen05.commit was wrapped in an ELECT + 5-7 x R2UR + branch sequence (the operands of those instructions must be
+        // uniform, and inside a divergent region the compiler has to re-establish that each time): ~70 issue slots per
+        // k-block for the producer and ~100 for the MMA warp, against 512 clocks of MMA work per k-block.
+        {
             int stage = 0;
             uint32_t phase = 0;
             int mit = 0;                                  // masked tiles so far (mask buffer = mit & 1)
@@ -311,10 +318,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     mbar_wait(mempty_bar(mb), ((uint32_t)(mit >> 1) & 1u) ^ 1u);
                     int nbox = (sargs[g].N - nt * BN + 63) / 64;
                     if (nbox > Cfg::MASK_BOXES) nbox = Cfg::MASK_BOXES;
-                    mbar_expect_tx(mfull_bar(mb), (uint32_t)nbox * BOX_BYTES);
-                    for (int bx = 0; bx < nbox; ++bx)
-                        tma_load_3d(mask_base + (uint32_t)(mb * Cfg::MASK_BOXES + bx) * BOX_BYTES, &grp.p[g].tmM,
-                                    mfull_bar(mb), nt * BN + bx * 64, mt * BM, b);
+                    if (elect_one()) {
+                        mbar_expect_tx(mfull_bar(mb), (uint32_t)nbox * BOX_BYTES);
+                        for (int bx = 0; bx < nbox; ++bx)
+                            tma_load_3d(mask_base + (uint32_t)(mb * Cfg::MASK_BOXES + bx) * BOX_BYTES, &grp.p[g].tmM,
+                                        mfull_bar(mb), nt * BN + bx * 64, mt * BM, b);
+                    }
                     ++mit;
                 }
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -322,6 +331,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + A_STAGE_BYTES;
                     const uint32_t fb = full0 + 8u * stage;
+                    if (elect_one()) {
                     if (!CTA2 || cta_rank == 0) mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * (CTA2 ? 2 : 1));
                     auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2) {
                         if (CTA2) tma_load_3d_2sm(dst, tm, fb, c0, c1, c2);
@@ -345,13 +355,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     } else {
                         load_b(sbh, tmB, kb * BK, n0, bb);
                     }
+                    }   // elected lane
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == W_MMA) {
         // ------------------------------ MMA issuer ------------------------------
-        if (lane == 0 && (cta_rank == 0 || MCB)) {
+        if (cta_rank == 0 || MCB) {            // whole warp, one elected lane issues (see the producer)
             constexpr uint32_t idesc = make_idesc_bf16(CTA2 ? 2 * BM : BM, BN, A_MN, B_MN);
             constexpr uint32_t A_LBO = A_MN ? 8192u : 16u;
             constexpr uint32_t B_LBO = B_MN ? 8192u : 16u;
@@ -373,20 +384,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + A_STAGE_BYTES;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t ad = make_smem_desc(sa + k * A_KSTEP, A_LBO, 1024u);
-                        const uint64_t bd = make_smem_desc(sb + k * B_KSTEP, B_LBO, 1024u);
-                        if (CTA2) tc_mma_bf16_2sm(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                        else tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t ad = make_smem_desc(sa + k * A_KSTEP, A_LBO, 1024u);
+                            const uint64_t bd = make_smem_desc(sb + k * B_KSTEP, B_LBO, 1024u);
+                            if (CTA2) tc_mma_bf16_2sm(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            else tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
+                        if (CTA2) tc_commit_2sm(empty_bar(stage), 3);     // frees the stage in both CTAs
+                        else if (MCB) tc_commit_mc(empty_bar(stage), 3);  // one of the two releases each CTA's producer waits for
+                        else tc_commit(empty_bar(stage));
                     }
-                    if (CTA2) tc_commit_2sm(empty_bar(stage), 3);     // frees the stage in both CTAs
-                    else if (MCB) tc_commit_mc(empty_bar(stage), 3);  // one of the two releases each CTA's producer waits for
-                    else tc_commit(empty_bar(stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                if (CTA2) tc_commit_2sm(tfull_bar(as), 3);
-                else tc_commit(tfull_bar(as));
+                if (elect_one()) {
+                    if (CTA2) tc_commit_2sm(tfull_bar(as), 3);
+                    else tc_commit(tfull_bar(as));
+                }
             }
         }
     } else {
