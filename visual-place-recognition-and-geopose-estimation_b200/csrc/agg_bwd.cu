@@ -80,7 +80,9 @@ agg_bwd_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ 
     uint8_t* smem_al = smem_raw + (base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - base));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: provably warp-uniform (see gemm.cu: single-thread instructions then take uniform-register
+    // operands directly instead of an election loop each)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int b = blockIdx.x;
     const int chunks = (args.n + 127) / 128;
 

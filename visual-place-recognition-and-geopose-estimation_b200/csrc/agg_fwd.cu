@@ -67,7 +67,9 @@ agg_fwd_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
     uint8_t* smem_al = smem_raw + (base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - base));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: provably warp-uniform (see gemm.cu: single-thread instructions then take uniform-register
+    // operands directly instead of an election loop each)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int b = blockIdx.x;
     const int chunks = (args.n + 127) / 128;
 
@@ -90,11 +92,11 @@ agg_fwd_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
     pdl_launch_dependents();
 
     if (warp == AG_W_PROD) {
-        if (lane == 0) {
-            for (int ch = 0; ch < chunks; ++ch) {
-                const int s = ch % AG_STAGES;
-                mbar_wait(empty(s), (((uint32_t)(ch / AG_STAGES)) & 1u) ^ 1u);
-                const uint32_t st = base + (uint32_t)s * AG_STAGE;
+        for (int ch = 0; ch < chunks; ++ch) {                // whole warp, one elected lane issues
+            const int s = ch % AG_STAGES;
+            mbar_wait(empty(s), (((uint32_t)(ch / AG_STAGES)) & 1u) ^ 1u);
+            const uint32_t st = base + (uint32_t)s * AG_STAGE;
+            if (elect_one()) {
                 mbar_expect_tx(full(s), AG_STAGE);
                 tma_load_3d(st, &tmF, full(s), 0, ch * 128, b);                  // rows beyond n are zero-filled
                 tma_load_3d(st + AG_BOX, &tmF, full(s), 64, ch * 128, b);
@@ -102,21 +104,21 @@ agg_fwd_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ 
             }
         }
     } else if (warp == AG_W_MMA) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, 64, true, true);
-            for (int ch = 0; ch < chunks; ++ch) {
-                const int s = ch % AG_STAGES;
-                mbar_wait(full(s), ((uint32_t)(ch / AG_STAGES)) & 1u);
-                tc_fence_after();
-                const uint32_t st = base + (uint32_t)s * AG_STAGE;
+        constexpr uint32_t idesc = make_idesc_bf16(128, 64, true, true);
+        for (int ch = 0; ch < chunks; ++ch) {
+            const int s = ch % AG_STAGES;
+            mbar_wait(full(s), ((uint32_t)(ch / AG_STAGES)) & 1u);
+            tc_fence_after();
+            const uint32_t st = base + (uint32_t)s * AG_STAGE;
+            if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
                     tc_mma_bf16(tmem_base, make_smem_desc(st + ks * 2048, AG_BOX, 1024u),
                                 make_smem_desc(st + 2 * AG_BOX + ks * 2048, AG_BOX, 1024u), idesc, (ch > 0 || ks > 0) ? 1u : 0u);
                 tc_commit(empty(s));
             }
-            tc_commit(tfull);
         }
+        if (elect_one()) tc_commit(tfull);
     } else {
         // ------------------------------ epilogue: thread = cluster-feature row l ------------------------------
         const int l = warp * 32 + lane;

@@ -83,7 +83,9 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
     uint8_t* smem_al = smem_raw + (base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - base));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: provably warp-uniform, so the producer and MMA warps run their loops convergently with
+    // uniform-register operands and one elected lane issuing (see gemm.cu)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     // this CTA's hidden-layer column slice and its share of the token tiles
     const int nct = 2 * args.ct_per_half;
     const int ct = (int)blockIdx.x % nct;
@@ -124,41 +126,49 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
     // Programmatic dependent launch: everything above overlapped the previous launch's tail.  The resident W1 slice
     // comes from the parameter pack of the forward pass (many launches back), so the producer fetches it before it
     // waits for the previous launch (the Sinkhorn backward, which produces dS) to complete.
-    if (!(warp == DH_W_PROD && lane == 0)) { pdl_wait(); pdl_launch_dependents(); }
+    if (warp != DH_W_PROD) { pdl_wait(); pdl_launch_dependents(); }
 
     if (warp == DH_W_PROD) {
         // ------------------------------ TMA producer ------------------------------
-        if (lane == 0) {
+        {   // whole warp, one elected lane issues
             const CUtensorMap* tmA = half == 0 ? &tmF : &tmS;
             const CUtensorMap* tmB = half == 0 ? &tmW1c : &tmW1s;
             // resident W1 slice, MN-major: per 64-row k-block two boxes of 64 h-columns
-            mbar_expect_tx(bfull, (uint32_t)kboxes * DH_BOX);
-            for (int kb = 0; kb < kboxes; ++kb)
-                for (int i = 0; i < 2; ++i)
-                    tma_load_3d(sB + (uint32_t)kb * DH_BOX + (uint32_t)i * 8192u, tmB, bfull, cn * 128 + i * 64, kb * 64, 0);
+            if (elect_one()) {
+                mbar_expect_tx(bfull, (uint32_t)kboxes * DH_BOX);
+                for (int kb = 0; kb < kboxes; ++kb)
+                    for (int i = 0; i < 2; ++i)
+                        tma_load_3d(sB + (uint32_t)kb * DH_BOX + (uint32_t)i * 8192u, tmB, bfull, cn * 128 + i * 64, kb * 64, 0);
+            }
+            __syncwarp();
             pdl_wait();
             pdl_launch_dependents();
+            const uint64_t pol_h = l2_evict_first_policy();
             int it = 0;
             for (int mt = j0; mt < args.tiles_m; mt += nj, ++it) {
                 const int s = it & 1;
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(aempty(s), ph ^ 1u);
-                mbar_expect_tx(afull(s), (uint32_t)kboxes * DH_BOX);
-                for (int kb = 0; kb < kboxes; ++kb)
-                    tma_load_3d(sA + (uint32_t)s * DH_A_STAGE + (uint32_t)kb * DH_BOX, tmA, afull(s), kb * 64, mt * 128, 0);
+                if (elect_one()) {
+                    mbar_expect_tx(afull(s), (uint32_t)kboxes * DH_BOX);
+                    for (int kb = 0; kb < kboxes; ++kb)
+                        tma_load_3d(sA + (uint32_t)s * DH_A_STAGE + (uint32_t)kb * DH_BOX, tmA, afull(s), kb * 64, mt * 128, 0);
+                }
                 mbar_wait(mempty(s), ph ^ 1u);
-                mbar_expect_tx(mfull(s), DH_MASK_BYTES);
-                for (int i = 0; i < 2; ++i)
-                    if (args.l2_hints != 0)
-                        tma_load_3d_hint(sM + (uint32_t)s * DH_MASK_BYTES + (uint32_t)i * DH_BOX, &tmH, mfull(s), col0 + i * 64, mt * 128, 0,
-                                         l2_evict_first_policy());
-                    else
-                        tma_load_3d(sM + (uint32_t)s * DH_MASK_BYTES + (uint32_t)i * DH_BOX, &tmH, mfull(s), col0 + i * 64, mt * 128, 0);
+                if (elect_one()) {
+                    mbar_expect_tx(mfull(s), DH_MASK_BYTES);
+                    for (int i = 0; i < 2; ++i)
+                        if (args.l2_hints != 0)
+                            tma_load_3d_hint(sM + (uint32_t)s * DH_MASK_BYTES + (uint32_t)i * DH_BOX, &tmH, mfull(s), col0 + i * 64, mt * 128, 0,
+                                             pol_h);
+                        else
+                            tma_load_3d(sM + (uint32_t)s * DH_MASK_BYTES + (uint32_t)i * DH_BOX, &tmH, mfull(s), col0 + i * 64, mt * 128, 0);
+                }
             }
         }
     } else if (warp == DH_W_MMA) {
         // ------------------------------ MMA issuer ------------------------------
-        if (lane == 0) {
+        {   // whole warp waits, one elected lane issues
             constexpr uint32_t idesc1 = make_idesc_bf16(128, 128, false, true);    // dH: A K-major, B MN-major
             constexpr uint32_t idesc2 = make_idesc_bf16(128, 128, true, true);     // dW1: both MN-major views
             constexpr uint32_t idesc3 = make_idesc_bf16(128, 16, true, false);     // column sums: A MN-major, ones K-major
@@ -170,13 +180,15 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
                 const int sb = tile_it & 1;
                 mbar_wait(sfull(sb), (uint32_t)(tile_it >> 1) & 1u);
                 tc_fence_after();
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const uint64_t ad = make_smem_desc(sStage + (uint32_t)sb * DH_STAGE_BYTES + ks * 2048, DH_BOX, 1024u);
-                    const uint64_t bd = make_smem_desc(sOnes + (ks & 3) * 32, 16u, 1024u);
-                    tc_mma_bf16(tmem_base + DH_TM_D3, ad, bd, idesc3, (tile_it > 0 || ks > 0) ? 1u : 0u);
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint64_t ad = make_smem_desc(sStage + (uint32_t)sb * DH_STAGE_BYTES + ks * 2048, DH_BOX, 1024u);
+                        const uint64_t bd = make_smem_desc(sOnes + (ks & 3) * 32, 16u, 1024u);
+                        tc_mma_bf16(tmem_base + DH_TM_D3, ad, bd, idesc3, (tile_it > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    tc_commit(sdone(sb));
                 }
-                tc_commit(sdone(sb));
             };
             for (int mt = j0; mt < args.tiles_m; mt += nj, ++it) {
                 const int s = it & 1;
@@ -186,38 +198,42 @@ dh_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
                 mbar_wait(afull(s), ph);
                 tc_fence_after();
                 // dH tile: D1[token, h] = sum_k A[token, k] W1[k, h]
-                for (int kb = 0; kb < kboxes; ++kb)
+                if (elect_one()) {
+                    for (int kb = 0; kb < kboxes; ++kb)
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t ad = make_smem_desc(a_s + (uint32_t)kb * DH_BOX + ks * 32, 16u, 1024u);
-                        const uint64_t bd = make_smem_desc(sB + (uint32_t)kb * DH_BOX + ks * 2048, 8192u, 1024u);
-                        tc_mma_bf16(tmem_base + (uint32_t)(s * 128), ad, bd, idesc1, (kb > 0 || ks > 0) ? 1u : 0u);
-                    }
-                tc_commit(tfull(s));
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t ad = make_smem_desc(a_s + (uint32_t)kb * DH_BOX + ks * 32, 16u, 1024u);
+                            const uint64_t bd = make_smem_desc(sB + (uint32_t)kb * DH_BOX + ks * 2048, 8192u, 1024u);
+                            tc_mma_bf16(tmem_base + (uint32_t)(s * 128), ad, bd, idesc1, (kb > 0 || ks > 0) ? 1u : 0u);
+                        }
+                    tc_commit(tfull(s));
+                }
                 // dW1 slice: D2[l, h] += sum_token A[token, l] H[token, h]   (same bytes, MN-major views)
                 mbar_wait(mfull(s), ph);
                 tc_fence_after();
                 const uint32_t m_s = sM + (uint32_t)s * DH_MASK_BYTES;
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const uint64_t ad = make_smem_desc(a_s + ks * 2048, DH_BOX, 1024u);
-                    const uint64_t bd = make_smem_desc(m_s + ks * 2048, DH_BOX, 1024u);
-                    tc_mma_bf16(tmem_base + DH_TM_D2, ad, bd, idesc2, (it > 0 || ks > 0) ? 1u : 0u);
-                }
-                if (do_db1) {                              // D4[l, .] += sum_token dF[token, l]
+                if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
                         const uint64_t ad = make_smem_desc(a_s + ks * 2048, DH_BOX, 1024u);
-                        const uint64_t bd = make_smem_desc(sOnes + (ks & 3) * 32, 16u, 1024u);
-                        tc_mma_bf16(tmem_base + DH_TM_D4, ad, bd, idesc3, (it > 0 || ks > 0) ? 1u : 0u);
+                        const uint64_t bd = make_smem_desc(m_s + ks * 2048, DH_BOX, 1024u);
+                        tc_mma_bf16(tmem_base + DH_TM_D2, ad, bd, idesc2, (it > 0 || ks > 0) ? 1u : 0u);
                     }
+                    if (do_db1) {                              // D4[l, .] += sum_token dF[token, l]
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+                            const uint64_t ad = make_smem_desc(a_s + ks * 2048, DH_BOX, 1024u);
+                            const uint64_t bd = make_smem_desc(sOnes + (ks & 3) * 32, 16u, 1024u);
+                            tc_mma_bf16(tmem_base + DH_TM_D4, ad, bd, idesc3, (it > 0 || ks > 0) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(aempty(s));
+                    tc_commit(mempty(s));
                 }
-                tc_commit(aempty(s));
-                tc_commit(mempty(s));
                 if (it > 0) colsum_mma(it - 1);
             }
             if (it > 0) colsum_mma(it - 1);
-            tc_commit(accdone);
+            if (elect_one()) tc_commit(accdone);
         }
     } else {
         // ------------------------------ epilogue ------------------------------

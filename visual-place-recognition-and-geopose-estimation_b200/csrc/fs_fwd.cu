@@ -49,7 +49,9 @@ fs_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sB = base;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: provably warp-uniform (see gemm.cu: single-thread instructions then take uniform-register
+    // operands directly instead of an election loop each)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     // what this CTA computes: 0 = F (cluster features), 1 = S (scores), 2 = TF (token features, half `thalf`)
     const int cta = (int)blockIdx.x;
     const int kind = cta < args.ctas_f ? 0 : cta < args.ctas_f + args.ctas_s ? 1 : 2;
@@ -93,16 +95,19 @@ fs_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
     const uint32_t tmem_base = *tmem_slot_ptr;
     // Programmatic dependent launch: everything above overlapped the previous launch's tail; the resident weights come
     // from the parameter pack (two launches back), so the producer fetches them before it waits for H to be complete.
-    if (!(warp == FS_W_PROD && lane == 0)) { pdl_wait(); pdl_launch_dependents(); }
+    if (warp != FS_W_PROD) { pdl_wait(); pdl_launch_dependents(); }
     const bool rev = args.rev != 0 && kind != 2;
     auto row_tile = [&](int mt) { return rev ? tiles_m - 1 - mt : mt; };
 
     if (warp == FS_W_PROD) {
-        if (lane == 0) {
+        {   // whole warp, one elected lane issues
             // resident weights, K-major: k-block kb = [nrows x 64 k] at sB + kb * nrows * 128
-            mbar_expect_tx(bfull, (uint32_t)(FS_KB * nrows * 128));
-            for (int kb = 0; kb < FS_KB; ++kb)
-                tma_load_3d(sB + (uint32_t)(kb * nrows * 128), tmB, bfull, kb * 64, thalf * 128, 0);
+            if (elect_one()) {
+                mbar_expect_tx(bfull, (uint32_t)(FS_KB * nrows * 128));
+                for (int kb = 0; kb < FS_KB; ++kb)
+                    tma_load_3d(sB + (uint32_t)(kb * nrows * 128), tmB, bfull, kb * 64, thalf * 128, 0);
+            }
+            __syncwarp();
             pdl_wait();
             pdl_launch_dependents();
             int stage = 0; uint32_t phase = 0;
@@ -113,14 +118,16 @@ fs_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
             for (int mt = j0; mt < tiles_m; mt += nj)
                 for (int kb = 0; kb < FS_KB; ++kb) {
                     mbar_wait(aempty(stage), phase ^ 1u);
-                    mbar_expect_tx(afull(stage), FS_A_STAGE);
-                    if (hint) tma_load_3d_hint(sA + (uint32_t)stage * FS_A_STAGE, tmA, afull(stage), koff + kb * 64, row_tile(mt) * 128, 0, pol_h);
-                    else tma_load_3d(sA + (uint32_t)stage * FS_A_STAGE, tmA, afull(stage), koff + kb * 64, row_tile(mt) * 128, 0);
+                    if (elect_one()) {
+                        mbar_expect_tx(afull(stage), FS_A_STAGE);
+                        if (hint) tma_load_3d_hint(sA + (uint32_t)stage * FS_A_STAGE, tmA, afull(stage), koff + kb * 64, row_tile(mt) * 128, 0, pol_h);
+                        else tma_load_3d(sA + (uint32_t)stage * FS_A_STAGE, tmA, afull(stage), koff + kb * 64, row_tile(mt) * 128, 0);
+                    }
                     if (++stage == nstages) { stage = 0; phase ^= 1u; }
                 }
         }
     } else if (warp == FS_W_MMA) {
-        if (lane == 0) {
+        {   // whole warp waits, one elected lane issues
             const uint32_t idesc = make_idesc_bf16(128, nrows, false, false);
             mbar_wait(bfull, 0);
             tc_fence_after();
@@ -134,14 +141,16 @@ fs_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
                     tc_fence_after();
                     const uint32_t a_s = sA + (uint32_t)stage * FS_A_STAGE;
                     const uint32_t b_s = sB + (uint32_t)(kb * nrows * 128);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        tc_mma_bf16(tmem_base + (uint32_t)(as * 128), make_smem_desc(a_s + ks * 32, 16u, 1024u),
-                                    make_smem_desc(b_s + ks * 32, 16u, 1024u), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-                    tc_commit(aempty(stage));
+                        for (int ks = 0; ks < 4; ++ks)
+                            tc_mma_bf16(tmem_base + (uint32_t)(as * 128), make_smem_desc(a_s + ks * 32, 16u, 1024u),
+                                        make_smem_desc(b_s + ks * 32, 16u, 1024u), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                        tc_commit(aempty(stage));
+                    }
                     if (++stage == nstages) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(tfull(as));
+                if (elect_one()) tc_commit(tfull(as));
             }
         }
     } else {

@@ -79,7 +79,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t tmem_slot = bar_base + 8u * (2 * K_STAGES + 4);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: branches on it are provably warp-uniform, so the producer and MMA warps below run their
+    // loops convergently with uniform-register operands and one elected lane issuing (see gemm.cu)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t cta_rank = cluster_ctarank();                 // 0 = leader of the pair
     const int w_first = (int)(blockIdx.x >> 1), w_step = (int)(gridDim.x >> 1);
     if (warp == K_W_PROD && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmG); }
@@ -119,7 +121,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     };
 
     if (warp == K_W_PROD) {
-        if (lane == 0) {
+        {
             int stage = 0; uint32_t phase = 0;
             const uint32_t full0 = mapa_shared(full_bar(0), 0u);     // both producers credit the leader's barrier
             const uint64_t pol_q = l2_policy_evict_last(), pol_g = l2_policy_evict_first();
@@ -140,6 +142,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 for (int nt = nt0; nt < nt1; ++nt)
                     for (int kb = 0; kb < args.kb_total; ++kb, ++kbi) {
                         if (paced && kbi % args.throttle == 0) {
+                          if (elect_one()) {
                             const int step = kbi / args.throttle;
                             prog[me] = step + 1;                                     // "I am issuing step `step`"
                             if (step > 0) {
@@ -154,18 +157,22 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                                         }
                                     }
                             }
+                          }
+                          __syncwarp();                                              // the other lanes wait for the paced one
                         }
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         const uint32_t sa = smem_base + stage * K_STAGE_BYTES, sb = sa + K_A_BYTES;
-                        if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * K_STAGE_BYTES);
-                        tma_load_3d_2sm_hint(sa, &tmQ, full0 + 8u * stage, kb * KBK, q0, 0, pol_q);
-                        tma_load_3d_2sm_hint(sb, &tmG, full0 + 8u * stage, kb * KBK, nt * KBN + (int)cta_rank * (KBN / 2), 0, pol_g);
+                        if (elect_one()) {
+                            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * K_STAGE_BYTES);
+                            tma_load_3d_2sm_hint(sa, &tmQ, full0 + 8u * stage, kb * KBK, q0, 0, pol_q);
+                            tma_load_3d_2sm_hint(sb, &tmG, full0 + 8u * stage, kb * KBK, nt * KBN + (int)cta_rank * (KBN / 2), 0, pol_g);
+                        }
                         if (++stage == K_STAGES) { stage = 0; phase ^= 1u; }
                     }
             }
         }
     } else if (warp == K_W_MMA) {
-        if (lane == 0 && cta_rank == 0) {
+        if (cta_rank == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(K_TILE_M, KBN, false, false);
             int stage = 0; uint32_t phase = 0; int it = 0;
             for (int w = w_first; w < total_work; w += w_step) {
@@ -181,14 +188,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_base + stage * K_STAGE_BYTES, sb = sa + K_A_BYTES;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < KBK / 16; ++k)
-                            tc_mma_bf16_2sm(d_tmem, make_smem_desc(sa + k * 32, 16u, 1024u),
-                                            make_smem_desc(sb + k * 32, 16u, 1024u), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        tc_commit_2sm(empty_bar(stage), 3);
+                            for (int k = 0; k < KBK / 16; ++k)
+                                tc_mma_bf16_2sm(d_tmem, make_smem_desc(sa + k * 32, 16u, 1024u),
+                                                make_smem_desc(sb + k * 32, 16u, 1024u), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            tc_commit_2sm(empty_bar(stage), 3);
+                        }
                         if (++stage == K_STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    tc_commit_2sm(tfull_bar(as), 3);
+                    if (elect_one()) tc_commit_2sm(tfull_bar(as), 3);
                 }
             }
         }

@@ -112,7 +112,8 @@ sink_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
     const uint32_t fullF0 = base + SA_BAR, fullF1 = fullF0 + 8, tfull = fullF0 + 16, tmem_slot = fullF0 + 24;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + SA_BAR + 24);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform (see gemm.cu)
     const int b = blockIdx.x;
     const int chunks = (a.n + 127) / 128;
 
