@@ -463,7 +463,7 @@ def test_graphed_finetune_step_with_huber_and_both_dropouts_redraws_masks(vpr):
 
 
 @pytest.mark.parametrize("env", [{"VPR_DH_FUSED": "0", "VPR_FS_FUSED": "0", "VPR_AGG_FUSED": "0"},
-                                 {"VPR_GEMM_2CTA": "0"}, {"VPR_GEMM_MCB": "1", "VPR_FS_REVERSE": "0"}])
+                                 {"VPR_GEMM_2CTA": "0"}, {"VPR_GEMM_MCB": "0", "VPR_FS_REVERSE": "0", "VPR_FS_L2HINT": "0", "VPR_DH_L2HINT": "0"}])
 def test_generic_paths_still_match_when_the_fused_kernels_are_switched_off(vpr, env):
     """The default head shape runs the column-owner / per-image fused kernels and CTA-pair tiles; other shapes fall
     back to the generic grouped GEMMs.  Switch the fused kernels off (environment knobs read once per process, hence

@@ -764,9 +764,11 @@ static int auto_bn(int N) { return (N > 128) ? 256 : (N > 64) ? 128 : 64; }
 // when that does not inflate the MMA work (short-M problems would leave the peer CTA's rows empty).
 static bool mcb_enabled() {
     static int v = -1;
-    // measured (B200, H = dropout(relu(X W0cat^T + b)) in the graphed step): 97.6 us with the multicast clusters vs
-    // 96.0 us with independent CTAs -- the L2->SM fabric is not what limits this launch -- so it stays opt-in
-    if (v < 0) { const char* e = getenv("VPR_GEMM_MCB"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }
+    // measured (B200, H = dropout(relu(X W0cat^T + b)) in the graphed step).  Round 1, election loops around every TMA /
+    // MMA instruction: 97.6 us with the multicast clusters vs 96.0 us with independent CTAs, so it was opt-in.  With the
+    // convergent producer / MMA warps the order flips: 0.3769 vs 0.3783 ms/step (two alternating pairs of runs, same box),
+    // so it is on unless VPR_GEMM_MCB=0.
+    if (v < 0) { const char* e = getenv("VPR_GEMM_MCB"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
     return v == 1;
 }
 
