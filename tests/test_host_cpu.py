@@ -181,6 +181,26 @@ def test_reference_model_wrapper_and_checkpoint_layout(built, tmp_path):
         built.load_upstream_salad_weights(head, {"state_dict": {"backbone.x": torch.zeros(1)}})
 
 
+def test_single_thread_roles_issue_from_uniform_registers(built):
+    """Regression guard for DESIGN.md 4.1: a TMA / tcgen05 instruction issued from inside `if (lane == 0) { loop }` gets
+    wrapped by the compiler in an election loop (ELECT, R2UR.BROADCAST x 5-7, branch) because its operands must be uniform
+    registers -- ~100 serial issue slots per k-block, which used to make the MMA issuer co-critical with the tensor pipe
+    (0.414 -> 0.391 ms/step, kNN 55 k -> 60 k queries/s when they went).  R2UR.BROADCAST appears nowhere else, so: none
+    of it in the kernels that run by default.  (sink_agg_fwd.cu is opt-in and keeps its single issuing lane.)"""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    obj_dir = os.path.join(ROOT, "visual-place-recognition-and-geopose-estimation_b200", "build")
+    for name in ("gemm", "knn", "dh_fused", "fs_fwd", "agg_fwd", "agg_bwd"):
+        obj = os.path.join(obj_dir, name + ".o")
+        if not os.path.exists(obj):
+            pytest.skip("object files not kept on this box (prebuilt library)")
+        sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
+        assert "UTCHMMA" in sass, name                       # the tensor-core path is there at all
+        assert sass.count("R2UR.BROADCAST") == 0, f"{name}.cu: a single-thread role issues from a divergent region again"
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "visual-place-recognition-and-geopose-estimation_b200")
     for dp, _, files in os.walk(pkg):
