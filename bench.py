@@ -537,7 +537,7 @@ def run_own(args, rank, local, world):
                 traffic = json.load(open(tp_path)).get("gemm_tc_kernel_H_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<A K-major,B K-major,BN=256> (H = dropout(relu(X W0cat^T + b)), "
+        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<A K-major,B K-major,BN=256, multicast-B clusters> (H = dropout(relu(X W0cat^T + b)), "
                     f"M={T} N=1024 K=768)", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peaks["source"] + " burst",
                     "kernel_ms": k_ms,
