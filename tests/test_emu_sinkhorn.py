@@ -141,6 +141,34 @@ def test_register_tile_range_guard_asks_for_the_log_domain_body(emu, nt):
     assert guards == 1 and torch.isfinite(dS[0]).all() and torch.isnan(dS[1]).all()
 
 
+def test_register_tile_kernels_on_seeded_random_shapes(emu):
+    """Eight seeded draws of (n, score scale, dustbin, thread count, images): forward and backward against the fp64 oracle,
+    plus the marginal identity the solver's last update makes exact (token rows sum to 1 - dustbin share)."""
+    rng = torch.Generator().manual_seed(20261018)
+    for _ in range(8):
+        n = int(torch.randint(65, 257, (1,), generator=rng))
+        scale = float(torch.rand(1, generator=rng) * 5 + 0.2)
+        dust = float(torch.randn(1, generator=rng) * 3)
+        nt = 512 if int(torch.randint(0, 2, (1,), generator=rng)) else 256
+        B = int(torch.randint(1, 4, (1,), generator=rng))
+        S = torch.randn(B, 64, n, generator=rng) * scale
+        db = torch.tensor([dust])
+        Sd = S.double().requires_grad_(True)
+        Pd = O.get_matching_probs(Sd, db.double()[0], 3, const_dtype=torch.float64).exp()
+        St = S.transpose(1, 2).contiguous()
+        P, U, V, guards = run_fwd(emu, St, db, 3, nt=nt)
+        tag = (n, scale, dust, nt, B)
+        assert guards == 0, tag
+        assert rel(P, Pd[:, :64].transpose(1, 2)) < 1e-5, tag
+        assert (P.double().sum(2) - (1 - Pd[:, 64])).abs().max() < 1e-5, tag      # token marginal
+        dP = torch.randn(B, n, 64, generator=rng)
+        (Pd[:, :64] * dP.double().transpose(1, 2)).sum().backward()
+        dS = torch.full((B, n, 64), float("nan"))
+        d_bias = torch.zeros(64)
+        assert emu.emu_sinkhorn_bwd_rt3(ptr(St), ptr(db), ptr(U), ptr(V), ptr(dP), ptr(dS), 0, ptr(d_bias), B, n, nt) == 0, tag
+        assert rel(dS, Sd.grad.transpose(1, 2)) < 2e-5, tag
+
+
 @pytest.mark.parametrize("n", [256, 196, 100])
 def test_plan_written_as_the_aggregation_mma_operand(emu, n):
     """The fused Sinkhorn + aggregation kernel never reads the plan back: the row owners write it, as bf16, straight into
